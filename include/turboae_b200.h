@@ -1,0 +1,128 @@
+/*
+ * turboae_b200.h -- C ABI of libturboae_b200.so
+ *
+ * B200 (sm_100a) implementation of ONE hot path of yihanjiang/turboae: the rate-1/3 CNN
+ * encoder ENC_interCNN, the iterative CNN turbo decoder DEC_LargeCNN and the interleaver
+ * gather they share.  The reference is pure Python/PyTorch and has no FFI; every entry
+ * point below names the reference lines (paths relative to the reference checkout) whose
+ * arithmetic it replaces.  Host language above this boundary is Python
+ * (turboae_b200/*.py, loaded with ctypes); INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in _host;
+ *  - tensors are dense, row-major, float32, "channel-last" exactly as the reference's
+ *    nn.Module.forward() sees them: (B, L, C);
+ *  - calls only ENQUEUE work on `stream` (a cudaStream_t passed as void*) and never
+ *    synchronise; inputs/outputs/workspace are borrowed for the duration of that work;
+ *  - return value: 0 (TAE_OK) or a negative TAE_E* code; tae_last_error() returns a
+ *    thread-local message for the last failing call.  There is no CPU fallback.
+ */
+#ifndef TURBOAE_B200_H_
+#define TURBOAE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAE_OK            0
+#define TAE_EINVAL       -1   /* bad pointer / shape / size                            */
+#define TAE_EUNSUPPORTED -2   /* configuration outside what the kernels implement      */
+#define TAE_ECUDA        -3   /* CUDA runtime error (message has cudaGetErrorString)   */
+#define TAE_EWORKSPACE   -4   /* workspace smaller than tae_*_workspace_bytes() asks   */
+
+#define TAE_PRECISION_FP32 0  /* CUDA-core fp32 FMA path: elementwise parity (<=1e-4)  */
+#define TAE_PRECISION_BF16 1  /* tcgen05 bf16 operands, fp32 TMEM accumulation          */
+
+/* Shape of a DEC_LargeCNN (reference decoders.py:158-192; get_args.py:83-84,89-100,122). */
+typedef struct TaeDecConfig {
+  int32_t block_len;      /* L            args.block_len                                 */
+  int32_t num_iteration;  /* I            args.num_iteration                             */
+  int32_t num_iter_ft;    /* F            args.num_iter_ft                               */
+  int32_t num_layer;      /*              args.dec_num_layer                             */
+  int32_t num_unit;       /*              args.dec_num_unit                              */
+  int32_t kernel_size;    /* odd          args.dec_kernel_size                           */
+  int32_t extrinsic;      /* 0/1          args.extrinsic (decoders.py:235,246,257)       */
+} TaeDecConfig;
+
+/* Shape of an ENC_interCNN (reference encoders.py:307-337). */
+typedef struct TaeEncConfig {
+  int32_t block_len;      /* L                                                           */
+  int32_t num_layer;      /* args.enc_num_layer                                          */
+  int32_t num_unit;       /* args.enc_num_unit                                           */
+  int32_t kernel_size;    /* args.enc_kernel_size (odd)                                  */
+} TaeEncConfig;
+
+/* ---- library ------------------------------------------------------------------------ */
+int          tae_version(void);
+const char*  tae_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
+uint64_t     tae_launch_count(void);
+
+/* ---- a1/a2: Interleaver.forward / DeInterleaver.forward ----------------------------------
+ * reference interleavers.py:15-21 and :43-48.  out[b,i,f] = in[b,perm[i],f] for an int32
+ * device permutation of length L; pass the inverse permutation (rp[p[i]] = i,
+ * interleavers.py:29-33) to de-interleave.  Pure data movement: bit-exact.              */
+int tae_interleave_f32(const float* in, float* out, const int32_t* perm,
+                       int32_t B, int32_t L, int32_t F, void* stream);
+
+/* ---- a3: one layer of SameShapeConv1d.forward ---------------------------------------------
+ * reference cnn_utils.py:36-46 (conv built at :15-22): channel-last
+ * y[b,l,o] = act(bias[o] + sum_c sum_t W[o,c,t] * x[b,l+t-K/2,c]), zero padded, act = ELU
+ * (alpha 1) when apply_elu != 0.  `weight` is torch's Conv1d layout (Cout, Cin, K).
+ * `workspace` needs tae_conv1d_workspace_bytes(Cin, Cout, K) bytes.                      */
+size_t tae_conv1d_workspace_bytes(int32_t Cin, int32_t Cout, int32_t K);
+int tae_conv1d_elu_f32(const float* in, float* out, const float* weight, const float* bias,
+                       int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t K,
+                       int32_t apply_elu, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a7/a8: DEC_LargeCNN -------------------------------------------------------------------
+ * Parameters travel as ONE flat float32 buffer in canonical order:
+ *   for idx in 0..I-1: for s in (dec1, dec2):
+ *       for j in 0..num_layer-1: cnns[j].weight (Cout,Cin,K) then cnns[j].bias (Cout)
+ *       outputs[idx].weight (Fout, num_unit) then outputs[idx].bias (Fout)
+ * with Cin = 2+F for j == 0 else num_unit, Fout = F except dec2 of the last iteration
+ * (Fout = 1) -- the order of reference decoders.py:178-192.
+ */
+size_t tae_dec_param_count(const TaeDecConfig* cfg);
+/* Size of / conversion into the bf16 tensor-core weight image (UMMA canonical K-major
+ * layout, zero padded), consumed by TAE_PRECISION_BF16.  Rebuild after every weight update. */
+size_t tae_dec_packed_bytes(const TaeDecConfig* cfg);
+int    tae_dec_pack_bf16(const TaeDecConfig* cfg, const float* params, void* packed, void* stream);
+size_t tae_dec_workspace_bytes(const TaeDecConfig* cfg, int32_t B, int32_t precision);
+/* DEC_LargeCNN.forward, reference decoders.py:206-269.
+ *   received (B,L,3) -> out (B,L,1) = sigmoid posteriors.
+ *   perm / inv_perm: int32[L] device arrays (Interleaver / DeInterleaver index).
+ *   packed: result of tae_dec_pack_bf16 (may be NULL for TAE_PRECISION_FP32).
+ *   trace: NULL, or (2I, B, L, F) floats receiving the output of every dec{1,2}_outputs
+ *          Linear before the extrinsic subtraction (last one has 1 feature, stored in [..,0]). */
+int tae_dec_forward(const TaeDecConfig* cfg, const float* params, const void* packed,
+                    const float* received, const int32_t* perm, const int32_t* inv_perm,
+                    float* out, float* trace, int32_t B, int32_t precision,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a4/a5/a6: ENC_interCNN ----------------------------------------------------------------
+ * Flat parameter order: for branch in 1..3: for j: enc_cnn_b.cnns[j].weight, .bias; then
+ * enc_linear_b.weight (1,num_unit), .bias (1)   (reference encoders.py:314-335).
+ */
+size_t tae_enc_param_count(const TaeEncConfig* cfg);
+size_t tae_enc_workspace_bytes(const TaeEncConfig* cfg, int32_t B);
+/* Branches + concat, reference encoders.py:362-373: u (B,L,1) in {0,1} -> x_tx (B,L,3),
+ * NOT yet normalised.  Adds (sum x, sum x^2, count) of this call's x_tx into stats[0..2]
+ * (device doubles; caller zeroes them, and all-reduces them across ranks when the batch is
+ * sharded, because power_constraint normalises over the WHOLE batch).                     */
+int tae_enc_forward(const TaeEncConfig* cfg, const float* params, const float* u,
+                    const int32_t* perm, float* x_tx, double* stats, int32_t B,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* ENCBase.power_constraint default branch, reference encoders.py:107-116:
+ * codes = (x - mean) / std, mean/std (unbiased, N-1) derived on the device from stats[0..2].
+ * mean_std: NULL or 2 device floats receiving (mean, std).  x may alias codes.            */
+int tae_power_norm_f32(const float* x, float* codes, size_t n, const double* stats,
+                       float* mean_std, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TURBOAE_B200_H_ */

@@ -1,0 +1,162 @@
+"""Generate the golden fixtures under tests/golden/ by executing the UNMODIFIED
+reference (/root/reference) on CPU in the build container.
+
+    python tests/golden/make_golden.py [--sweep-blocks 10000]
+
+The reference cannot travel to the GPU box, so its outputs are committed here:
+
+  weights_c1.npz   state_dict of models/dta_cont_cnn2_cnn5_enctrain2_dectrainneg15_2.pt (enc2/dec5)
+  weights_c3.npz   state_dict of models/enc5_dec5_cont_1dBenc.pt                        (enc5/dec5)
+  kat_c1_b4.npz    SURVEY.md Appendix C known-answer run (torch.manual_seed(0), B=4)
+  io_c1_b8.npz     B=8 @ 0 dB, numpy-RandomState inputs, with every dec Linear output (hooks)
+  io_c3_b6.npz     same for the enc5/dec5 checkpoint, B=6 @ 1 dB
+  perm.npz         interleaver goldens (p, inverse, gather of arange through the reference modules)
+  ber_c1.json      12-point BER/BLER sweep (reference trainer.py:157-178 loop restated with seeded
+                   numpy inputs, batch 500) -- per-point bit/block error counts
+
+All random inputs come from numpy's legacy RandomState (stream-stable by
+numpy's compatibility policy) except the Appendix-C KAT, which stores the torch
+tensors themselves.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import compat  # noqa: E402
+
+C1_ARGS = ["-encoder", "TurboAE_rate3_cnn", "-decoder", "TurboAE_rate3_cnn", "-enc_num_unit", "100",
+           "-enc_num_layer", "2", "-enc_kernel_size", "5", "-dec_num_layer", "5", "-dec_num_unit", "100",
+           "-dec_kernel_size", "5", "-channel", "awgn", "-num_train_dec", "5", "-num_train_enc", "1",
+           "-code_rate_k", "1", "-code_rate_n", "3", "-block_len", "100", "--no-cuda"]
+C3_ARGS = [a if a != "2" or C1_ARGS[i - 1] != "-enc_num_layer" else "5" for i, a in enumerate(C1_ARGS)]
+CKPT = {"c1": "models/dta_cont_cnn2_cnn5_enctrain2_dectrainneg15_2.pt", "c3": "models/enc5_dec5_cont_1dBenc.pt"}
+
+
+def build_reference_model(cfg, batch_size):
+    compat.install()
+    args = compat.reference_args((C1_ARGS if cfg == "c1" else C3_ARGS) + ["-batch_size", str(batch_size)])
+    from numpy import arange
+    from numpy.random import mtrand
+    from encoders import ENC_interCNN          # reference main.py:35-36
+    from decoders import DEC_LargeCNN          # reference main.py:75-76
+    from channel_ae import Channel_AE
+    p_array = mtrand.RandomState(0).permutation(arange(args.block_len))   # main.py:123-127
+    enc, dec = ENC_interCNN(args, p_array), DEC_LargeCNN(args, p_array)
+    enc.set_parallel(); dec.set_parallel()      # main.py:157-159 (gives the '.module.' keys)
+    model = Channel_AE(args, enc, dec)
+    sd = torch.load(os.path.join(compat.REFERENCE_ROOT, CKPT[cfg]), weights_only=True)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    return model, args, p_array
+
+
+def gen_inputs(seed, B, L, snr_db):
+    rs = np.random.mtrand.RandomState(seed)
+    u = rs.randint(0, 2, size=(B, L, 1)).astype(np.float32)
+    sigma = 10 ** (-snr_db / 20.0)
+    noise = (sigma * rs.standard_normal((B, L, 3))).astype(np.float32)
+    return u, noise
+
+
+def dump_weights(cfg):
+    model, _, _ = build_reference_model(cfg, 4)
+    sd = {k: v.detach().cpu().numpy().astype(np.float32) for k, v in model.state_dict().items()}
+    np.savez_compressed(os.path.join(HERE, "weights_%s.npz" % cfg), **sd)
+    print("weights_%s.npz: %d tensors, %d params" % (cfg, len(sd), sum(v.size for v in sd.values())))
+
+
+def dump_io(cfg, B, seed, snr_db, name):
+    model, args, p = build_reference_model(cfg, B)
+    u, noise = gen_inputs(seed, B, args.block_len, snr_db)
+    lin_out = []
+    hooks = []
+    for i in range(args.num_iteration):
+        for mod in (model.dec.dec1_outputs[i], model.dec.dec2_outputs[i]):
+            hooks.append(mod.register_forward_hook(lambda m, a, o: lin_out.append(o.detach().numpy().copy())))
+    with torch.no_grad():
+        y, codes = model(torch.from_numpy(u), torch.from_numpy(noise))
+        x_tx = None
+    for h in hooks:
+        h.remove()
+    out = dict(u=u, noise=noise, codes=codes.numpy(), received=(codes + torch.from_numpy(noise)).numpy(),
+               y=y.numpy(), p=np.asarray(p, dtype=np.int64), snr_db=np.float32(snr_db))
+    assert len(lin_out) == 2 * args.num_iteration
+    for j, a in enumerate(lin_out):
+        out["lin_%02d" % j] = a
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, "BER", float(np.mean(np.round(y.numpy()) != u)))
+
+
+def dump_kat():
+    model, args, p = build_reference_model("c1", 4)
+    torch.manual_seed(0)
+    X = torch.randint(0, 2, (4, 100, 1), dtype=torch.float)
+    noise = torch.randn(4, 100, 3)
+    with torch.no_grad():
+        y, codes = model(X, noise)
+    np.savez_compressed(os.path.join(HERE, "kat_c1_b4.npz"), X=X.numpy(), noise=noise.numpy(),
+                        codes=codes.numpy(), y=y.numpy(), p=np.asarray(p, dtype=np.int64))
+    print("KAT bit errors", int((torch.round(y) != X).sum()), "of 400; y[0,:4]", y[0, :4, 0].tolist())
+
+
+def dump_perm():
+    compat.install()
+    from interleavers import Interleaver, DeInterleaver
+    from numpy import arange
+    from numpy.random import mtrand
+    out = {}
+    for L, seed in ((100, 0), (100, 7), (10, 0), (1000, 0), (1, 0)):
+        p = mtrand.RandomState(seed).permutation(arange(L))
+        x = torch.arange(3 * L * 5, dtype=torch.float32).view(3, L, 5)
+        out["p_%d_%d" % (L, seed)] = np.asarray(p, dtype=np.int64)
+        out["fwd_%d_%d" % (L, seed)] = Interleaver(None, p)(x).contiguous().numpy()
+        out["inv_%d_%d" % (L, seed)] = DeInterleaver(None, p)(x).contiguous().numpy()
+    np.savez_compressed(os.path.join(HERE, "perm.npz"), **out)
+    print("perm.npz written")
+
+
+def dump_ber(blocks, batch=500):
+    model, args, p = build_reference_model("c1", batch)
+    snrs = [-1.5 + 0.5 * i for i in range(12)]          # trainer.py:157-158 with the default flags
+    res = {"batch": batch, "blocks": blocks, "snrs": snrs, "bit_errors": [], "block_errors": [], "first_batch_bit_errors": [],
+           "seed_rule": "seed = 100000 + 1000*snr_index + batch_index; gen_inputs() in make_golden.py"}
+    for si, snr in enumerate(snrs):
+        be = ble = 0
+        for bi in range(blocks // batch):
+            u, noise = gen_inputs(100000 + 1000 * si + bi, batch, args.block_len, snr)
+            with torch.no_grad():
+                y, _ = model(torch.from_numpy(u), torch.from_numpy(noise))
+            wrong = np.round(y.numpy()) != u
+            be += int(wrong.sum()); ble += int(wrong.reshape(batch, -1).any(axis=1).sum())
+            if bi == 0:
+                res["first_batch_bit_errors"].append(int(wrong.sum()))
+        res["bit_errors"].append(be); res["block_errors"].append(ble)
+        print("snr %+.1f dB  BER %.6f  BLER %.5f" % (snr, be / (blocks * 100.0), ble / float(blocks)), flush=True)
+    json.dump(res, open(os.path.join(HERE, "ber_c1.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sweep-blocks", type=int, default=10000)
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    torch.set_num_threads(os.cpu_count())
+    todo = a.only.split(",") if a.only else ["weights", "kat", "io", "perm", "ber"]
+    if "weights" in todo:
+        dump_weights("c1"); dump_weights("c3")
+    if "kat" in todo:
+        dump_kat()
+    if "io" in todo:
+        dump_io("c1", 8, 4242, 0.0, "io_c1_b8.npz"); dump_io("c3", 6, 777, 1.0, "io_c3_b6.npz")
+    if "perm" in todo:
+        dump_perm()
+    if "ber" in todo:
+        dump_ber(a.sweep_blocks)

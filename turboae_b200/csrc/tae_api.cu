@@ -1,0 +1,203 @@
+// C ABI of libturboae_b200.so (see include/turboae_b200.h): argument validation, the error
+// convention and dispatch to the fp32 (tae_f32.cu) and bf16 tcgen05 (tae_dec_bf16.cu) paths.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "tae_common.cuh"
+
+namespace tae {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int after_launch(const char* kernel_name) {
+  count_launch();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s launch failed: %s", kernel_name, cudaGetErrorString(e));
+    return TAE_ECUDA;
+  }
+  return TAE_OK;
+}
+
+int check_dec_config(const TaeDecConfig* c) {
+  if (!c) { set_error("TaeDecConfig is NULL"); return TAE_EINVAL; }
+  if (c->block_len < 1 || c->num_iteration < 1 || c->num_iter_ft < 1 || c->num_layer < 1 || c->num_unit < 1) {
+    set_error("TaeDecConfig: non-positive dimension (L=%d I=%d F=%d layers=%d units=%d)", c->block_len,
+              c->num_iteration, c->num_iter_ft, c->num_layer, c->num_unit);
+    return TAE_EINVAL;
+  }
+  if (c->num_iteration > 32 || c->num_layer > 16) {
+    set_error("TaeDecConfig: num_iteration <= 32 and num_layer <= 16 supported (got %d, %d)", c->num_iteration,
+              c->num_layer);
+    return TAE_EUNSUPPORTED;
+  }
+  if (c->kernel_size < 1 || c->kernel_size > 9 || (c->kernel_size & 1) == 0) {
+    set_error("TaeDecConfig: kernel_size %d unsupported (odd sizes 1..9)", c->kernel_size);
+    return TAE_EUNSUPPORTED;
+  }
+  return TAE_OK;
+}
+
+int check_enc_config(const TaeEncConfig* c) {
+  if (!c) { set_error("TaeEncConfig is NULL"); return TAE_EINVAL; }
+  if (c->block_len < 1 || c->num_layer < 1 || c->num_unit < 1) {
+    set_error("TaeEncConfig: non-positive dimension (L=%d layers=%d units=%d)", c->block_len, c->num_layer,
+              c->num_unit);
+    return TAE_EINVAL;
+  }
+  if (c->num_layer > 16) { set_error("TaeEncConfig: num_layer <= 16 supported (got %d)", c->num_layer); return TAE_EUNSUPPORTED; }
+  if (c->kernel_size < 1 || c->kernel_size > 9 || (c->kernel_size & 1) == 0) {
+    set_error("TaeEncConfig: kernel_size %d unsupported (odd sizes 1..9)", c->kernel_size);
+    return TAE_EUNSUPPORTED;
+  }
+  return TAE_OK;
+}
+
+}  // namespace tae
+
+using namespace tae;
+
+#define TAE_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      set_error(__VA_ARGS__);             \
+      return TAE_EINVAL;                  \
+    }                                     \
+  } while (0)
+
+extern "C" {
+
+int tae_version(void) { return 100; }   // 0.1.0
+
+const char* tae_last_error(void) { return g_err; }
+
+uint64_t tae_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int tae_interleave_f32(const float* in, float* out, const int32_t* perm, int32_t B, int32_t L, int32_t F,
+                       void* stream) {
+  TAE_REQUIRE(B >= 0 && L >= 1 && F >= 1, "tae_interleave_f32: bad shape B=%d L=%d F=%d", B, L, F);
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(in && out && perm, "tae_interleave_f32: NULL pointer");
+  TAE_REQUIRE(in != out, "tae_interleave_f32: in-place permutation is not supported");
+  return launch_interleave_f32(in, out, perm, B, L, F, (cudaStream_t)stream);
+}
+
+size_t tae_conv1d_workspace_bytes(int32_t Cin, int32_t Cout, int32_t K) {
+  if (Cin < 1 || Cout < 1 || K < 1) return 0;
+  return conv_packed_floats(Cin, Cout, K) * sizeof(float) + 256;
+}
+
+int tae_conv1d_elu_f32(const float* in, float* out, const float* weight, const float* bias, int32_t B, int32_t L,
+                       int32_t Cin, int32_t Cout, int32_t K, int32_t apply_elu, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  TAE_REQUIRE(B >= 0 && L >= 1 && Cin >= 1 && Cout >= 1, "tae_conv1d_elu_f32: bad shape B=%d L=%d Cin=%d Cout=%d", B,
+              L, Cin, Cout);
+  if (K < 1 || K > 9 || (K & 1) == 0) {
+    set_error("tae_conv1d_elu_f32: kernel_size %d unsupported (odd sizes 1..9)", K);
+    return TAE_EUNSUPPORTED;
+  }
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(in && out && weight && bias && workspace, "tae_conv1d_elu_f32: NULL pointer");
+  if (workspace_bytes < tae_conv1d_workspace_bytes(Cin, Cout, K)) {
+    set_error("tae_conv1d_elu_f32: workspace %zu < %zu bytes", workspace_bytes, tae_conv1d_workspace_bytes(Cin, Cout, K));
+    return TAE_EWORKSPACE;
+  }
+  float* packed = reinterpret_cast<float*>(align_up(reinterpret_cast<uintptr_t>(workspace), 256));
+  int rc = launch_pack_conv_f32(weight, packed, Cin, Cout, K, (cudaStream_t)stream);
+  if (rc) return rc;
+  return launch_conv_f32(in, out, packed, bias, B, L, Cin, Cout, K, apply_elu, (cudaStream_t)stream);
+}
+
+size_t tae_dec_param_count(const TaeDecConfig* cfg) {
+  if (check_dec_config(cfg)) return 0;
+  return dec_layout(*cfg, nullptr);
+}
+
+size_t tae_dec_packed_bytes(const TaeDecConfig* cfg) {
+  if (check_dec_config(cfg)) return 0;
+  const char* why = nullptr;
+  if (!dec_bf16_supported(*cfg, &why)) { set_error("bf16 path: %s", why); return 0; }
+  return dec_packed_bytes_bf16(*cfg);
+}
+
+int tae_dec_pack_bf16(const TaeDecConfig* cfg, const float* params, void* packed, void* stream) {
+  int rc = check_dec_config(cfg);
+  if (rc) return rc;
+  const char* why = nullptr;
+  if (!dec_bf16_supported(*cfg, &why)) { set_error("bf16 path: %s", why); return TAE_EUNSUPPORTED; }
+  TAE_REQUIRE(params && packed, "tae_dec_pack_bf16: NULL pointer");
+  return dec_pack_bf16(*cfg, params, packed, (cudaStream_t)stream);
+}
+
+size_t tae_dec_workspace_bytes(const TaeDecConfig* cfg, int32_t B, int32_t precision) {
+  if (check_dec_config(cfg) || B < 0) return 0;
+  if (precision == TAE_PRECISION_FP32) return dec_workspace_bytes_f32(*cfg, B);
+  if (precision == TAE_PRECISION_BF16) {
+    const char* why = nullptr;
+    if (!dec_bf16_supported(*cfg, &why)) { set_error("bf16 path: %s", why); return 0; }
+    return dec_workspace_bytes_bf16(*cfg, B);
+  }
+  set_error("unknown precision %d", precision);
+  return 0;
+}
+
+int tae_dec_forward(const TaeDecConfig* cfg, const float* params, const void* packed, const float* received,
+                    const int32_t* perm, const int32_t* inv_perm, float* out, float* trace, int32_t B,
+                    int32_t precision, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_dec_config(cfg);
+  if (rc) return rc;
+  TAE_REQUIRE(B >= 0, "tae_dec_forward: negative batch %d", B);
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(params && received && perm && inv_perm && out && workspace, "tae_dec_forward: NULL pointer");
+  if (precision == TAE_PRECISION_FP32)
+    return dec_forward_f32(*cfg, params, received, perm, inv_perm, out, trace, B, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
+  if (precision == TAE_PRECISION_BF16) {
+    const char* why = nullptr;
+    if (!dec_bf16_supported(*cfg, &why)) { set_error("bf16 path: %s", why); return TAE_EUNSUPPORTED; }
+    TAE_REQUIRE(packed, "tae_dec_forward(bf16): packed weight image is NULL (call tae_dec_pack_bf16)");
+    return dec_forward_bf16(*cfg, params, packed, received, perm, inv_perm, out, trace, B, workspace,
+                            workspace_bytes, (cudaStream_t)stream);
+  }
+  set_error("tae_dec_forward: unknown precision %d", precision);
+  return TAE_EINVAL;
+}
+
+size_t tae_enc_param_count(const TaeEncConfig* cfg) {
+  if (check_enc_config(cfg)) return 0;
+  return enc_layout(*cfg, nullptr);
+}
+
+size_t tae_enc_workspace_bytes(const TaeEncConfig* cfg, int32_t B) {
+  if (check_enc_config(cfg) || B < 0) return 0;
+  return enc_workspace_bytes_f32(*cfg, B);
+}
+
+int tae_enc_forward(const TaeEncConfig* cfg, const float* params, const float* u, const int32_t* perm, float* x_tx,
+                    double* stats, int32_t B, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_enc_config(cfg);
+  if (rc) return rc;
+  TAE_REQUIRE(B >= 0, "tae_enc_forward: negative batch %d", B);
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(params && u && perm && x_tx && stats && workspace, "tae_enc_forward: NULL pointer");
+  return enc_forward_f32(*cfg, params, u, perm, x_tx, stats, B, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int tae_power_norm_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std, void* stream) {
+  if (n == 0) return TAE_OK;
+  TAE_REQUIRE(x && codes && stats, "tae_power_norm_f32: NULL pointer");
+  return launch_power_norm_f32(x, codes, n, stats, mean_std, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// Shared helpers of libturboae_b200.so (error convention, launch accounting, layouts).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "turboae_b200.h"
+
+namespace tae {
+
+// Thread-local error message behind tae_last_error().
+void set_error(const char* fmt, ...);
+// Records a launch (bench.py's "gpu_launches") and converts a launch failure into TAE_ECUDA.
+int after_launch(const char* kernel_name);
+void count_launch();
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- canonical flat-parameter layouts (see include/turboae_b200.h) ---------------------
+struct ConvLayer {
+  size_t w_off;   // offset (floats) of weight (Cout, Cin, K) in the flat parameter buffer
+  size_t b_off;   // offset of bias (Cout)
+  int cin, cout;
+};
+
+struct DecStackLayout {
+  ConvLayer conv[16];
+  size_t lin_w_off, lin_b_off;
+  int fout;
+};
+
+// stack index = 2*idx + s  (s = 0: dec1, s = 1: dec2)
+inline size_t dec_layout(const TaeDecConfig& c, DecStackLayout* out /* 2*I entries or nullptr */) {
+  size_t off = 0;
+  for (int idx = 0; idx < c.num_iteration; ++idx) {
+    for (int s = 0; s < 2; ++s) {
+      DecStackLayout st{};
+      for (int j = 0; j < c.num_layer; ++j) {
+        int cin = (j == 0) ? (2 + c.num_iter_ft) : c.num_unit;
+        st.conv[j].cin = cin;
+        st.conv[j].cout = c.num_unit;
+        st.conv[j].w_off = off; off += (size_t)c.num_unit * cin * c.kernel_size;
+        st.conv[j].b_off = off; off += (size_t)c.num_unit;
+      }
+      st.fout = (s == 1 && idx == c.num_iteration - 1) ? 1 : c.num_iter_ft;
+      st.lin_w_off = off; off += (size_t)st.fout * c.num_unit;
+      st.lin_b_off = off; off += (size_t)st.fout;
+      if (out) out[2 * idx + s] = st;
+    }
+  }
+  return off;
+}
+
+struct EncBranchLayout {
+  ConvLayer conv[16];
+  size_t lin_w_off, lin_b_off;
+};
+
+inline size_t enc_layout(const TaeEncConfig& c, EncBranchLayout* out /* 3 entries or nullptr */) {
+  size_t off = 0;
+  for (int br = 0; br < 3; ++br) {
+    EncBranchLayout st{};
+    for (int j = 0; j < c.num_layer; ++j) {
+      int cin = (j == 0) ? 1 : c.num_unit;
+      st.conv[j].cin = cin;
+      st.conv[j].cout = c.num_unit;
+      st.conv[j].w_off = off; off += (size_t)c.num_unit * cin * c.kernel_size;
+      st.conv[j].b_off = off; off += (size_t)c.num_unit;
+    }
+    st.lin_w_off = off; off += (size_t)c.num_unit;
+    st.lin_b_off = off; off += 1;
+    if (out) out[br] = st;
+  }
+  return off;
+}
+
+int check_dec_config(const TaeDecConfig* cfg);
+int check_enc_config(const TaeEncConfig* cfg);
+
+// ---- fp32 CUDA-core path (tae_f32.cu) -----------------------------------------------------
+size_t conv_packed_floats(int cin, int cout, int k);
+int launch_pack_conv_f32(const float* w, float* packed, int cin, int cout, int k, cudaStream_t s);
+int launch_conv_f32(const float* in, float* out, const float* packed, const float* bias, int B, int L,
+                    int cin, int cout, int k, int apply_elu, cudaStream_t s);
+int launch_interleave_f32(const float* in, float* out, const int32_t* perm, int B, int L, int F, cudaStream_t s);
+size_t dec_workspace_bytes_f32(const TaeDecConfig& c, int B);
+int dec_forward_f32(const TaeDecConfig& c, const float* params, const float* received, const int32_t* perm,
+                    const int32_t* inv_perm, float* out, float* trace, int B, void* ws, size_t ws_bytes,
+                    cudaStream_t s);
+size_t enc_workspace_bytes_f32(const TaeEncConfig& c, int B);
+int enc_forward_f32(const TaeEncConfig& c, const float* params, const float* u, const int32_t* perm, float* x_tx,
+                    double* stats, int B, void* ws, size_t ws_bytes, cudaStream_t s);
+int launch_power_norm_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std,
+                          cudaStream_t s);
+
+// ---- bf16 tcgen05 path (tae_dec_bf16.cu) --------------------------------------------------
+bool dec_bf16_supported(const TaeDecConfig& c, const char** why);
+size_t dec_packed_bytes_bf16(const TaeDecConfig& c);
+int dec_pack_bf16(const TaeDecConfig& c, const float* params, void* packed, cudaStream_t s);
+size_t dec_workspace_bytes_bf16(const TaeDecConfig& c, int B);
+int dec_forward_bf16(const TaeDecConfig& c, const float* params, const void* packed, const float* received,
+                     const int32_t* perm, const int32_t* inv_perm, float* out, float* trace, int B, void* ws,
+                     size_t ws_bytes, cudaStream_t s);
+
+}  // namespace tae

@@ -1,0 +1,501 @@
+// fp32 CUDA-core path of the TurboAE hot path (TAE_PRECISION_FP32).
+//
+// This is the elementwise-parity anchor (<= 1e-4 vs the reference's fp32 forward, measured
+// ~1e-6): layer-at-a-time kernels with fp32 FMA accumulation, activations in HBM between
+// layers.  The throughput path is the fused tcgen05 kernel in tae_dec_bf16.cu.
+//
+// Reference lines restated here (paths relative to the reference checkout):
+//   conv layer + ELU ............ cnn_utils.py:15-22, 36-46
+//   Interleaver / DeInterleaver . interleavers.py:15-21, 43-48
+//   DEC_LargeCNN.forward ........ decoders.py:219-269
+//   ENC_interCNN.forward ........ encoders.py:362-375 ; power_constraint encoders.py:107-116
+#include <algorithm>
+
+#include "tae_common.cuh"
+
+namespace tae {
+
+namespace {
+
+constexpr int CONV_TN = 128;  // output channels per CTA (4 per lane)
+constexpr int CONV_CC = 16;   // input channels staged per shared-memory chunk
+
+__device__ __forceinline__ float elu1(float z) { return z > 0.f ? z : expm1f(z); }
+
+// ---------------------------------------------------------------------------------------
+// weight re-layout: torch Conv1d (Cout, Cin, K)  ->  [Cin][K][CoutPad] (zero padded), so that
+// one (c, t) row of 128 output channels is a contiguous, 16-byte aligned run.
+// ---------------------------------------------------------------------------------------
+__global__ void pack_conv_f32_kernel(const float* __restrict__ w, float* __restrict__ packed, int cin, int cout,
+                                     int k, int cout_pad) {
+  size_t n = (size_t)cin * k * cout_pad;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    int o = (int)(idx % cout_pad);
+    int t = (int)((idx / cout_pad) % k);
+    int c = (int)(idx / ((size_t)cout_pad * k));
+    packed[idx] = (o < cout) ? w[((size_t)o * cin + c) * k + t] : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// One Conv1d(K, stride 1, pad K/2) + bias (+ ELU) on a channel-last (B, L, Cin) tensor.
+// CTA = one tile of TM (= 8 * warps) consecutive positions of ONE codeword x 128 output
+// channels; zero padding at the codeword edges is materialised while staging, so the inner
+// loop has no masks.  Warp w owns rows 8w..8w+7, lane owns channels 4*lane..4*lane+3:
+// per input channel a lane keeps a sliding window of 8+K-1 inputs in registers and issues
+// 8*K*4 FMAs against K float4 weight loads.
+// ---------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(512)
+conv1d_f32_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ wp,
+                  const float* __restrict__ bias, int L, int cin, int cout, int cout_pad, int tiles_per_cw, int TM,
+                  int AS, int apply_elu) {
+  extern __shared__ __align__(16) float smem[];
+  float* W_s = smem;                          // [CC][K][128]
+  float* A_s = smem + CONV_CC * K * CONV_TN;  // [CC][AS]
+  constexpr int PAD = K / 2;
+  constexpr int NWIN = 8 + K - 1;
+  constexpr int NV = (NWIN + 3) / 4;
+
+  const int b = blockIdx.x / tiles_per_cw;
+  const int l0 = (blockIdx.x % tiles_per_cw) * TM;
+  const int n0 = blockIdx.y * CONV_TN;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* in_cw = in + (size_t)b * L * cin;
+  const int rows = TM + K - 1;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int c0 = 0; c0 < cin; c0 += CONV_CC) {
+    const int cc_n = min(CONV_CC, cin - c0);
+    for (int i = threadIdx.x; i < cc_n * K * 32; i += blockDim.x) {
+      const int v = i & 31, ct = i >> 5;
+      const float4 val = *reinterpret_cast<const float4*>(wp + ((size_t)c0 * K + ct) * cout_pad + n0 + v * 4);
+      *reinterpret_cast<float4*>(W_s + ct * CONV_TN + v * 4) = val;
+    }
+    for (int i = threadIdx.x; i < rows * cc_n; i += blockDim.x) {
+      const int cc = i % cc_n, r = i / cc_n;
+      const int l = l0 - PAD + r;
+      A_s[cc * AS + r] = (l >= 0 && l < L) ? in_cw[(size_t)l * cin + c0 + cc] : 0.f;
+    }
+    __syncthreads();
+    for (int cc = 0; cc < cc_n; ++cc) {
+      float win[4 * NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const float4 a = *reinterpret_cast<const float4*>(A_s + cc * AS + warp * 8 + v * 4);
+        win[4 * v + 0] = a.x; win[4 * v + 1] = a.y; win[4 * v + 2] = a.z; win[4 * v + 3] = a.w;
+      }
+#pragma unroll
+      for (int t = 0; t < K; ++t) {
+        const float4 w = *reinterpret_cast<const float4*>(W_s + (cc * K + t) * CONV_TN + lane * 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a = win[i + t];
+          acc[i][0] = fmaf(a, w.x, acc[i][0]);
+          acc[i][1] = fmaf(a, w.y, acc[i][1]);
+          acc[i][2] = fmaf(a, w.z, acc[i][2]);
+          acc[i][3] = fmaf(a, w.w, acc[i][3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  const int o = n0 + lane * 4;
+  if (o >= cout) return;
+  float bv[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) bv[j] = (o + j < cout) ? bias[o + j] : 0.f;
+  const bool vec = ((cout & 3) == 0) && (o + 3 < cout);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int l = l0 + warp * 8 + i;
+    if (l >= L) continue;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = acc[i][j] + bv[j];
+      if (apply_elu) v[j] = elu1(v[j]);
+    }
+    float* dst = out + ((size_t)b * L + l) * cout + o;
+    if (vec) {
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      for (int j = 0; j < 4 && o + j < cout; ++j) dst[j] = v[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Interleaver / DeInterleaver gather (reference interleavers.py:15-21, 43-48).
+// ---------------------------------------------------------------------------------------
+__global__ void interleave_f32_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                      const int32_t* __restrict__ perm, size_t n, int L, int F) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int f = (int)(idx % F);
+    const size_t bi = idx / F;
+    const int i = (int)(bi % L);
+    const size_t b = bi / L;
+    out[idx] = in[(b * L + perm[i]) * F + f];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Decoder glue.  x_in of a stack is (B, L, 2+F) = [sys, parity, prior_0..F-1] (decoders.py:230,240).
+// ---------------------------------------------------------------------------------------
+__global__ void dec_init_kernel(const float* __restrict__ received, float* __restrict__ xin, size_t n_rows, int F) {
+  const int C = 2 + F;
+  for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < n_rows; g += (size_t)gridDim.x * blockDim.x) {
+    xin[g * C + 0] = received[g * 3 + 0];
+    xin[g * C + 1] = received[g * 3 + 1];
+    for (int q = 0; q < F; ++q) xin[g * C + 2 + q] = 0.f;   // prior = zeros (decoders.py:227)
+  }
+}
+
+// One warp per OUTPUT row (b, i); source row s = map[i] (perm: interleave, inv_perm: de-interleave).
+//   lin[q]  = lb[q] + sum_o lw[q,o] * h[b,s,o]                         (dec*_outputs Linear)
+//   middle:  ext[q] = lin[q] - x_in_prev[b,s,2+q]   (extrinsic, decoders.py:235-236, 246-247)
+//            x_in_next[b,i,:] = [sys, parity, ext]  (interleave/deinterleave + cat, :238-240, :249 + :230)
+//   final :  out[b,i] = sigmoid(lin[0])             (decoders.py:267)
+__global__ void dec_tail_kernel(const float* __restrict__ h, const float* __restrict__ lw,
+                                const float* __restrict__ lb, const float* __restrict__ xin_prev,
+                                const float* __restrict__ received, const int32_t* __restrict__ map,
+                                float* __restrict__ xin_next, float* __restrict__ out_final,
+                                float* __restrict__ trace, size_t n_rows, int L, int units, int F, int fout,
+                                int extrinsic, int to_dec2, int final_mode) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp0 = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarp = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const int C = 2 + F;
+  for (size_t g = warp0; g < n_rows; g += nwarp) {
+    const size_t b = g / L;
+    const int i = (int)(g % L);
+    const int s = map[i];
+    const size_t src = b * L + s;
+    const float* hrow = h + src * units;
+    for (int q = 0; q < fout; ++q) {
+      float part = 0.f;
+      for (int o = lane; o < units; o += 32) part = fmaf(lw[q * units + o], hrow[o], part);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+      if (lane == 0) {
+        const float lin = part + lb[q];
+        if (trace) trace[src * F + q] = lin;
+        if (final_mode) {
+          out_final[g] = 1.f / (1.f + expf(-lin));
+        } else {
+          const float prior = extrinsic ? xin_prev[src * C + 2 + q] : 0.f;
+          xin_next[g * C + 2 + q] = lin - prior;
+        }
+      }
+    }
+    if (!final_mode && lane == 0) {
+      xin_next[g * C + 0] = received[(to_dec2 ? src : g) * 3 + 0];   // r_sys_int (decoders.py:222) or r_sys
+      xin_next[g * C + 1] = received[g * 3 + (to_dec2 ? 2 : 1)];     // r_par2 or r_par1
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Encoder glue.
+// ---------------------------------------------------------------------------------------
+__global__ void enc_prep_kernel(const float* __restrict__ u, const int32_t* __restrict__ perm, float* __restrict__ x,
+                                float* __restrict__ x_int, size_t n_rows, int L) {
+  for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < n_rows; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = g / L;
+    const int i = (int)(g % L);
+    x[g] = 2.0f * u[g] - 1.0f;                               // encoders.py:362
+    x_int[g] = 2.0f * u[b * L + perm[i]] - 1.0f;             // encoders.py:369
+  }
+}
+
+// warp per row: x_tx[g, branch] = ELU(lb + <lw, h[g,:]>) (encoders.py:364,367,371) and the running
+// (sum, sum of squares) of everything written, for power_constraint.
+__global__ void enc_tail_kernel(const float* __restrict__ h, const float* __restrict__ lw,
+                                const float* __restrict__ lb, float* __restrict__ x_tx, size_t n_rows, int units,
+                                int branch, double* __restrict__ stats) {
+  __shared__ double red[2][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const size_t warp0 = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+  const size_t nwarp = ((size_t)gridDim.x * blockDim.x) >> 5;
+  double s1 = 0.0, s2 = 0.0;
+  for (size_t g = warp0; g < n_rows; g += nwarp) {
+    const float* hrow = h + g * units;
+    float part = 0.f;
+    for (int o = lane; o < units; o += 32) part = fmaf(lw[o], hrow[o], part);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (lane == 0) {
+      const float v = elu1(part + lb[0]);
+      x_tx[g * 3 + branch] = v;
+      s1 += (double)v;
+      s2 += (double)v * (double)v;
+    }
+  }
+  if (lane == 0) { red[0][wib] = s1; red[1][wib] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, c = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += red[0][w]; c += red[1][w]; }
+    atomicAdd(stats + 0, a);
+    atomicAdd(stats + 1, c);
+  }
+}
+
+__global__ void add_count_kernel(double* stats, double n) { stats[2] += n; }
+
+// codes = (x - mean) / std with unbiased std over everything counted in stats (encoders.py:107-116).
+__global__ void power_norm_kernel(const float* __restrict__ x, float* __restrict__ codes, size_t n,
+                                  const double* __restrict__ stats, float* __restrict__ mean_std) {
+  const double cnt = stats[2];
+  const double mean = stats[0] / cnt;
+  const double var = (stats[1] - cnt * mean * mean) / (cnt - 1.0);
+  const float meanf = (float)mean;
+  const float stdf = (float)sqrt(var > 0.0 ? var : 0.0);
+  if (mean_std && blockIdx.x == 0 && threadIdx.x == 0) { mean_std[0] = meanf; mean_std[1] = stdf; }
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x)
+    codes[idx] = (x[idx] - meanf) / stdf;
+}
+
+inline int grid_for(size_t n, int block, int max_blocks = 148 * 16) {
+  size_t g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > (size_t)max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+template <int K>
+int launch_conv_k(const float* in, float* out, const float* packed, const float* bias, int B, int L, int cin,
+                  int cout, int apply_elu, cudaStream_t s) {
+  const int cout_pad = (int)align_up(cout, CONV_TN);
+  const int tiles_per_cw = (L + 127) / 128;
+  int TM = (L + tiles_per_cw - 1) / tiles_per_cw;
+  TM = (int)align_up(TM, 8);
+  int AS = TM + 8;
+  while (AS % 32 != 4) AS += 4;
+  const size_t smem = (size_t)(CONV_CC * K * CONV_TN + CONV_CC * AS) * sizeof(float);
+  static bool attr_done = false;   // per instantiation
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv1d_f32_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv1d_f32): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+    attr_done = true;
+  }
+  if (smem > 96 * 1024) { set_error("conv1d_f32: kernel_size %d needs %zu B shared memory", K, smem); return TAE_EUNSUPPORTED; }
+  dim3 grid((unsigned)((size_t)B * tiles_per_cw), (unsigned)(cout_pad / CONV_TN));
+  conv1d_f32_kernel<K><<<grid, 32 * (TM / 8), smem, s>>>(in, out, packed, bias, L, cin, cout, cout_pad, tiles_per_cw,
+                                                         TM, AS, apply_elu);
+  return after_launch("conv1d_f32_kernel");
+}
+
+}  // namespace
+
+size_t conv_packed_floats(int cin, int cout, int k) { return (size_t)cin * k * align_up(cout, CONV_TN); }
+
+int launch_pack_conv_f32(const float* w, float* packed, int cin, int cout, int k, cudaStream_t s) {
+  const size_t n = conv_packed_floats(cin, cout, k);
+  pack_conv_f32_kernel<<<grid_for(n, 256), 256, 0, s>>>(w, packed, cin, cout, k, (int)align_up(cout, CONV_TN));
+  return after_launch("pack_conv_f32_kernel");
+}
+
+int launch_conv_f32(const float* in, float* out, const float* packed, const float* bias, int B, int L, int cin,
+                    int cout, int k, int apply_elu, cudaStream_t s) {
+  if (B == 0) return TAE_OK;
+  switch (k) {
+    case 1: return launch_conv_k<1>(in, out, packed, bias, B, L, cin, cout, apply_elu, s);
+    case 3: return launch_conv_k<3>(in, out, packed, bias, B, L, cin, cout, apply_elu, s);
+    case 5: return launch_conv_k<5>(in, out, packed, bias, B, L, cin, cout, apply_elu, s);
+    case 7: return launch_conv_k<7>(in, out, packed, bias, B, L, cin, cout, apply_elu, s);
+    case 9: return launch_conv_k<9>(in, out, packed, bias, B, L, cin, cout, apply_elu, s);
+    default:
+      set_error("kernel_size %d unsupported (odd sizes 1..9 only: SameShapeConv1d pads K/2, cnn_utils.py:16)", k);
+      return TAE_EUNSUPPORTED;
+  }
+}
+
+int launch_interleave_f32(const float* in, float* out, const int32_t* perm, int B, int L, int F, cudaStream_t s) {
+  const size_t n = (size_t)B * L * F;
+  if (n == 0) return TAE_OK;
+  interleave_f32_kernel<<<grid_for(n, 256, 148 * 32), 256, 0, s>>>(in, out, perm, n, L, F);
+  return after_launch("interleave_f32_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
+// DEC_LargeCNN.forward, fp32 (reference decoders.py:219-269)
+// ---------------------------------------------------------------------------------------
+static constexpr int DEC_F32_CHUNK = 8192;  // codewords per pass: bounds the activation workspace
+
+static size_t dec_packed_floats_f32(const TaeDecConfig& c) {
+  size_t n = 0;
+  for (int j = 0; j < c.num_layer; ++j)
+    n += conv_packed_floats(j == 0 ? 2 + c.num_iter_ft : c.num_unit, c.num_unit, c.kernel_size);
+  return n * 2 * c.num_iteration;
+}
+
+size_t dec_workspace_bytes_f32(const TaeDecConfig& c, int B) {
+  const size_t chunk = (size_t)std::min(B, DEC_F32_CHUNK);
+  const size_t rows = chunk * c.block_len;
+  size_t fl = align_up(dec_packed_floats_f32(c), 64);
+  fl += 2 * align_up(rows * (2 + c.num_iter_ft), 64);
+  fl += 2 * align_up(rows * c.num_unit, 64);
+  return fl * sizeof(float) + 256;
+}
+
+int dec_forward_f32(const TaeDecConfig& c, const float* params, const float* received, const int32_t* perm,
+                    const int32_t* inv_perm, float* out, float* trace, int B, void* ws, size_t ws_bytes,
+                    cudaStream_t s) {
+  if (ws_bytes < dec_workspace_bytes_f32(c, B)) {
+    set_error("tae_dec_forward(fp32): workspace %zu < %zu bytes", ws_bytes, dec_workspace_bytes_f32(c, B));
+    return TAE_EWORKSPACE;
+  }
+  const int L = c.block_len, F = c.num_iter_ft, U = c.num_unit, K = c.kernel_size, I = c.num_iteration;
+  DecStackLayout lay[64];
+  dec_layout(c, lay);
+
+  float* base = reinterpret_cast<float*>(align_up(reinterpret_cast<uintptr_t>(ws), 256));
+  const size_t chunk = (size_t)std::min(B, DEC_F32_CHUNK);
+  const size_t rows_max = chunk * L;
+  float* wpk = base;
+  float* xin[2];
+  xin[0] = wpk + align_up(dec_packed_floats_f32(c), 64);
+  xin[1] = xin[0] + align_up(rows_max * (2 + F), 64);
+  float* hbuf[2];
+  hbuf[0] = xin[1] + align_up(rows_max * (2 + F), 64);
+  hbuf[1] = hbuf[0] + align_up(rows_max * U, 64);
+
+  // re-layout every conv weight once per call (2.4 M floats: negligible next to the convs)
+  const float* wp_ptr[64][16];
+  {
+    float* p = wpk;
+    for (int st = 0; st < 2 * I; ++st)
+      for (int j = 0; j < c.num_layer; ++j) {
+        const ConvLayer& cl = lay[st].conv[j];
+        int rc = launch_pack_conv_f32(params + cl.w_off, p, cl.cin, cl.cout, K, s);
+        if (rc) return rc;
+        wp_ptr[st][j] = p;
+        p += conv_packed_floats(cl.cin, cl.cout, K);
+      }
+  }
+
+  for (size_t b0 = 0; b0 < (size_t)B; b0 += chunk) {
+    const int nb = (int)std::min(chunk, (size_t)B - b0);
+    const size_t rows = (size_t)nb * L;
+    const float* rec = received + b0 * L * 3;
+    dec_init_kernel<<<grid_for(rows, 256), 256, 0, s>>>(rec, xin[0], rows, F);
+    int rc = after_launch("dec_init_kernel");
+    if (rc) return rc;
+    for (int st = 0; st < 2 * I; ++st) {
+      const int sidx = st & 1;           // 0: dec1 stack (natural order), 1: dec2 stack (interleaved order)
+      const float* cur = xin[sidx];
+      int hb = 0;
+      for (int j = 0; j < c.num_layer; ++j) {
+        const ConvLayer& cl = lay[st].conv[j];
+        rc = launch_conv_f32(cur, hbuf[hb], wp_ptr[st][j], params + cl.b_off, nb, L, cl.cin, cl.cout, K, 1, s);
+        if (rc) return rc;
+        cur = hbuf[hb];
+        hb ^= 1;
+      }
+      const bool final_mode = (st == 2 * I - 1);
+      float* tr = trace ? trace + ((size_t)st * B + b0) * L * F : nullptr;
+      const int threads = 256;
+      const int blocks = grid_for(rows * 32, threads);
+      dec_tail_kernel<<<blocks, threads, 0, s>>>(cur, params + lay[st].lin_w_off, params + lay[st].lin_b_off,
+                                                 xin[sidx], rec, sidx == 0 ? perm : inv_perm, xin[sidx ^ 1],
+                                                 out + b0 * L, tr, rows, L, U, F, lay[st].fout, c.extrinsic,
+                                                 sidx == 0 ? 1 : 0, final_mode ? 1 : 0);
+      rc = after_launch("dec_tail_kernel");
+      if (rc) return rc;
+    }
+  }
+  return TAE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// ENC_interCNN.forward up to the concat, fp32 (reference encoders.py:362-373)
+// ---------------------------------------------------------------------------------------
+static constexpr int ENC_F32_CHUNK = 8192;
+
+static size_t enc_packed_floats_f32(const TaeEncConfig& c) {
+  size_t n = 0;
+  for (int j = 0; j < c.num_layer; ++j) n += conv_packed_floats(j == 0 ? 1 : c.num_unit, c.num_unit, c.kernel_size);
+  return n * 3;
+}
+
+size_t enc_workspace_bytes_f32(const TaeEncConfig& c, int B) {
+  const size_t rows = (size_t)std::min(B, ENC_F32_CHUNK) * c.block_len;
+  size_t fl = align_up(enc_packed_floats_f32(c), 64);
+  fl += 2 * align_up(rows, 64);
+  fl += 2 * align_up(rows * c.num_unit, 64);
+  return fl * sizeof(float) + 256;
+}
+
+int enc_forward_f32(const TaeEncConfig& c, const float* params, const float* u, const int32_t* perm, float* x_tx,
+                    double* stats, int B, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (ws_bytes < enc_workspace_bytes_f32(c, B)) {
+    set_error("tae_enc_forward: workspace %zu < %zu bytes", ws_bytes, enc_workspace_bytes_f32(c, B));
+    return TAE_EWORKSPACE;
+  }
+  const int L = c.block_len, U = c.num_unit, K = c.kernel_size;
+  EncBranchLayout lay[3];
+  enc_layout(c, lay);
+  float* base = reinterpret_cast<float*>(align_up(reinterpret_cast<uintptr_t>(ws), 256));
+  const size_t chunk = (size_t)std::min(B, ENC_F32_CHUNK);
+  const size_t rows_max = chunk * L;
+  float* wpk = base;
+  float* x = wpk + align_up(enc_packed_floats_f32(c), 64);
+  float* x_int = x + align_up(rows_max, 64);
+  float* hbuf[2];
+  hbuf[0] = x_int + align_up(rows_max, 64);
+  hbuf[1] = hbuf[0] + align_up(rows_max * U, 64);
+
+  const float* wp_ptr[3][16];
+  {
+    float* p = wpk;
+    for (int br = 0; br < 3; ++br)
+      for (int j = 0; j < c.num_layer; ++j) {
+        const ConvLayer& cl = lay[br].conv[j];
+        int rc = launch_pack_conv_f32(params + cl.w_off, p, cl.cin, cl.cout, K, s);
+        if (rc) return rc;
+        wp_ptr[br][j] = p;
+        p += conv_packed_floats(cl.cin, cl.cout, K);
+      }
+  }
+  for (size_t b0 = 0; b0 < (size_t)B; b0 += chunk) {
+    const int nb = (int)std::min(chunk, (size_t)B - b0);
+    const size_t rows = (size_t)nb * L;
+    enc_prep_kernel<<<grid_for(rows, 256), 256, 0, s>>>(u + b0 * L, perm, x, x_int, rows, L);
+    int rc = after_launch("enc_prep_kernel");
+    if (rc) return rc;
+    for (int br = 0; br < 3; ++br) {
+      const float* cur = (br == 2) ? x_int : x;
+      int hb = 0;
+      for (int j = 0; j < c.num_layer; ++j) {
+        const ConvLayer& cl = lay[br].conv[j];
+        rc = launch_conv_f32(cur, hbuf[hb], wp_ptr[br][j], params + cl.b_off, nb, L, cl.cin, cl.cout, K, 1, s);
+        if (rc) return rc;
+        cur = hbuf[hb];
+        hb ^= 1;
+      }
+      enc_tail_kernel<<<grid_for(rows * 32, 256, 148 * 8), 256, 0, s>>>(cur, params + lay[br].lin_w_off,
+                                                                         params + lay[br].lin_b_off,
+                                                                         x_tx + b0 * L * 3, rows, U, br, stats);
+      rc = after_launch("enc_tail_kernel");
+      if (rc) return rc;
+    }
+  }
+  add_count_kernel<<<1, 1, 0, s>>>(stats, (double)B * L * 3);
+  return after_launch("add_count_kernel");
+}
+
+int launch_power_norm_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std,
+                          cudaStream_t s) {
+  if (n == 0) return TAE_OK;
+  power_norm_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, codes, n, stats, mean_std);
+  return after_launch("power_norm_kernel");
+}
+
+}  // namespace tae

@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""Headline benchmark: codewords/sec of the fused 6-iteration DEC_LargeCNN decode at block_len=100
+(BASELINE.json configs[1]: enc2/dec5, unit 100, B = 50 000 codewords per GPU, AWGN 0 dB).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]           # this repo's CUDA path (one rank per GPU)
+    python bench.py --impl reference [...]                         # the reference's PyTorch-CPU operator path
+
+A "step" is one decode pass over one batch of B codewords.  `value` is timed with the inputs resident in HBM;
+`e2e` goes through the module's forward() with pinned HOST buffers (H2D of `received`, D2H of the posteriors
+inside the timed region).  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "codewords/sec (block_len=100, 6-iter decode)"
+UNIT = "codewords/s"
+DEC_FLOP_PER_CW = 489_520_000          # SURVEY.md 8(d); oracle.decoder_flops_per_codeword()
+HBM_BYTES_PER_CW = 1600                # read (100,3) fp32 + write (100,1) fp32
+
+
+def workload_name(B):
+    return "TurboAE_rate3_cnn enc2/dec5 unit=100 block_len=100 num_iteration=6 AWGN 0dB, batch=%d per GPU, " \
+           "checkpoint dta_cont_cnn2_cnn5_enctrain2_dectrainneg15_2" % B
+
+
+def measured_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["bf16_tflops"]), float(p.get("bf16_tflops_sustained", 0.0)), "measured"
+    except Exception:
+        return 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def cpu_reference_rate(sample_b, min_seconds, max_reps, warmup=1):
+    """The reference's operator sequence on torch CPU kernels (oracle/turboae_torch.py), all host threads."""
+    import numpy as np
+    import torch
+    from helpers import load_npz
+    from oracle import turboae_oracle as O
+    from oracle import turboae_torch as TT
+    torch.set_num_threads(os.cpu_count())
+    w = TT.to_torch(load_npz("weights_c1.npz"))
+    p = O.make_perm(100, 0)
+    g = torch.Generator().manual_seed(1)
+    rec = torch.randn(sample_b, 100, 3, generator=g) + (2.0 * torch.randint(0, 2, (sample_b, 100, 3), generator=g) - 1.0)
+    times = []
+    with torch.no_grad():
+        for _ in range(warmup):
+            TT.dec_forward(rec, w, p)
+        t_all = time.perf_counter()
+        while len(times) < max_reps and (len(times) < 3 or time.perf_counter() - t_all < min_seconds):
+            t0 = time.perf_counter()
+            TT.dec_forward(rec, w, p)
+            times.append(time.perf_counter() - t0)
+    return sample_b / statistics.median(times), times, torch.get_num_threads()
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample_b = a.cpu_sample
+    import torch
+    from helpers import load_npz
+    from oracle import turboae_oracle as O
+    from oracle import turboae_torch as TT
+    torch.set_num_threads(os.cpu_count())
+    w = TT.to_torch(load_npz("weights_c1.npz"))
+    p = O.make_perm(100, 0)
+    g = torch.Generator().manual_seed(1)
+    rec = torch.randn(sample_b, 100, 3, generator=g) + (2.0 * torch.randint(0, 2, (sample_b, 100, 3), generator=g) - 1.0)
+    with torch.no_grad():
+        for _ in range(a.warmup):
+            TT.dec_forward(rec, w, p)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            TT.dec_forward(rec, w, p)
+        dt = time.perf_counter() - t0
+    val = sample_b * a.steps / dt
+    sample = "%d of the %d codewords of one batch per step (same decoder, same checkpoint, torch CPU operators, " \
+             "%d threads)" % (sample_b, a.batch, torch.get_num_threads())
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a.batch), "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_b200(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from helpers import build_codec
+    from turboae_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- turboae_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = a.batch, a.steps, max(a.warmup, 3)
+
+    m, w, p = build_codec("c1", device=dev, batch_size=B)
+    m.dec.precision = a.precision
+    NBUF = 4          # 4 resident batches x (60 MB in + 20 MB out) = 320 MB rotated: larger than the 126 MB L2
+    torch.manual_seed(1234 + rank)
+    bits, recs = [], []
+    with torch.no_grad():
+        for i in range(NBUF):
+            u = torch.randint(0, 2, (B, 100, 1), device=dev).float()
+            codes = m.enc(u)
+            recs.append((codes + torch.randn(B, 100, 3, device=dev)).contiguous())      # AWGN, sigma = 1 (0 dB)
+            bits.append(u)
+        outs = [None] * NBUF
+        for i in range(W):
+            outs[i % NBUF] = m.dec(recs[i % NBUF])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        n0 = _lib.launch_count()
+        ev[0].record()
+        for i in range(K):
+            outs[i % NBUF] = m.dec(recs[i % NBUF])
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        launches = _lib.launch_count() - n0
+        sampler.stop_flag = True
+        sampler.join()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total_ms = ev[0].elapsed_time(ev[K])
+        per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        max_ms = float(t.item())
+        value = world * B * K / (max_ms * 1e-3)
+
+        # BER of the timed outputs at 0 dB (sanity that the timed kernel did the work)
+        j = (K - 1) % NBUF
+        ber = float((torch.round(outs[j]) != bits[j]).float().mean())
+
+        # ---- end to end through forward() with pinned host buffers ---------------------------------------
+        rec_host = [r.cpu().pin_memory() for r in recs[:2]]
+        out_host = torch.empty((B, 100, 1), dtype=torch.float32).pin_memory()
+        for i in range(2):
+            out_host.copy_(m.dec(rec_host[i % 2]))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(K):
+            y = m.dec(rec_host[i % 2])              # forward(): H2D of `received`, fused decode
+            out_host.copy_(y)                       # D2H of the posteriors
+        e1.record()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e2e_ms = max(e0.elapsed_time(e1), wall_ms)
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_value = world * B * K / (float(t.item()) * 1e-3)
+
+    if rank == 0:
+        peak, peak_sus, which = measured_peaks()
+        launch_ms = statistics.mean(per_launch_ms)
+        achieved = B * DEC_FLOP_PER_CW / (launch_ms * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dec_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": a.precision, "data": "synthetic",
+                "config": {"workload": workload_name(B), "l2": "4 resident batches (320 MB) rotated, > 126 MB L2",
+                           "weights": "tests/golden/weights_c1.npz (reference checkpoint values)",
+                           "parallelism": "dp%d, whole codewords per rank, no collective in decode" % world},
+                "ber_0db": ber,
+                "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                             "frac": achieved / peak, "frac_of_sustained": (achieved / peak_sus) if peak_sus else None,
+                             "peak_source": which + " bf16 burst", "traffic": traffic,
+                             "algorithmic_flop_per_launch": B * DEC_FLOP_PER_CW,
+                             "algorithmic_hbm_bytes_per_launch": B * HBM_BYTES_PER_CW,
+                             "launch_ms_mean": launch_ms, "launch_ms_min": min(per_launch_ms)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 100 * 3 * 4,
+                        "d2h_bytes_per_step": B * 100 * 4},
+                "gpu_launches": int(launches), "clocks": sampler.result()}
+        if world == 1 and not a.no_cpu_baseline:
+            v, times, cores = cpu_reference_rate(a.cpu_sample, 10.0, 30)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d codewords x %d repetitions (median), torch CPU operators of the "
+                                              "reference's decode path" % (a.cpu_sample, len(times))}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=50000)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample", type=int, default=500)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        return run_reference(a)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29541"), __file__] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_b200(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

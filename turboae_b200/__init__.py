@@ -1,0 +1,14 @@
+"""turboae_b200 -- B200 (sm_100a) implementation of the TurboAE CNN encode / turbo-decode hot path.
+
+Drop-in for the reference's ``encoders.ENC_interCNN`` / ``decoders.DEC_LargeCNN`` (and the
+``Interleaver`` / ``DeInterleaver`` / ``SameShapeConv1d`` building blocks): same constructor,
+``forward`` surface, parameter names and checkpoint keys, backed by hand-written CUDA kernels in
+``libturboae_b200.so`` (C ABI in ``include/turboae_b200.h``).  There is no CPU fallback: without
+the library or without a CUDA device every forward raises.
+"""
+from .interleavers import Interleaver, DeInterleaver          # noqa: F401
+from .cnn_utils import SameShapeConv1d                        # noqa: F401
+from .encoders import ENCBase, ENC_interCNN                   # noqa: F401
+from .decoders import DEC_LargeCNN                            # noqa: F401
+
+__version__ = "0.1.0"

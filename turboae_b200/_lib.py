@@ -1,0 +1,105 @@
+"""ctypes binding of libturboae_b200.so (the C ABI declared in include/turboae_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libturboae_b200.so")
+
+PRECISION_FP32 = 0
+PRECISION_BF16 = 1
+PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16}
+
+
+class TaeDecConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("block_len", "num_iteration", "num_iter_ft", "num_layer", "num_unit",
+                                         "kernel_size", "extrinsic")]
+
+
+class TaeEncConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("block_len", "num_layer", "num_unit", "kernel_size")]
+
+
+class TaeError(RuntimeError):
+    pass
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    "tae_version": (C.c_int, []),
+    "tae_last_error": (C.c_char_p, []),
+    "tae_launch_count": (C.c_uint64, []),
+    "tae_interleave_f32": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "tae_conv1d_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "tae_conv1d_elu_f32": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_int32, _P, C.c_size_t, _P]),
+    "tae_dec_param_count": (C.c_size_t, [C.POINTER(TaeDecConfig)]),
+    "tae_dec_packed_bytes": (C.c_size_t, [C.POINTER(TaeDecConfig)]),
+    "tae_dec_pack_bf16": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P]),
+    "tae_dec_workspace_bytes": (C.c_size_t, [C.POINTER(TaeDecConfig), C.c_int32, C.c_int32]),
+    "tae_dec_forward": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P,
+                                  C.c_size_t, _P]),
+    "tae_enc_param_count": (C.c_size_t, [C.POINTER(TaeEncConfig)]),
+    "tae_enc_workspace_bytes": (C.c_size_t, [C.POINTER(TaeEncConfig), C.c_int32]),
+    "tae_enc_forward": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P, _P, _P, C.c_int32, _P, C.c_size_t, _P]),
+    "tae_power_norm_f32": (C.c_int, [_P, _P, C.c_size_t, _P, _P, _P]),
+    # debug / self-test entry points
+    "tae_debug_set_dump": (None, [_P]),
+    "tae_debug_umma_probe": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, _P, _P]),
+}
+# symbols every build must export (checked by tests/test_cabi.py against include/turboae_b200.h)
+PUBLIC_SYMBOLS = [s for s in _SIGNATURES if not s.startswith("tae_debug_")]
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """Load the shared library (building it first if nvcc is present and it is stale/missing).
+    Raises loudly when it cannot be had -- the product has no CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH) or os.environ.get("TURBOAE_B200_REBUILD"):
+            from . import build as _build
+            _build.build(force=True)
+        try:
+            lib = C.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise TaeError("cannot load %s (%s); run `python -m turboae_b200.build` -- there is no CPU fallback"
+                           % (LIB_PATH, e)) from e
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise TaeError("libturboae_b200 error %d: %s" % (rc, load().tae_last_error().decode()))
+
+
+def ptr(t: torch.Tensor | None):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise TaeError("%s must live on a CUDA device (got %s): turboae_b200 has no CPU fallback" % (what, t.device))
+
+
+def launch_count() -> int:
+    return int(load().tae_launch_count())

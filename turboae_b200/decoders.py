@@ -1,0 +1,124 @@
+"""DEC_LargeCNN with the reference's nn.Module surface (reference decoders.py:157-269).
+
+forward: ``received (B, L, 3)`` -> ``(B, L, 1)`` posteriors.  The whole turbo schedule (2*num_iteration conv
+stacks, Linear projections, extrinsic subtractions, interleave / de-interleave, sigmoid) is one call into
+libturboae_b200.so: ``precision='bf16'`` runs the fused tcgen05 kernel, ``precision='fp32'`` the CUDA-core
+elementwise-parity path.  No CPU fallback and no silent switch between the two."""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib
+from ._flat import FlatCache, ParallelShim, Workspace, unwrap
+from .cnn_utils import SameShapeConv1d
+from .interleavers import DeInterleaver, Interleaver
+
+
+class DEC_LargeCNN(torch.nn.Module):
+    def __init__(self, args, p_array):
+        super().__init__()
+        self.args = args
+        use_cuda = not args.no_cuda and torch.cuda.is_available()
+        self.this_device = torch.device("cuda" if use_cuda else "cpu")
+        if args.encoder != "TurboAE_rate3_cnn":        # decoders.py:173 keys the layer type on args.encoder
+            raise NotImplementedError("turboae_b200.DEC_LargeCNN builds the SameShapeConv1d variant only "
+                                      "(-encoder TurboAE_rate3_cnn); got %r" % (args.encoder,))
+        self.interleaver = Interleaver(args, p_array)
+        self.deinterleaver = DeInterleaver(args, p_array)
+        self.dec1_cnns = torch.nn.ModuleList()
+        self.dec2_cnns = torch.nn.ModuleList()
+        self.dec1_outputs = torch.nn.ModuleList()
+        self.dec2_outputs = torch.nn.ModuleList()
+        for idx in range(args.num_iteration):
+            for lst in (self.dec1_cnns, self.dec2_cnns):
+                lst.append(SameShapeConv1d(num_layer=args.dec_num_layer, in_channels=2 + args.num_iter_ft,
+                                           out_channels=args.dec_num_unit, kernel_size=args.dec_kernel_size))
+            self.dec1_outputs.append(torch.nn.Linear(args.dec_num_unit, args.num_iter_ft))
+            self.dec2_outputs.append(torch.nn.Linear(args.dec_num_unit,
+                                                     1 if idx == args.num_iteration - 1 else args.num_iter_ft))
+        self._flat = FlatCache()
+        self._ws = Workspace()
+        #: 'bf16' (fused tcgen05 kernel) or 'fp32' (CUDA-core parity path)
+        self.precision = getattr(args, "tae_precision", None) or os.environ.get("TURBOAE_B200_PRECISION", "bf16")
+
+    def set_parallel(self):
+        for lst in (self.dec1_cnns, self.dec2_cnns, self.dec1_outputs, self.dec2_outputs):
+            for idx in range(len(lst)):
+                if not isinstance(lst[idx], ParallelShim):
+                    lst[idx] = ParallelShim(lst[idx])
+
+    def set_interleaver(self, p_array):
+        self.interleaver.set_parray(p_array)
+        self.deinterleaver.set_parray(p_array)
+
+    # -- canonical flat order of include/turboae_b200.h ------------------------------------------------
+    def ordered_parameters(self):
+        out = []
+        for idx in range(self.args.num_iteration):
+            for cnns, outs in ((self.dec1_cnns, self.dec1_outputs), (self.dec2_cnns, self.dec2_outputs)):
+                for conv in unwrap(cnns[idx]).cnns:
+                    out += [conv.weight, conv.bias]
+                lin = unwrap(outs[idx])
+                out += [lin.weight, lin.bias]
+        return out
+
+    def config(self, block_len):
+        a = self.args
+        return _lib.TaeDecConfig(block_len, a.num_iteration, a.num_iter_ft, a.dec_num_layer, a.dec_num_unit,
+                                 a.dec_kernel_size, 1 if a.extrinsic else 0)
+
+    def decode(self, received, precision=None, trace=None):
+        """received: contiguous float32 CUDA (B, L, 3) -> (B, L, 1).  `trace`: optional (2I, B, L, F) tensor that
+        receives every dec{1,2}_outputs Linear output (pre-subtraction), for parity debugging."""
+        lib = _lib.load()
+        precision = precision or self.precision
+        if precision not in _lib.PRECISIONS:
+            raise _lib.TaeError("precision must be 'bf16' or 'fp32', got %r" % (precision,))
+        prec = _lib.PRECISIONS[precision]
+        _lib.require_cuda(received, "DEC_LargeCNN input")
+        B, L, three = received.shape
+        if three != 3:
+            raise _lib.TaeError("DEC_LargeCNN expects (B, L, 3), got %s" % (tuple(received.shape),))
+        dev = received.device
+        cfg = self.config(L)
+        flat = self._flat.get(self.ordered_parameters())
+        if flat.device != dev:
+            raise _lib.TaeError("decoder parameters are on %s but the input is on %s" % (flat.device, dev))
+        if flat.numel() != lib.tae_dec_param_count(cfg):
+            raise _lib.TaeError("parameter count mismatch: module %d vs library %d"
+                                % (flat.numel(), lib.tae_dec_param_count(cfg)))
+        perm, inv = self.interleaver.device_index(dev)
+        out = torch.empty((B, L, 1), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            packed = None
+            if prec == _lib.PRECISION_BF16:
+                packed = self._flat.derived.get("bf16")
+                if packed is None:
+                    nbytes = lib.tae_dec_packed_bytes(cfg)
+                    if nbytes == 0:
+                        raise _lib.TaeError("bf16 tensor path unavailable for this configuration (%s); "
+                                            "set precision='fp32'" % lib.tae_last_error().decode())
+                    packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                    _lib.check(lib.tae_dec_pack_bf16(cfg, _lib.ptr(flat), _lib.ptr(packed), _lib.stream_ptr(dev)))
+                    self._flat.derived["bf16"] = packed
+            ws_bytes = lib.tae_dec_workspace_bytes(cfg, B, prec)
+            ws = self._ws.get(ws_bytes, dev)
+            _lib.check(lib.tae_dec_forward(cfg, _lib.ptr(flat), _lib.ptr(packed), _lib.ptr(received), _lib.ptr(perm),
+                                           _lib.ptr(inv), _lib.ptr(out), _lib.ptr(trace), B, prec, _lib.ptr(ws),
+                                           ws.numel(), _lib.stream_ptr(dev)))
+        return out
+
+    def forward(self, received):
+        if getattr(self.args, "is_variable_block_len", False):
+            raise NotImplementedError("--is_variable_block_len is not supported by turboae_b200")
+        if self.this_device.type != "cuda":
+            raise _lib.TaeError("no CUDA device: turboae_b200 has no CPU fallback")
+        if torch.is_grad_enabled() and (received.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("turboae_b200: decoder backward is not built yet (SURVEY.md 8(f) row 1); "
+                                      "use torch.no_grad()")
+        # reference decoders.py:219: received.type(torch.FloatTensor).to(self.this_device) -- here without the
+        # device->host->device round trip when the tensor is already resident.
+        x = received.to(device=self.this_device, dtype=torch.float32).contiguous()
+        return self.decode(x)

@@ -1,0 +1,137 @@
+"""ENC_interCNN with the reference's nn.Module surface (reference encoders.py:63-125, 306-377).
+
+forward: ``u (B, L, 1) in {0,1}`` -> ``codes (B, L, 3)``: three conv branches (the third on interleaved bits),
+Linear(100->1) + ELU each, concat, then the batch-global power normalisation -- all in libturboae_b200.so
+(``tae_enc_forward`` + ``tae_power_norm_f32``)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._flat import FlatCache, ParallelShim, Workspace, unwrap
+from .cnn_utils import SameShapeConv1d
+from .interleavers import Interleaver
+
+
+class ENCBase(torch.nn.Module):
+    """reference encoders.py:63-125."""
+
+    def __init__(self, args):
+        super().__init__()
+        use_cuda = not args.no_cuda and torch.cuda.is_available()
+        self.this_device = torch.device("cuda" if use_cuda else "cpu")
+        self.args = args
+        self.reset_precomp()
+
+    def set_parallel(self):
+        pass
+
+    def set_precomp(self, mean_scalar, std_scalar):
+        self.mean_scalar = mean_scalar.to(self.this_device)
+        self.std_scalar = std_scalar.to(self.this_device)
+
+    def reset_precomp(self):
+        self.mean_scalar = torch.zeros(1).type(torch.FloatTensor).to(self.this_device)
+        self.std_scalar = torch.ones(1).type(torch.FloatTensor).to(self.this_device)
+        self.num_test_block = 0.0
+
+
+class ENC_interCNN(ENCBase):
+    """reference encoders.py:306-377."""
+
+    def __init__(self, args, p_array):
+        super().__init__(args)
+        self.args = args
+        if args.encoder != "TurboAE_rate3_cnn":
+            raise NotImplementedError("turboae_b200.ENC_interCNN builds the SameShapeConv1d variant only "
+                                      "(-encoder TurboAE_rate3_cnn); got %r" % (args.encoder,))
+        if args.code_rate_k != 1:
+            raise NotImplementedError("code_rate_k must be 1 (got %r)" % (args.code_rate_k,))
+        mk = lambda: SameShapeConv1d(num_layer=args.enc_num_layer, in_channels=args.code_rate_k,
+                                     out_channels=args.enc_num_unit, kernel_size=args.enc_kernel_size)
+        self.enc_cnn_1, self.enc_cnn_2, self.enc_cnn_3 = mk(), mk(), mk()
+        self.enc_linear_1 = torch.nn.Linear(args.enc_num_unit, 1)
+        self.enc_linear_2 = torch.nn.Linear(args.enc_num_unit, 1)
+        self.enc_linear_3 = torch.nn.Linear(args.enc_num_unit, 1)
+        self.interleaver = Interleaver(args, p_array)
+        self._flat = FlatCache()
+        self._ws = Workspace()
+        self.shard_group = None      # set to a torch.distributed group when the batch is sharded across ranks
+
+    def set_interleaver(self, p_array):
+        self.interleaver.set_parray(p_array)
+
+    def set_parallel(self):
+        for n in ("enc_cnn_1", "enc_cnn_2", "enc_cnn_3", "enc_linear_1", "enc_linear_2", "enc_linear_3"):
+            m = getattr(self, n)
+            if not isinstance(m, ParallelShim):
+                setattr(self, n, ParallelShim(m))
+
+    # -- canonical flat order of include/turboae_b200.h ------------------------------------------------
+    def ordered_parameters(self):
+        out = []
+        for i in (1, 2, 3):
+            for conv in unwrap(getattr(self, "enc_cnn_%d" % i)).cnns:
+                out += [conv.weight, conv.bias]
+            lin = unwrap(getattr(self, "enc_linear_%d" % i))
+            out += [lin.weight, lin.bias]
+        return out
+
+    def config(self, block_len):
+        a = self.args
+        return _lib.TaeEncConfig(block_len, a.enc_num_layer, a.enc_num_unit, a.enc_kernel_size)
+
+    def _check_supported(self):
+        a = self.args
+        if getattr(a, "is_variable_block_len", False):
+            raise NotImplementedError("--is_variable_block_len is not supported by turboae_b200")
+        if getattr(a, "enc_act", "elu") != "elu":
+            raise NotImplementedError("enc_act=%r: only 'elu' is built (get_args.py:100 'only elu works')" % a.enc_act)
+        if getattr(a, "precompute_norm_stats", False):
+            raise NotImplementedError("--precompute_norm_stats is not supported by turboae_b200")
+        if getattr(a, "train_channel_mode", "block_norm") == "block_norm_ste":
+            raise NotImplementedError("train_channel_mode=block_norm_ste (STEQuantize) is not built yet")
+
+    def encode_unnormalised(self, inputs, stats):
+        """x_tx (B, L, 3) before power_constraint; adds (sum, sumsq, count) into the 3 device doubles `stats`."""
+        lib = _lib.load()
+        B, L = inputs.shape[0], inputs.shape[1]
+        dev = inputs.device
+        cfg = self.config(L)
+        flat = self._flat.get(self.ordered_parameters())
+        if flat.device != dev:
+            raise _lib.TaeError("encoder parameters are on %s but the input is on %s" % (flat.device, dev))
+        perm, _ = self.interleaver.device_index(dev)
+        ws_bytes = lib.tae_enc_workspace_bytes(cfg, B)
+        ws = self._ws.get(ws_bytes, dev)
+        x_tx = torch.empty((B, L, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.tae_enc_forward(cfg, _lib.ptr(flat), _lib.ptr(inputs), _lib.ptr(perm), _lib.ptr(x_tx),
+                                           _lib.ptr(stats), B, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+        return x_tx
+
+    def forward(self, inputs):
+        self._check_supported()
+        if self.this_device.type != "cuda":
+            raise _lib.TaeError("no CUDA device: turboae_b200 has no CPU fallback")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("turboae_b200: encoder backward is not built yet (SURVEY.md 8(f) row 1); "
+                                      "use torch.no_grad()")
+        x = inputs.to(device=self.this_device, dtype=torch.float32).contiguous()
+        if x.dim() != 3 or x.shape[2] != 1:
+            raise _lib.TaeError("ENC_interCNN expects (B, L, 1) bits, got %s" % (tuple(x.shape),))
+        lib = _lib.load()
+        stats = torch.zeros(3, dtype=torch.float64, device=x.device)
+        x_tx = self.encode_unnormalised(x, stats)
+        if self.args.no_code_norm:
+            return x_tx
+        if self.shard_group is not None:
+            # power_constraint normalises over the WHOLE batch (encoders.py:107-116): merge the per-rank sums
+            torch.distributed.all_reduce(stats, group=self.shard_group)
+        codes = torch.empty_like(x_tx)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.tae_power_norm_f32(_lib.ptr(x_tx), _lib.ptr(codes), x_tx.numel(), _lib.ptr(stats), None,
+                                              _lib.stream_ptr(x.device)))
+        if self.args.enc_truncate_limit > 0:
+            codes = torch.clamp(codes, -self.args.enc_truncate_limit, self.args.enc_truncate_limit)
+        return codes

@@ -138,6 +138,40 @@ def test_umma_descriptor_probe(K, N, shift):
     np.testing.assert_allclose(D.cpu().numpy(), ref.cpu().numpy(), atol=1e-3, rtol=1e-3)
 
 
+@pytest.mark.parametrize("N,shift,lbo_rows", [(112, 0, 1), (112, 3, 1), (112, 0, 2), (16, 4, 2), (112, 2, 7)])
+def test_umma_probe_two_taps_in_one_kstep(N, shift, lbo_rows):
+    """K chunk 1 of the A operand = the same 8-channel chunk `lbo_rows` rows further down (LBO = 16*lbo_rows bytes):
+    the packed-K scheme of the CTA-pair decoder (taps t, t+1 of one chunk in a single k-step)."""
+    from turboae_b200 import _lib
+    lib = _lib.load()
+    R = 144
+    rs = np.random.RandomState(N * 100 + shift * 10 + lbo_rows)
+    X = torch.from_numpy(rs.standard_normal((R, 8)).astype(np.float32)).to(DEV).to(torch.bfloat16)
+    Bm = torch.from_numpy(rs.standard_normal((N, 16)).astype(np.float32)).to(DEV).to(torch.bfloat16)
+    D = torch.zeros(128, N, device=DEV)
+    err = torch.zeros(4, dtype=torch.int32, device=DEV)
+    _lib.check(lib.tae_debug_probe_lbo(_lib.ptr(X), _lib.ptr(Bm), _lib.ptr(D), R, N, shift, lbo_rows, _lib.ptr(err),
+                                       _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    A = torch.cat([X[shift:shift + 128], X[shift + lbo_rows:shift + lbo_rows + 128]], dim=1).float()
+    np.testing.assert_allclose(D.cpu().numpy(), (A @ Bm.float().t()).cpu().numpy(), atol=1e-3, rtol=1e-3)
+
+
+@pytest.mark.parametrize("K,N", [(16, 112), (64, 112), (112, 16), (32, 32)])
+def test_umma_probe_cta_pair(K, N):
+    """tcgen05.mma.cta_group::2 (M = 256): CTA r supplies rows 128r.. of A and columns r*N/2.. of B."""
+    from turboae_b200 import _lib
+    lib = _lib.load()
+    rs = np.random.RandomState(K * 7 + N)
+    A = torch.from_numpy(rs.standard_normal((256, K)).astype(np.float32)).to(DEV).to(torch.bfloat16)
+    Bm = torch.from_numpy(rs.standard_normal((N, K)).astype(np.float32)).to(DEV).to(torch.bfloat16)
+    D = torch.zeros(256, N, device=DEV)
+    err = torch.zeros(4, dtype=torch.int32, device=DEV)
+    _lib.check(lib.tae_debug_probe_pair(_lib.ptr(A), _lib.ptr(Bm), _lib.ptr(D), K, N, _lib.ptr(err), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(D.cpu().numpy(), (A.float() @ Bm.float().t()).cpu().numpy(), atol=2e-3, rtol=2e-3)
+
+
 # ------------------------------------------------------------------------------------------------- a8 bf16
 def _bf16_checks(y, tr, g, n_flip_max):
     for j in range(12):

@@ -50,6 +50,8 @@ _SIGNATURES = {
     # debug / self-test entry points
     "tae_debug_set_dump": (None, [_P]),
     "tae_debug_umma_probe": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, _P, _P]),
+    "tae_debug_probe_lbo": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "tae_debug_probe_pair": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
 }
 # symbols every build must export (checked by tests/test_cabi.py against include/turboae_b200.h)
 PUBLIC_SYMBOLS = [s for s in _SIGNATURES if not s.startswith("tae_debug_")]

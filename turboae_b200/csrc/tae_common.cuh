@@ -103,4 +103,13 @@ int dec_forward_bf16(const TaeDecConfig& c, const float* params, const void* pac
                      const int32_t* perm, const int32_t* inv_perm, float* out, float* trace, int B, void* ws,
                      size_t ws_bytes, cudaStream_t s);
 
+// ---- bf16 tcgen05 path, CTA-pair version (tae_dec_pair.cu): the default --------------------
+bool dec_pair_supported(const TaeDecConfig& c, const char** why);
+size_t dec_pair_packed_bytes(const TaeDecConfig& c);
+int dec_pair_pack(const TaeDecConfig& c, const float* params, void* packed, cudaStream_t s);
+int dec_forward_pair(const TaeDecConfig& c, const void* packed, const float* received, const int32_t* perm,
+                     const int32_t* inv_perm, float* out, float* trace, int B, void* ws, size_t ws_bytes, cudaStream_t s);
+// TURBOAE_B200_DEC_IMPL=v1 selects the older single-CTA kernel (development A/B only)
+bool use_dec_v1();
+
 }  // namespace tae

@@ -1,0 +1,935 @@
+// Fused DEC_LargeCNN.forward on 5th-gen tensor cores, CTA-pair version (TAE_PRECISION_BF16), sm_100a only.
+//
+// Reference arithmetic restated (paths relative to the reference checkout):
+//   decoders.py:219-269 (turbo schedule), cnn_utils.py:36-46 (conv + ELU stack),
+//   interleavers.py:15-21, 43-48 (row permutations).
+//
+// Execution model
+//   * cluster of 2 CTAs (one per SM of a TPC), persistent; each CTA owns one "group" = a 512-row activation
+//     buffer holding floor(514/(L+2)) codewords, each followed by 2 all-zero separator rows (= the zero
+//     padding of cnn_utils.py:16 for free).  4 MMA tiles of 128 rows per CTA.
+//   * every conv layer is tcgen05.mma.cta_group::2, M = 256 (tile m of both CTAs), N = 112 (100 output
+//     channels, padded), issued by ONE thread of the leader CTA.  Each CTA stages only ITS half of the weight
+//     columns (56 of 112), so a whole layer (57 KB per CTA) is resident while the four tiles run through it:
+//     tile-outer order => the epilogue of tile m overlaps the MMAs of tile m+1, and the next layer's tile 0 can
+//     start as soon as tiles 0 and 1 of this layer are written back.
+//   * K is packed to exactly 32 k-steps of 16: 5 taps x 96 channels = 30 k-steps from the canonical
+//     no-swizzle K-major activation layout [C/8][rows][8] (tap t = descriptor start address + 16*t bytes), and
+//     channels 96..99 live in a "combined" chunk whose row r holds [x[r][96..99], x[r+1][96..99]], so that one
+//     16-byte chunk carries two taps; the last k-step pairs tap 4 of those channels with a constant-one chunk
+//     that injects the bias (bf16 hi + lo split) -- no output channel, no epilogue add.
+//   * activations are updated IN PLACE: the epilogue of tile m may not touch the two rows that tile m+1's MMAs
+//     still read (its last two), so those go to a side buffer and are flushed by the next tile's epilogue.
+//   * priors stay in shared memory (fp32) for all 2*I half-iterations; (de)interleave is the row index of the
+//     Linear epilogue's store.  HBM sees `received` once and `out` once; weights stream from L2 once per CTA
+//     pair and layer through a bulk-copy (UBLKCP) ring.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "tae_common.cuh"
+
+namespace tae {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// geometry
+// ------------------------------------------------------------------------------------------
+constexpr int GROUP_ROWS = 512;
+constexpr int BUF_ROWS = GROUP_ROWS + 4;          // 2 halo rows in front and behind
+constexpr int N_TILES = 4;
+constexpr int NPAD = 112;                         // UMMA N of a conv layer (both CTAs together)
+constexpr int NHALF = NPAD / 2;                   // weight columns staged per CTA
+constexpr int LIN_N = 16, LIN_NHALF = 8;
+constexpr int N_REG_CH = 96;                      // channels in regular chunks
+constexpr int N_REG_CHUNKS = N_REG_CH / 8;        // 12
+constexpr int UNITS_MAX = 100;
+constexpr int TAPS = 5;
+constexpr int KS_CONV = 32;                       // k-steps of a units->units layer
+constexpr int KS_L0 = 3;                          // k-steps of the (2+F)->units layer
+constexpr int KS_LIN = 7;                         // k-steps of the Linear
+constexpr int KS_PER_SLOT = 4;
+constexpr int SLOTS_CONV = KS_CONV / KS_PER_SLOT; // 8
+constexpr uint32_t ROW_B = 16;
+constexpr uint32_t CHUNK_B = BUF_ROWS * ROW_B;                  // 8256
+constexpr uint32_t WCHUNK_B = NHALF * ROW_B;                    // 896: one 8-channel K chunk of 56 weight columns
+constexpr uint32_t SLOT_B = KS_PER_SLOT * 2 * WCHUNK_B;         // 7168
+constexpr uint32_t L0_B = KS_L0 * 2 * WCHUNK_B;                 // 5376
+constexpr uint32_t LIN_WCHUNK_B = LIN_NHALF * ROW_B;            // 128
+constexpr uint32_t LIN_B = KS_LIN * 2 * LIN_WCHUNK_B;           // 1792
+constexpr int NS = 10;                                          // weight ring slots
+constexpr int SIDE_ENTRIES = 13;                                // 12 regular chunks + (ch 96..99)
+constexpr int N_EPI_WARPS = 8;
+constexpr int N_EPI_THREADS = N_EPI_WARPS * 32;
+constexpr int WARP_PRODUCER = 0;
+constexpr int WARP_MMA = 1;
+constexpr int EPI_WARP0 = 2;
+constexpr int N_THREADS = 320;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TMEM_LIN_COL = N_TILES * NPAD;               // 448
+
+// instruction descriptor (kind::f16): D fp32, A/B bf16, both K-major
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct Smem {
+  uint32_t act, comb, xin[2], ones, pri[2], side, wslot, perm, inv_perm, bars, tmem_ptr, total;
+};
+// barrier slots (8 bytes each)
+enum { B_WFULL = 0, B_WEMPTY = NS, B_PFULL = 2 * NS, B_ACC = 3 * NS, B_ACT = 3 * NS + 4, N_BARS = 3 * NS + 8 };
+
+__host__ __device__ inline Smem make_smem(int F) {
+  Smem s{};
+  uint32_t o = 0;
+  s.act = o; o += N_REG_CHUNKS * CHUNK_B;
+  s.comb = o; o += CHUNK_B;
+  s.xin[0] = o; o += CHUNK_B;
+  s.xin[1] = o; o += CHUNK_B;
+  s.ones = o; o += CHUNK_B;                        // after comb and xin: positive LBO towards it
+  s.pri[0] = o; o += (uint32_t)F * BUF_ROWS * 4;
+  s.pri[1] = o; o += (uint32_t)F * BUF_ROWS * 4;
+  o = (o + 15) / 16 * 16;
+  s.side = o; o += 3 * 2 * SIDE_ENTRIES * 16;
+  s.wslot = o; o += NS * SLOT_B;
+  s.perm = o; o += 1024;
+  s.inv_perm = o; o += 1024;
+  s.bars = o; o += N_BARS * 8;
+  s.tmem_ptr = o; o += 16;
+  s.total = o;
+  return s;
+}
+
+struct PairArgs {
+  const uint8_t* wimg;
+  const float* received;
+  float* out;
+  float* trace;
+  int* err;
+  const int32_t* perm;
+  const int32_t* inv_perm;
+  int B, L, F, I, n_layer, extrinsic, n_groups, n_pairs, cw_per_group;
+  uint32_t stack_bytes;        // bytes of one stack's image (both halves)
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t n_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// arrive (release at cluster scope) on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded waits: a protocol bug traps (context error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) {
+      if (err) atomicExch(err, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* err, int code) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > (1u << 22)) {
+      if (err) atomicExch(err, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  if (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  if (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// Shared-memory matrix descriptor, no swizzle, K-major: rows 16 bytes apart inside an 8-row core matrix,
+// SBO = byte distance between 8-row groups (128: rows are contiguous), LBO = byte distance between the two
+// 8-element K chunks of one UMMA_K = 16 slice.  Bits [46,48) = 1: Blackwell descriptor version.
+// low word (start address, LBO) and full descriptor (high word = SBO 128 B + version, a constant)
+__device__ __forceinline__ uint32_t dlo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ uint64_t dfull(uint32_t lo) { return ((uint64_t)((128u >> 4) | (1u << 14)) << 32) | lo; }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128u >> 4) << 32) |
+         (1ull << 46);
+}
+
+template <int CG>
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+// Arrives on the mbarrier (same offset in every CTA of `mask`) when all previously issued MMAs have completed.
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit_1(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// true in exactly one lane of a converged warp (ptxas keeps the surrounding values in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred px;\n\t"
+      "elect.sync _|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float elu_fast(float v) {
+  const float e = fast_exp2(v * 1.4426950408889634f) - 1.0f;
+  return v > 0.f ? v : e;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint16_t ld_shared_u16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint16_t bf16_bits(float v) {
+  __nv_bfloat16 t = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&t);
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_THREADS) : "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// weight image (bf16), per stack:  [slot][cta half][bytes];  slot 0 = layer 0 (3 k-steps), then
+// (n_layer-1) x 8 slots of 4 k-steps, then the Linear (7 k-steps, 8 columns per half).
+// One k-step of a half = 2 chunks [columns of this half][8 K elements].
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// K element e (0..15) of k-step ks of a units->units layer  ->  (channel, tap) or bias / zero
+__device__ __forceinline__ float conv_w_elem(const float* __restrict__ w, const float* __restrict__ b, int units, int o,
+                                             int ks, int e) {
+  if (o >= units) return 0.f;
+  if (ks < 30) {
+    const int t = ks / 6, c = 16 * (ks % 6) + e;
+    return c < units ? w[((size_t)o * units + c) * TAPS + t] : 0.f;
+  }
+  if (ks == 30) {
+    const int t = e >> 2, c = N_REG_CH + (e & 3);
+    return c < units ? w[((size_t)o * units + c) * TAPS + t] : 0.f;
+  }
+  if (e < 4) {
+    const int c = N_REG_CH + e;
+    return c < units ? w[((size_t)o * units + c) * TAPS + 4] : 0.f;
+  }
+  if (e == 8) return bf16_round(b[o]);
+  if (e == 9) return b[o] - bf16_round(b[o]);
+  return 0.f;
+}
+__device__ __forceinline__ float l0_w_elem(const float* __restrict__ w, const float* __restrict__ b, int units, int cin,
+                                           int o, int ks, int e) {
+  if (o >= units) return 0.f;
+  const int t = 2 * ks + (e >> 3), c = e & 7;
+  if (t < TAPS) return c < cin ? w[((size_t)o * cin + c) * TAPS + t] : 0.f;
+  if (e == 8) return bf16_round(b[o]);
+  if (e == 9) return b[o] - bf16_round(b[o]);
+  return 0.f;
+}
+__device__ __forceinline__ float lin_w_elem(const float* __restrict__ w, const float* __restrict__ b, int units, int fout,
+                                            int o, int ks, int e) {
+  if (o >= fout) return 0.f;
+  if (ks < 6) {
+    const int c = 16 * ks + e;
+    return c < units ? w[(size_t)o * units + c] : 0.f;
+  }
+  if (e < 4) {
+    const int c = N_REG_CH + e;
+    return c < units ? w[(size_t)o * units + c] : 0.f;
+  }
+  if (e == 8) return bf16_round(b[o]);
+  if (e == 9) return b[o] - bf16_round(b[o]);
+  return 0.f;
+}
+
+__global__ void pack_pair_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ img,
+                                 const DecStackLayout* __restrict__ lay, int n_stacks, int n_layer, int units, int F,
+                                 uint32_t stack_elems) {
+  const size_t total = (size_t)n_stacks * stack_elems;
+  const uint32_t l0_elems = 2 * L0_B / 2, slot_elems = 2 * SLOT_B / 2;
+  const uint32_t conv_elems = (uint32_t)(n_layer - 1) * SLOTS_CONV * slot_elems;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int st = (int)(idx / stack_elems);
+    uint32_t r = (uint32_t)(idx % stack_elems);
+    const DecStackLayout& S = lay[st];
+    float v;
+    if (r < l0_elems) {
+      const int half = r / (L0_B / 2);
+      r %= (L0_B / 2);
+      const int ks = r / (2 * NHALF * 8), ch = (r / (NHALF * 8)) & 1, n = (r / 8) % NHALF, e8 = r % 8;
+      v = l0_w_elem(params + S.conv[0].w_off, params + S.conv[0].b_off, units, 2 + F, half * NHALF + n, ks, ch * 8 + e8);
+    } else if (r < l0_elems + conv_elems) {
+      r -= l0_elems;
+      const int sl = r / slot_elems;                 // slot within the stack's conv layers
+      r %= slot_elems;
+      const int half = r / (SLOT_B / 2);
+      r %= (SLOT_B / 2);
+      const int j = 1 + sl / SLOTS_CONV;
+      const int ks = (sl % SLOTS_CONV) * KS_PER_SLOT + r / (2 * NHALF * 8);
+      const int ch = (r / (NHALF * 8)) & 1, n = (r / 8) % NHALF, e8 = r % 8;
+      v = conv_w_elem(params + S.conv[j].w_off, params + S.conv[j].b_off, units, half * NHALF + n, ks, ch * 8 + e8);
+    } else {
+      r -= l0_elems + conv_elems;
+      const int half = r / (LIN_B / 2);
+      r %= (LIN_B / 2);
+      const int ks = r / (2 * LIN_NHALF * 8), ch = (r / (LIN_NHALF * 8)) & 1, n = (r / 8) % LIN_NHALF, e8 = r % 8;
+      v = lin_w_elem(params + S.lin_w_off, params + S.lin_b_off, units, S.fout, half * LIN_NHALF + n, ks, ch * 8 + e8);
+    }
+    img[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// the fused decoder kernel (cluster of 2)
+// ------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pair_kernel(const PairArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const Smem S = make_smem(a.F);
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int L = a.L, F = a.F, CW_ROWS = a.L + 2;
+  const int n_stacks = 2 * a.I;
+  const int slots_per_stack = 2 + SLOTS_CONV * (a.n_layer - 1);
+
+  auto bar = [&](int i) { return sbase + S.bars + 8u * (uint32_t)i; };
+
+  // ---- one-time setup ----------------------------------------------------------------------
+  for (uint32_t i = threadIdx.x * 16; i < S.bars; i += N_THREADS * 16) st_shared_v4(sbase + i, 0u, 0u, 0u, 0u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); mbar_init(bar(B_PFULL + i), 1); }
+    for (int m = 0; m < N_TILES; ++m) { mbar_init(bar(B_ACC + m), 1); mbar_init(bar(B_ACT + m), 2); }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < L; i += N_THREADS) {
+    st_shared_u16(sbase + S.perm + 2 * i, (uint16_t)a.perm[i]);
+    st_shared_u16(sbase + S.inv_perm + 2 * i, (uint16_t)a.inv_perm[i]);
+  }
+  if (warp == WARP_PRODUCER) tmem_alloc<2>(sbase + S.tmem_ptr, TMEM_COLS);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                       // both CTAs' barriers are initialised before any remote arrive
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sbase + S.tmem_ptr) : "memory");
+
+  const int pair0 = (int)cluster_id_x(), pair_stride = (int)n_clusters_x();
+
+  if (warp == WARP_PRODUCER) {
+    // ================= weight producer: this CTA's half of every slot ==============================
+    if (lane == 0) {
+      uint32_t pos = 0, phase = 0;
+      for (int pr = pair0; pr < a.n_pairs; pr += pair_stride) {
+        for (int st = 0; st < n_stacks; ++st) {
+          const uint8_t* src = a.wimg + (size_t)st * a.stack_bytes;
+          for (int i = 0; i < slots_per_stack; ++i) {
+            const uint32_t bytes = (i == 0) ? L0_B : (i == slots_per_stack - 1 ? LIN_B : SLOT_B);
+            mbar_wait(bar(B_WEMPTY + pos), phase ^ 1, a.err, 1);
+            mbar_arrive_expect_tx(bar(B_WFULL + pos), bytes);
+            bulk_g2s(sbase + S.wslot + pos * SLOT_B, src + rank * bytes, bytes, bar(B_WFULL + pos));
+            src += 2 * bytes;
+            if (++pos == NS) { pos = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    if (rank == 1) {
+      // ================= peer relay: tell the leader that this CTA's half of a slot has landed ======
+      uint32_t pos = 0, phase = 0;
+      for (int pr = pair0; pr < a.n_pairs; pr += pair_stride)
+        for (int i = 0; i < n_stacks * slots_per_stack; ++i) {
+          mbar_wait(bar(B_WFULL + pos), phase, a.err, 2);
+          if (elect_one()) mbar_arrive_cluster(bar(B_PFULL + pos), 0);
+          __syncwarp();
+          if (++pos == NS) { pos = 0; phase ^= 1; }
+        }
+    } else {
+      // ================= MMA issuer: the warp of the leader CTA runs converged, one elected lane issues =====
+      constexpr uint32_t IDESC_CONV = make_idesc(256, NPAD), IDESC_LIN = make_idesc(256, LIN_N);
+      uint32_t pos = 0, wphase = 0, step = 0;
+      const uint32_t act = sbase + S.act, comb = sbase + S.comb, ones = sbase + S.ones;
+      auto wait_w = [&](uint32_t p, uint32_t ph) {
+        mbar_wait(bar(B_WFULL + p), ph, a.err, 3);
+        mbar_wait_cluster(bar(B_PFULL + p), ph, a.err, 4);
+      };
+      for (int pr = pair0; pr < a.n_pairs; pr += pair_stride) {
+        for (int st = 0; st < n_stacks; ++st) {
+          const uint32_t xin = sbase + S.xin[st & 1];
+          for (int layer = 0; layer <= a.n_layer; ++layer, ++step) {
+            const uint32_t par = step & 1;
+            const int n_slots = (layer == 0 || layer == a.n_layer) ? 1 : SLOTS_CONV;
+#pragma unroll 1
+            for (int m = 0; m < N_TILES; ++m) {
+              // inputs of tile m: rows of tiles m-1 (done earlier), m and the first rows of m+1; the deferred
+              // last two rows of tile m are flushed by the epilogue of tile m+1.  Layer 0 reads the stack input,
+              // which the previous Linear epilogue scatters across the whole group.
+              if (m == 0) {
+                mbar_wait_cluster(bar(B_ACT + 0), par, a.err, 5);
+                mbar_wait_cluster(bar(B_ACT + 1), par, a.err, 5);
+                if (layer == 0) { mbar_wait_cluster(bar(B_ACT + 2), par, a.err, 5); mbar_wait_cluster(bar(B_ACT + 3), par, a.err, 5); }
+              } else if (m < N_TILES - 1) {
+                mbar_wait_cluster(bar(B_ACT + m + 1), par, a.err, 5);
+              }
+              tc_fence_after();
+              const uint32_t rowoff = (uint32_t)(128 * m) * ROW_B;
+              uint32_t p = pos, ph = wphase;
+              // descriptors are assembled from per-tile base words plus compile-time constants (the loops below
+              // are fully unrolled): ONE thread has to issue an MMA every 56 cycles.
+              uint32_t wlo = dlo(sbase + S.wslot + p * SLOT_B, WCHUNK_B);
+              const uint32_t d_tmem = tmem_base + m * NPAD;
+              if (layer == 0) {
+                if (m == 0) { wait_w(p, ph); tc_fence_after(); }
+                const uint32_t x_lo = dlo(xin + rowoff, ROW_B);
+                const uint32_t x2_lo = dlo(xin + rowoff + 4 * ROW_B, (ones + 2 * ROW_B) - (xin + 4 * ROW_B));
+                if (elect_one()) {
+                  umma_bf16<2>(d_tmem, dfull(x_lo), dfull(wlo), IDESC_CONV, 0);                                 // taps 0,1
+                  umma_bf16<2>(d_tmem, dfull(x_lo + 2), dfull(wlo + ((2 * WCHUNK_B) >> 4)), IDESC_CONV, 1);     // taps 2,3
+                  umma_bf16<2>(d_tmem, dfull(x2_lo), dfull(wlo + ((4 * WCHUNK_B) >> 4)), IDESC_CONV, 1);        // tap 4, bias
+                  if (m == N_TILES - 1) umma_commit_pair(bar(B_WEMPTY + p), 3);
+                }
+                __syncwarp();
+              } else if (layer < a.n_layer) {
+                const uint32_t act_lo = dlo(act + rowoff, CHUNK_B);
+                const uint32_t c30_lo = dlo(comb + rowoff, 2 * ROW_B);             // [taps 0,1 | taps 2,3] of channels 96..99
+                const uint32_t c31_lo = dlo(comb + rowoff + 4 * ROW_B, (ones + 2 * ROW_B) - (comb + 4 * ROW_B));   // [tap 4 | ones (bias)]
+#pragma unroll
+                for (int s = 0; s < SLOTS_CONV; ++s) {
+                  if (m == 0) { wait_w(p, ph); tc_fence_after(); }   // resident until tile 3 releases the slot
+                  if (elect_one()) {
+#pragma unroll
+                    for (int k4 = 0; k4 < KS_PER_SLOT; ++k4) {
+                      const int ks = s * KS_PER_SLOT + k4;
+                      const uint32_t alo = ks < 30 ? act_lo + ((uint32_t)(2 * (ks % 6)) * CHUNK_B + (uint32_t)(ks / 6) * ROW_B) / 16
+                                                   : (ks == 30 ? c30_lo : c31_lo);
+                      umma_bf16<2>(d_tmem, dfull(alo), dfull(wlo + (uint32_t)(k4 * 2 * WCHUNK_B) / 16), IDESC_CONV, ks > 0);
+                    }
+                    if (m == N_TILES - 1) umma_commit_pair(bar(B_WEMPTY + p), 3);
+                  }
+                  __syncwarp();
+                  wlo += SLOT_B / 16;
+                  if (++p == NS) { p = 0; ph ^= 1; wlo -= NS * SLOT_B / 16; }
+                }
+              } else {
+                if (m == 0) { wait_w(p, ph); tc_fence_after(); }
+                const uint32_t act_lo = dlo(act + rowoff + 2 * ROW_B, CHUNK_B);                      // centre row only
+                const uint32_t c_lo = dlo(comb + rowoff + 2 * ROW_B, ones - comb);
+                const uint32_t wl = dlo(sbase + S.wslot + p * SLOT_B, LIN_WCHUNK_B);
+                if (elect_one()) {
+#pragma unroll
+                  for (int ks = 0; ks < KS_LIN; ++ks)
+                    umma_bf16<2>(tmem_base + TMEM_LIN_COL + m * LIN_N, dfull(ks < 6 ? act_lo + (uint32_t)(2 * ks) * CHUNK_B / 16 : c_lo),
+                                 dfull(wl + (uint32_t)(ks * 2 * LIN_WCHUNK_B) / 16), IDESC_LIN, ks > 0);
+                  if (m == N_TILES - 1) umma_commit_pair(bar(B_WEMPTY + p), 3);
+                }
+                __syncwarp();
+              }
+              if (elect_one()) umma_commit_pair(bar(B_ACC + m), 3);
+              __syncwarp();
+            }
+            // advance the ring past this layer's slots
+            for (int s = 0; s < n_slots; ++s)
+              if (++pos == NS) { pos = 0; wphase ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps (8): TMEM -> ELU -> bf16 -> shared memory =================
+    const int ew = warp - EPI_WARP0;           // 0..7
+    const int q = warp & 3;                    // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;                  // column half: 0 -> channels 0..47, 1 -> channels 48..99
+    const int tid = threadIdx.x - EPI_WARP0 * 32;
+    uint32_t step = 0;
+    for (int pr = pair0; pr < a.n_pairs; pr += pair_stride) {
+      const int grp = 2 * pr + (int)rank;
+      const int cw0 = grp * a.cw_per_group;
+      const int n_cw = max(0, min(a.cw_per_group, a.B - cw0));
+
+      // ---- group start: stack inputs, zero prior, ones chunk ----------------------------------------
+      for (uint32_t i = tid * 16; i < 3 * CHUNK_B; i += N_EPI_THREADS * 16) st_shared_v4(sbase + S.xin[0] + i, 0u, 0u, 0u, 0u);
+      for (uint32_t i = tid * 16; i < (uint32_t)F * BUF_ROWS * 4; i += N_EPI_THREADS * 16)
+        st_shared_v4(sbase + S.pri[0] + i, 0u, 0u, 0u, 0u);
+      epi_bar_sync();
+      for (int i = tid; i < n_cw * L; i += N_EPI_THREADS) {
+        const int c = i / L, l = i % L;
+        const float* r = a.received + ((size_t)(cw0 + c) * L + l) * 3;
+        const float r0 = r[0], r1 = r[1], r2 = r[2];
+        const uint32_t row = (uint32_t)(c * CW_ROWS + l + 2) * ROW_B;
+        const uint32_t row_i = (uint32_t)(c * CW_ROWS + ld_shared_u16(sbase + S.inv_perm + 2 * l) + 2) * ROW_B;
+        st_shared_u16(sbase + S.xin[0] + row + 0, bf16_bits(r0));        // r_sys          (decoders.py:221)
+        st_shared_u16(sbase + S.xin[0] + row + 2, bf16_bits(r1));        // r_par1         (decoders.py:223)
+        st_shared_u16(sbase + S.xin[1] + row_i + 0, bf16_bits(r0));      // r_sys_int[i] = r_sys[p[i]]  (:222)
+        st_shared_u16(sbase + S.xin[1] + row + 2, bf16_bits(r2));        // r_par2         (decoders.py:224)
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + S.ones + row), "r"(0x3F803F80u) : "memory");   // bias inputs
+      }
+      fence_proxy_async();
+      epi_bar_sync();
+      if (tid == 0)
+        for (int m = 0; m < N_TILES; ++m) mbar_arrive_cluster(bar(B_ACT + m), 0);
+
+      for (int st = 0; st < n_stacks; ++st) {
+        for (int layer = 0; layer <= a.n_layer; ++layer, ++step) {
+          const uint32_t par = step & 1;
+          const bool last_step = (st == n_stacks - 1 && layer == a.n_layer);
+#pragma unroll 1
+          for (int m = 0; m < N_TILES; ++m) {
+            mbar_wait(bar(B_ACC + m), par, a.err, 6);
+            tc_fence_after();
+            const int g_row = 128 * m + 32 * q + lane;
+            const int g_cw = g_row / CW_ROWS, g_l = g_row % CW_ROWS;
+            const bool valid = (g_l < L) && (g_cw < n_cw);
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
+            if (layer < a.n_layer) {
+              // -- flush the deferred last two rows of tile m-1 (its readers, the MMAs of tile m, are done) --
+              if (m > 0 && tid < 2 * SIDE_ENTRIES) {
+                const int r = tid / SIDE_ENTRIES, c = tid % SIDE_ENTRIES;
+                const uint32_t src = sbase + S.side + (uint32_t)(((m - 1) * 2 + r) * SIDE_ENTRIES + c) * 16;
+                const uint32_t brow = (uint32_t)(128 * m - 2 + r + 2);            // buffer row
+                uint32_t x0, x1, x2, x3;
+                ld_shared_v4(src, x0, x1, x2, x3);
+                if (c < N_REG_CHUNKS) {
+                  st_shared_v4(sbase + S.act + (uint32_t)c * CHUNK_B + brow * ROW_B, x0, x1, x2, x3);
+                } else {
+                  st_shared_v2(sbase + S.comb + brow * ROW_B, x0, x1);
+                  st_shared_v2(sbase + S.comb + (brow - 1) * ROW_B + 8, x0, x1);
+                }
+              }
+              // -- this thread's row, its half of the channels ------------------------------------------
+              const bool defer = (m < N_TILES - 1) && (q == 3) && (lane >= 30);
+              const uint32_t brow = (uint32_t)(g_row + 2);
+              const uint32_t side_row = sbase + S.side + (uint32_t)((m * 2 + (lane - 30)) * SIDE_ENTRIES) * 16;
+              const uint32_t col0 = (uint32_t)(m * NPAD + half * 48);
+              uint32_t r[56];
+              tmem_ld16(lane_addr + col0, r);
+              tmem_ld16(lane_addr + col0 + 16, r + 16);
+              tmem_ld16(lane_addr + col0 + 32, r + 32);
+              if (half == 1) tmem_ld8(lane_addr + col0 + 48, r + 48);
+              tmem_ld_wait();
+              const uint32_t keep = valid ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+              for (int c = 0; c < 6; ++c) {
+                uint32_t p[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  p[j] = pack_bf16x2(elu_fast(__uint_as_float(r[8 * c + 2 * j])), elu_fast(__uint_as_float(r[8 * c + 2 * j + 1]))) & keep;
+                const int chunk = half * 6 + c;
+                const uint32_t dst = defer ? side_row + (uint32_t)chunk * 16 : sbase + S.act + (uint32_t)chunk * CHUNK_B + brow * ROW_B;
+                st_shared_v4(dst, p[0], p[1], p[2], p[3]);
+              }
+              if (half == 1) {
+                const uint32_t p0 = pack_bf16x2(elu_fast(__uint_as_float(r[48])), elu_fast(__uint_as_float(r[49]))) & keep;
+                const uint32_t p1 = pack_bf16x2(elu_fast(__uint_as_float(r[50])), elu_fast(__uint_as_float(r[51]))) & keep;
+                if (defer) {
+                  st_shared_v2(side_row + 12 * 16, p0, p1);
+                } else {
+                  st_shared_v2(sbase + S.comb + brow * ROW_B, p0, p1);              // x[r][96..99]  -> comb[r][0:4]
+                  st_shared_v2(sbase + S.comb + (brow - 1) * ROW_B + 8, p0, p1);    //               -> comb[r-1][4:8]
+                }
+              }
+            } else if (half == 0) {
+              // -- Linear epilogue: extrinsic subtraction + (de)interleave into the next stack's input ------
+              const bool last = (st == n_stacks - 1);
+              const int fout = last ? 1 : F;
+              const uint32_t pri_cur = sbase + S.pri[st & 1], pri_nxt = sbase + S.pri[(st & 1) ^ 1];
+              const uint32_t xin_nxt = sbase + S.xin[(st & 1) ^ 1];
+              const uint32_t map = sbase + ((st & 1) ? S.perm : S.inv_perm);   // where position l lands
+              uint32_t r[8];
+              tmem_ld8(lane_addr + TMEM_LIN_COL + (uint32_t)(m * LIN_N), r);
+              tmem_ld_wait();
+              if (valid) {
+                const int cw = cw0 + g_cw, l = g_l;
+                if (a.trace) {
+                  float* tr = a.trace + (((size_t)st * a.B + cw) * L + l) * F;
+                  for (int f = 0; f < fout; ++f) tr[f] = __uint_as_float(r[f]);
+                }
+                if (last) {
+                  const int dl = ld_shared_u16(sbase + S.perm + 2 * l);         // deinterleave: out[p[l]] = x[l]
+                  a.out[(size_t)cw * L + dl] = 1.f / (1.f + __expf(-__uint_as_float(r[0])));   // decoders.py:267
+                } else {
+                  const int dl = ld_shared_u16(map + 2 * l);
+                  const uint32_t drow = (uint32_t)(g_cw * CW_ROWS + dl + 2);
+                  for (int f = 0; f < F; ++f) {
+                    const float prior = a.extrinsic ? ld_shared_f32(pri_cur + ((uint32_t)f * BUF_ROWS + g_row + 2) * 4) : 0.f;
+                    const float ext = __uint_as_float(r[f]) - prior;             // decoders.py:235-236, 246-247
+                    st_shared_f32(pri_nxt + ((uint32_t)f * BUF_ROWS + drow) * 4, ext);
+                    st_shared_u16(xin_nxt + drow * ROW_B + 2 * (2 + f), bf16_bits(ext));
+                  }
+                }
+              }
+            }
+            if (!last_step) {
+              fence_proxy_async();
+              tc_fence_before();
+              epi_bar_sync();
+              if (tid == 0) mbar_arrive_cluster(bar(B_ACT + m), 0);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      epi_bar_sync();        // every epilogue thread is done with this group before its buffers are reloaded
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == WARP_PRODUCER) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<2>(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// UMMA probes (self-tests of the operand schemes the decoder relies on)
+// ------------------------------------------------------------------------------------------
+// (1) one CTA: D[128 x N] = A_eff[128 x K] * B[N x K]^T where A is ONE 8-column chunk X[R][8] and K chunk j of
+//     A_eff is X shifted down by j*lbo_rows rows (LBO = 16*lbo_rows bytes): the "two taps in one k-step" scheme.
+__global__ void __launch_bounds__(128, 1)
+probe_lbo_kernel(const __nv_bfloat16* __restrict__ X, const __nv_bfloat16* __restrict__ Bm, float* __restrict__ D, int R,
+                 int N, int shift, int lbo_rows, int* err) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t b_off = (uint32_t)R * 16, lbo_b = (uint32_t)N * 16;
+  const uint32_t bar_off = (b_off + 2 * lbo_b + 15) / 16 * 16, tptr_off = bar_off + 16;
+  for (int i = threadIdx.x; i < R * 8; i += blockDim.x) reinterpret_cast<__nv_bfloat16*>(smem)[i] = X[i];
+  for (int i = threadIdx.x; i < N * 16; i += blockDim.x) {
+    const int n = i / 16, c = i % 16;
+    reinterpret_cast<__nv_bfloat16*>(smem + b_off)[(size_t)(c / 8) * N * 8 + n * 8 + (c % 8)] = Bm[i];
+  }
+  if (threadIdx.x == 0) { mbar_init(sbase + bar_off, 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) tmem_alloc<1>(sbase + tptr_off, 128);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sbase + tptr_off) : "memory");
+  if (threadIdx.x == 0) {
+    umma_bf16<1>(tmem_base, make_desc(sbase + shift * 16, (uint32_t)lbo_rows * 16), make_desc(sbase + b_off, lbo_b),
+                 make_idesc(128, N), 0);
+    umma_commit_1(sbase + bar_off);
+  }
+  mbar_wait(sbase + bar_off, 0, err, 7);
+  tc_fence_after();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int cb = 0; cb < N / 16; ++cb) {
+    uint32_t r[16];
+    tmem_ld16(tmem_base + ((uint32_t)(32 * warp) << 16) + cb * 16, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[(size_t)(32 * warp + lane) * N + cb * 16 + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc<1>(tmem_base, 128); }
+}
+
+// (2) CTA pair: D[256 x N] = A[256 x K] * B[N x K]^T with cta_group::2; CTA r stages rows 128r.. of A and
+//     columns r*N/2.. of B (the decoder's assumption), reads back its own 128 rows of D.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+probe_pair_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ Bm, float* __restrict__ D, int K,
+                  int N, int* err) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t rank = cluster_ctarank();
+  const int NH = N / 2;
+  const uint32_t lbo_a = 128 * 16, lbo_b = (uint32_t)NH * 16;
+  const uint32_t b_off = (uint32_t)(K / 8) * lbo_a;
+  const uint32_t bar_off = (b_off + (uint32_t)(K / 8) * lbo_b + 15) / 16 * 16, tptr_off = bar_off + 16;
+  for (int i = threadIdx.x; i < 128 * K; i += blockDim.x) {
+    const int r = i / K, c = i % K;
+    reinterpret_cast<__nv_bfloat16*>(smem)[(size_t)(c / 8) * 128 * 8 + r * 8 + (c % 8)] = A[(size_t)(128 * rank + r) * K + c];
+  }
+  for (int i = threadIdx.x; i < NH * K; i += blockDim.x) {
+    const int n = i / K, c = i % K;
+    reinterpret_cast<__nv_bfloat16*>(smem + b_off)[(size_t)(c / 8) * NH * 8 + n * 8 + (c % 8)] = Bm[(size_t)(NH * rank + n) * K + c];
+  }
+  if (threadIdx.x == 0) { mbar_init(sbase + bar_off, 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) tmem_alloc<2>(sbase + tptr_off, 128);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sbase + tptr_off) : "memory");
+  if (threadIdx.x == 0 && rank == 0) {
+    for (int ks = 0; ks < K / 16; ++ks)
+      umma_bf16<2>(tmem_base, make_desc(sbase + 2 * ks * lbo_a, lbo_a), make_desc(sbase + b_off + 2 * ks * lbo_b, lbo_b),
+                   make_idesc(256, N), ks > 0);
+    umma_commit_pair(sbase + bar_off, 3);
+  }
+  mbar_wait(sbase + bar_off, 0, err, 8);
+  tc_fence_after();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int cb = 0; cb < N / 16; ++cb) {
+    uint32_t r[16];
+    tmem_ld16(tmem_base + ((uint32_t)(32 * warp) << 16) + cb * 16, r);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) D[(size_t)(128 * rank + 32 * warp + lane) * N + cb * 16 + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc<2>(tmem_base, 128); }
+}
+
+static uint32_t stack_image_bytes(const TaeDecConfig& c) {
+  return 2 * (L0_B + (uint32_t)(c.num_layer - 1) * SLOTS_CONV * SLOT_B + LIN_B);
+}
+
+}  // namespace
+
+bool dec_pair_supported(const TaeDecConfig& c, const char** why) {
+  static thread_local char msg[160];
+  *why = msg;
+  if (c.kernel_size != TAPS) { snprintf(msg, sizeof msg, "kernel_size %d (only 5 is built for the tensor path)", c.kernel_size); return false; }
+  if (c.num_unit > UNITS_MAX || c.num_unit < 1) { snprintf(msg, sizeof msg, "num_unit %d > %d", c.num_unit, UNITS_MAX); return false; }
+  if (c.num_iter_ft > 5) { snprintf(msg, sizeof msg, "num_iter_ft %d > 5", c.num_iter_ft); return false; }
+  if (c.num_layer < 2) { snprintf(msg, sizeof msg, "num_layer %d < 2", c.num_layer); return false; }
+  if (c.block_len > GROUP_ROWS) { snprintf(msg, sizeof msg, "block_len %d > %d (one codeword must fit a 512-row group)", c.block_len, GROUP_ROWS); return false; }
+  if (make_smem(c.num_iter_ft).total > 227 * 1024) { snprintf(msg, sizeof msg, "shared memory budget exceeded"); return false; }
+  *why = nullptr;
+  return true;
+}
+
+size_t dec_pair_packed_bytes(const TaeDecConfig& c) { return (size_t)2 * c.num_iteration * stack_image_bytes(c); }
+
+int dec_pair_pack(const TaeDecConfig& c, const float* params, void* packed, cudaStream_t s) {
+  DecStackLayout lay[64];
+  dec_layout(c, lay);
+  const int n_stacks = 2 * c.num_iteration;
+  DecStackLayout* d_lay = nullptr;
+  cudaError_t e = cudaMallocAsync(&d_lay, sizeof(DecStackLayout) * n_stacks, s);
+  if (e != cudaSuccess) { set_error("cudaMallocAsync: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+  e = cudaMemcpyAsync(d_lay, lay, sizeof(DecStackLayout) * n_stacks, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) { set_error("cudaMemcpyAsync: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+  const uint32_t stack_elems = stack_image_bytes(c) / 2;
+  const size_t total = (size_t)n_stacks * stack_elems;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  pack_pair_kernel<<<blocks, 256, 0, s>>>(params, reinterpret_cast<__nv_bfloat16*>(packed), d_lay, n_stacks, c.num_layer,
+                                          c.num_unit, c.num_iter_ft, stack_elems);
+  int rc = after_launch("pack_pair_kernel");
+  cudaFreeAsync(d_lay, s);
+  return rc;
+}
+
+int dec_forward_pair(const TaeDecConfig& c, const void* packed, const float* received, const int32_t* perm,
+                     const int32_t* inv_perm, float* out, float* trace, int B, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (ws_bytes < 256) { set_error("tae_dec_forward(bf16): workspace %zu < 256 bytes", ws_bytes); return TAE_EWORKSPACE; }
+  static int n_sm = 0;
+  static bool attr_done = false;
+  const Smem S = make_smem(c.num_iter_ft);
+  if (!attr_done) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) { set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+    if (prop.major != 10) { set_error("bf16 path needs an sm_100a device (found sm_%d%d)", prop.major, prop.minor); return TAE_EUNSUPPORTED; }
+    n_sm = prop.multiProcessorCount;
+    e = cudaFuncSetAttribute(dec_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dec_pair_kernel): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+    attr_done = true;
+  }
+  PairArgs a{};
+  a.wimg = reinterpret_cast<const uint8_t*>(packed);
+  a.received = received;
+  a.out = out;
+  a.trace = trace;
+  a.err = reinterpret_cast<int*>(align_up(reinterpret_cast<uintptr_t>(ws), 16));
+  a.perm = perm;
+  a.inv_perm = inv_perm;
+  a.B = B; a.L = c.block_len; a.F = c.num_iter_ft; a.I = c.num_iteration; a.n_layer = c.num_layer;
+  a.extrinsic = c.extrinsic;
+  a.cw_per_group = (GROUP_ROWS + 2) / (c.block_len + 2);
+  a.n_groups = (B + a.cw_per_group - 1) / a.cw_per_group;
+  a.n_pairs = (a.n_groups + 1) / 2;
+  a.stack_bytes = stack_image_bytes(c);
+  const int n_clusters = std::min(a.n_pairs, n_sm / 2);
+  dec_pair_kernel<<<2 * n_clusters, N_THREADS, S.total, s>>>(a);
+  return after_launch("dec_pair_kernel");
+}
+
+}  // namespace tae
+
+// ---- self-test entry points (not part of the drop-in surface) ------------------------------------------
+extern "C" {
+
+// D (128, N) = A_eff @ Bm^T, A_eff[r, 8j + e] = X[shift + r + j*lbo_rows, e] (j = 0, 1).  X: (R, 8) bf16, Bm: (N, 16) bf16.
+int tae_debug_probe_lbo(const void* X, const void* Bm, float* D, int32_t R, int32_t N, int32_t shift, int32_t lbo_rows,
+                        int* err, void* stream) {
+  using namespace tae;
+  if (N % 16 || N > 128 || shift < 0 || lbo_rows < 1 || shift + lbo_rows + 128 > R) { set_error("probe_lbo: bad shape"); return TAE_EINVAL; }
+  const size_t smem = (size_t)R * 16 + 2 * (size_t)N * 16 + 64;
+  cudaError_t e = cudaFuncSetAttribute(probe_lbo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(probe_lbo): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+  if (smem > 100 * 1024) { set_error("probe_lbo: too large"); return TAE_EINVAL; }
+  probe_lbo_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(X),
+                                                         reinterpret_cast<const __nv_bfloat16*>(Bm), D, R, N, shift, lbo_rows, err);
+  return after_launch("probe_lbo_kernel");
+}
+
+// D (256, N) = A (256, K) @ Bm (N, K)^T with one cta_group::2 MMA chain.
+int tae_debug_probe_pair(const void* A, const void* Bm, float* D, int32_t K, int32_t N, int* err, void* stream) {
+  using namespace tae;
+  if (K % 16 || N % 16 || N > 128 || K > 128) { set_error("probe_pair: bad shape"); return TAE_EINVAL; }
+  const size_t smem = (size_t)(K / 8) * 128 * 16 + (size_t)(K / 8) * (N / 2) * 16 + 64;
+  cudaError_t e = cudaFuncSetAttribute(probe_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(probe_pair): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+  probe_pair_kernel<<<2, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(A),
+                                                          reinterpret_cast<const __nv_bfloat16*>(Bm), D, K, N, err);
+  return after_launch("probe_pair_kernel");
+}
+
+}  // extern "C"

@@ -50,6 +50,8 @@ _SIGNATURES = {
     # debug / self-test entry points
     "tae_debug_set_dump": (None, [_P]),
     "tae_debug_umma_probe": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, _P, _P]),
+    "tae_debug_set_timeline": (None, [_P]),
+    "tae_debug_probe_rate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int32, _P]),
     "tae_debug_probe_lbo": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "tae_debug_probe_pair": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P]),
 }

@@ -19,7 +19,8 @@
 //     16-byte chunk carries two taps; the last k-step pairs tap 4 of those channels with a constant-one chunk
 //     that injects the bias (bf16 hi + lo split) -- no output channel, no epilogue add.
 //   * activations are updated IN PLACE: the epilogue of tile m may not touch the two rows that tile m+1's MMAs
-//     still read (its last two), so those go to a side buffer and are flushed by the next tile's epilogue.
+//     still read (its last two), so the two lanes owning them keep their packed outputs in registers and store
+//     them at the start of the next tile's epilogue.  Epilogue warps report per warp (no CTA-wide barrier).
 //   * priors stay in shared memory (fp32) for all 2*I half-iterations; (de)interleave is the row index of the
 //     Linear epilogue's store.  HBM sees `received` once and `out` once; weights stream from L2 once per CTA
 //     pair and layer through a bulk-copy (UBLKCP) ring.
@@ -60,14 +61,13 @@ constexpr uint32_t SLOT_B = KS_PER_SLOT * 2 * WCHUNK_B;         // 7168
 constexpr uint32_t L0_B = KS_L0 * 2 * WCHUNK_B;                 // 5376
 constexpr uint32_t LIN_WCHUNK_B = LIN_NHALF * ROW_B;            // 128
 constexpr uint32_t LIN_B = KS_LIN * 2 * LIN_WCHUNK_B;           // 1792
-constexpr int NS = 10;                                          // weight ring slots
-constexpr int SIDE_ENTRIES = 13;                                // 12 regular chunks + (ch 96..99)
+constexpr int NS = 10;                                          // weight ring slots (a layer uses 8; 2 are prefetch headroom)
 constexpr int N_EPI_WARPS = 8;
 constexpr int N_EPI_THREADS = N_EPI_WARPS * 32;
 constexpr int WARP_PRODUCER = 0;
-constexpr int WARP_MMA = 1;
-constexpr int EPI_WARP0 = 2;
-constexpr int N_THREADS = 320;
+constexpr int WARP_MMA = 1;                                     // warps 1..4 of the leader: one MMA issuer per tile
+constexpr int EPI_WARP0 = 1 + N_TILES;
+constexpr int N_THREADS = 32 * (1 + N_TILES + N_EPI_WARPS);      // 416
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TMEM_LIN_COL = N_TILES * NPAD;               // 448
 
@@ -77,10 +77,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 }
 
 struct Smem {
-  uint32_t act, comb, xin[2], ones, pri[2], side, wslot, perm, inv_perm, bars, tmem_ptr, total;
+  uint32_t act, comb, xin[2], ones, pri[2], wslot, perm, inv_perm, bars, tmem_ptr, total;
 };
 // barrier slots (8 bytes each)
-enum { B_WFULL = 0, B_WEMPTY = NS, B_PFULL = 2 * NS, B_ACC = 3 * NS, B_ACT = 3 * NS + 4, N_BARS = 3 * NS + 8 };
+// B_WFULL[p]: ring slot p resident in BOTH CTAs (leader: own bulk copy + one arrival forwarded by the peer's relay, so an
+// MMA issuer does ONE wait per slot).  B_WEMPTY[p]: the MMAs of all four tiles reading slot p have completed (one commit
+// per tile issuer, multicast to both CTAs).
+// B_ACC[m]: accumulators of tile m complete (commit, multicast).  B_ACT[m] (leader): tile m written back by all 16 epilogue
+// warps of the pair (each warp arrives on its own).
+enum { B_WFULL = 0, B_WEMPTY = NS, B_ACC = 2 * NS, B_ACT = 2 * NS + 4, N_BARS = 2 * NS + 8 };
 
 __host__ __device__ inline Smem make_smem(int F) {
   Smem s{};
@@ -93,7 +98,6 @@ __host__ __device__ inline Smem make_smem(int F) {
   s.pri[0] = o; o += (uint32_t)F * BUF_ROWS * 4;
   s.pri[1] = o; o += (uint32_t)F * BUF_ROWS * 4;
   o = (o + 15) / 16 * 16;
-  s.side = o; o += 3 * 2 * SIDE_ENTRIES * 16;
   s.wslot = o; o += NS * SLOT_B;
   s.perm = o; o += 1024;
   s.inv_perm = o; o += 1024;
@@ -113,6 +117,7 @@ struct PairArgs {
   const int32_t* inv_perm;
   int B, L, F, I, n_layer, extrinsic, n_groups, n_pairs, cw_per_group;
   uint32_t stack_bytes;        // bytes of one stack's image (both halves)
+  unsigned long long* tl;      // optional timeline buffer (tae_debug_set_timeline): clock64 stamps of cluster 0, leader CTA
 };
 
 // ------------------------------------------------------------------------------------------
@@ -150,6 +155,19 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
       "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// plain arrive on the barrier at the same offset in CTA `rank` (CTA-scope release: the data it publishes stays in
+// the arriving CTA's own shared memory and was already made visible to the async proxy by fence.proxy.async)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
       "r"(rank)
       : "memory");
 }
@@ -310,9 +328,6 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 __device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
-__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
-  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
-}
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
   asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
 }
@@ -391,8 +406,8 @@ __global__ void pack_pair_kernel(const float* __restrict__ params, __nv_bfloat16
                                  const DecStackLayout* __restrict__ lay, int n_stacks, int n_layer, int units, int F,
                                  uint32_t stack_elems) {
   const size_t total = (size_t)n_stacks * stack_elems;
-  const uint32_t l0_elems = 2 * L0_B / 2, slot_elems = 2 * SLOT_B / 2;
-  const uint32_t conv_elems = (uint32_t)(n_layer - 1) * SLOTS_CONV * slot_elems;
+  const uint32_t l0_elems = 2 * L0_B / 2;
+  const uint32_t conv_elems = (uint32_t)(n_layer - 1) * SLOTS_CONV * (2 * SLOT_B / 2);
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int st = (int)(idx / stack_elems);
     uint32_t r = (uint32_t)(idx % stack_elems);
@@ -405,7 +420,8 @@ __global__ void pack_pair_kernel(const float* __restrict__ params, __nv_bfloat16
       v = l0_w_elem(params + S.conv[0].w_off, params + S.conv[0].b_off, units, 2 + F, half * NHALF + n, ks, ch * 8 + e8);
     } else if (r < l0_elems + conv_elems) {
       r -= l0_elems;
-      const int sl = r / slot_elems;                 // slot within the stack's conv layers
+      const uint32_t slot_elems = 2 * SLOT_B / 2;      // both halves of one slot
+      const int sl = r / slot_elems;                   // slot within the stack's units->units layers
       r %= slot_elems;
       const int half = r / (SLOT_B / 2);
       r %= (SLOT_B / 2);
@@ -435,7 +451,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
   const uint32_t rank = cluster_ctarank();
   const int L = a.L, F = a.F, CW_ROWS = a.L + 2;
   const int n_stacks = 2 * a.I;
-  const int slots_per_stack = 2 + SLOTS_CONV * (a.n_layer - 1);
+  const int slots_per_stack = 2 + SLOTS_CONV * (a.n_layer - 1);    // weight transfers: layer 0, 8 per layer, Linear
 
   auto bar = [&](int i) { return sbase + S.bars + 8u * (uint32_t)i; };
 
@@ -443,8 +459,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
   for (uint32_t i = threadIdx.x * 16; i < S.bars; i += N_THREADS * 16) st_shared_v4(sbase + i, 0u, 0u, 0u, 0u);
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); mbar_init(bar(B_PFULL + i), 1); }
-    for (int m = 0; m < N_TILES; ++m) { mbar_init(bar(B_ACC + m), 1); mbar_init(bar(B_ACT + m), 2); }
+    for (int i = 0; i < NS; ++i) { mbar_init(bar(B_WFULL + i), rank == 0 ? 2 : 1); mbar_init(bar(B_WEMPTY + i), N_TILES); }
+    for (int m = 0; m < N_TILES; ++m) { mbar_init(bar(B_ACC + m), 1); mbar_init(bar(B_ACT + m), 2 * N_EPI_WARPS); }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < L; i += N_THREADS) {
@@ -461,9 +477,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sbase + S.tmem_ptr) : "memory");
 
   const int pair0 = (int)cluster_id_x(), pair_stride = (int)n_clusters_x();
+  unsigned long long t_start_ns = 0, t_start_clk = 0;
+  if (a.tl && threadIdx.x == 0) {
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start_ns));
+    t_start_clk = clock64();
+  }
 
   if (warp == WARP_PRODUCER) {
-    // ================= weight producer: this CTA's half of every slot ==============================
+    // ================= weight producer: this CTA's half of every slot =================================
     if (lane == 0) {
       uint32_t pos = 0, phase = 0;
       for (int pr = pair0; pr < a.n_pairs; pr += pair_stride) {
@@ -480,69 +501,75 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
         }
       }
     }
-  } else if (warp == WARP_MMA) {
+  } else if (warp >= WARP_MMA && warp < WARP_MMA + N_TILES) {
     if (rank == 1) {
-      // ================= peer relay: tell the leader that this CTA's half of a slot has landed ======
+      if (warp == WARP_MMA) {
+      // ================= peer relay: tell the leader that this CTA's half of a slot has landed ==========
       uint32_t pos = 0, phase = 0;
       for (int pr = pair0; pr < a.n_pairs; pr += pair_stride)
         for (int i = 0; i < n_stacks * slots_per_stack; ++i) {
           mbar_wait(bar(B_WFULL + pos), phase, a.err, 2);
-          if (elect_one()) mbar_arrive_cluster(bar(B_PFULL + pos), 0);
+          if (elect_one()) mbar_arrive_remote(bar(B_WFULL + pos), 0);   // data was written by the async proxy: no fence needed
           __syncwarp();
           if (++pos == NS) { pos = 0; phase ^= 1; }
         }
+      }
     } else {
-      // ================= MMA issuer: the warp of the leader CTA runs converged, one elected lane issues =====
+      // ================= MMA issuers: warp 1+m of the leader CTA owns tile m; the warp runs converged and one elected
+      // lane issues.  tcgen05.mma issue is nearly synchronous (the queue is about one instruction deep), so a single
+      // issuer would expose every barrier wait as tensor-pipe idle time; with one issuer per tile the waits of tile
+      // m+1 (inputs written back, weight slots resident) overlap the MMAs of tile m.  Tiles use disjoint accumulators,
+      // so the order in which the tensor core interleaves the four streams does not matter.
+      const int m = warp - WARP_MMA;
       constexpr uint32_t IDESC_CONV = make_idesc(256, NPAD), IDESC_LIN = make_idesc(256, LIN_N);
       uint32_t pos = 0, wphase = 0, step = 0;
       const uint32_t act = sbase + S.act, comb = sbase + S.comb, ones = sbase + S.ones;
-      auto wait_w = [&](uint32_t p, uint32_t ph) {
-        mbar_wait(bar(B_WFULL + p), ph, a.err, 3);
-        mbar_wait_cluster(bar(B_PFULL + p), ph, a.err, 4);
-      };
       for (int pr = pair0; pr < a.n_pairs; pr += pair_stride) {
         for (int st = 0; st < n_stacks; ++st) {
           const uint32_t xin = sbase + S.xin[st & 1];
           for (int layer = 0; layer <= a.n_layer; ++layer, ++step) {
             const uint32_t par = step & 1;
-            const int n_slots = (layer == 0 || layer == a.n_layer) ? 1 : SLOTS_CONV;
-#pragma unroll 1
-            for (int m = 0; m < N_TILES; ++m) {
-              // inputs of tile m: rows of tiles m-1 (done earlier), m and the first rows of m+1; the deferred
-              // last two rows of tile m are flushed by the epilogue of tile m+1.  Layer 0 reads the stack input,
-              // which the previous Linear epilogue scatters across the whole group.
-              if (m == 0) {
-                mbar_wait_cluster(bar(B_ACT + 0), par, a.err, 5);
-                mbar_wait_cluster(bar(B_ACT + 1), par, a.err, 5);
-                if (layer == 0) { mbar_wait_cluster(bar(B_ACT + 2), par, a.err, 5); mbar_wait_cluster(bar(B_ACT + 3), par, a.err, 5); }
-              } else if (m < N_TILES - 1) {
-                mbar_wait_cluster(bar(B_ACT + m + 1), par, a.err, 5);
+            const bool conv = (layer > 0 && layer < a.n_layer);
+            {
+              const bool stamp = a.tl && pr == 0 && lane == 0;
+              if (stamp) a.tl[(step * 4 + m) * 8 + 0] = clock64();
+              // inputs of tile m: its own rows and the last rows of tile m-1 (both covered by B_ACT[m]), the first rows of
+              // tile m+1 and the deferred last two rows of tile m, stored by the epilogue of tile m+1 (B_ACT[m+1]).  Layer 0 reads the stack input, which the
+              // previous Linear epilogue scatters across the whole group.
+              if (layer == 0) {
+                for (int t = 0; t < N_TILES; ++t) mbar_wait(bar(B_ACT + t), par, a.err, 5);
+              } else {
+                mbar_wait(bar(B_ACT + m), par, a.err, 5);
+                if (m < N_TILES - 1) mbar_wait(bar(B_ACT + m + 1), par, a.err, 5);
               }
               tc_fence_after();
+              if (stamp) a.tl[(step * 4 + m) * 8 + 1] = clock64();
               const uint32_t rowoff = (uint32_t)(128 * m) * ROW_B;
               uint32_t p = pos, ph = wphase;
-              // descriptors are assembled from per-tile base words plus compile-time constants (the loops below
-              // are fully unrolled): ONE thread has to issue an MMA every 56 cycles.
+              // descriptors = per-tile base words + compile-time constants (everything below is fully unrolled)
               uint32_t wlo = dlo(sbase + S.wslot + p * SLOT_B, WCHUNK_B);
               const uint32_t d_tmem = tmem_base + m * NPAD;
               if (layer == 0) {
-                if (m == 0) { wait_w(p, ph); tc_fence_after(); }
+                mbar_wait(bar(B_WFULL + p), ph, a.err, 3);
+                tc_fence_after();
                 const uint32_t x_lo = dlo(xin + rowoff, ROW_B);
                 const uint32_t x2_lo = dlo(xin + rowoff + 4 * ROW_B, (ones + 2 * ROW_B) - (xin + 4 * ROW_B));
                 if (elect_one()) {
                   umma_bf16<2>(d_tmem, dfull(x_lo), dfull(wlo), IDESC_CONV, 0);                                 // taps 0,1
                   umma_bf16<2>(d_tmem, dfull(x_lo + 2), dfull(wlo + ((2 * WCHUNK_B) >> 4)), IDESC_CONV, 1);     // taps 2,3
                   umma_bf16<2>(d_tmem, dfull(x2_lo), dfull(wlo + ((4 * WCHUNK_B) >> 4)), IDESC_CONV, 1);        // tap 4, bias
-                  if (m == N_TILES - 1) umma_commit_pair(bar(B_WEMPTY + p), 3);
+                  umma_commit_pair(bar(B_WEMPTY + p), 3);
+                  umma_commit_pair(bar(B_ACC + m), 3);
                 }
                 __syncwarp();
-              } else if (layer < a.n_layer) {
+              } else if (conv) {
                 const uint32_t act_lo = dlo(act + rowoff, CHUNK_B);
                 const uint32_t c30_lo = dlo(comb + rowoff, 2 * ROW_B);             // [taps 0,1 | taps 2,3] of channels 96..99
                 const uint32_t c31_lo = dlo(comb + rowoff + 4 * ROW_B, (ones + 2 * ROW_B) - (comb + 4 * ROW_B));   // [tap 4 | ones (bias)]
 #pragma unroll
                 for (int s = 0; s < SLOTS_CONV; ++s) {
-                  if (m == 0) { wait_w(p, ph); tc_fence_after(); }   // resident until tile 3 releases the slot
+                  mbar_wait(bar(B_WFULL + p), ph, a.err, 3);
+                  tc_fence_after();
                   if (elect_one()) {
 #pragma unroll
                     for (int k4 = 0; k4 < KS_PER_SLOT; ++k4) {
@@ -551,14 +578,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
                                                    : (ks == 30 ? c30_lo : c31_lo);
                       umma_bf16<2>(d_tmem, dfull(alo), dfull(wlo + (uint32_t)(k4 * 2 * WCHUNK_B) / 16), IDESC_CONV, ks > 0);
                     }
-                    if (m == N_TILES - 1) umma_commit_pair(bar(B_WEMPTY + p), 3);
+                    umma_commit_pair(bar(B_WEMPTY + p), 3);
+                    if (s == SLOTS_CONV - 1) umma_commit_pair(bar(B_ACC + m), 3);
                   }
                   __syncwarp();
                   wlo += SLOT_B / 16;
                   if (++p == NS) { p = 0; ph ^= 1; wlo -= NS * SLOT_B / 16; }
                 }
               } else {
-                if (m == 0) { wait_w(p, ph); tc_fence_after(); }
+                mbar_wait(bar(B_WFULL + p), ph, a.err, 3);
+                tc_fence_after();
                 const uint32_t act_lo = dlo(act + rowoff + 2 * ROW_B, CHUNK_B);                      // centre row only
                 const uint32_t c_lo = dlo(comb + rowoff + 2 * ROW_B, ones - comb);
                 const uint32_t wl = dlo(sbase + S.wslot + p * SLOT_B, LIN_WCHUNK_B);
@@ -567,15 +596,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
                   for (int ks = 0; ks < KS_LIN; ++ks)
                     umma_bf16<2>(tmem_base + TMEM_LIN_COL + m * LIN_N, dfull(ks < 6 ? act_lo + (uint32_t)(2 * ks) * CHUNK_B / 16 : c_lo),
                                  dfull(wl + (uint32_t)(ks * 2 * LIN_WCHUNK_B) / 16), IDESC_LIN, ks > 0);
-                  if (m == N_TILES - 1) umma_commit_pair(bar(B_WEMPTY + p), 3);
+                  umma_commit_pair(bar(B_WEMPTY + p), 3);
+                  umma_commit_pair(bar(B_ACC + m), 3);
                 }
                 __syncwarp();
               }
-              if (elect_one()) umma_commit_pair(bar(B_ACC + m), 3);
-              __syncwarp();
+              if (stamp) a.tl[(step * 4 + m) * 8 + 2] = clock64();
             }
             // advance the ring past this layer's slots
-            for (int s = 0; s < n_slots; ++s)
+            const int n_adv = conv ? SLOTS_CONV : 1;
+            for (int s = 0; s < n_adv; ++s)
               if (++pos == NS) { pos = 0; wphase ^= 1; }
           }
         }
@@ -588,11 +618,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
     const int half = ew >> 2;                  // column half: 0 -> channels 0..47, 1 -> channels 48..99
     const int tid = threadIdx.x - EPI_WARP0 * 32;
     uint32_t step = 0;
+    // this thread's row in each of the four tiles: codeword slot and position inside it (fixed for the whole kernel)
+    int row_cw[N_TILES], row_l[N_TILES];
+#pragma unroll
+    for (int m = 0; m < N_TILES; ++m) {
+      const int g = 128 * m + 32 * q + lane;
+      row_cw[m] = g / CW_ROWS;
+      row_l[m] = g % CW_ROWS;
+    }
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
     for (int pr = pair0; pr < a.n_pairs; pr += pair_stride) {
       const int grp = 2 * pr + (int)rank;
       const int cw0 = grp * a.cw_per_group;
       const int n_cw = max(0, min(a.cw_per_group, a.B - cw0));
+      uint32_t vmask = 0;      // bit m: this thread's row of tile m holds a real codeword position
+#pragma unroll
+      for (int m = 0; m < N_TILES; ++m) vmask |= ((row_l[m] < L) && (row_cw[m] < n_cw)) ? (1u << m) : 0u;
 
+      if (a.tl && pair0 == 0 && rank == 0 && tid == 0) a.tl[72 * 4 * 8 + 148 * 4 + (pr / pair_stride)] = clock64();
       // ---- group start: stack inputs, zero prior, ones chunk ----------------------------------------
       for (uint32_t i = tid * 16; i < 3 * CHUNK_B; i += N_EPI_THREADS * 16) st_shared_v4(sbase + S.xin[0] + i, 0u, 0u, 0u, 0u);
       for (uint32_t i = tid * 16; i < (uint32_t)F * BUF_ROWS * 4; i += N_EPI_THREADS * 16)
@@ -612,105 +655,152 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
       }
       fence_proxy_async();
       epi_bar_sync();
-      if (tid == 0)
-        for (int m = 0; m < N_TILES; ++m) mbar_arrive_cluster(bar(B_ACT + m), 0);
+      if (lane == 0)
+        for (int m = 0; m < N_TILES; ++m) mbar_arrive_remote(bar(B_ACT + m), 0);
+
+      // Deferred rows: the last two rows of tile m are still read by the MMAs of tile m+1 (taps 0, 1), so the two
+      // lanes that own them keep their packed outputs in registers and store them at the start of the next tile.
+      uint32_t dq[26];
+#pragma unroll
+      for (int i = 0; i < 26; ++i) dq[i] = 0u;
 
       for (int st = 0; st < n_stacks; ++st) {
         for (int layer = 0; layer <= a.n_layer; ++layer, ++step) {
           const uint32_t par = step & 1;
           const bool last_step = (st == n_stacks - 1 && layer == a.n_layer);
-#pragma unroll 1
-          for (int m = 0; m < N_TILES; ++m) {
-            mbar_wait(bar(B_ACC + m), par, a.err, 6);
+          if (layer == a.n_layer) {
+            // -- Linear epilogue, all four tiles in one pass (their MMAs are tiny and complete together): extrinsic
+            //    subtraction + (de)interleave into the next stack's input.  The two warps of a quadrant split the
+            //    features (half 0: f = 0..2, half 1: f = 3..4); all loads are issued before the first store. ----------
+            const bool last = (st == n_stacks - 1);
+            const uint32_t pri_cur = sbase + S.pri[st & 1], pri_nxt = sbase + S.pri[(st & 1) ^ 1];
+            const uint32_t xin_nxt = sbase + S.xin[(st & 1) ^ 1];
+            const uint32_t map = sbase + (last ? S.perm : ((st & 1) ? S.perm : S.inv_perm));   // where position l lands
+            const int f0 = half ? 3 : 0, f1 = half ? F : min(F, 3);
+            const bool stamp = a.tl && pr == 0 && rank == 0 && lane == 0 && (ew == 0 || ew == 7);
+            if (stamp && ew == 0) a.tl[(step * 4 + 0) * 8 + 3] = clock64();
+#pragma unroll
+            for (int m = 0; m < N_TILES; ++m) mbar_wait(bar(B_ACC + m), par, a.err, 6);
             tc_fence_after();
-            const int g_row = 128 * m + 32 * q + lane;
-            const int g_cw = g_row / CW_ROWS, g_l = g_row % CW_ROWS;
-            const bool valid = (g_l < L) && (g_cw < n_cw);
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
-            if (layer < a.n_layer) {
-              // -- flush the deferred last two rows of tile m-1 (its readers, the MMAs of tile m, are done) --
-              if (m > 0 && tid < 2 * SIDE_ENTRIES) {
-                const int r = tid / SIDE_ENTRIES, c = tid % SIDE_ENTRIES;
-                const uint32_t src = sbase + S.side + (uint32_t)(((m - 1) * 2 + r) * SIDE_ENTRIES + c) * 16;
-                const uint32_t brow = (uint32_t)(128 * m - 2 + r + 2);            // buffer row
-                uint32_t x0, x1, x2, x3;
-                ld_shared_v4(src, x0, x1, x2, x3);
-                if (c < N_REG_CHUNKS) {
-                  st_shared_v4(sbase + S.act + (uint32_t)c * CHUNK_B + brow * ROW_B, x0, x1, x2, x3);
-                } else {
-                  st_shared_v2(sbase + S.comb + brow * ROW_B, x0, x1);
-                  st_shared_v2(sbase + S.comb + (brow - 1) * ROW_B + 8, x0, x1);
-                }
-              }
-              // -- this thread's row, its half of the channels ------------------------------------------
-              const bool defer = (m < N_TILES - 1) && (q == 3) && (lane >= 30);
-              const uint32_t brow = (uint32_t)(g_row + 2);
-              const uint32_t side_row = sbase + S.side + (uint32_t)((m * 2 + (lane - 30)) * SIDE_ENTRIES) * 16;
-              const uint32_t col0 = (uint32_t)(m * NPAD + half * 48);
-              uint32_t r[56];
-              tmem_ld16(lane_addr + col0, r);
-              tmem_ld16(lane_addr + col0 + 16, r + 16);
-              tmem_ld16(lane_addr + col0 + 32, r + 32);
-              if (half == 1) tmem_ld8(lane_addr + col0 + 48, r + 48);
-              tmem_ld_wait();
-              const uint32_t keep = valid ? 0xFFFFFFFFu : 0u;
+            if (stamp) a.tl[(step * 4 + 0) * 8 + (ew == 0 ? 4 : 6)] = clock64();
+            uint32_t r[N_TILES][8];
+            float prior[N_TILES][3];
+            uint32_t dl[N_TILES];
 #pragma unroll
-              for (int c = 0; c < 6; ++c) {
-                uint32_t p[4];
+            for (int m = 0; m < N_TILES; ++m) tmem_ld8(lane_addr + TMEM_LIN_COL + (uint32_t)(m * LIN_N), r[m]);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  p[j] = pack_bf16x2(elu_fast(__uint_as_float(r[8 * c + 2 * j])), elu_fast(__uint_as_float(r[8 * c + 2 * j + 1]))) & keep;
-                const int chunk = half * 6 + c;
-                const uint32_t dst = defer ? side_row + (uint32_t)chunk * 16 : sbase + S.act + (uint32_t)chunk * CHUNK_B + brow * ROW_B;
-                st_shared_v4(dst, p[0], p[1], p[2], p[3]);
-              }
-              if (half == 1) {
-                const uint32_t p0 = pack_bf16x2(elu_fast(__uint_as_float(r[48])), elu_fast(__uint_as_float(r[49]))) & keep;
-                const uint32_t p1 = pack_bf16x2(elu_fast(__uint_as_float(r[50])), elu_fast(__uint_as_float(r[51]))) & keep;
-                if (defer) {
-                  st_shared_v2(side_row + 12 * 16, p0, p1);
-                } else {
-                  st_shared_v2(sbase + S.comb + brow * ROW_B, p0, p1);              // x[r][96..99]  -> comb[r][0:4]
-                  st_shared_v2(sbase + S.comb + (brow - 1) * ROW_B + 8, p0, p1);    //               -> comb[r-1][4:8]
+            for (int m = 0; m < N_TILES; ++m) {
+              const bool valid = (row_l[m] < L) && (row_cw[m] < n_cw);
+              dl[m] = valid ? ld_shared_u16(map + 2 * row_l[m]) : 0u;
+#pragma unroll
+              for (int i = 0; i < 3; ++i)
+                prior[m][i] = (valid && a.extrinsic && !last && f0 + i < f1)
+                                  ? ld_shared_f32(pri_cur + ((uint32_t)(f0 + i) * BUF_ROWS + 128 * m + 32 * q + lane + 2) * 4) : 0.f;
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int m = 0; m < N_TILES; ++m) {
+              const bool valid = (row_l[m] < L) && (row_cw[m] < n_cw);
+              if (!valid) continue;
+              const int cw = cw0 + row_cw[m], l = row_l[m];
+              if (a.trace) {
+                float* tr = a.trace + (((size_t)st * a.B + cw) * L + l) * F;
+                if (last) { if (half == 0) tr[0] = __uint_as_float(r[m][0]); }
+                else {
+#pragma unroll
+                  for (int i = 0; i < 3; ++i)
+                    if (f0 + i < f1) tr[f0 + i] = __uint_as_float(half ? r[m][(3 + i) & 7] : r[m][i]);
                 }
               }
-            } else if (half == 0) {
-              // -- Linear epilogue: extrinsic subtraction + (de)interleave into the next stack's input ------
-              const bool last = (st == n_stacks - 1);
-              const int fout = last ? 1 : F;
-              const uint32_t pri_cur = sbase + S.pri[st & 1], pri_nxt = sbase + S.pri[(st & 1) ^ 1];
-              const uint32_t xin_nxt = sbase + S.xin[(st & 1) ^ 1];
-              const uint32_t map = sbase + ((st & 1) ? S.perm : S.inv_perm);   // where position l lands
-              uint32_t r[8];
-              tmem_ld8(lane_addr + TMEM_LIN_COL + (uint32_t)(m * LIN_N), r);
-              tmem_ld_wait();
-              if (valid) {
-                const int cw = cw0 + g_cw, l = g_l;
-                if (a.trace) {
-                  float* tr = a.trace + (((size_t)st * a.B + cw) * L + l) * F;
-                  for (int f = 0; f < fout; ++f) tr[f] = __uint_as_float(r[f]);
-                }
-                if (last) {
-                  const int dl = ld_shared_u16(sbase + S.perm + 2 * l);         // deinterleave: out[p[l]] = x[l]
-                  a.out[(size_t)cw * L + dl] = 1.f / (1.f + __expf(-__uint_as_float(r[0])));   // decoders.py:267
-                } else {
-                  const int dl = ld_shared_u16(map + 2 * l);
-                  const uint32_t drow = (uint32_t)(g_cw * CW_ROWS + dl + 2);
-                  for (int f = 0; f < F; ++f) {
-                    const float prior = a.extrinsic ? ld_shared_f32(pri_cur + ((uint32_t)f * BUF_ROWS + g_row + 2) * 4) : 0.f;
-                    const float ext = __uint_as_float(r[f]) - prior;             // decoders.py:235-236, 246-247
-                    st_shared_f32(pri_nxt + ((uint32_t)f * BUF_ROWS + drow) * 4, ext);
-                    st_shared_u16(xin_nxt + drow * ROW_B + 2 * (2 + f), bf16_bits(ext));
+              if (last) {
+                // deinterleave: out[p[l]] = sigmoid(x[l])                                         (decoders.py:267)
+                if (half == 0) a.out[(size_t)cw * L + dl[m]] = 1.f / (1.f + __expf(-__uint_as_float(r[m][0])));
+              } else {
+                const uint32_t drow = (uint32_t)(row_cw[m] * CW_ROWS) + dl[m] + 2;
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+                  if (f0 + i < f1) {
+                    const float ext = __uint_as_float(half ? r[m][(3 + i) & 7] : r[m][i]) - prior[m][i];   // decoders.py:235-236, 246-247
+                    st_shared_f32(pri_nxt + ((uint32_t)(f0 + i) * BUF_ROWS + drow) * 4, ext);
+                    st_shared_u16(xin_nxt + drow * ROW_B + 2 * (2 + f0 + i), bf16_bits(ext));
                   }
-                }
               }
             }
             if (!last_step) {
               fence_proxy_async();
               tc_fence_before();
-              epi_bar_sync();
-              if (tid == 0) mbar_arrive_cluster(bar(B_ACT + m), 0);
+              __syncwarp();
+              if (lane == 0)
+                for (int m = 0; m < N_TILES; ++m) mbar_arrive_remote(bar(B_ACT + m), 0);
             }
+            if (stamp) a.tl[(step * 4 + 0) * 8 + (ew == 0 ? 5 : 7)] = clock64();
+            continue;
+          }
+#pragma unroll 1
+          for (int m = 0; m < N_TILES; ++m) {
+            const bool stamp = a.tl && pr == 0 && rank == 0 && lane == 0 && (ew == 0 || ew == 7);
+            if (stamp && ew == 0) a.tl[(step * 4 + m) * 8 + 3] = clock64();
+            mbar_wait(bar(B_ACC + m), par, a.err, 6);
+            tc_fence_after();
+            if (stamp) a.tl[(step * 4 + m) * 8 + (ew == 0 ? 4 : 6)] = clock64();
+            const int g_row = 128 * m + 32 * q + lane;
+            const bool valid = (vmask >> m) & 1u;
+            {
+              const bool owns_tail = (q == 3) && (lane >= 30);
+              const bool defer = owns_tail && (m < N_TILES - 1);
+              const uint32_t brow = (uint32_t)(g_row + 2);
+              const uint32_t col0 = (uint32_t)(m * NPAD + half * 48);
+              uint32_t r[56];
+              tmem_ld16(lane_addr + col0, r);
+              tmem_ld16(lane_addr + col0 + 16, r + 16);
+              // -- store the rows deferred from tile m-1 (their readers, the MMAs of tile m, have completed) -----
+              if (owns_tail && m > 0) {
+                const uint32_t prow = brow - 128;
+#pragma unroll
+                for (int c = 0; c < 6; ++c)
+                  st_shared_v4(sbase + S.act + (uint32_t)(half * 6 + c) * CHUNK_B + prow * ROW_B, dq[4 * c], dq[4 * c + 1],
+                               dq[4 * c + 2], dq[4 * c + 3]);
+                if (half == 1) {
+                  st_shared_v2(sbase + S.comb + prow * ROW_B, dq[24], dq[25]);
+                  st_shared_v2(sbase + S.comb + (prow - 1) * ROW_B + 8, dq[24], dq[25]);
+                }
+              }
+              tmem_ld_wait();
+              tmem_ld16(lane_addr + col0 + 32, r + 32);
+              if (half == 1) tmem_ld8(lane_addr + col0 + 48, r + 48);
+              const uint32_t keep = valid ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+              for (int c = 0; c < 6; ++c) {
+                if (c == 4) tmem_ld_wait();
+                uint32_t p[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  p[j] = pack_bf16x2(elu_fast(__uint_as_float(r[8 * c + 2 * j])), elu_fast(__uint_as_float(r[8 * c + 2 * j + 1]))) & keep;
+                if (defer) {
+                  dq[4 * c] = p[0]; dq[4 * c + 1] = p[1]; dq[4 * c + 2] = p[2]; dq[4 * c + 3] = p[3];
+                } else {
+                  st_shared_v4(sbase + S.act + (uint32_t)(half * 6 + c) * CHUNK_B + brow * ROW_B, p[0], p[1], p[2], p[3]);
+                }
+              }
+              if (half == 1) {
+                const uint32_t p0 = pack_bf16x2(elu_fast(__uint_as_float(r[48])), elu_fast(__uint_as_float(r[49]))) & keep;
+                const uint32_t p1 = pack_bf16x2(elu_fast(__uint_as_float(r[50])), elu_fast(__uint_as_float(r[51]))) & keep;
+                if (defer) {
+                  dq[24] = p0; dq[25] = p1;
+                } else {
+                  st_shared_v2(sbase + S.comb + brow * ROW_B, p0, p1);              // x[r][96..99]  -> comb[r][0:4]
+                  st_shared_v2(sbase + S.comb + (brow - 1) * ROW_B + 8, p0, p1);    //               -> comb[r-1][4:8]
+                }
+              }
+            }
+            {
+              // every warp reports on its own: no CTA-wide barrier on the tile-to-tile critical path
+              fence_proxy_async();
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_remote(bar(B_ACT + m), 0);
+            }
+            if (stamp) a.tl[(step * 4 + m) * 8 + (ew == 0 ? 5 : 7)] = clock64();
           }
         }
       }
@@ -722,6 +812,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
   // ---- teardown ---------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
+  if (a.tl && threadIdx.x == 0) {
+    unsigned long long t_end_ns;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end_ns));
+    unsigned long long* o = a.tl + 72 * 4 * 8 + (size_t)blockIdx.x * 4;
+    o[0] = t_start_ns; o[1] = t_end_ns; o[2] = clock64() - t_start_clk;
+    unsigned int smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    o[3] = smid;
+  }
   cluster_sync_all();
   if (warp == WARP_PRODUCER) {
     __syncwarp();
@@ -824,6 +923,100 @@ probe_pair_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __re
   if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc<2>(tmem_base, 128); }
 }
 
+
+// (3) MMA issue-rate probe: one CTA (CG = 1) or CTA pair (CG = 2) per launch streams `n_mma` accumulating MMAs whose
+//     operands rotate through shared memory (A: 512 rows x 96 ch layout of the decoder, B: 8 k-step slots), with no
+//     epilogue; reports clock64 cycles from first issue to completion.  Measures the operand-fetch-limited MMA rate.
+template <int CG>
+__device__ __forceinline__ void probe_rate_body(int N, int n_mma, int same_operands, long long* cycles, const uint8_t* src, int tma_on, int sts_warps) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0;
+  const uint32_t a_off = 0, a_bytes = 12 * CHUNK_B;                 // activation-like region
+  const uint32_t nh = (uint32_t)N / CG;
+  const uint32_t b_off = a_bytes, b_bytes = 16 * 2 * nh * 16;        // 16 k-steps of B
+  const uint32_t tma_off = (b_off + b_bytes + 1023) / 1024 * 1024;   // 4 x 7168 B landing slots for concurrent bulk copies
+  const uint32_t sts_off = tma_off + 4 * SLOT_B;                     // 16 KB scratch for concurrent st.shared traffic
+  const uint32_t bar_off = sts_off + 16384, tptr_off = bar_off + 64;
+  for (uint32_t i = threadIdx.x * 16; i < bar_off; i += blockDim.x * 16) st_shared_v4(sbase + i, 0u, 0u, 0u, 0u);
+  if (threadIdx.x == 0) { for (int i = 0; i < 6; ++i) mbar_init(sbase + bar_off + 8 * i, 1); fence_barrier_init(); }
+  volatile uint32_t* stop = reinterpret_cast<volatile uint32_t*>(smem + bar_off + 48);
+  if (threadIdx.x == 0) *stop = 0;
+  if (threadIdx.x < 32) tmem_alloc<CG>(sbase + tptr_off, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sbase + tptr_off) : "memory");
+  long long t0 = 0;
+  if (threadIdx.x < 32 && rank == 0) {
+    t0 = clock64();
+    const uint32_t idesc = make_idesc(128 * CG, N);
+    const uint32_t act_lo = dlo(sbase + a_off, CHUNK_B);
+    const uint32_t w_lo = dlo(sbase + b_off, nh * 16);
+    for (int i = 0; i < n_mma; i += 32) {
+      const uint32_t m = (uint32_t)(i >> 5) & 3u;
+      const uint32_t d_tmem = tmem_base + (N <= 128 ? m * 128u : 0u);
+      const uint32_t a_m = act_lo + (same_operands ? 0u : m * 128u);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 32; ++ks) {
+          const uint32_t alo = a_m + (same_operands ? 0u : ((uint32_t)(2 * (ks % 6)) * CHUNK_B + (uint32_t)(ks / 6) * ROW_B) / 16);
+          const uint32_t blo = w_lo + (same_operands ? 0u : (uint32_t)(ks % 16) * 2 * nh);
+          umma_bf16<CG>(d_tmem, dfull(alo), dfull(blo), idesc, 1);
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) {
+      if (CG == 2) umma_commit_pair(sbase + bar_off, 3); else umma_commit_1(sbase + bar_off);
+    }
+    __syncwarp();
+  }
+  const int warp = threadIdx.x >> 5;
+  if (warp == 1 && tma_on && (threadIdx.x & 31) == 0) {
+    // concurrent bulk copies global -> shared, 4 in flight, until the MMA stream has drained
+    uint32_t n = 0, ph = 0;
+    for (int i = 0; i < 4; ++i) { mbar_arrive_expect_tx(sbase + bar_off + 8 * (1 + i), SLOT_B); bulk_g2s(sbase + tma_off + i * SLOT_B, src + (size_t)((blockIdx.x * 4 + i) % 64) * SLOT_B, SLOT_B, sbase + bar_off + 8 * (1 + i)); }
+    while (!*stop) {
+      for (int i = 0; i < 4; ++i) {
+        mbar_wait(sbase + bar_off + 8 * (1 + i), ph, nullptr, 9);
+        ++n;
+        mbar_arrive_expect_tx(sbase + bar_off + 8 * (1 + i), SLOT_B);
+        bulk_g2s(sbase + tma_off + i * SLOT_B, src + (size_t)((n + blockIdx.x) % 64) * SLOT_B, SLOT_B, sbase + bar_off + 8 * (1 + i));
+      }
+      ph ^= 1;
+    }
+    for (int i = 0; i < 4; ++i) mbar_wait(sbase + bar_off + 8 * (1 + i), ph, nullptr, 9);
+    if (rank == 0) cycles[128 + blockIdx.x / CG] = (long long)n * SLOT_B;
+  } else if (warp >= 2 && warp < 2 + sts_warps) {
+    uint32_t n = 0;
+    const uint32_t dst = sbase + sts_off + (uint32_t)(warp - 2) * 2048 + (threadIdx.x & 31) * 16;
+    while (!*stop) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) st_shared_v4(dst + u * 512, n, n, n, n);
+      ++n;
+    }
+    if (rank == 0 && (threadIdx.x & 31) == 0 && warp == 2) cycles[192 + blockIdx.x / CG] = (long long)n * 2048 * sts_warps;
+  }
+  if (warp == 0) {
+    mbar_wait(sbase + bar_off, 0, nullptr, 9);
+    if (threadIdx.x == 0) { if (rank == 0) cycles[blockIdx.x / CG] = clock64() - t0; *stop = 1; }
+  }
+  __syncthreads();
+  tc_fence_after();
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc<CG>(tmem_base, 512); }
+}
+__global__ void __launch_bounds__(256, 1) probe_rate_kernel_1(int N, int n_mma, int same, long long* cycles, const uint8_t* src, int tma_on, int sts_warps) { probe_rate_body<1>(N, n_mma, same, cycles, src, tma_on, sts_warps); }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) probe_rate_kernel_2(int N, int n_mma, int same, long long* cycles, const uint8_t* src, int tma_on, int sts_warps) { probe_rate_body<2>(N, n_mma, same, cycles, src, tma_on, sts_warps); }
+
+static unsigned long long* g_timeline = nullptr;
+
 static uint32_t stack_image_bytes(const TaeDecConfig& c) {
   return 2 * (L0_B + (uint32_t)(c.num_layer - 1) * SLOTS_CONV * SLOT_B + LIN_B);
 }
@@ -896,6 +1089,7 @@ int dec_forward_pair(const TaeDecConfig& c, const void* packed, const float* rec
   a.n_groups = (B + a.cw_per_group - 1) / a.cw_per_group;
   a.n_pairs = (a.n_groups + 1) / 2;
   a.stack_bytes = stack_image_bytes(c);
+  a.tl = g_timeline;
   const int n_clusters = std::min(a.n_pairs, n_sm / 2);
   dec_pair_kernel<<<2 * n_clusters, N_THREADS, S.total, s>>>(a);
   return after_launch("dec_pair_kernel");
@@ -905,6 +1099,10 @@ int dec_forward_pair(const TaeDecConfig& c, const void* packed, const float* rec
 
 // ---- self-test entry points (not part of the drop-in surface) ------------------------------------------
 extern "C" {
+
+// When non-NULL, later CTA-pair decodes record clock64 stamps of cluster 0's leader CTA: (steps*4, 8) uint64
+// [mma wait start, mma wait done, mma issued+committed, epi warp0 wait start, acc ready, done, epi warp7 acc ready, done].
+void tae_debug_set_timeline(unsigned long long* dev) { tae::g_timeline = dev; }
 
 // D (128, N) = A_eff @ Bm^T, A_eff[r, 8j + e] = X[shift + r + j*lbo_rows, e] (j = 0, 1).  X: (R, 8) bf16, Bm: (N, 16) bf16.
 int tae_debug_probe_lbo(const void* X, const void* Bm, float* D, int32_t R, int32_t N, int32_t shift, int32_t lbo_rows,
@@ -918,6 +1116,22 @@ int tae_debug_probe_lbo(const void* X, const void* Bm, float* D, int32_t R, int3
   probe_lbo_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(X),
                                                          reinterpret_cast<const __nv_bfloat16*>(Bm), D, R, N, shift, lbo_rows, err);
   return after_launch("probe_lbo_kernel");
+}
+
+// Issue-rate probe: `grid` CTAs (CG = 1) or CTA pairs (CG = 2), each streaming n_mma MMAs of shape (128*CG, N, 16).
+int tae_debug_probe_rate(int32_t cg, int32_t N, int32_t n_mma, int32_t same_operands, int32_t grid, long long* cycles, const void* src,
+                         int32_t tma_on, int32_t sts_warps, void* stream) {
+  using namespace tae;
+  if ((cg != 1 && cg != 2) || N % 16 || N < 16 || N > 256 || n_mma % 4) { set_error("probe_rate: bad arguments"); return TAE_EINVAL; }
+  const size_t smem = 12 * CHUNK_B + 16 * 2 * (size_t)(N / cg) * 16 + 1024 + 4 * SLOT_B + 16384 + 128;
+  if (sts_warps < 0 || sts_warps > 6 || (tma_on && !src)) { set_error("probe_rate: bad arguments"); return TAE_EINVAL; }
+  cudaError_t e = cg == 1 ? cudaFuncSetAttribute(probe_rate_kernel_1, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                          : cudaFuncSetAttribute(probe_rate_kernel_2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(probe_rate): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+  const uint8_t* sp = reinterpret_cast<const uint8_t*>(src);
+  if (cg == 1) probe_rate_kernel_1<<<grid, 256, smem, (cudaStream_t)stream>>>(N, n_mma, same_operands, cycles, sp, tma_on, sts_warps);
+  else probe_rate_kernel_2<<<2 * grid, 256, smem, (cudaStream_t)stream>>>(N, n_mma, same_operands, cycles, sp, tma_on, sts_warps);
+  return after_launch("probe_rate_kernel");
 }
 
 // D (256, N) = A (256, K) @ Bm (N, K)^T with one cta_group::2 MMA chain.

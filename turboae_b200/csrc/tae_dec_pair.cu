@@ -32,6 +32,10 @@
 
 #include "tae_common.cuh"
 
+#ifndef TAE_TIMELINE
+#define TAE_TIMELINE 0      // 1: record clock64 stamps (scripts/dec_timeline.py); costs code size, keep off in production
+#endif
+
 namespace tae {
 
 namespace {
@@ -171,6 +175,11 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) 
       "r"(rank)
       : "memory");
 }
+// arrive on the LEADER's barrier: a plain local arrive when executed in the leader CTA itself
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar, uint32_t my_rank) {
+  if (my_rank == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  else mbar_arrive_remote(bar, 0);
+}
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -193,8 +202,23 @@ __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t
       : "memory");
   return ok;
 }
-// Bounded waits: a protocol bug traps (context error) instead of hanging the GPU box.
+// Bounded waits: a protocol bug traps (context error) instead of hanging the GPU box.  The slow path lives in ONE
+// out-of-line function: the kernel must stay small enough for the instruction cache (rarely executed straight-line
+// code was measured at ~20 cycles per instruction when it did not).
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* err, int code) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) {
+      if (err) atomicExch(err, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, err, code);
+}
+__device__ __forceinline__ void mbar_wait_unused(uint32_t bar, uint32_t parity, int* err, int code) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 22)) {
@@ -478,7 +502,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
 
   const int pair0 = (int)cluster_id_x(), pair_stride = (int)n_clusters_x();
   unsigned long long t_start_ns = 0, t_start_clk = 0;
-  if (a.tl && threadIdx.x == 0) {
+  if (TAE_TIMELINE && a.tl && threadIdx.x == 0) {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start_ns));
     t_start_clk = clock64();
   }
@@ -531,7 +555,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
             const uint32_t par = step & 1;
             const bool conv = (layer > 0 && layer < a.n_layer);
             {
-              const bool stamp = a.tl && pr == 0 && lane == 0;
+              const bool stamp = TAE_TIMELINE && a.tl && pr == 0 && lane == 0;
               if (stamp) a.tl[(step * 4 + m) * 8 + 0] = clock64();
               // inputs of tile m: its own rows and the last rows of tile m-1 (both covered by B_ACT[m]), the first rows of
               // tile m+1 and the deferred last two rows of tile m, stored by the epilogue of tile m+1 (B_ACT[m+1]).  Layer 0 reads the stack input, which the
@@ -618,14 +642,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
     const int half = ew >> 2;                  // column half: 0 -> channels 0..47, 1 -> channels 48..99
     const int tid = threadIdx.x - EPI_WARP0 * 32;
     uint32_t step = 0;
-    // this thread's row in each of the four tiles: codeword slot and position inside it (fixed for the whole kernel)
-    int row_cw[N_TILES], row_l[N_TILES];
-#pragma unroll
-    for (int m = 0; m < N_TILES; ++m) {
-      const int g = 128 * m + 32 * q + lane;
-      row_cw[m] = g / CW_ROWS;
-      row_l[m] = g % CW_ROWS;
-    }
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
     for (int pr = pair0; pr < a.n_pairs; pr += pair_stride) {
       const int grp = 2 * pr + (int)rank;
@@ -633,9 +649,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
       const int n_cw = max(0, min(a.cw_per_group, a.B - cw0));
       uint32_t vmask = 0;      // bit m: this thread's row of tile m holds a real codeword position
 #pragma unroll
-      for (int m = 0; m < N_TILES; ++m) vmask |= ((row_l[m] < L) && (row_cw[m] < n_cw)) ? (1u << m) : 0u;
+      for (int m = 0; m < N_TILES; ++m) {
+        const int g = 128 * m + 32 * q + lane;
+        vmask |= ((g % CW_ROWS < L) && (g / CW_ROWS < n_cw)) ? (1u << m) : 0u;
+      }
 
-      if (a.tl && pair0 == 0 && rank == 0 && tid == 0) a.tl[72 * 4 * 8 + 148 * 4 + (pr / pair_stride)] = clock64();
+      if (TAE_TIMELINE && a.tl && pair0 == 0 && rank == 0 && tid == 0) a.tl[72 * 4 * 8 + 148 * 4 + (pr / pair_stride)] = clock64();
       // ---- group start: stack inputs, zero prior, ones chunk ----------------------------------------
       for (uint32_t i = tid * 16; i < 3 * CHUNK_B; i += N_EPI_THREADS * 16) st_shared_v4(sbase + S.xin[0] + i, 0u, 0u, 0u, 0u);
       for (uint32_t i = tid * 16; i < (uint32_t)F * BUF_ROWS * 4; i += N_EPI_THREADS * 16)
@@ -656,7 +675,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
       fence_proxy_async();
       epi_bar_sync();
       if (lane == 0)
-        for (int m = 0; m < N_TILES; ++m) mbar_arrive_remote(bar(B_ACT + m), 0);
+        for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_ACT + m), rank);
 
       // Deferred rows: the last two rows of tile m are still read by the MMAs of tile m+1 (taps 0, 1), so the two
       // lanes that own them keep their packed outputs in registers and store them at the start of the next tile.
@@ -677,50 +696,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
             const uint32_t xin_nxt = sbase + S.xin[(st & 1) ^ 1];
             const uint32_t map = sbase + (last ? S.perm : ((st & 1) ? S.perm : S.inv_perm));   // where position l lands
             const int f0 = half ? 3 : 0, f1 = half ? F : min(F, 3);
-            const bool stamp = a.tl && pr == 0 && rank == 0 && lane == 0 && (ew == 0 || ew == 7);
+            const bool stamp = TAE_TIMELINE && a.tl && pr == 0 && rank == 0 && lane == 0 && (ew == 0 || ew == 7);
             if (stamp && ew == 0) a.tl[(step * 4 + 0) * 8 + 3] = clock64();
 #pragma unroll
             for (int m = 0; m < N_TILES; ++m) mbar_wait(bar(B_ACC + m), par, a.err, 6);
             tc_fence_after();
             if (stamp) a.tl[(step * 4 + 0) * 8 + (ew == 0 ? 4 : 6)] = clock64();
-            uint32_t r[N_TILES][8];
-            float prior[N_TILES][3];
-            uint32_t dl[N_TILES];
-#pragma unroll
-            for (int m = 0; m < N_TILES; ++m) tmem_ld8(lane_addr + TMEM_LIN_COL + (uint32_t)(m * LIN_N), r[m]);
-#pragma unroll
+            // rolled on purpose (cold code, executed once per stack: instruction fetch dominates its cost)
+#pragma unroll 1
             for (int m = 0; m < N_TILES; ++m) {
-              const bool valid = (row_l[m] < L) && (row_cw[m] < n_cw);
-              dl[m] = valid ? ld_shared_u16(map + 2 * row_l[m]) : 0u;
+              uint32_t r[8];
+              tmem_ld8(lane_addr + TMEM_LIN_COL + (uint32_t)(m * LIN_N), r);
+              const int g_row = 128 * m + 32 * q + lane;
+              const int g_cw = g_row / CW_ROWS, g_l = g_row - g_cw * CW_ROWS;
+              const bool valid = (vmask >> m) & 1u;
+              uint32_t dl = 0;
+              float prior[3] = {0.f, 0.f, 0.f};
+              if (valid) {
+                dl = ld_shared_u16(map + 2 * g_l);
+                if (a.extrinsic && !last)
 #pragma unroll
-              for (int i = 0; i < 3; ++i)
-                prior[m][i] = (valid && a.extrinsic && !last && f0 + i < f1)
-                                  ? ld_shared_f32(pri_cur + ((uint32_t)(f0 + i) * BUF_ROWS + 128 * m + 32 * q + lane + 2) * 4) : 0.f;
-            }
-            tmem_ld_wait();
-#pragma unroll
-            for (int m = 0; m < N_TILES; ++m) {
-              const bool valid = (row_l[m] < L) && (row_cw[m] < n_cw);
+                  for (int i = 0; i < 3; ++i)
+                    if (f0 + i < f1) prior[i] = ld_shared_f32(pri_cur + ((uint32_t)(f0 + i) * BUF_ROWS + g_row + 2) * 4);
+              }
+              tmem_ld_wait();
               if (!valid) continue;
-              const int cw = cw0 + row_cw[m], l = row_l[m];
+              const int cw = cw0 + g_cw, l = g_l;
               if (a.trace) {
                 float* tr = a.trace + (((size_t)st * a.B + cw) * L + l) * F;
-                if (last) { if (half == 0) tr[0] = __uint_as_float(r[m][0]); }
+                if (last) { if (half == 0) tr[0] = __uint_as_float(r[0]); }
                 else {
 #pragma unroll
                   for (int i = 0; i < 3; ++i)
-                    if (f0 + i < f1) tr[f0 + i] = __uint_as_float(half ? r[m][(3 + i) & 7] : r[m][i]);
+                    if (f0 + i < f1) tr[f0 + i] = __uint_as_float(half ? r[(3 + i) & 7] : r[i]);
                 }
               }
               if (last) {
                 // deinterleave: out[p[l]] = sigmoid(x[l])                                         (decoders.py:267)
-                if (half == 0) a.out[(size_t)cw * L + dl[m]] = 1.f / (1.f + __expf(-__uint_as_float(r[m][0])));
+                if (half == 0) a.out[(size_t)cw * L + dl] = 1.f / (1.f + __expf(-__uint_as_float(r[0])));
               } else {
-                const uint32_t drow = (uint32_t)(row_cw[m] * CW_ROWS) + dl[m] + 2;
+                const uint32_t drow = (uint32_t)(g_cw * CW_ROWS) + dl + 2;
 #pragma unroll
                 for (int i = 0; i < 3; ++i)
                   if (f0 + i < f1) {
-                    const float ext = __uint_as_float(half ? r[m][(3 + i) & 7] : r[m][i]) - prior[m][i];   // decoders.py:235-236, 246-247
+                    const float ext = __uint_as_float(half ? r[(3 + i) & 7] : r[i]) - prior[i];   // decoders.py:235-236, 246-247
                     st_shared_f32(pri_nxt + ((uint32_t)(f0 + i) * BUF_ROWS + drow) * 4, ext);
                     st_shared_u16(xin_nxt + drow * ROW_B + 2 * (2 + f0 + i), bf16_bits(ext));
                   }
@@ -731,14 +750,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
               tc_fence_before();
               __syncwarp();
               if (lane == 0)
-                for (int m = 0; m < N_TILES; ++m) mbar_arrive_remote(bar(B_ACT + m), 0);
+                for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_ACT + m), rank);
             }
             if (stamp) a.tl[(step * 4 + 0) * 8 + (ew == 0 ? 5 : 7)] = clock64();
             continue;
           }
 #pragma unroll 1
           for (int m = 0; m < N_TILES; ++m) {
-            const bool stamp = a.tl && pr == 0 && rank == 0 && lane == 0 && (ew == 0 || ew == 7);
+            const bool stamp = TAE_TIMELINE && a.tl && pr == 0 && rank == 0 && lane == 0 && (ew == 0 || ew == 7);
             if (stamp && ew == 0) a.tl[(step * 4 + m) * 8 + 3] = clock64();
             mbar_wait(bar(B_ACC + m), par, a.err, 6);
             tc_fence_after();
@@ -798,7 +817,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
               fence_proxy_async();
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive_remote(bar(B_ACT + m), 0);
+              if (lane == 0) mbar_arrive_leader(bar(B_ACT + m), rank);
             }
             if (stamp) a.tl[(step * 4 + m) * 8 + (ew == 0 ? 5 : 7)] = clock64();
           }
@@ -812,7 +831,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
   // ---- teardown ---------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (a.tl && threadIdx.x == 0) {
+  if (TAE_TIMELINE && a.tl && threadIdx.x == 0) {
     unsigned long long t_end_ns;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end_ns));
     unsigned long long* o = a.tl + 72 * 4 * 8 + (size_t)blockIdx.x * 4;

@@ -103,6 +103,17 @@ int tae_dec_forward(const TaeDecConfig* cfg, const float* params, const void* pa
                     float* out, float* trace, int32_t B, int32_t precision,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* DEC_LargeCNN.forward for HOST buffers (reference decoders.py:219 moves `received` to the device itself, and
+ * trainer.py:176-177 reads the result back): `received_host` / `out_host` are host pointers (pinned memory makes the
+ * copies asynchronous).  The batch is cut into chunks whose H2D copy, decode and D2H copy overlap on internal
+ * streams; on return everything is ENQUEUED and `stream` waits for the last D2H copy, so synchronising `stream`
+ * makes `out_host` valid.  `workspace` (device) needs tae_dec_host_workspace_bytes().                          */
+size_t tae_dec_host_workspace_bytes(const TaeDecConfig* cfg, int32_t B, int32_t precision);
+int tae_dec_forward_host(const TaeDecConfig* cfg, const float* params, const void* packed,
+                         const float* received_host, const int32_t* perm, const int32_t* inv_perm,
+                         float* out_host, int32_t B, int32_t precision,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a4/a5/a6: ENC_interCNN ----------------------------------------------------------------
  * Flat parameter order: for branch in 1..3: for j: enc_cnn_b.cnns[j].weight, .bias; then
  * enc_linear_b.weight (1,num_unit), .bias (1)   (reference encoders.py:314-335).

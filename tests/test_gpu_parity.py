@@ -244,6 +244,23 @@ def test_decoder_empty_batch_and_errors():
         m.dec(torch.zeros(2, 100, 3, device=DEV))        # autograd path is not built yet: loud, not silent
 
 
+def test_decode_host_matches_device_path():
+    """tae_dec_forward_host (chunked H2D / decode / D2H pipeline) == device-resident decode, bit for bit."""
+    m, w, p = build_codec("c1")
+    for B in (3, 4000, 10007):
+        u, noise = gen_inputs(B, B, 100, 0.0)
+        with torch.no_grad():
+            rec = m.enc(_t(u)) + _t(noise)
+            ref = m.dec.decode(rec)
+            host = rec.cpu().pin_memory()
+            out = m.dec.decode_host(host)
+            torch.cuda.synchronize()
+            assert torch.equal(out, ref.cpu()), B
+            out32 = m.dec.decode_host(rec.cpu(), precision="fp32")        # pageable memory works too
+            torch.cuda.synchronize()
+            assert torch.equal(out32, m.dec.decode(rec, precision="fp32").cpu()), B
+
+
 # ------------------------------------------------------------------------------------------------- metric: BER at 0 dB
 def _ber_point(m, si, snr, n_batches, batch, prec):
     be = 0

@@ -1,0 +1,89 @@
+"""N > 1 host logic on CPU: world_size-2 `gloo` process group.
+
+What is exercised is exactly what the GPU ranks run around the kernels: the contiguous codeword split, the 3-double
+all-reduce that makes ENCBase.power_constraint (reference encoders.py:107-116) see the WHOLE batch, and the
+max-over-ranks timing reduction of bench.py.  The per-rank kernel outputs are stood in for by the CPU oracle
+(test infrastructure), so the check is: sharded statistics -> same codes as the unsharded reference computation."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import ROOT, gen_inputs, load_npz
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, B, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import turboae_oracle as O
+    from turboae_b200 import shard
+    w = load_npz("weights_c1.npz")
+    p = O.make_perm(100, 0)
+    u, _ = gen_inputs(4321, B, 100, 0.0)                      # every rank draws the same full batch, keeps its shard
+    lo, hi = shard.shard_range(B, rank, world)
+    x_tx = O.enc_forward_unnormalised(u[lo:hi], w, p)         # stands in for tae_enc_forward on this rank's codewords
+    xd = x_tx.astype(np.float64)
+    stats = torch.tensor([xd.sum(), (xd * xd).sum(), float(xd.size)], dtype=torch.float64)
+    shard.merge_power_stats(stats)                            # the collective under test
+    mean, std = shard.mean_std_from_stats(stats)
+    codes = ((x_tx - np.float32(mean)) / np.float32(std)).astype(np.float32)
+    slowest = shard.max_over_ranks(10.0 + rank)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), codes=codes, lo=lo, hi=hi, mean=mean, std=std, slowest=slowest,
+             count=float(stats[2]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_range_covers_batch_exactly():
+    from turboae_b200 import shard
+    for B in (0, 1, 7, 500, 50000, 50001):
+        for world in (1, 2, 3, 8):
+            edges = [shard.shard_range(B, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == B
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard.shard_range(10, 2, 2)
+
+
+def test_two_rank_power_normalisation_matches_unsharded_reference(tmp_path):
+    from oracle import turboae_oracle as O
+    B, world = 37, 2                                          # odd batch: ranks own 19 and 18 codewords
+    mp.spawn(_worker, args=(world, _free_port(), B, str(tmp_path)), nprocs=world, join=True)
+    w = load_npz("weights_c1.npz")
+    u, _ = gen_inputs(4321, B, 100, 0.0)
+    ref = O.enc_forward(u, w, O.make_perm(100, 0))            # the reference's batch-global normalisation
+    got = np.zeros_like(ref)
+    for r in range(world):
+        z = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
+        got[int(z["lo"]):int(z["hi"])] = z["codes"]
+        assert float(z["slowest"]) == 10.0 + world - 1        # MAX over ranks
+        assert float(z["count"]) == B * 100 * 3               # statistics cover the WHOLE batch
+    np.testing.assert_allclose(got, ref, atol=2e-6, rtol=0)
+    # per-rank statistics instead would miss the tolerance: the all-reduce is what keeps parity
+    local = O.enc_forward(u[:19], w, O.make_perm(100, 0))
+    assert np.abs(local - ref[:19]).max() > 1e-4
+
+
+def test_single_process_is_a_no_op():
+    from turboae_b200 import shard
+    s = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)
+    assert shard.merge_power_stats(s.clone()).tolist() == s.tolist()
+    assert shard.max_over_ranks(3.5) == 3.5
+    with pytest.raises(ValueError):
+        shard.merge_power_stats(torch.zeros(3))

@@ -43,6 +43,8 @@ _SIGNATURES = {
     "tae_dec_workspace_bytes": (C.c_size_t, [C.POINTER(TaeDecConfig), C.c_int32, C.c_int32]),
     "tae_dec_forward": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P,
                                   C.c_size_t, _P]),
+    "tae_dec_host_workspace_bytes": (C.c_size_t, [C.POINTER(TaeDecConfig), C.c_int32, C.c_int32]),
+    "tae_dec_forward_host": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_size_t, _P]),
     "tae_enc_param_count": (C.c_size_t, [C.POINTER(TaeEncConfig)]),
     "tae_enc_workspace_bytes": (C.c_size_t, [C.POINTER(TaeEncConfig), C.c_int32]),
     "tae_enc_forward": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P, _P, _P, C.c_int32, _P, C.c_size_t, _P]),

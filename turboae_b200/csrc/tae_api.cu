@@ -1,5 +1,6 @@
 // C ABI of libturboae_b200.so (see include/turboae_b200.h): argument validation, the error
 // convention and dispatch to the fp32 (tae_f32.cu) and bf16 tcgen05 (tae_dec_bf16.cu) paths.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -191,6 +192,95 @@ int tae_dec_forward(const TaeDecConfig* cfg, const float* params, const void* pa
   }
   set_error("tae_dec_forward: unknown precision %d", precision);
   return TAE_EINVAL;
+}
+
+// ---- host-buffer decode: chunked H2D / decode / D2H pipeline ---------------------------------------------------
+static constexpr int HOST_CHUNKS = 4;
+
+static int host_chunk(int B) {
+  if (B < 4000) return B;                                   // too small to be worth splitting
+  const int c = (B + HOST_CHUNKS - 1) / HOST_CHUNKS;
+  return (c + 9) / 10 * 10;                                 // whole CTA-pair groups (10 codewords at L = 100)
+}
+
+size_t tae_dec_host_workspace_bytes(const TaeDecConfig* cfg, int32_t B, int32_t precision) {
+  if (check_dec_config(cfg) || B < 0) return 0;
+  const size_t chunk = (size_t)host_chunk(B);
+  const size_t kernel_ws = tae_dec_workspace_bytes(cfg, (int32_t)chunk, precision);
+  if (B > 0 && kernel_ws == 0) return 0;
+  return 2 * align_up(chunk * cfg->block_len * 3 * sizeof(float), 256) + 2 * align_up(chunk * cfg->block_len * sizeof(float), 256) +
+         align_up(kernel_ws, 256) + 256;
+}
+
+int tae_dec_forward_host(const TaeDecConfig* cfg, const float* params, const void* packed, const float* received_host,
+                         const int32_t* perm, const int32_t* inv_perm, float* out_host, int32_t B, int32_t precision,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_dec_config(cfg);
+  if (rc) return rc;
+  TAE_REQUIRE(B >= 0, "tae_dec_forward_host: negative batch %d", B);
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(params && received_host && out_host && perm && inv_perm && workspace, "tae_dec_forward_host: NULL pointer");
+  if (workspace_bytes < tae_dec_host_workspace_bytes(cfg, B, precision)) {
+    set_error("tae_dec_forward_host: workspace %zu < %zu bytes", workspace_bytes, tae_dec_host_workspace_bytes(cfg, B, precision));
+    return TAE_EWORKSPACE;
+  }
+  // per-device copy streams and events, created once
+  struct Pipe { cudaStream_t in = nullptr, out = nullptr; cudaEvent_t h2d[2], dec[2], d2h[2], start; bool ok = false; };
+  static Pipe pipes[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  TAE_REQUIRE(dev >= 0 && dev < 64, "tae_dec_forward_host: device index %d out of range", dev);
+  Pipe& P = pipes[dev];
+  if (!P.ok) {
+    cudaError_t e = cudaStreamCreateWithFlags(&P.in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&P.out, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+      e = cudaEventCreateWithFlags(&P.h2d[i], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&P.dec[i], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&P.d2h[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&P.start, cudaEventDisableTiming);
+    if (e != cudaSuccess) { set_error("tae_dec_forward_host: stream/event setup: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+    P.ok = true;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int L = cfg->block_len;
+  const size_t chunk = (size_t)host_chunk(B);
+  const size_t in_b = align_up(chunk * L * 3 * sizeof(float), 256), out_b = align_up(chunk * L * sizeof(float), 256);
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(workspace), 256));
+  float* d_in[2] = {reinterpret_cast<float*>(base), reinterpret_cast<float*>(base + in_b)};
+  float* d_out[2] = {reinterpret_cast<float*>(base + 2 * in_b), reinterpret_cast<float*>(base + 2 * in_b + out_b)};
+  void* kws = base + 2 * in_b + 2 * out_b;
+  const size_t kws_b = tae_dec_workspace_bytes(cfg, (int32_t)chunk, precision);
+#define TAE_CU(call)                                                                        \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) { set_error("tae_dec_forward_host: %s: %s", #call, cudaGetErrorString(e_)); return TAE_ECUDA; } \
+  } while (0)
+  // the copy streams start after whatever precedes this call on `stream` (e.g. a weight update / pack)
+  TAE_CU(cudaEventRecord(P.start, s));
+  TAE_CU(cudaStreamWaitEvent(P.in, P.start, 0));
+  TAE_CU(cudaStreamWaitEvent(P.out, P.start, 0));
+  int i = 0;
+  for (size_t b0 = 0; b0 < (size_t)B; b0 += chunk, ++i) {
+    const int nb = (int)std::min(chunk, (size_t)B - b0);
+    const int k = i & 1;
+    if (i >= 2) TAE_CU(cudaStreamWaitEvent(P.in, P.dec[k], 0));          // staging buffer k: its previous decode is done
+    TAE_CU(cudaMemcpyAsync(d_in[k], received_host + b0 * L * 3, (size_t)nb * L * 3 * sizeof(float), cudaMemcpyHostToDevice, P.in));
+    TAE_CU(cudaEventRecord(P.h2d[k], P.in));
+    TAE_CU(cudaStreamWaitEvent(s, P.h2d[k], 0));
+    if (i >= 2) TAE_CU(cudaStreamWaitEvent(s, P.d2h[k], 0));             // output buffer k has been read back
+    rc = tae_dec_forward(cfg, params, packed, d_in[k], perm, inv_perm, d_out[k], nullptr, nb, precision, kws, kws_b, s);
+    if (rc) return rc;
+    TAE_CU(cudaEventRecord(P.dec[k], s));
+    TAE_CU(cudaStreamWaitEvent(P.out, P.dec[k], 0));
+    TAE_CU(cudaMemcpyAsync(out_host + b0 * L, d_out[k], (size_t)nb * L * sizeof(float), cudaMemcpyDeviceToHost, P.out));
+    TAE_CU(cudaEventRecord(P.d2h[k], P.out));
+  }
+  TAE_CU(cudaStreamWaitEvent(s, P.d2h[(i - 1) & 1], 0));                 // `stream` completes when out_host is complete
+  if (i >= 2) TAE_CU(cudaStreamWaitEvent(s, P.d2h[i & 1], 0));
+#undef TAE_CU
+  return TAE_OK;
 }
 
 size_t tae_enc_param_count(const TaeEncConfig* cfg) {

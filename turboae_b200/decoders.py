@@ -40,6 +40,7 @@ class DEC_LargeCNN(torch.nn.Module):
                                                      1 if idx == args.num_iteration - 1 else args.num_iter_ft))
         self._flat = FlatCache()
         self._ws = Workspace()
+        self._ws_host = Workspace()
         #: 'bf16' (fused tcgen05 kernel) or 'fp32' (CUDA-core parity path)
         self.precision = getattr(args, "tae_precision", None) or os.environ.get("TURBOAE_B200_PRECISION", "bf16")
 
@@ -72,43 +73,74 @@ class DEC_LargeCNN(torch.nn.Module):
     def decode(self, received, precision=None, trace=None):
         """received: contiguous float32 CUDA (B, L, 3) -> (B, L, 1).  `trace`: optional (2I, B, L, F) tensor that
         receives every dec{1,2}_outputs Linear output (pre-subtraction), for parity debugging."""
-        lib = _lib.load()
-        precision = precision or self.precision
-        if precision not in _lib.PRECISIONS:
-            raise _lib.TaeError("precision must be 'bf16' or 'fp32', got %r" % (precision,))
-        prec = _lib.PRECISIONS[precision]
         _lib.require_cuda(received, "DEC_LargeCNN input")
         B, L, three = received.shape
         if three != 3:
             raise _lib.TaeError("DEC_LargeCNN expects (B, L, 3), got %s" % (tuple(received.shape),))
         dev = received.device
-        cfg = self.config(L)
-        flat = self._flat.get(self.ordered_parameters())
-        if flat.device != dev:
-            raise _lib.TaeError("decoder parameters are on %s but the input is on %s" % (flat.device, dev))
-        if flat.numel() != lib.tae_dec_param_count(cfg):
-            raise _lib.TaeError("parameter count mismatch: module %d vs library %d"
-                                % (flat.numel(), lib.tae_dec_param_count(cfg)))
-        perm, inv = self.interleaver.device_index(dev)
         out = torch.empty((B, L, 1), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            packed = None
-            if prec == _lib.PRECISION_BF16:
-                packed = self._flat.derived.get("bf16")
-                if packed is None:
-                    nbytes = lib.tae_dec_packed_bytes(cfg)
-                    if nbytes == 0:
-                        raise _lib.TaeError("bf16 tensor path unavailable for this configuration (%s); "
-                                            "set precision='fp32'" % lib.tae_last_error().decode())
-                    packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-                    _lib.check(lib.tae_dec_pack_bf16(cfg, _lib.ptr(flat), _lib.ptr(packed), _lib.stream_ptr(dev)))
-                    self._flat.derived["bf16"] = packed
+            lib, cfg, flat, packed, prec = self._prepare(L, dev, precision)
+            if flat.numel() != lib.tae_dec_param_count(cfg):
+                raise _lib.TaeError("parameter count mismatch: module %d vs library %d"
+                                    % (flat.numel(), lib.tae_dec_param_count(cfg)))
+            perm, inv = self.interleaver.device_index(dev)
             ws_bytes = lib.tae_dec_workspace_bytes(cfg, B, prec)
             ws = self._ws.get(ws_bytes, dev)
             _lib.check(lib.tae_dec_forward(cfg, _lib.ptr(flat), _lib.ptr(packed), _lib.ptr(received), _lib.ptr(perm),
                                            _lib.ptr(inv), _lib.ptr(out), _lib.ptr(trace), B, prec, _lib.ptr(ws),
                                            ws.numel(), _lib.stream_ptr(dev)))
         return out
+
+    def _prepare(self, L, dev, precision):
+        lib = _lib.load()
+        precision = precision or self.precision
+        if precision not in _lib.PRECISIONS:
+            raise _lib.TaeError("precision must be 'bf16' or 'fp32', got %r" % (precision,))
+        prec = _lib.PRECISIONS[precision]
+        cfg = self.config(L)
+        flat = self._flat.get(self.ordered_parameters())
+        if flat.device != dev:
+            raise _lib.TaeError("decoder parameters are on %s but the device buffers are on %s" % (flat.device, dev))
+        packed = None
+        if prec == _lib.PRECISION_BF16:
+            packed = self._flat.derived.get("bf16")
+            if packed is None:
+                nbytes = lib.tae_dec_packed_bytes(cfg)
+                if nbytes == 0:
+                    raise _lib.TaeError("bf16 tensor path unavailable for this configuration (%s); set precision='fp32'"
+                                        % lib.tae_last_error().decode())
+                packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                _lib.check(lib.tae_dec_pack_bf16(cfg, _lib.ptr(flat), _lib.ptr(packed), _lib.stream_ptr(dev)))
+                self._flat.derived["bf16"] = packed
+        return lib, cfg, flat, packed, prec
+
+    def decode_host(self, received_host, out_host=None, precision=None):
+        """Host-buffer decode: ``received_host`` (B, L, 3) float32 on the CPU (pin it for asynchronous copies) ->
+        ``out_host`` (B, L, 1) on the CPU.  H2D copy, fused decode and D2H copy of successive chunks of the batch overlap
+        inside ``tae_dec_forward_host``; the call returns after enqueueing, synchronise the current stream (or call
+        ``torch.cuda.synchronize()``) before reading ``out_host``."""
+        if received_host.is_cuda or received_host.dtype != torch.float32 or not received_host.is_contiguous():
+            raise _lib.TaeError("decode_host expects a contiguous float32 CPU tensor")
+        if self.this_device.type != "cuda":
+            raise _lib.TaeError("no CUDA device: turboae_b200 has no CPU fallback")
+        B, L, three = received_host.shape
+        if three != 3:
+            raise _lib.TaeError("DEC_LargeCNN expects (B, L, 3), got %s" % (tuple(received_host.shape),))
+        dev = next(self.parameters()).device
+        if out_host is None:
+            out_host = torch.empty((B, L, 1), dtype=torch.float32).pin_memory()
+        if out_host.is_cuda or out_host.dtype != torch.float32 or out_host.numel() != B * L or not out_host.is_contiguous():
+            raise _lib.TaeError("out_host must be a contiguous float32 CPU tensor with B*L elements")
+        with torch.cuda.device(dev):
+            lib, cfg, flat, packed, prec = self._prepare(L, dev, precision)
+            perm, inv = self.interleaver.device_index(dev)
+            ws_bytes = lib.tae_dec_host_workspace_bytes(cfg, B, prec)
+            ws = self._ws_host.get(ws_bytes, dev)
+            _lib.check(lib.tae_dec_forward_host(cfg, _lib.ptr(flat), _lib.ptr(packed), _lib.ptr(received_host), _lib.ptr(perm),
+                                                _lib.ptr(inv), _lib.ptr(out_host), B, prec, _lib.ptr(ws), ws.numel(),
+                                                _lib.stream_ptr(dev)))
+        return out_host
 
     def forward(self, received):
         if getattr(self.args, "is_variable_block_len", False):

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
+from . import _lib, shard
 from ._flat import FlatCache, ParallelShim, Workspace, unwrap
 from .cnn_utils import SameShapeConv1d
 from .interleavers import Interleaver
@@ -127,7 +127,7 @@ class ENC_interCNN(ENCBase):
             return x_tx
         if self.shard_group is not None:
             # power_constraint normalises over the WHOLE batch (encoders.py:107-116): merge the per-rank sums
-            torch.distributed.all_reduce(stats, group=self.shard_group)
+            shard.merge_power_stats(stats, self.shard_group)
         codes = torch.empty_like(x_tx)
         with torch.cuda.device(x.device):
             _lib.check(lib.tae_power_norm_f32(_lib.ptr(x_tx), _lib.ptr(codes), x_tx.numel(), _lib.ptr(stats), None,

@@ -127,6 +127,14 @@ size_t tae_enc_workspace_bytes(const TaeEncConfig* cfg, int32_t B);
 int tae_enc_forward(const TaeEncConfig* cfg, const float* params, const float* u,
                     const int32_t* perm, float* x_tx, double* stats, int32_t B,
                     void* workspace, size_t workspace_bytes, void* stream);
+/* The same forward on the tensor cores (bf16 operands, fp32 accumulation; the fused CTA-pair kernel of the decoder with
+ * the three branches as three conv stacks).  `packed` from tae_enc_pack_bf16 (rebuild after every weight update);
+ * needs perm AND inverse perm; workspace >= 256 bytes.  Same x_tx / stats contract as tae_enc_forward.            */
+size_t tae_enc_packed_bytes(const TaeEncConfig* cfg);
+int    tae_enc_pack_bf16(const TaeEncConfig* cfg, const float* params, void* packed, void* stream);
+int tae_enc_forward_bf16(const TaeEncConfig* cfg, const void* packed, const float* u, const int32_t* perm,
+                         const int32_t* inv_perm, float* x_tx, double* stats, int32_t B,
+                         void* workspace, size_t workspace_bytes, void* stream);
 /* ENCBase.power_constraint default branch, reference encoders.py:107-116:
  * codes = (x - mean) / std, mean/std (unbiased, N-1) derived on the device from stats[0..2].
  * mean_std: NULL or 2 device floats receiving (mean, std).  x may alias codes.            */

@@ -90,6 +90,45 @@ def test_encoder_edge_cases():
         m.enc.args.no_code_norm = False
 
 
+@pytest.mark.parametrize("cfg,name", [("c1", "io_c1_b8.npz"), ("c3", "io_c3_b6.npz")])
+def test_encoder_bf16_tensor_path_vs_reference_fixture(cfg, name):
+    """ENC_interCNN on the fused tcgen05 kernel (bf16 operands): codes within bf16 rounding noise of the reference's,
+    power constraint exact (mean 0, std 1), hard agreement of the decoded bits."""
+    g = load_npz(name)
+    m, w, p = build_codec(cfg, batch_size=g["u"].shape[0])
+    m.enc.precision = "bf16"
+    with torch.no_grad():
+        codes = m.enc(_t(g["u"]))
+        y = m.dec.decode(codes + _t(g["noise"]), precision="fp32").cpu().numpy()
+    c = codes.cpu().numpy()
+    err = np.abs(c - g["codes"])
+    assert err.max() < 0.08 and err.mean() < 0.01, (err.max(), err.mean())
+    assert abs(float(c.mean())) < 1e-5 and abs(float(c.std(ddof=1)) - 1) < 1e-4
+    assert int((np.round(y) != np.round(g["y"])).sum()) <= 2
+
+
+def test_encoder_bf16_ragged_batches_and_ber():
+    m, w, p = build_codec("c1")
+    ref = json.load(open(os.path.join(GOLDEN, "ber_c1.json")))
+    with torch.no_grad():
+        for B in (1, 7, 1003):
+            u, _ = gen_inputs(50 + B, B, 100, 0.0)
+            m.enc.precision = "fp32"
+            c32 = m.enc(_t(u))
+            m.enc.precision = "bf16"
+            c16 = m.enc(_t(u))
+            assert c16.shape == (B, 100, 3) and torch.isfinite(c16).all()
+            assert float((c16 - c32).abs().mean()) < 0.01, B
+        # BER at 0 dB with BOTH halves on the tensor path, same seeded bits/noise as the reference sweep
+        be = 0
+        for bi in range(ref["blocks"] // ref["batch"]):
+            u, noise = gen_inputs(100000 + 1000 * 3 + bi, ref["batch"], 100, 0.0)
+            ud = _t(u)
+            y = m.dec.decode(m.enc(ud) + _t(noise), precision="bf16")
+            be += int((torch.round(y) != ud).sum())
+    assert abs(be - ref["bit_errors"][3]) / (ref["blocks"] * 100) < 1e-4, (be, ref["bit_errors"][3])
+
+
 # ------------------------------------------------------------------------------------------------- a8 fp32
 @pytest.mark.parametrize("cfg,name", [("c1", "io_c1_b8.npz"), ("c3", "io_c3_b6.npz")])
 def test_decoder_fp32_vs_reference_fixture(cfg, name):

@@ -48,6 +48,9 @@ _SIGNATURES = {
     "tae_enc_param_count": (C.c_size_t, [C.POINTER(TaeEncConfig)]),
     "tae_enc_workspace_bytes": (C.c_size_t, [C.POINTER(TaeEncConfig), C.c_int32]),
     "tae_enc_forward": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P, _P, _P, C.c_int32, _P, C.c_size_t, _P]),
+    "tae_enc_packed_bytes": (C.c_size_t, [C.POINTER(TaeEncConfig)]),
+    "tae_enc_pack_bf16": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P]),
+    "tae_enc_forward_bf16": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_size_t, _P]),
     "tae_power_norm_f32": (C.c_int, [_P, _P, C.c_size_t, _P, _P, _P]),
     # debug / self-test entry points
     "tae_debug_set_dump": (None, [_P]),

@@ -303,6 +303,37 @@ int tae_enc_forward(const TaeEncConfig* cfg, const float* params, const float* u
   return enc_forward_f32(*cfg, params, u, perm, x_tx, stats, B, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+size_t tae_enc_packed_bytes(const TaeEncConfig* cfg) {
+  if (check_enc_config(cfg)) return 0;
+  const char* why = nullptr;
+  if (!enc_pair_supported(*cfg, &why)) { set_error("bf16 encoder path: %s", why); return 0; }
+  return enc_pair_packed_bytes(*cfg);
+}
+
+int tae_enc_pack_bf16(const TaeEncConfig* cfg, const float* params, void* packed, void* stream) {
+  int rc = check_enc_config(cfg);
+  if (rc) return rc;
+  const char* why = nullptr;
+  if (!enc_pair_supported(*cfg, &why)) { set_error("bf16 encoder path: %s", why); return TAE_EUNSUPPORTED; }
+  TAE_REQUIRE(params && packed, "tae_enc_pack_bf16: NULL pointer");
+  return enc_pair_pack(*cfg, params, packed, (cudaStream_t)stream);
+}
+
+int tae_enc_forward_bf16(const TaeEncConfig* cfg, const void* packed, const float* u, const int32_t* perm,
+                         const int32_t* inv_perm, float* x_tx, double* stats, int32_t B, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  int rc = check_enc_config(cfg);
+  if (rc) return rc;
+  const char* why = nullptr;
+  if (!enc_pair_supported(*cfg, &why)) { set_error("bf16 encoder path: %s", why); return TAE_EUNSUPPORTED; }
+  TAE_REQUIRE(B >= 0, "tae_enc_forward_bf16: negative batch %d", B);
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(packed && u && perm && inv_perm && x_tx && stats && workspace, "tae_enc_forward_bf16: NULL pointer");
+  rc = enc_forward_pair(*cfg, packed, u, perm, inv_perm, x_tx, stats, B, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (rc) return rc;
+  return launch_add_count(stats, (double)B * cfg->block_len * 3, (cudaStream_t)stream);
+}
+
 int tae_power_norm_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std, void* stream) {
   if (n == 0) return TAE_OK;
   TAE_REQUIRE(x && codes && stats, "tae_power_norm_f32: NULL pointer");

@@ -109,6 +109,13 @@ size_t dec_pair_packed_bytes(const TaeDecConfig& c);
 int dec_pair_pack(const TaeDecConfig& c, const float* params, void* packed, cudaStream_t s);
 int dec_forward_pair(const TaeDecConfig& c, const void* packed, const float* received, const int32_t* perm,
                      const int32_t* inv_perm, float* out, float* trace, int B, void* ws, size_t ws_bytes, cudaStream_t s);
+// ENC_interCNN on the same CTA-pair kernel (three branches as three stacks)
+bool enc_pair_supported(const TaeEncConfig& c, const char** why);
+size_t enc_pair_packed_bytes(const TaeEncConfig& c);
+int enc_pair_pack(const TaeEncConfig& c, const float* params, void* packed, cudaStream_t s);
+int enc_forward_pair(const TaeEncConfig& c, const void* packed, const float* u, const int32_t* perm, const int32_t* inv_perm,
+                     float* x_tx, double* stats, int B, void* ws, size_t ws_bytes, cudaStream_t s);
+int launch_add_count(double* stats, double n, cudaStream_t s);
 // TURBOAE_B200_DEC_IMPL=v1 selects the older single-CTA kernel (development A/B only)
 bool use_dec_v1();
 

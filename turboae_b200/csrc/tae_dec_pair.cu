@@ -119,7 +119,11 @@ struct PairArgs {
   int* err;
   const int32_t* perm;
   const int32_t* inv_perm;
-  int B, L, F, I, n_layer, extrinsic, n_groups, n_pairs, cw_per_group;
+  int B, L, F, n_stacks, n_layer, extrinsic, n_groups, n_pairs, cw_per_group;
+  int enc;                     // 0: DEC_LargeCNN schedule; 1: ENC_interCNN (three branches, Linear(units,1) + ELU, power sums)
+  const float* u;              // enc: bits (B, L, 1)
+  float* x_tx;                 // enc: un-normalised codes (B, L, 3)
+  double* stats;               // enc: running (sum, sum of squares)
   uint32_t stack_bytes;        // bytes of one stack's image (both halves)
   unsigned long long* tl;      // optional timeline buffer (tae_debug_set_timeline): clock64 stamps of cluster 0, leader CTA
 };
@@ -427,7 +431,7 @@ __device__ __forceinline__ float lin_w_elem(const float* __restrict__ w, const f
 }
 
 __global__ void pack_pair_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ img,
-                                 const DecStackLayout* __restrict__ lay, int n_stacks, int n_layer, int units, int F,
+                                 const DecStackLayout* __restrict__ lay, int n_stacks, int n_layer, int units, int cin0,
                                  uint32_t stack_elems) {
   const size_t total = (size_t)n_stacks * stack_elems;
   const uint32_t l0_elems = 2 * L0_B / 2;
@@ -441,7 +445,7 @@ __global__ void pack_pair_kernel(const float* __restrict__ params, __nv_bfloat16
       const int half = r / (L0_B / 2);
       r %= (L0_B / 2);
       const int ks = r / (2 * NHALF * 8), ch = (r / (NHALF * 8)) & 1, n = (r / 8) % NHALF, e8 = r % 8;
-      v = l0_w_elem(params + S.conv[0].w_off, params + S.conv[0].b_off, units, 2 + F, half * NHALF + n, ks, ch * 8 + e8);
+      v = l0_w_elem(params + S.conv[0].w_off, params + S.conv[0].b_off, units, cin0, half * NHALF + n, ks, ch * 8 + e8);
     } else if (r < l0_elems + conv_elems) {
       r -= l0_elems;
       const uint32_t slot_elems = 2 * SLOT_B / 2;      // both halves of one slot
@@ -474,7 +478,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int L = a.L, F = a.F, CW_ROWS = a.L + 2;
-  const int n_stacks = 2 * a.I;
+  const int n_stacks = a.n_stacks;
   const int slots_per_stack = 2 + SLOTS_CONV * (a.n_layer - 1);    // weight transfers: layer 0, 8 per layer, Linear
 
   auto bar = [&](int i) { return sbase + S.bars + 8u * (uint32_t)i; };
@@ -550,7 +554,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
       const uint32_t act = sbase + S.act, comb = sbase + S.comb, ones = sbase + S.ones;
       for (int pr = pair0; pr < a.n_pairs; pr += pair_stride) {
         for (int st = 0; st < n_stacks; ++st) {
-          const uint32_t xin = sbase + S.xin[st & 1];
+          const uint32_t xin = sbase + S.xin[a.enc ? (st == 2) : (st & 1)];   // enc: branch 3 reads the interleaved bits
           for (int layer = 0; layer <= a.n_layer; ++layer, ++step) {
             const uint32_t par = step & 1;
             const bool conv = (layer > 0 && layer < a.n_layer);
@@ -660,6 +664,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
       for (uint32_t i = tid * 16; i < (uint32_t)F * BUF_ROWS * 4; i += N_EPI_THREADS * 16)
         st_shared_v4(sbase + S.pri[0] + i, 0u, 0u, 0u, 0u);
       epi_bar_sync();
+      if (a.enc) {
+        for (int i = tid; i < n_cw * L; i += N_EPI_THREADS) {
+          const int c = i / L, l = i % L;
+          const uint16_t x = bf16_bits(2.0f * a.u[(size_t)(cw0 + c) * L + l] - 1.0f);                  // encoders.py:362
+          const uint32_t row = (uint32_t)(c * CW_ROWS + l + 2) * ROW_B;
+          const uint32_t row_i = (uint32_t)(c * CW_ROWS + ld_shared_u16(sbase + S.inv_perm + 2 * l) + 2) * ROW_B;
+          st_shared_u16(sbase + S.xin[0] + row, x);            // branches 1, 2
+          st_shared_u16(sbase + S.xin[1] + row_i, x);          // branch 3: x_int[i] = x[p[i]]          (encoders.py:369)
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + S.ones + row), "r"(0x3F803F80u) : "memory");
+        }
+      } else
       for (int i = tid; i < n_cw * L; i += N_EPI_THREADS) {
         const int c = i / L, l = i % L;
         const float* r = a.received + ((size_t)(cw0 + c) * L + l) * 3;
@@ -687,6 +702,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
         for (int layer = 0; layer <= a.n_layer; ++layer, ++step) {
           const uint32_t par = step & 1;
           const bool last_step = (st == n_stacks - 1 && layer == a.n_layer);
+          if (layer == a.n_layer && a.enc) {
+            // -- ENC_interCNN tail: x_tx[:, :, branch] = ELU(Linear(h)) (encoders.py:364,367,371) + the power sums ------
+#pragma unroll
+            for (int m = 0; m < N_TILES; ++m) mbar_wait(bar(B_ACC + m), par, a.err, 6);
+            tc_fence_after();
+            double s1 = 0.0, s2 = 0.0;
+            if (half == 0) {
+#pragma unroll 1
+              for (int m = 0; m < N_TILES; ++m) {
+                uint32_t r[8];
+                tmem_ld8(lane_addr + TMEM_LIN_COL + (uint32_t)(m * LIN_N), r);
+                tmem_ld_wait();
+                if (!((vmask >> m) & 1u)) continue;
+                const int g_row = 128 * m + 32 * q + lane;
+                const int g_cw = g_row / CW_ROWS, g_l = g_row - g_cw * CW_ROWS;
+                const float z = __uint_as_float(r[0]);
+                const float v = z > 0.f ? z : expm1f(z);
+                a.x_tx[((size_t)(cw0 + g_cw) * L + g_l) * 3 + st] = v;
+                s1 += (double)v;
+                s2 += (double)v * (double)v;
+              }
+#pragma unroll
+              for (int d = 16; d > 0; d >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+              }
+              if (lane == 0) { atomicAdd(a.stats + 0, s1); atomicAdd(a.stats + 1, s2); }
+            }
+            if (!last_step) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0)
+                for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_ACT + m), rank);
+            }
+            continue;
+          }
           if (layer == a.n_layer) {
             // -- Linear epilogue, all four tiles in one pass (their MMAs are tiny and complete together): extrinsic
             //    subtraction + (de)interleave into the next stack's input.  The two warps of a quadrant split the
@@ -1070,18 +1121,15 @@ int dec_pair_pack(const TaeDecConfig& c, const float* params, void* packed, cuda
   const size_t total = (size_t)n_stacks * stack_elems;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
   pack_pair_kernel<<<blocks, 256, 0, s>>>(params, reinterpret_cast<__nv_bfloat16*>(packed), d_lay, n_stacks, c.num_layer,
-                                          c.num_unit, c.num_iter_ft, stack_elems);
+                                          c.num_unit, 2 + c.num_iter_ft, stack_elems);
   int rc = after_launch("pack_pair_kernel");
   cudaFreeAsync(d_lay, s);
   return rc;
 }
 
-int dec_forward_pair(const TaeDecConfig& c, const void* packed, const float* received, const int32_t* perm,
-                     const int32_t* inv_perm, float* out, float* trace, int B, void* ws, size_t ws_bytes, cudaStream_t s) {
-  if (ws_bytes < 256) { set_error("tae_dec_forward(bf16): workspace %zu < 256 bytes", ws_bytes); return TAE_EWORKSPACE; }
+static int pair_launch_setup(const TaeDecConfig&, int* n_sm_out) {
   static int n_sm = 0;
   static bool attr_done = false;
-  const Smem S = make_smem(c.num_iter_ft);
   if (!attr_done) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1090,9 +1138,22 @@ int dec_forward_pair(const TaeDecConfig& c, const void* packed, const float* rec
     if (e != cudaSuccess) { set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
     if (prop.major != 10) { set_error("bf16 path needs an sm_100a device (found sm_%d%d)", prop.major, prop.minor); return TAE_EUNSUPPORTED; }
     n_sm = prop.multiProcessorCount;
-    e = cudaFuncSetAttribute(dec_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S.total);
+    e = cudaFuncSetAttribute(dec_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)make_smem(5).total);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dec_pair_kernel): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
     attr_done = true;
+  }
+  *n_sm_out = n_sm;
+  return TAE_OK;
+}
+
+int dec_forward_pair(const TaeDecConfig& c, const void* packed, const float* received, const int32_t* perm,
+                     const int32_t* inv_perm, float* out, float* trace, int B, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (ws_bytes < 256) { set_error("tae_dec_forward(bf16): workspace %zu < 256 bytes", ws_bytes); return TAE_EWORKSPACE; }
+  const Smem S = make_smem(c.num_iter_ft);
+  int n_sm = 0;
+  {
+    int rc = pair_launch_setup(c, &n_sm);
+    if (rc) return rc;
   }
   PairArgs a{};
   a.wimg = reinterpret_cast<const uint8_t*>(packed);
@@ -1102,7 +1163,8 @@ int dec_forward_pair(const TaeDecConfig& c, const void* packed, const float* rec
   a.err = reinterpret_cast<int*>(align_up(reinterpret_cast<uintptr_t>(ws), 16));
   a.perm = perm;
   a.inv_perm = inv_perm;
-  a.B = B; a.L = c.block_len; a.F = c.num_iter_ft; a.I = c.num_iteration; a.n_layer = c.num_layer;
+  a.B = B; a.L = c.block_len; a.F = c.num_iter_ft; a.n_stacks = 2 * c.num_iteration; a.n_layer = c.num_layer;
+  a.enc = 0;
   a.extrinsic = c.extrinsic;
   a.cw_per_group = (GROUP_ROWS + 2) / (c.block_len + 2);
   a.n_groups = (B + a.cw_per_group - 1) / a.cw_per_group;
@@ -1112,6 +1174,76 @@ int dec_forward_pair(const TaeDecConfig& c, const void* packed, const float* rec
   const int n_clusters = std::min(a.n_pairs, n_sm / 2);
   dec_pair_kernel<<<2 * n_clusters, N_THREADS, S.total, s>>>(a);
   return after_launch("dec_pair_kernel");
+}
+
+
+// ---- ENC_interCNN on the same kernel ----------------------------------------------------------------------------
+static TaeDecConfig enc_as_dec(const TaeEncConfig& c) {
+  TaeDecConfig d{};
+  d.block_len = c.block_len; d.num_iteration = 2; d.num_iter_ft = 1; d.num_layer = c.num_layer; d.num_unit = c.num_unit;
+  d.kernel_size = c.kernel_size; d.extrinsic = 0;
+  return d;
+}
+
+bool enc_pair_supported(const TaeEncConfig& c, const char** why) {
+  static thread_local char msg[160];
+  const TaeDecConfig d = enc_as_dec(c);
+  if (!dec_pair_supported(d, why)) return false;
+  *why = msg;
+  if (c.num_layer < 2) { snprintf(msg, sizeof msg, "enc_num_layer %d < 2", c.num_layer); return false; }
+  *why = nullptr;
+  return true;
+}
+
+size_t enc_pair_packed_bytes(const TaeEncConfig& c) { return (size_t)3 * stack_image_bytes(enc_as_dec(c)); }
+
+int enc_pair_pack(const TaeEncConfig& c, const float* params, void* packed, cudaStream_t s) {
+  EncBranchLayout el[3];
+  enc_layout(c, el);
+  DecStackLayout lay[3];
+  for (int b = 0; b < 3; ++b) {
+    lay[b] = DecStackLayout{};
+    for (int j = 0; j < c.num_layer; ++j) lay[b].conv[j] = el[b].conv[j];
+    lay[b].lin_w_off = el[b].lin_w_off; lay[b].lin_b_off = el[b].lin_b_off; lay[b].fout = 1;
+  }
+  DecStackLayout* d_lay = nullptr;
+  cudaError_t e = cudaMallocAsync(&d_lay, sizeof(lay), s);
+  if (e != cudaSuccess) { set_error("cudaMallocAsync: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+  e = cudaMemcpyAsync(d_lay, lay, sizeof(lay), cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) { set_error("cudaMemcpyAsync: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+  const TaeDecConfig d = enc_as_dec(c);
+  const uint32_t stack_elems = stack_image_bytes(d) / 2;
+  const size_t total = (size_t)3 * stack_elems;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  pack_pair_kernel<<<blocks, 256, 0, s>>>(params, reinterpret_cast<__nv_bfloat16*>(packed), d_lay, 3, c.num_layer, c.num_unit, 1,
+                                          stack_elems);
+  int rc = after_launch("pack_pair_kernel");
+  cudaFreeAsync(d_lay, s);
+  return rc;
+}
+
+int enc_forward_pair(const TaeEncConfig& c, const void* packed, const float* u, const int32_t* perm, const int32_t* inv_perm,
+                     float* x_tx, double* stats, int B, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (ws_bytes < 256) { set_error("tae_enc_forward_bf16: workspace %zu < 256 bytes", ws_bytes); return TAE_EWORKSPACE; }
+  const TaeDecConfig d = enc_as_dec(c);
+  // reuse the decoder launcher's one-time setup by going through the same code path
+  PairArgs a{};
+  int n_sm = 0;
+  int rc = pair_launch_setup(d, &n_sm);
+  if (rc) return rc;
+  a.wimg = reinterpret_cast<const uint8_t*>(packed);
+  a.u = u; a.x_tx = x_tx; a.stats = stats; a.enc = 1;
+  a.err = reinterpret_cast<int*>(align_up(reinterpret_cast<uintptr_t>(ws), 16));
+  a.perm = perm; a.inv_perm = inv_perm;
+  a.B = B; a.L = c.block_len; a.F = 1; a.n_stacks = 3; a.n_layer = c.num_layer; a.extrinsic = 0;
+  a.cw_per_group = (GROUP_ROWS + 2) / (c.block_len + 2);
+  a.n_groups = (B + a.cw_per_group - 1) / a.cw_per_group;
+  a.n_pairs = (a.n_groups + 1) / 2;
+  a.stack_bytes = stack_image_bytes(d);
+  a.tl = nullptr;
+  const int n_clusters = std::min(a.n_pairs, n_sm / 2);
+  dec_pair_kernel<<<2 * n_clusters, N_THREADS, make_smem(1).total, s>>>(a);
+  return after_launch("dec_pair_kernel(enc)");
 }
 
 }  // namespace tae

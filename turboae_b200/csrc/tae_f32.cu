@@ -491,6 +491,11 @@ int enc_forward_f32(const TaeEncConfig& c, const float* params, const float* u, 
   return after_launch("add_count_kernel");
 }
 
+int launch_add_count(double* stats, double n, cudaStream_t s) {
+  add_count_kernel<<<1, 1, 0, s>>>(stats, n);
+  return after_launch("add_count_kernel");
+}
+
 int launch_power_norm_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std,
                           cudaStream_t s) {
   if (n == 0) return TAE_OK;

@@ -5,6 +5,8 @@ Linear(100->1) + ELU each, concat, then the batch-global power normalisation -- 
 (``tae_enc_forward`` + ``tae_power_norm_f32``)."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib, shard
@@ -57,6 +59,9 @@ class ENC_interCNN(ENCBase):
         self._flat = FlatCache()
         self._ws = Workspace()
         self.shard_group = None      # set to a torch.distributed group when the batch is sharded across ranks
+        #: 'fp32' (CUDA-core path, elementwise parity <= 1e-4) or 'bf16' (the decoder's fused tcgen05 kernel with the three
+        #: branches as three conv stacks: ~25x faster, codes within bf16 rounding of the reference's)
+        self.precision = getattr(args, "tae_enc_precision", None) or os.environ.get("TURBOAE_B200_ENC_PRECISION", "fp32")
 
     def set_interleaver(self, p_array):
         self.interleaver.set_parray(p_array)
@@ -101,10 +106,28 @@ class ENC_interCNN(ENCBase):
         flat = self._flat.get(self.ordered_parameters())
         if flat.device != dev:
             raise _lib.TaeError("encoder parameters are on %s but the input is on %s" % (flat.device, dev))
-        perm, _ = self.interleaver.device_index(dev)
+        perm, inv = self.interleaver.device_index(dev)
+        x_tx = torch.empty((B, L, 3), dtype=torch.float32, device=dev)
+        if self.precision not in ("fp32", "bf16"):
+            raise _lib.TaeError("encoder precision must be 'fp32' or 'bf16', got %r" % (self.precision,))
+        if self.precision == "bf16":
+            with torch.cuda.device(dev):
+                packed = self._flat.derived.get("bf16")
+                if packed is None:
+                    nbytes = lib.tae_enc_packed_bytes(cfg)
+                    if nbytes == 0:
+                        raise _lib.TaeError("bf16 encoder path unavailable for this configuration (%s); set precision='fp32'"
+                                            % lib.tae_last_error().decode())
+                    packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                    _lib.check(lib.tae_enc_pack_bf16(cfg, _lib.ptr(flat), _lib.ptr(packed), _lib.stream_ptr(dev)))
+                    self._flat.derived["bf16"] = packed
+                ws = self._ws.get(256, dev)
+                _lib.check(lib.tae_enc_forward_bf16(cfg, _lib.ptr(packed), _lib.ptr(inputs), _lib.ptr(perm), _lib.ptr(inv),
+                                                    _lib.ptr(x_tx), _lib.ptr(stats), B, _lib.ptr(ws), ws.numel(),
+                                                    _lib.stream_ptr(dev)))
+            return x_tx
         ws_bytes = lib.tae_enc_workspace_bytes(cfg, B)
         ws = self._ws.get(ws_bytes, dev)
-        x_tx = torch.empty((B, L, 3), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.tae_enc_forward(cfg, _lib.ptr(flat), _lib.ptr(inputs), _lib.ptr(perm), _lib.ptr(x_tx),
                                            _lib.ptr(stats), B, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))

@@ -249,11 +249,53 @@ def run_b200(a):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 100 * 3 * 4,
                         "d2h_bytes_per_step": B * 100 * 4},
                 "gpu_launches": int(launches), "clocks": sampler.result()}
+        # ---- secondary metrics: encoder and whole Channel_AE forward, device-resident ------------
+        def timed(fn, reps):
+            fn()
+            torch.cuda.synchronize()
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record()
+            for _ in range(reps):
+                fn()
+            t1e.record()
+            torch.cuda.synchronize()
+            return t0e.elapsed_time(t1e) / reps
+
+        with torch.no_grad():
+            sec = {}
+            noise = torch.randn(B, 100, 3, device=dev)
+            for prec in ("fp32", "bf16"):
+                m.enc.precision = prec
+                ms = timed(lambda: m.enc(bits[0]), 3)
+                sec["encoder_%s_cw_per_s" % prec] = B / (ms * 1e-3)
+            m.enc.precision = "bf16"
+            ms = timed(lambda: m.dec(m.enc(bits[0]) + noise), 3)
+            sec["channel_ae_forward_bf16_cw_per_s"] = B / (ms * 1e-3)
+            m.enc.precision = "fp32"
+            sec["encoder_flop_per_cw"] = 30_360_000
+        line["secondary"] = sec
         if world == 1 and not a.no_cpu_baseline:
             v, times, cores = cpu_reference_rate(a.cpu_sample, 10.0, 30)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d codewords x %d repetitions (median), torch CPU operators of the "
                                               "reference's decode path" % (a.cpu_sample, len(times))}
+            # the reference's operator sequence executed by torch eager ON THIS GPU (cuDNN/cuBLAS): "what you get today"
+            try:
+                from oracle import turboae_oracle as O
+                from oracle import turboae_torch as TT
+                wt = {k: torch.from_numpy(v).to(dev) for k, v in w.items()}
+                eg = {}
+                for tf32 in (False, True):
+                    torch.backends.cudnn.allow_tf32 = tf32
+                    torch.backends.cuda.matmul.allow_tf32 = tf32
+                    with torch.no_grad():
+                        ms = timed(lambda: TT.dec_forward(recs[0], wt, p), 2)
+                    eg["tf32" if tf32 else "fp32"] = B / (ms * 1e-3)
+                line["eager_gpu_baseline"] = {"value_fp32": eg["fp32"], "value_tf32": eg["tf32"], "unit": UNIT,
+                                              "what": "reference operator sequence (oracle/turboae_torch.py) on torch eager CUDA, "
+                                                      "B=%d, same weights" % B}
+            except Exception as e:  # pragma: no cover
+                line["eager_gpu_baseline"] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

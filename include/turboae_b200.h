@@ -141,6 +141,16 @@ int tae_enc_forward_bf16(const TaeEncConfig* cfg, const void* packed, const floa
 int tae_power_norm_f32(const float* x, float* codes, size_t n, const double* stats,
                        float* mean_std, void* stream);
 
+/* ---- around the path: on-device channel and metrics -------------------------------------
+ * AWGN channel, reference channel_ae.py:41-42 with channels.py:21-35: received = codes + sigma * N(0,1).
+ * The reference draws torch.randn on the CPU (unseeded); this stream is Philox4x32-10 + Box-Muller, element i uses
+ * counter (offset + i/4), word i%4, key = seed -- reproducible, restated in oracle/turboae_oracle.py.  codes may alias
+ * received.                                                                                                      */
+int tae_awgn_f32(const float* codes, float* received, size_t n, float sigma, uint64_t seed, uint64_t offset, void* stream);
+/* reference utils.py:6-18 (errors_ber) and :49-66 (errors_bler): adds sum(round(y_true) != round(y_pred)) to counts[0]
+ * and the number of codewords with at least one such error to counts[1] (device uint64[2], caller zeroes).        */
+int tae_error_count_f32(const float* y_true, const float* y_pred, int32_t B, int32_t L, unsigned long long* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -254,3 +254,58 @@ def decoder_flops_per_codeword(L=100, n_iter=6, n_ft=5, units=100, n_layer=5, k=
 def encoder_flops_per_codeword(L=100, units=100, n_layer=2, k=5) -> int:
     macs = 3 * L * (1 * units * k + (n_layer - 1) * units * units * k) + 3 * L * units
     return 2 * macs
+
+
+# --------------------------------------------------------------------------- #
+# on-device channel                            #
+# --------------------------------------------------------------------------- #
+def philox4x32_10(counter: np.ndarray, seed: int) -> np.ndarray:
+    """Philox4x32-10 (Salmon et al., SC'11; the generator behind curand / torch CUDA RNG) for 64-bit counters
+    ``counter`` (uint64 array) and a 64-bit key: returns uint32 array of shape (len(counter), 4).  This is the
+    published algorithm restated -- turboae_b200's ``tae_awgn_f32`` must reproduce it bit for bit."""
+    c = np.asarray(counter, dtype=np.uint64)
+    c0 = (c & np.uint64(0xFFFFFFFF)).astype(np.uint64)
+    c1 = (c >> np.uint64(32)).astype(np.uint64)
+    c2 = np.zeros_like(c0)
+    c3 = np.zeros_like(c0)
+    k0 = np.uint64(seed & 0xFFFFFFFF)
+    k1 = np.uint64((seed >> 32) & 0xFFFFFFFF)
+    M0, M1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = M0 * c0
+        p1 = M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
+        hi1, lo1 = p1 >> np.uint64(32), p1 & MASK
+        c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+        k0 = (k0 + np.uint64(0x9E3779B9)) & MASK
+        k1 = (k1 + np.uint64(0xBB67AE85)) & MASK
+    return np.stack([c0, c1, c2, c3], axis=1).astype(np.uint32)
+
+
+def awgn_noise(n: int, seed: int, offset: int = 0) -> np.ndarray:
+    """The N(0,1) stream of ``tae_awgn_f32``: element i = Box-Muller of words (2*(i%4//2), +1) of Philox counter
+    offset + i//4 -- cos branch for even i, sin branch for odd i."""
+    n4 = (n + 3) // 4
+    x = philox4x32_10(np.arange(offset, offset + n4, dtype=np.uint64), seed)
+    u = (x.astype(np.float32) + F32(0.5)) * F32(2.3283064365386963e-10)
+    z = np.empty((n4, 4), dtype=F32)
+    for j in (0, 2):
+        r = np.sqrt(F32(-2.0) * np.log(u[:, j])).astype(F32)
+        ang = (F32(2.0) * u[:, j + 1]).astype(np.float64) * np.pi
+        z[:, j] = r * np.cos(ang).astype(F32)
+        z[:, j + 1] = r * np.sin(ang).astype(F32)
+    return z.reshape(-1)[:n]
+
+
+def awgn(codes: np.ndarray, sigma: float, seed: int, offset: int = 0) -> np.ndarray:
+    """reference channel_ae.py:41-42: received = codes + fwd_noise, fwd_noise = sigma * N(0,1) (channels.py:31-35)."""
+    z = awgn_noise(codes.size, seed, offset).reshape(codes.shape)
+    return (codes.astype(F32) + F32(sigma) * z).astype(F32)
+
+
+def error_counts(y_true: np.ndarray, y_pred: np.ndarray):
+    """(bit errors, block errors): the numerators of reference utils.py:6-18 (errors_ber) and :49-66 (errors_bler)."""
+    t = np.round(y_true.reshape(y_true.shape[0], -1))
+    q = np.round(y_pred.reshape(y_pred.shape[0], -1))
+    wrong = t != q
+    return int(wrong.sum()), int(wrong.any(axis=1).sum())

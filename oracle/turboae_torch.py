@@ -69,12 +69,13 @@ def dec_forward(received, weights, p, num_iteration=6, num_iter_ft=5, extrinsic=
     p = torch.as_tensor(np.asarray(p), dtype=torch.long)
     rp = torch.empty_like(p)
     rp[p] = torch.arange(len(p))                                      # interleavers.py:29-33
+    p, rp = p.to(received.device), rp.to(received.device)
     B, L, _ = received.shape
     r_sys = received[:, :, 0].view(B, L, 1)
     r_sys_int = interleave(r_sys, p)
     r_par1 = received[:, :, 1].view(B, L, 1)
     r_par2 = received[:, :, 2].view(B, L, 1)
-    prior = torch.zeros(B, L, num_iter_ft)
+    prior = torch.zeros(B, L, num_iter_ft, device=received.device)
     x_plr = None
     for idx in range(num_iteration):
         last = idx == num_iteration - 1

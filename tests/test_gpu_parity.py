@@ -348,6 +348,46 @@ def test_ber_sweep_all_points_bf16():
               open(os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out", "ber_sweep_bf16.json"), "w"))
 
 
+# ------------------------------------------------------------------------------------------------- f3: channel + metrics
+@pytest.mark.parametrize("n,offset", [(1, 0), (7, 3), (4096, 0), (300007, 1 << 33)])
+def test_awgn_stream_vs_oracle(n, offset):
+    import turboae_b200 as T
+    codes = torch.linspace(-2, 2, n, device=DEV)
+    got = T.channel.awgn(codes, 0.75, seed=0x1234567890ABCDEF, offset=offset).cpu().numpy()
+    ref = O.awgn(codes.cpu().numpy(), 0.75, 0x1234567890ABCDEF, offset)
+    # integer stream bit-exact => any difference is libm rounding inside Box-Muller
+    np.testing.assert_allclose(got, ref, atol=2e-5, rtol=0)
+    z = (got - codes.cpu().numpy()) / 0.75
+    zr = O.awgn_noise(n, 0x1234567890ABCDEF, offset)
+    assert np.abs(z - zr).max() < 5e-5
+
+
+def test_error_counts_bit_exact_vs_oracle():
+    import turboae_b200 as T
+    rs = np.random.RandomState(11)
+    for B, L in ((1, 100), (500, 100), (33, 7), (50000, 100)):
+        u = rs.randint(0, 2, size=(B, L, 1)).astype(np.float32)
+        y = np.clip(u + 0.7 * rs.standard_normal(u.shape), 0, 1).astype(np.float32)
+        y[0, 0, 0] = 0.5                                                   # round-half-to-even corner
+        c = T.channel.error_counts(_t(u), _t(y)).tolist()
+        assert tuple(c) == O.error_counts(u, y), (B, L)
+
+
+def test_device_ber_sweep_statistics():
+    """On-device trainer.test loop: BER at 0 dB over 200 000 fresh blocks agrees with the reference's 10 000-block figure
+    within their joint sampling error (different noise realisations, so statistical only)."""
+    import turboae_b200 as T
+    m, w, p = build_codec("c1", batch_size=50000)
+    m.enc.precision = "bf16"
+    ref = json.load(open(os.path.join(GOLDEN, "ber_c1.json")))
+    bers, blers, raw = T.channel.ber_sweep(m.enc, m.dec, [0.0, 2.0], num_block=200000, batch_size=50000, seed=99)
+    ref_ber0 = ref["bit_errors"][3] / (ref["blocks"] * 100.0)
+    assert abs(bers[0] - ref_ber0) < 4e-4, (bers, ref_ber0)               # ~3 sigma of the reference's own estimate
+    assert bers[1] < 2e-4 and blers[0] > blers[1]
+    json.dump({"snrs": [0.0, 2.0], "ber": bers, "bler": blers, "counts": raw, "blocks": 200000},
+              open(os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out", "device_ber_sweep.json"), "w"))
+
+
 # ------------------------------------------------------------------------------------------------- full size
 def test_full_size_batch_properties():
     """BASELINE config 2 size (B = 50 000): size-independent properties -- finite posteriors in (0,1), agreement

@@ -340,4 +340,18 @@ int tae_power_norm_f32(const float* x, float* codes, size_t n, const double* sta
   return launch_power_norm_f32(x, codes, n, stats, mean_std, (cudaStream_t)stream);
 }
 
+int tae_awgn_f32(const float* codes, float* received, size_t n, float sigma, uint64_t seed, uint64_t offset, void* stream) {
+  if (n == 0) return TAE_OK;
+  TAE_REQUIRE(codes && received, "tae_awgn_f32: NULL pointer");
+  TAE_REQUIRE(sigma >= 0.f, "tae_awgn_f32: negative sigma");
+  return launch_awgn(codes, received, n, sigma, seed, offset, (cudaStream_t)stream);
+}
+
+int tae_error_count_f32(const float* y_true, const float* y_pred, int32_t B, int32_t L, unsigned long long* counts, void* stream) {
+  TAE_REQUIRE(B >= 0 && L >= 1, "tae_error_count_f32: bad shape B=%d L=%d", B, L);
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(y_true && y_pred && counts, "tae_error_count_f32: NULL pointer");
+  return launch_error_count(y_true, y_pred, B, L, counts, (cudaStream_t)stream);
+}
+
 }  // extern "C"

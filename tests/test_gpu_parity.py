@@ -158,25 +158,6 @@ def test_kat_appendix_c_fp32():
 
 
 # ------------------------------------------------------------------------------------------------- tensor-core plumbing
-@pytest.mark.parametrize("K,N,shift", [(16, 16, 0), (112, 112, 0), (112, 112, 1), (112, 112, 4), (16, 112, 3), (112, 16, 2)])
-def test_umma_descriptor_probe(K, N, shift):
-    """tcgen05.mma with the decoder's operand scheme (no-swizzle K-major, tap shift = descriptor start address)."""
-    from turboae_b200 import _lib
-    lib = _lib.load()
-    R = 136
-    rs = np.random.RandomState(K * 1000 + N + shift)
-    A = torch.from_numpy(rs.standard_normal((R, K)).astype(np.float32)).to(DEV).to(torch.bfloat16)
-    Bm = torch.from_numpy(rs.standard_normal((N, K)).astype(np.float32)).to(DEV).to(torch.bfloat16)
-    D = torch.zeros(128, N, device=DEV)
-    err = torch.zeros(4, dtype=torch.int32, device=DEV)
-    _lib.check(lib.tae_debug_umma_probe(_lib.ptr(A), _lib.ptr(Bm), _lib.ptr(D), R, K, N, shift, 0, _lib.ptr(err),
-                                        _lib.stream_ptr()))
-    torch.cuda.synchronize()
-    ref = A[shift:shift + 128].float() @ Bm.float().t()
-    assert int(err[0]) == 0
-    np.testing.assert_allclose(D.cpu().numpy(), ref.cpu().numpy(), atol=1e-3, rtol=1e-3)
-
-
 @pytest.mark.parametrize("N,shift,lbo_rows", [(112, 0, 1), (112, 3, 1), (112, 0, 2), (16, 4, 2), (112, 2, 7)])
 def test_umma_probe_two_taps_in_one_kstep(N, shift, lbo_rows):
     """K chunk 1 of the A operand = the same 8-channel chunk `lbo_rows` rows further down (LBO = 16*lbo_rows bytes):

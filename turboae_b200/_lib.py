@@ -8,7 +8,7 @@ import threading
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libturboae_b200.so")
+LIB_PATH = os.environ.get("TURBOAE_B200_LIB") or os.path.join(_PKG, "lib", "libturboae_b200.so")   # env: A/B builds
 
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
@@ -55,8 +55,6 @@ _SIGNATURES = {
     "tae_awgn_f32": (C.c_int, [_P, _P, C.c_size_t, C.c_float, C.c_uint64, C.c_uint64, _P]),
     "tae_error_count_f32": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     # debug / self-test entry points
-    "tae_debug_set_dump": (None, [_P]),
-    "tae_debug_umma_probe": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, _P, _P]),
     "tae_debug_set_timeline": (None, [_P]),
     "tae_debug_probe_rate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int32, _P]),
     "tae_debug_probe_lbo": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),

@@ -10,8 +10,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
-LIB = os.path.join(LIBDIR, "libturboae_b200.so")
-SOURCES = ["tae_api.cu", "tae_f32.cu", "tae_dec_bf16.cu", "tae_dec_pair.cu", "tae_channel.cu"]
+LIB = os.environ.get("TURBOAE_B200_LIB") or os.path.join(LIBDIR, "libturboae_b200.so")
+SOURCES = ["tae_api.cu", "tae_f32.cu", "tae_dec_pair.cu", "tae_channel.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -33,18 +33,7 @@ int after_launch(const char* kernel_name) {
   return TAE_OK;
 }
 
-bool use_dec_v1() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TURBOAE_B200_DEC_IMPL");
-    v = (e && !strcmp(e, "v1")) ? 1 : 0;
-  }
-  return v == 1;
-}
-
-static bool bf16_supported(const TaeDecConfig& c, const char** why) {
-  return use_dec_v1() ? dec_bf16_supported(c, why) : dec_pair_supported(c, why);
-}
+static bool bf16_supported(const TaeDecConfig& c, const char** why) { return dec_pair_supported(c, why); }
 
 int check_dec_config(const TaeDecConfig* c) {
   if (!c) { set_error("TaeDecConfig is NULL"); return TAE_EINVAL; }
@@ -144,7 +133,7 @@ size_t tae_dec_packed_bytes(const TaeDecConfig* cfg) {
   if (check_dec_config(cfg)) return 0;
   const char* why = nullptr;
   if (!bf16_supported(*cfg, &why)) { set_error("bf16 path: %s", why); return 0; }
-  return use_dec_v1() ? dec_packed_bytes_bf16(*cfg) : dec_pair_packed_bytes(*cfg);
+  return dec_pair_packed_bytes(*cfg);
 }
 
 int tae_dec_pack_bf16(const TaeDecConfig* cfg, const float* params, void* packed, void* stream) {
@@ -153,8 +142,7 @@ int tae_dec_pack_bf16(const TaeDecConfig* cfg, const float* params, void* packed
   const char* why = nullptr;
   if (!bf16_supported(*cfg, &why)) { set_error("bf16 path: %s", why); return TAE_EUNSUPPORTED; }
   TAE_REQUIRE(params && packed, "tae_dec_pack_bf16: NULL pointer");
-  return use_dec_v1() ? dec_pack_bf16(*cfg, params, packed, (cudaStream_t)stream)
-                      : dec_pair_pack(*cfg, params, packed, (cudaStream_t)stream);
+  return dec_pair_pack(*cfg, params, packed, (cudaStream_t)stream);
 }
 
 size_t tae_dec_workspace_bytes(const TaeDecConfig* cfg, int32_t B, int32_t precision) {
@@ -163,7 +151,7 @@ size_t tae_dec_workspace_bytes(const TaeDecConfig* cfg, int32_t B, int32_t preci
   if (precision == TAE_PRECISION_BF16) {
     const char* why = nullptr;
     if (!bf16_supported(*cfg, &why)) { set_error("bf16 path: %s", why); return 0; }
-    return dec_workspace_bytes_bf16(*cfg, B);
+    return 256;
   }
   set_error("unknown precision %d", precision);
   return 0;
@@ -184,11 +172,8 @@ int tae_dec_forward(const TaeDecConfig* cfg, const float* params, const void* pa
     const char* why = nullptr;
     if (!bf16_supported(*cfg, &why)) { set_error("bf16 path: %s", why); return TAE_EUNSUPPORTED; }
     TAE_REQUIRE(packed, "tae_dec_forward(bf16): packed weight image is NULL (call tae_dec_pack_bf16)");
-    if (!use_dec_v1())
-      return dec_forward_pair(*cfg, packed, received, perm, inv_perm, out, trace, B, workspace, workspace_bytes,
-                              (cudaStream_t)stream);
-    return dec_forward_bf16(*cfg, params, packed, received, perm, inv_perm, out, trace, B, workspace,
-                            workspace_bytes, (cudaStream_t)stream);
+    return dec_forward_pair(*cfg, packed, received, perm, inv_perm, out, trace, B, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
   }
   set_error("tae_dec_forward: unknown precision %d", precision);
   return TAE_EINVAL;

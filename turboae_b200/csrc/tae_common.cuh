@@ -96,16 +96,7 @@ int enc_forward_f32(const TaeEncConfig& c, const float* params, const float* u, 
 int launch_power_norm_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std,
                           cudaStream_t s);
 
-// ---- bf16 tcgen05 path (tae_dec_bf16.cu) --------------------------------------------------
-bool dec_bf16_supported(const TaeDecConfig& c, const char** why);
-size_t dec_packed_bytes_bf16(const TaeDecConfig& c);
-int dec_pack_bf16(const TaeDecConfig& c, const float* params, void* packed, cudaStream_t s);
-size_t dec_workspace_bytes_bf16(const TaeDecConfig& c, int B);
-int dec_forward_bf16(const TaeDecConfig& c, const float* params, const void* packed, const float* received,
-                     const int32_t* perm, const int32_t* inv_perm, float* out, float* trace, int B, void* ws,
-                     size_t ws_bytes, cudaStream_t s);
-
-// ---- bf16 tcgen05 path, CTA-pair version (tae_dec_pair.cu): the default --------------------
+// ---- bf16 tcgen05 path: fused CTA-pair kernel (tae_dec_pair.cu) -----------------------------
 bool dec_pair_supported(const TaeDecConfig& c, const char** why);
 size_t dec_pair_packed_bytes(const TaeDecConfig& c);
 int dec_pair_pack(const TaeDecConfig& c, const float* params, void* packed, cudaStream_t s);
@@ -121,7 +112,5 @@ int launch_add_count(double* stats, double n, cudaStream_t s);
 // ---- channel + metrics (tae_channel.cu) ------------------------------------------------------
 int launch_awgn(const float* codes, float* received, size_t n, float sigma, uint64_t seed, uint64_t offset, cudaStream_t s);
 int launch_error_count(const float* y_true, const float* y_pred, int B, int L, unsigned long long* counts, cudaStream_t s);
-// TURBOAE_B200_DEC_IMPL=v1 selects the older single-CTA kernel (development A/B only)
-bool use_dec_v1();
 
 }  // namespace tae

@@ -65,13 +65,19 @@ constexpr uint32_t SLOT_B = KS_PER_SLOT * 2 * WCHUNK_B;         // 7168
 constexpr uint32_t L0_B = KS_L0 * 2 * WCHUNK_B;                 // 5376
 constexpr uint32_t LIN_WCHUNK_B = LIN_NHALF * ROW_B;            // 128
 constexpr uint32_t LIN_B = KS_LIN * 2 * LIN_WCHUNK_B;           // 1792
-constexpr int NS = 10;                                          // weight ring slots (a layer uses 8; 2 are prefetch headroom)
-constexpr int N_EPI_WARPS = 8;
+constexpr int NS = 12;                                          // weight ring slots (a layer uses 8; 4 are prefetch headroom)
+#ifndef TAE_EPI_WARPS
+#define TAE_EPI_WARPS 16
+#endif
+constexpr int N_EPI_WARPS = TAE_EPI_WARPS;                      // 4 lane quadrants x PARTS column parts (8 or 16)
+constexpr int PARTS = N_EPI_WARPS / 4;                          // column parts per lane quadrant
+constexpr int CPP = N_REG_CHUNKS / PARTS;                       // regular 8-channel chunks per part
+constexpr int NDQ = CPP * 4 + 2;                                // registers holding one deferred row of a part
 constexpr int N_EPI_THREADS = N_EPI_WARPS * 32;
 constexpr int WARP_PRODUCER = 0;
 constexpr int WARP_MMA = 1;                                     // warps 1..4 of the leader: one MMA issuer per tile
 constexpr int EPI_WARP0 = 1 + N_TILES;
-constexpr int N_THREADS = 32 * (1 + N_TILES + N_EPI_WARPS);      // 416
+constexpr int N_THREADS = 32 * (1 + N_TILES + N_EPI_WARPS);      // 672
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TMEM_LIN_COL = N_TILES * NPAD;               // 448
 
@@ -81,7 +87,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
 }
 
 struct Smem {
-  uint32_t act, comb, xin[2], ones, pri[2], wslot, perm, inv_perm, bars, tmem_ptr, total;
+  uint32_t act, comb, xin[2], ones, wslot, perm, inv_perm, bars, tmem_ptr, total;
 };
 // barrier slots (8 bytes each)
 // B_WFULL[p]: ring slot p resident in BOTH CTAs (leader: own bulk copy + one arrival forwarded by the peer's relay, so an
@@ -99,9 +105,7 @@ __host__ __device__ inline Smem make_smem(int F) {
   s.xin[0] = o; o += CHUNK_B;
   s.xin[1] = o; o += CHUNK_B;
   s.ones = o; o += CHUNK_B;                        // after comb and xin: positive LBO towards it
-  s.pri[0] = o; o += (uint32_t)F * BUF_ROWS * 4;
-  s.pri[1] = o; o += (uint32_t)F * BUF_ROWS * 4;
-  o = (o + 15) / 16 * 16;
+  (void)F;
   s.wslot = o; o += NS * SLOT_B;
   s.perm = o; o += 1024;
   s.inv_perm = o; o += 1024;
@@ -334,6 +338,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr)
                : "memory");
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -640,10 +649,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
       }
     }
   } else {
-    // ================= epilogue warps (8): TMEM -> ELU -> bf16 -> shared memory =================
-    const int ew = warp - EPI_WARP0;           // 0..7
+    // ================= epilogue warps: TMEM -> ELU -> bf16 -> shared memory ======================
+    const int ew = warp - EPI_WARP0;
     const int q = warp & 3;                    // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;                  // column half: 0 -> channels 0..47, 1 -> channels 48..99
+    const int part = ew >> 2;                  // column part: channels [8*CPP*part, 8*CPP*(part+1)); the last part adds 96..99
     const int tid = threadIdx.x - EPI_WARP0 * 32;
     uint32_t step = 0;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
@@ -659,10 +668,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
       }
 
       if (TAE_TIMELINE && a.tl && pair0 == 0 && rank == 0 && tid == 0) a.tl[72 * 4 * 8 + 148 * 4 + (pr / pair_stride)] = clock64();
-      // ---- group start: stack inputs, zero prior, ones chunk ----------------------------------------
+      // ---- group start: stack inputs (prior channels = 0, decoders.py:227), ones chunk ----------------------------------------
       for (uint32_t i = tid * 16; i < 3 * CHUNK_B; i += N_EPI_THREADS * 16) st_shared_v4(sbase + S.xin[0] + i, 0u, 0u, 0u, 0u);
-      for (uint32_t i = tid * 16; i < (uint32_t)F * BUF_ROWS * 4; i += N_EPI_THREADS * 16)
-        st_shared_v4(sbase + S.pri[0] + i, 0u, 0u, 0u, 0u);
       epi_bar_sync();
       if (a.enc) {
         for (int i = tid; i < n_cw * L; i += N_EPI_THREADS) {
@@ -694,9 +701,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
 
       // Deferred rows: the last two rows of tile m are still read by the MMAs of tile m+1 (taps 0, 1), so the two
       // lanes that own them keep their packed outputs in registers and store them at the start of the next tile.
-      uint32_t dq[26];
+      uint32_t dq[NDQ];
 #pragma unroll
-      for (int i = 0; i < 26; ++i) dq[i] = 0u;
+      for (int i = 0; i < NDQ; ++i) dq[i] = 0u;
 
       for (int st = 0; st < n_stacks; ++st) {
         for (int layer = 0; layer <= a.n_layer; ++layer, ++step) {
@@ -708,16 +715,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
             for (int m = 0; m < N_TILES; ++m) mbar_wait(bar(B_ACC + m), par, a.err, 6);
             tc_fence_after();
             double s1 = 0.0, s2 = 0.0;
-            if (half == 0) {
+            if (part == 0) {
 #pragma unroll 1
               for (int m = 0; m < N_TILES; ++m) {
-                uint32_t r[8];
-                tmem_ld8(lane_addr + TMEM_LIN_COL + (uint32_t)(m * LIN_N), r);
+                const uint32_t r0 = tmem_ld1(lane_addr + TMEM_LIN_COL + (uint32_t)(m * LIN_N));
                 tmem_ld_wait();
                 if (!((vmask >> m) & 1u)) continue;
                 const int g_row = 128 * m + 32 * q + lane;
                 const int g_cw = g_row / CW_ROWS, g_l = g_row - g_cw * CW_ROWS;
-                const float z = __uint_as_float(r[0]);
+                const float z = __uint_as_float(r0);
                 const float v = z > 0.f ? z : expm1f(z);
                 a.x_tx[((size_t)(cw0 + g_cw) * L + g_l) * 3 + st] = v;
                 s1 += (double)v;
@@ -740,60 +746,66 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
           }
           if (layer == a.n_layer) {
             // -- Linear epilogue, all four tiles in one pass (their MMAs are tiny and complete together): extrinsic
-            //    subtraction + (de)interleave into the next stack's input.  The two warps of a quadrant split the
-            //    features (half 0: f = 0..2, half 1: f = 3..4); all loads are issued before the first store. ----------
+            //    subtraction + (de)interleave into the next stack's input.  The PARTS warps of a quadrant split the
+            //    features; all loads of a tile are issued before its first store. ------------------------------------
             const bool last = (st == n_stacks - 1);
-            const uint32_t pri_cur = sbase + S.pri[st & 1], pri_nxt = sbase + S.pri[(st & 1) ^ 1];
-            const uint32_t xin_nxt = sbase + S.xin[(st & 1) ^ 1];
+            const uint32_t xin_cur = sbase + S.xin[st & 1], xin_nxt = sbase + S.xin[(st & 1) ^ 1];
             const uint32_t map = sbase + (last ? S.perm : ((st & 1) ? S.perm : S.inv_perm));   // where position l lands
-            const int f0 = half ? 3 : 0, f1 = half ? F : min(F, 3);
-            const bool stamp = TAE_TIMELINE && a.tl && pr == 0 && rank == 0 && lane == 0 && (ew == 0 || ew == 7);
-            if (stamp && ew == 0) a.tl[(step * 4 + 0) * 8 + 3] = clock64();
+            const bool stamp = TAE_TIMELINE && a.tl && pr == 0 && rank == 0 && lane == 0 && ew == 0;
+            if (stamp) a.tl[(step * 4 + 0) * 8 + 3] = clock64();
 #pragma unroll
             for (int m = 0; m < N_TILES; ++m) mbar_wait(bar(B_ACC + m), par, a.err, 6);
             tc_fence_after();
-            if (stamp) a.tl[(step * 4 + 0) * 8 + (ew == 0 ? 4 : 6)] = clock64();
-            // rolled on purpose (cold code, executed once per stack: instruction fetch dominates its cost)
+            if (stamp) a.tl[(step * 4 + 0) * 8 + 4] = clock64();
+            // One warp per lane quadrant (part 0) does the whole row: the prior that is subtracted is the bf16 value the
+            // stack actually saw (channels 2.. of its own input row), so no separate fp32 prior buffer exists, and the
+            // extrinsic values of a row go out as one 4-byte and one 8-byte store (scattered rows => bank conflicts,
+            // which is why as few store instructions as possible are issued).
+            if (part == 0) {
 #pragma unroll 1
-            for (int m = 0; m < N_TILES; ++m) {
-              uint32_t r[8];
-              tmem_ld8(lane_addr + TMEM_LIN_COL + (uint32_t)(m * LIN_N), r);
-              const int g_row = 128 * m + 32 * q + lane;
-              const int g_cw = g_row / CW_ROWS, g_l = g_row - g_cw * CW_ROWS;
-              const bool valid = (vmask >> m) & 1u;
-              uint32_t dl = 0;
-              float prior[3] = {0.f, 0.f, 0.f};
-              if (valid) {
-                dl = ld_shared_u16(map + 2 * g_l);
-                if (a.extrinsic && !last)
-#pragma unroll
-                  for (int i = 0; i < 3; ++i)
-                    if (f0 + i < f1) prior[i] = ld_shared_f32(pri_cur + ((uint32_t)(f0 + i) * BUF_ROWS + g_row + 2) * 4);
-              }
-              tmem_ld_wait();
-              if (!valid) continue;
-              const int cw = cw0 + g_cw, l = g_l;
-              if (a.trace) {
-                float* tr = a.trace + (((size_t)st * a.B + cw) * L + l) * F;
-                if (last) { if (half == 0) tr[0] = __uint_as_float(r[0]); }
-                else {
-#pragma unroll
-                  for (int i = 0; i < 3; ++i)
-                    if (f0 + i < f1) tr[f0 + i] = __uint_as_float(half ? r[(3 + i) & 7] : r[i]);
+              for (int m = 0; m < N_TILES; ++m) {
+                const int g_row = 128 * m + 32 * q + lane;
+                const int g_cw = g_row / CW_ROWS, g_l = g_row - g_cw * CW_ROWS;
+                const bool valid = (vmask >> m) & 1u;
+                uint32_t r[8];
+                tmem_ld8(lane_addr + TMEM_LIN_COL + (uint32_t)(m * LIN_N), r);
+                uint32_t x0 = 0, x1 = 0, x2 = 0, x3 = 0, dl = 0;
+                if (valid) {
+                  dl = ld_shared_u16(map + 2 * g_l);
+                  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                               : "r"(xin_cur + (uint32_t)(g_row + 2) * ROW_B) : "memory");
                 }
-              }
-              if (last) {
-                // deinterleave: out[p[l]] = sigmoid(x[l])                                         (decoders.py:267)
-                if (half == 0) a.out[(size_t)cw * L + dl] = 1.f / (1.f + __expf(-__uint_as_float(r[0])));
-              } else {
-                const uint32_t drow = (uint32_t)(g_cw * CW_ROWS) + dl + 2;
+                tmem_ld_wait();
+                if (!valid) continue;
+                const int cw = cw0 + g_cw, l = g_l;
+                if (a.trace) {
+                  float* tr = a.trace + (((size_t)st * a.B + cw) * L + l) * F;
+                  const int nf = last ? 1 : F;
 #pragma unroll
-                for (int i = 0; i < 3; ++i)
-                  if (f0 + i < f1) {
-                    const float ext = __uint_as_float(half ? r[(3 + i) & 7] : r[i]) - prior[i];   // decoders.py:235-236, 246-247
-                    st_shared_f32(pri_nxt + ((uint32_t)(f0 + i) * BUF_ROWS + drow) * 4, ext);
-                    st_shared_u16(xin_nxt + drow * ROW_B + 2 * (2 + f0 + i), bf16_bits(ext));
-                  }
+                  for (int f = 0; f < 5; ++f)
+                    if (f < nf) tr[f] = __uint_as_float(r[f]);
+                }
+                if (last) {
+                  // deinterleave: out[p[l]] = sigmoid(x[l])                                       (decoders.py:267)
+                  a.out[(size_t)cw * L + dl] = 1.f / (1.f + __expf(-__uint_as_float(r[0])));
+                } else {
+                  // input channels of this row: [sys, par, prior_0..4, 0] as bf16 pairs (x0 = ch0,1  x1 = ch2,3 ...)
+                  const bool ex = a.extrinsic != 0;
+                  float e[6];
+                  e[0] = __uint_as_float(r[0]) - (ex ? __uint_as_float(x1 << 16) : 0.f);            // decoders.py:235-236, 246-247
+                  e[1] = __uint_as_float(r[1]) - (ex ? __uint_as_float(x1 & 0xFFFF0000u) : 0.f);
+                  e[2] = __uint_as_float(r[2]) - (ex ? __uint_as_float(x2 << 16) : 0.f);
+                  e[3] = __uint_as_float(r[3]) - (ex ? __uint_as_float(x2 & 0xFFFF0000u) : 0.f);
+                  e[4] = __uint_as_float(r[4]) - (ex ? __uint_as_float(x3 << 16) : 0.f);
+                  e[5] = 0.f;
+#pragma unroll
+                  for (int f = 0; f < 5; ++f)
+                    if (f >= F) e[f] = 0.f;
+                  const uint32_t drow = (uint32_t)(g_cw * CW_ROWS) + dl + 2;
+                  const uint32_t dst = xin_nxt + drow * ROW_B;
+                  asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + 4), "r"(pack_bf16x2(e[0], e[1])) : "memory");
+                  st_shared_v2(dst + 8, pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]));
+                }
               }
             }
             if (!last_step) {
@@ -803,12 +815,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
               if (lane == 0)
                 for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_ACT + m), rank);
             }
-            if (stamp) a.tl[(step * 4 + 0) * 8 + (ew == 0 ? 5 : 7)] = clock64();
+            if (stamp) a.tl[(step * 4 + 0) * 8 + 5] = clock64();
             continue;
           }
 #pragma unroll 1
           for (int m = 0; m < N_TILES; ++m) {
-            const bool stamp = TAE_TIMELINE && a.tl && pr == 0 && rank == 0 && lane == 0 && (ew == 0 || ew == 7);
+            const bool stamp = TAE_TIMELINE && a.tl && pr == 0 && rank == 0 && lane == 0 && ew == 0;
             if (stamp && ew == 0) a.tl[(step * 4 + m) * 8 + 3] = clock64();
             mbar_wait(bar(B_ACC + m), par, a.err, 6);
             tc_fence_after();
@@ -818,30 +830,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
             {
               const bool owns_tail = (q == 3) && (lane >= 30);
               const bool defer = owns_tail && (m < N_TILES - 1);
+              const bool has_comb = (part == PARTS - 1);               // this part also owns channels 96..99
               const uint32_t brow = (uint32_t)(g_row + 2);
-              const uint32_t col0 = (uint32_t)(m * NPAD + half * 48);
-              uint32_t r[56];
-              tmem_ld16(lane_addr + col0, r);
-              tmem_ld16(lane_addr + col0 + 16, r + 16);
+              const uint32_t col0 = (uint32_t)(m * NPAD + part * CPP * 8);
+              const uint32_t act_part = sbase + S.act + (uint32_t)(part * CPP) * CHUNK_B;
+              uint32_t r[CPP * 8 + 8];
+#pragma unroll
+              for (int c = 0; c + 1 < CPP; c += 2) tmem_ld16(lane_addr + col0 + 8 * c, r + 8 * c);
+              if (CPP & 1) tmem_ld8(lane_addr + col0 + 8 * (CPP - 1), r + 8 * (CPP - 1));
+              if (has_comb) tmem_ld8(lane_addr + (uint32_t)(m * NPAD + N_REG_CH), r + 8 * CPP);
               // -- store the rows deferred from tile m-1 (their readers, the MMAs of tile m, have completed) -----
               if (owns_tail && m > 0) {
                 const uint32_t prow = brow - 128;
 #pragma unroll
-                for (int c = 0; c < 6; ++c)
-                  st_shared_v4(sbase + S.act + (uint32_t)(half * 6 + c) * CHUNK_B + prow * ROW_B, dq[4 * c], dq[4 * c + 1],
-                               dq[4 * c + 2], dq[4 * c + 3]);
-                if (half == 1) {
-                  st_shared_v2(sbase + S.comb + prow * ROW_B, dq[24], dq[25]);
-                  st_shared_v2(sbase + S.comb + (prow - 1) * ROW_B + 8, dq[24], dq[25]);
+                for (int c = 0; c < CPP; ++c)
+                  st_shared_v4(act_part + (uint32_t)c * CHUNK_B + prow * ROW_B, dq[4 * c], dq[4 * c + 1], dq[4 * c + 2], dq[4 * c + 3]);
+                if (has_comb) {
+                  st_shared_v2(sbase + S.comb + prow * ROW_B, dq[4 * CPP], dq[4 * CPP + 1]);
+                  st_shared_v2(sbase + S.comb + (prow - 1) * ROW_B + 8, dq[4 * CPP], dq[4 * CPP + 1]);
                 }
               }
               tmem_ld_wait();
-              tmem_ld16(lane_addr + col0 + 32, r + 32);
-              if (half == 1) tmem_ld8(lane_addr + col0 + 48, r + 48);
+              if (stamp && ew == 0) a.tl[(step * 4 + m) * 8 + 6] = clock64();
               const uint32_t keep = valid ? 0xFFFFFFFFu : 0u;
 #pragma unroll
-              for (int c = 0; c < 6; ++c) {
-                if (c == 4) tmem_ld_wait();
+              for (int c = 0; c < CPP; ++c) {
                 uint32_t p[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -849,14 +862,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
                 if (defer) {
                   dq[4 * c] = p[0]; dq[4 * c + 1] = p[1]; dq[4 * c + 2] = p[2]; dq[4 * c + 3] = p[3];
                 } else {
-                  st_shared_v4(sbase + S.act + (uint32_t)(half * 6 + c) * CHUNK_B + brow * ROW_B, p[0], p[1], p[2], p[3]);
+                  st_shared_v4(act_part + (uint32_t)c * CHUNK_B + brow * ROW_B, p[0], p[1], p[2], p[3]);
                 }
               }
-              if (half == 1) {
-                const uint32_t p0 = pack_bf16x2(elu_fast(__uint_as_float(r[48])), elu_fast(__uint_as_float(r[49]))) & keep;
-                const uint32_t p1 = pack_bf16x2(elu_fast(__uint_as_float(r[50])), elu_fast(__uint_as_float(r[51]))) & keep;
+              if (has_comb) {
+                const uint32_t p0 = pack_bf16x2(elu_fast(__uint_as_float(r[8 * CPP])), elu_fast(__uint_as_float(r[8 * CPP + 1]))) & keep;
+                const uint32_t p1 = pack_bf16x2(elu_fast(__uint_as_float(r[8 * CPP + 2])), elu_fast(__uint_as_float(r[8 * CPP + 3]))) & keep;
                 if (defer) {
-                  dq[24] = p0; dq[25] = p1;
+                  dq[4 * CPP] = p0; dq[4 * CPP + 1] = p1;
                 } else {
                   st_shared_v2(sbase + S.comb + brow * ROW_B, p0, p1);              // x[r][96..99]  -> comb[r][0:4]
                   st_shared_v2(sbase + S.comb + (brow - 1) * ROW_B + 8, p0, p1);    //               -> comb[r-1][4:8]
@@ -865,6 +878,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
             }
             {
               // every warp reports on its own: no CTA-wide barrier on the tile-to-tile critical path
+              if (stamp && ew == 0) a.tl[(step * 4 + m) * 8 + 7] = clock64();
               fence_proxy_async();
               tc_fence_before();
               __syncwarp();

@@ -233,6 +233,32 @@ def test_decoder_bf16_matches_fp32_path_ragged_batches():
             assert float((y32 - y16).abs().mean()) < 5e-3
 
 
+@pytest.mark.parametrize("L,F,n_layer,n_iter,units,B", [(100, 5, 5, 6, 100, 23), (64, 3, 3, 2, 100, 41), (37, 5, 2, 3, 64, 9),
+                                                       (200, 4, 4, 1, 96, 7), (510, 5, 3, 2, 100, 3), (10, 1, 2, 2, 8, 101)])
+def test_fused_decoder_other_configurations_vs_fp32_path(L, F, n_layer, n_iter, units, B):
+    """The fused kernel is not specialised to the shipped checkpoint: block lengths 10..510 (1..46 codewords per 512-row
+    group), 1..5 prior features, 2..5 layers, 8..100 units, random weights -- against the fp32 CUDA-core path, which is
+    itself pinned to the oracle below."""
+    import turboae_b200 as T
+    torch.manual_seed(L * 7 + F)
+    args = make_args(block_len=L, num_iter_ft=F, dec_num_layer=n_layer, num_iteration=n_iter, dec_num_unit=units, batch_size=B)
+    p = O.make_perm(L, 1)
+    dec = T.DEC_LargeCNN(args, p).to(DEV).eval()
+    rec = torch.randn(B, L, 3, device=DEV)
+    tr16 = torch.zeros(2 * n_iter, B, L, F, device=DEV)
+    tr32 = torch.zeros(2 * n_iter, B, L, F, device=DEV)
+    with torch.no_grad():
+        y32 = dec.decode(rec, precision="fp32", trace=tr32)
+        y16 = dec.decode(rec, precision="bf16", trace=tr16)
+    # oracle check of the fp32 path for this configuration (state_dict keys without the '.module.' level)
+    w = {"dec." + k: v.detach().cpu().numpy() for k, v in dec.state_dict().items()}
+    ref = O.dec_forward(rec.cpu().numpy(), w, p, num_iteration=n_iter, num_iter_ft=F)
+    np.testing.assert_allclose(y32.cpu().numpy(), ref, atol=5e-5, rtol=0)
+    scale = float(tr32.abs().max())
+    assert float((tr16 - tr32).abs().max()) < 0.05 * max(scale, 1.0), (float((tr16 - tr32).abs().max()), scale)
+    assert float((y16 - y32).abs().max()) < 0.05 and torch.isfinite(y16).all()
+
+
 def test_decoder_batch_independence_and_order():
     """Codewords are independent units: decoding a batch == decoding its pieces, in any order."""
     m, w, p = build_codec("c1")

@@ -78,6 +78,16 @@ int tae_conv1d_elu_f32(const float* in, float* out, const float* weight, const f
                        int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t K,
                        int32_t apply_elu, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Backward of that layer (training, reference trainer.py:74 `loss.backward()` through cnn_utils.py:36-46):
+ *   x (B,L,Cin) = the layer's input, y (B,L,Cout) = its forward output, dy = gradient w.r.t. y.
+ *   dx (B,L,Cin) or NULL; dweight (Cout,Cin,K) and dbias (Cout) are ACCUMULATED into (caller zeroes), NULL to skip.
+ *   With apply_elu the ELU derivative is taken from y (ELU'(z) = y > 0 ? 1 : y + 1).                              */
+size_t tae_conv1d_bwd_workspace_bytes(int32_t Cin, int32_t Cout, int32_t K);
+int tae_conv1d_elu_bwd_f32(const float* x, const float* y, const float* dy, const float* weight,
+                           float* dx, float* dweight, float* dbias,
+                           int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t K, int32_t apply_elu,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a7/a8: DEC_LargeCNN -------------------------------------------------------------------
  * Parameters travel as ONE flat float32 buffer in canonical order:
  *   for idx in 0..I-1: for s in (dec1, dec2):

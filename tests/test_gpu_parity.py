@@ -286,8 +286,8 @@ def test_decoder_empty_batch_and_errors():
         with pytest.raises(_lib.TaeError):
             m.dec.decode(torch.zeros(2, 100, 3))         # decode() refuses host tensors (forward() moves them)
         assert m.dec(torch.zeros(2, 100, 3)).is_cuda     # reference decoders.py:219 semantics: moved to the device
-    with pytest.raises(NotImplementedError):
-        m.dec(torch.zeros(2, 100, 3, device=DEV))        # autograd path is not built yet: loud, not silent
+    y = m.dec(torch.zeros(2, 100, 3, device=DEV))        # grad mode: the autograd (training) path
+    assert y.requires_grad and y.shape == (2, 100, 1)
 
 
 def test_decode_host_matches_device_path():
@@ -393,6 +393,89 @@ def test_device_ber_sweep_statistics():
     assert bers[1] < 2e-4 and blers[0] > blers[1]
     json.dump({"snrs": [0.0, 2.0], "ber": bers, "bler": blers, "counts": raw, "blocks": 200000},
               open(os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out", "device_ber_sweep.json"), "w"))
+
+
+# ------------------------------------------------------------------------------------------------- f1: backward / training
+@pytest.mark.parametrize("B,L,cin,cout,k,n_layer", [(3, 100, 7, 100, 5, 5), (2, 33, 4, 20, 3, 2), (5, 100, 1, 100, 5, 2), (1, 9, 3, 130, 7, 1)])
+def test_conv_stack_backward_vs_torch_autograd(B, L, cin, cout, k, n_layer):
+    """tae_conv1d_elu_bwd_f32 (weight-gradient kernel + transposed conv on dy*ELU') against torch autograd of the same
+    stack on the CPU (the reference's own backward)."""
+    import torch.nn.functional as Fn
+    import turboae_b200 as T
+    torch.manual_seed(3)
+    m = T.SameShapeConv1d(n_layer, cin, cout, k).to(DEV)
+    x = torch.randn(B, L, cin)
+    gout = torch.randn(B, L, cout)
+    xd = x.to(DEV).requires_grad_(True)
+    y = m(xd)
+    y.backward(gout.to(DEV))
+    # reference: torch CPU autograd of cnn_utils.py:36-46
+    xr = x.clone().requires_grad_(True)
+    ws = [(c.weight.detach().cpu().clone().requires_grad_(True), c.bias.detach().cpu().clone().requires_grad_(True)) for c in m.cnns]
+    h = xr.transpose(1, 2)
+    for w, b in ws:
+        h = Fn.elu(Fn.conv1d(h, w, b, padding=k // 2))
+    yr = h.transpose(1, 2)
+    yr.backward(gout)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().numpy(), atol=2e-5, rtol=1e-5)
+    np.testing.assert_allclose(xd.grad.cpu().numpy(), xr.grad.numpy(), atol=5e-5, rtol=1e-4)
+    for c, (w, b) in zip(m.cnns, ws):
+        sc = max(1.0, float(w.grad.abs().max()))
+        np.testing.assert_allclose(c.weight.grad.cpu().numpy(), w.grad.numpy(), atol=1e-4 * sc, rtol=1e-4)
+        np.testing.assert_allclose(c.bias.grad.cpu().numpy(), b.grad.numpy(), atol=1e-4 * sc, rtol=1e-4)
+
+
+def test_training_step_gradients_vs_reference_autograd():
+    """One trainer.train step (reference trainer.py:53-74: forward through enc -> +noise -> dec, clamp, BCE, backward) with the
+    shipped checkpoint: every parameter gradient of the CUDA path against torch autograd of the CPU restatement."""
+    import torch.nn.functional as Fn
+    from oracle import turboae_torch as TT
+    B = 6
+    m, w, p = build_codec("c1", batch_size=B)
+    m.train()
+    u, noise = gen_inputs(2718, B, 100, 0.0)
+    ud, nd = _t(u), _t(noise)
+    codes = m.enc(ud)
+    out = m.dec(codes + nd)
+    loss = Fn.binary_cross_entropy(torch.clamp(out, 0.0, 1.0), ud)              # loss.py:32-35 ; trainer.py:65
+    loss.backward()
+    wt = {k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in w.items()}
+    codes_r = TT.enc_forward(torch.from_numpy(u), wt, p)
+    out_r = TT.dec_forward(codes_r + torch.from_numpy(noise), wt, p)
+    loss_r = Fn.binary_cross_entropy(torch.clamp(out_r, 0.0, 1.0), torch.from_numpy(u))
+    loss_r.backward()
+    assert abs(float(loss) - float(loss_r)) < 1e-5
+    sd = dict(m.named_parameters())
+    worst = 0.0
+    for k, ref in wt.items():
+        got = sd[k].grad
+        assert got is not None, k
+        scale = max(float(ref.grad.abs().max()), 1e-6)
+        err = float((got.cpu() - ref.grad).abs().max()) / scale
+        worst = max(worst, err)
+        assert err < 2e-3, (k, err, scale)
+    assert worst > 0.0
+
+
+def test_reference_training_loop_reduces_loss():
+    """A few decoder-mode Adam steps in the reference's training pattern (trainer.py:33-76) on a fresh model: loss falls."""
+    import torch.nn.functional as Fn
+    import turboae_b200 as T
+    torch.manual_seed(0)
+    args = make_args(batch_size=200)
+    p = O.make_perm(100, 0)
+    enc, dec = T.ENC_interCNN(args, p).to(DEV), T.DEC_LargeCNN(args, p).to(DEV)
+    opt = torch.optim.Adam(dec.parameters(), lr=1e-3)
+    losses = []
+    for it in range(12):
+        opt.zero_grad()
+        u = torch.randint(0, 2, (200, 100, 1), device=DEV).float()
+        out = dec(enc(u) + 0.7 * torch.randn(200, 100, 3, device=DEV))
+        loss = Fn.binary_cross_entropy(torch.clamp(out, 0.0, 1.0), u)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0] - 0.02, losses
 
 
 # ------------------------------------------------------------------------------------------------- full size

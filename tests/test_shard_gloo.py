@@ -80,6 +80,51 @@ def test_two_rank_power_normalisation_matches_unsharded_reference(tmp_path):
     assert np.abs(local - ref[:19]).max() > 1e-4
 
 
+def _grad_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from turboae_b200 import shard
+    torch.manual_seed(5)
+    full = torch.randn(8, 10, 3)
+    g_full = torch.randn(8, 10, 3)
+    lo, hi = shard.shard_range(8, rank, world)
+    x = full[lo:hi].clone().requires_grad_(True)
+    y = shard.PowerNorm.apply(x, None)                       # default group = WORLD
+    y.backward(g_full[lo:hi])
+    # data-parallel gradient averaging through the optimizer hook
+    lin = torch.nn.Linear(4, 2)
+    torch.manual_seed(100 + rank)
+    lin(torch.randn(3, 4)).sum().backward()
+    local = [p.grad.clone() for p in lin.parameters()]
+    handle = shard.install_optimizer_hook()
+    opt = torch.optim.SGD(lin.parameters(), lr=0.0)
+    opt.step()
+    handle.remove()
+    torch.save({"y": y.detach(), "dx": x.grad, "lo": lo, "hi": hi, "local": local, "avg": [p.grad.clone() for p in lin.parameters()]},
+               os.path.join(out_dir, "g%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_power_norm_backward_and_gradient_all_reduce(tmp_path):
+    world = 2
+    mp.spawn(_grad_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    torch.manual_seed(5)
+    full = torch.randn(8, 10, 3, requires_grad=True)
+    g_full = torch.randn(8, 10, 3)
+    y = (full - torch.mean(full)) / torch.std(full)          # reference encoders.py:107-116 on the unsharded batch
+    y.backward(g_full)
+    parts = [torch.load(os.path.join(str(tmp_path), "g%d.pt" % r)) for r in range(world)]
+    for z in parts:
+        np.testing.assert_allclose(z["y"].numpy(), y.detach()[z["lo"]:z["hi"]].numpy(), atol=1e-6)
+        np.testing.assert_allclose(z["dx"].numpy(), full.grad[z["lo"]:z["hi"]].numpy(), atol=1e-6)
+    for i in range(2):
+        mean = (parts[0]["local"][i] + parts[1]["local"][i]) / 2
+        for z in parts:
+            np.testing.assert_allclose(z["avg"][i].numpy(), mean.numpy(), atol=1e-7)
+
+
 def test_single_process_is_a_no_op():
     from turboae_b200 import shard
     s = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64)

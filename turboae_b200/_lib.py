@@ -37,6 +37,9 @@ _SIGNATURES = {
     "tae_conv1d_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "tae_conv1d_elu_f32": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                      C.c_int32, _P, C.c_size_t, _P]),
+    "tae_conv1d_bwd_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "tae_conv1d_elu_bwd_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         _P, C.c_size_t, _P]),
     "tae_dec_param_count": (C.c_size_t, [C.POINTER(TaeDecConfig)]),
     "tae_dec_packed_bytes": (C.c_size_t, [C.POINTER(TaeDecConfig)]),
     "tae_dec_pack_bf16": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P]),

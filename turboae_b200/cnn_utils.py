@@ -27,21 +27,81 @@ class SameShapeConv1d(torch.nn.Module):
 
     def forward(self, inputs):
         _lib.require_cuda(inputs, "SameShapeConv1d input")
-        if torch.is_grad_enabled() and (inputs.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("turboae_b200: backward of the conv stack is not built yet "
-                                      "(SURVEY.md section 8(f) row 1); wrap inference in torch.no_grad()")
-        lib = _lib.load()
         x = inputs.to(torch.float32).contiguous()
-        B, L, _ = x.shape
-        with torch.cuda.device(x.device):
-            for conv in self.cnns:
-                cout, cin, k = conv.weight.shape
-                ws_bytes = lib.tae_conv1d_workspace_bytes(cin, cout, k)
-                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-                out = torch.empty((B, L, cout), dtype=torch.float32, device=x.device)
-                _lib.check(lib.tae_conv1d_elu_f32(_lib.ptr(x), _lib.ptr(out), _lib.ptr(conv.weight.detach().contiguous()),
-                                                  _lib.ptr(conv.bias.detach().contiguous()), B, L, cin, cout, k,
-                                                  0 if self.no_act else 1, _lib.ptr(ws), ws_bytes,
-                                                  _lib.stream_ptr(x.device)))
-                x = out
-        return x
+        params = []
+        for conv in self.cnns:
+            params += [conv.weight, conv.bias]
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
+            return _ConvStackFn.apply(x, not self.no_act, *params)           # training: activations are kept
+        return _conv_stack_forward(x, params, not self.no_act, keep=False)[-1]
+
+
+def _conv_layer(x, w, b, apply_elu):
+    lib = _lib.load()
+    B, L, _ = x.shape
+    cout, cin, k = w.shape
+    ws_bytes = lib.tae_conv1d_workspace_bytes(cin, cout, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    out = torch.empty((B, L, cout), dtype=torch.float32, device=x.device)
+    _lib.check(lib.tae_conv1d_elu_f32(_lib.ptr(x), _lib.ptr(out), _lib.ptr(w), _lib.ptr(b), B, L, cin, cout, k,
+                                      1 if apply_elu else 0, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(x.device)))
+    return out
+
+
+def _conv_stack_forward(x, params, apply_elu, keep):
+    """[x, h_1, ..., h_n] (keep) or [h_n]: every layer is one fused conv + bias + ELU kernel (cnn_utils.py:36-46)."""
+    acts = [x]
+    with torch.cuda.device(x.device):
+        for j in range(0, len(params), 2):
+            h = _conv_layer(acts[-1], params[j].detach().contiguous(), params[j + 1].detach().contiguous(), apply_elu)
+            if keep:
+                acts.append(h)
+            else:
+                acts = [h]
+    return acts
+
+
+class _ConvStackFn(torch.autograd.Function):
+    """Training path of SameShapeConv1d (reference trainer.py:74 backpropagates through cnn_utils.py:36-46): forward keeps
+    every layer's output; backward runs, per layer, the weight-gradient kernel and the same conv kernel with transposed,
+    tap-flipped weights on g = dy * ELU'(z) (``tae_conv1d_elu_bwd_f32``)."""
+
+    @staticmethod
+    def forward(ctx, x, apply_elu, *params):
+        acts = _conv_stack_forward(x, params, apply_elu, keep=True)
+        ctx.apply_elu = apply_elu
+        ctx.save_for_backward(*acts, *[p for p in params[0::2]])
+        ctx.n_layer = len(params) // 2
+        ctx.needs = [x.requires_grad] + [p.requires_grad for p in params]
+        return acts[-1]
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        n = ctx.n_layer
+        saved = ctx.saved_tensors
+        acts, weights = saved[:n + 1], saved[n + 1:]
+        dy = dy.contiguous()
+        grads = [None] * (2 * n)
+        dev = dy.device
+        with torch.cuda.device(dev):
+            for j in range(n - 1, -1, -1):
+                w = weights[j].detach().contiguous()
+                cout, cin, k = w.shape
+                x, y = acts[j], acts[j + 1]
+                B, L, _ = x.shape
+                need_dx = j > 0 or ctx.needs[0]
+                need_dw = ctx.needs[1 + 2 * j] or ctx.needs[2 + 2 * j]
+                dx = torch.empty_like(x) if need_dx else None
+                dw = torch.zeros_like(w) if need_dw else None
+                db = torch.zeros(cout, dtype=torch.float32, device=dev) if need_dw else None
+                ws_bytes = lib.tae_conv1d_bwd_workspace_bytes(cin, cout, k)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                if need_dx or need_dw:
+                    _lib.check(lib.tae_conv1d_elu_bwd_f32(_lib.ptr(x), _lib.ptr(y), _lib.ptr(dy), _lib.ptr(w), _lib.ptr(dx),
+                                                          _lib.ptr(dw), _lib.ptr(db), B, L, cin, cout, k,
+                                                          1 if ctx.apply_elu else 0, _lib.ptr(ws), ws_bytes,
+                                                          _lib.stream_ptr(dev)))
+                grads[2 * j], grads[2 * j + 1] = dw, db
+                dy = dx
+        return (dy if ctx.needs[0] else None, None, *grads)

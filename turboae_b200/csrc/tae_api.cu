@@ -124,6 +124,27 @@ int tae_conv1d_elu_f32(const float* in, float* out, const float* weight, const f
   return launch_conv_f32(in, out, packed, bias, B, L, Cin, Cout, K, apply_elu, (cudaStream_t)stream);
 }
 
+size_t tae_conv1d_bwd_workspace_bytes(int32_t Cin, int32_t Cout, int32_t K) {
+  if (Cin < 1 || Cout < 1 || K < 1) return 0;
+  return conv_bwd_packed_floats(Cin, Cout, K) * sizeof(float) + 256;
+}
+
+int tae_conv1d_elu_bwd_f32(const float* x, const float* y, const float* dy, const float* weight, float* dx, float* dweight,
+                           float* dbias, int32_t B, int32_t L, int32_t Cin, int32_t Cout, int32_t K, int32_t apply_elu,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  TAE_REQUIRE(B >= 0 && L >= 1 && Cin >= 1 && Cout >= 1, "tae_conv1d_elu_bwd_f32: bad shape B=%d L=%d Cin=%d Cout=%d", B, L, Cin, Cout);
+  if (K < 1 || K > 9 || (K & 1) == 0) { set_error("tae_conv1d_elu_bwd_f32: kernel_size %d unsupported (odd sizes 1..9)", K); return TAE_EUNSUPPORTED; }
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(x && y && dy && weight && workspace, "tae_conv1d_elu_bwd_f32: NULL pointer");
+  TAE_REQUIRE(dx || dweight, "tae_conv1d_elu_bwd_f32: nothing to compute (dx and dweight are NULL)");
+  if (workspace_bytes < tae_conv1d_bwd_workspace_bytes(Cin, Cout, K)) {
+    set_error("tae_conv1d_elu_bwd_f32: workspace %zu < %zu bytes", workspace_bytes, tae_conv1d_bwd_workspace_bytes(Cin, Cout, K));
+    return TAE_EWORKSPACE;
+  }
+  float* packed = reinterpret_cast<float*>(align_up(reinterpret_cast<uintptr_t>(workspace), 256));
+  return launch_conv_bwd_f32(x, y, dy, weight, dx, dweight, dbias, B, L, Cin, Cout, K, apply_elu, packed, (cudaStream_t)stream);
+}
+
 size_t tae_dec_param_count(const TaeDecConfig* cfg) {
   if (check_dec_config(cfg)) return 0;
   return dec_layout(*cfg, nullptr);

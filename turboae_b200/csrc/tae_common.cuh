@@ -85,6 +85,9 @@ size_t conv_packed_floats(int cin, int cout, int k);
 int launch_pack_conv_f32(const float* w, float* packed, int cin, int cout, int k, cudaStream_t s);
 int launch_conv_f32(const float* in, float* out, const float* packed, const float* bias, int B, int L,
                     int cin, int cout, int k, int apply_elu, cudaStream_t s);
+size_t conv_bwd_packed_floats(int cin, int cout, int k);
+int launch_conv_bwd_f32(const float* x, const float* y, const float* dy, const float* w, float* dx, float* dw, float* db, int B, int L,
+                        int cin, int cout, int k, int apply_elu, float* packed_ws, cudaStream_t s);
 int launch_interleave_f32(const float* in, float* out, const int32_t* perm, int B, int L, int F, cudaStream_t s);
 size_t dec_workspace_bytes_f32(const TaeDecConfig& c, int B);
 int dec_forward_f32(const TaeDecConfig& c, const float* params, const float* received, const int32_t* perm,

@@ -45,11 +45,14 @@ __global__ void pack_conv_f32_kernel(const float* __restrict__ w, float* __restr
 // per input channel a lane keeps a sliding window of 8+K-1 inputs in registers and issues
 // 8*K*4 FMAs against K float4 weight loads.
 // ---------------------------------------------------------------------------------------
-template <int K>
+// BWD: `in` is dy and `yfwd` the forward output of the same layer; the staged value is g = dy * ELU'(z) with
+// ELU'(z) = 1 for y > 0 and y + 1 otherwise (y = e^z - 1  =>  e^z = y + 1), i.e. the backward-data pass of a layer is this same
+// kernel run with transposed, tap-flipped weights on g.
+template <int K, bool BWD>
 __global__ void __launch_bounds__(512)
-conv1d_f32_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ wp,
-                  const float* __restrict__ bias, int L, int cin, int cout, int cout_pad, int tiles_per_cw, int TM,
-                  int AS, int apply_elu) {
+conv1d_f32_kernel(const float* __restrict__ in, const float* __restrict__ yfwd, float* __restrict__ out,
+                  const float* __restrict__ wp, const float* __restrict__ bias, int L, int cin, int cout, int cout_pad,
+                  int tiles_per_cw, int TM, int AS, int apply_elu) {
   extern __shared__ __align__(16) float smem[];
   float* W_s = smem;                          // [CC][K][128]
   float* A_s = smem + CONV_CC * K * CONV_TN;  // [CC][AS]
@@ -62,6 +65,7 @@ conv1d_f32_kernel(const float* __restrict__ in, float* __restrict__ out, const f
   const int n0 = blockIdx.y * CONV_TN;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* in_cw = in + (size_t)b * L * cin;
+  const float* y_cw = BWD ? yfwd + (size_t)b * L * cin : nullptr;
   const int rows = TM + K - 1;
 
   float acc[8][4];
@@ -80,7 +84,15 @@ conv1d_f32_kernel(const float* __restrict__ in, float* __restrict__ out, const f
     for (int i = threadIdx.x; i < rows * cc_n; i += blockDim.x) {
       const int cc = i % cc_n, r = i / cc_n;
       const int l = l0 - PAD + r;
-      A_s[cc * AS + r] = (l >= 0 && l < L) ? in_cw[(size_t)l * cin + c0 + cc] : 0.f;
+      float v = 0.f;
+      if (l >= 0 && l < L) {
+        v = in_cw[(size_t)l * cin + c0 + cc];
+        if (BWD && apply_elu) {
+          const float y = y_cw[(size_t)l * cin + c0 + cc];
+          v *= (y > 0.f) ? 1.f : (y + 1.f);
+        }
+      }
+      A_s[cc * AS + r] = v;
     }
     __syncthreads();
     for (int cc = 0; cc < cc_n; ++cc) {
@@ -110,7 +122,7 @@ conv1d_f32_kernel(const float* __restrict__ in, float* __restrict__ out, const f
   if (o >= cout) return;
   float bv[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) bv[j] = (o + j < cout) ? bias[o + j] : 0.f;
+  for (int j = 0; j < 4; ++j) bv[j] = (!BWD && o + j < cout) ? bias[o + j] : 0.f;
   const bool vec = ((cout & 3) == 0) && (o + 3 < cout);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -120,7 +132,7 @@ conv1d_f32_kernel(const float* __restrict__ in, float* __restrict__ out, const f
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       v[j] = acc[i][j] + bv[j];
-      if (apply_elu) v[j] = elu1(v[j]);
+      if (!BWD && apply_elu) v[j] = elu1(v[j]);
     }
     float* dst = out + ((size_t)b * L + l) * cout + o;
     if (vec) {
@@ -128,6 +140,97 @@ conv1d_f32_kernel(const float* __restrict__ in, float* __restrict__ out, const f
     } else {
       for (int j = 0; j < 4 && o + j < cout; ++j) dst[j] = v[j];
     }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Backward of one Conv1d(K, pad K/2) + ELU layer (training).
+//   g        = dy * ELU'(z)                                   (fused into both kernels' loads)
+//   dx[l,c]  = sum_o sum_t g[l - t + K/2, o] W[o,c,t]          = conv(g) with W'[c][o][t'] = W[o][c][K-1-t']
+//   dW[o,c,t]= sum_{b,l} g[b,l,o] x[b,l+t-K/2,c]   db[o] = sum_{b,l} g[b,l,o]
+// ---------------------------------------------------------------------------------------
+__global__ void pack_conv_bwd_f32_kernel(const float* __restrict__ w, float* __restrict__ packed, int cin, int cout, int k,
+                                         int cin_pad) {
+  // packed as a forward weight of a (Cout -> Cin) layer: [o][t'][c_pad]
+  size_t n = (size_t)cout * k * cin_pad;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(idx % cin_pad);
+    int t = (int)((idx / cin_pad) % k);
+    int o = (int)(idx / ((size_t)cin_pad * k));
+    packed[idx] = (c < cin) ? w[((size_t)o * cin + c) * k + (k - 1 - t)] : 0.f;
+  }
+}
+
+constexpr int WG_T = 13;            // 13 x 13 threads, 8 x 8 accumulators each: up to 104 x 104 (Cout x Cin) per tap
+constexpr int WG_R = 32;            // rows staged per step
+constexpr int WG_LD = 104 + 4;      // padded row stride of the staged tiles (floats)
+
+__global__ void __launch_bounds__(WG_T * WG_T)
+conv1d_wgrad_f32_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
+                        float* __restrict__ dw, float* __restrict__ db, int B, int L, int cin, int cout, int K, int apply_elu) {
+  __shared__ __align__(16) float G_s[WG_R][WG_LD];
+  __shared__ __align__(16) float X_s[WG_R][WG_LD];
+  const int t = blockIdx.y, pad = K / 2;
+  const int o0 = blockIdx.z / ((cin + 103) / 104) * 104, c0 = blockIdx.z % ((cin + 103) / 104) * 104;
+  const int ty = threadIdx.x / WG_T, tx = threadIdx.x % WG_T;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float gsum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) gsum[i] = 0.f;
+
+  const int chunks_per_cw = (L + WG_R - 1) / WG_R;
+  const long long n_chunks = (long long)B * chunks_per_cw;
+  for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const int b = (int)(ch / chunks_per_cw), l0 = (int)(ch % chunks_per_cw) * WG_R;
+    __syncthreads();
+    for (int i = threadIdx.x; i < WG_R * 104; i += blockDim.x) {
+      const int r = i / 104, cc = i % 104, l = l0 + r;
+      float g = 0.f, xv = 0.f;
+      if (l < L) {
+        const int o = o0 + cc;
+        if (o < cout) {
+          g = dy[((size_t)b * L + l) * cout + o];
+          if (apply_elu) {
+            const float yy = y[((size_t)b * L + l) * cout + o];
+            g *= (yy > 0.f) ? 1.f : (yy + 1.f);
+          }
+        }
+        const int ls = l + t - pad, c = c0 + cc;
+        if (ls >= 0 && ls < L && c < cin) xv = x[((size_t)b * L + ls) * cin + c];
+      }
+      G_s[r][cc] = g;
+      X_s[r][cc] = xv;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < WG_R; ++r) {
+      const float4 g0 = *reinterpret_cast<const float4*>(&G_s[r][8 * ty]), g1 = *reinterpret_cast<const float4*>(&G_s[r][8 * ty + 4]);
+      const float4 x0 = *reinterpret_cast<const float4*>(&X_s[r][8 * tx]), x1 = *reinterpret_cast<const float4*>(&X_s[r][8 * tx + 4]);
+      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(gv[i], xv[j], acc[i][j]);
+        if (tx == 0) gsum[i] += gv[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int o = o0 + 8 * ty + i;
+    if (o >= cout) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + 8 * tx + j;
+      if (c < cin) atomicAdd(dw + ((size_t)o * cin + c) * K + t, acc[i][j]);
+    }
+    if (tx == 0 && t == pad && c0 == 0 && db) atomicAdd(db + o, gsum[i]);
   }
 }
 
@@ -269,8 +372,8 @@ inline int grid_for(size_t n, int block, int max_blocks = 148 * 16) {
   return (int)g;
 }
 
-template <int K>
-int launch_conv_k(const float* in, float* out, const float* packed, const float* bias, int B, int L, int cin,
+template <int K, bool BWD>
+int launch_conv_k(const float* in, const float* yfwd, float* out, const float* packed, const float* bias, int B, int L, int cin,
                   int cout, int apply_elu, cudaStream_t s) {
   const int cout_pad = (int)align_up(cout, CONV_TN);
   const int tiles_per_cw = (L + 127) / 128;
@@ -281,14 +384,14 @@ int launch_conv_k(const float* in, float* out, const float* packed, const float*
   const size_t smem = (size_t)(CONV_CC * K * CONV_TN + CONV_CC * AS) * sizeof(float);
   static bool attr_done = false;   // per instantiation
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv1d_f32_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv1d_f32_kernel<K, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv1d_f32): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
     attr_done = true;
   }
   if (smem > 96 * 1024) { set_error("conv1d_f32: kernel_size %d needs %zu B shared memory", K, smem); return TAE_EUNSUPPORTED; }
   dim3 grid((unsigned)((size_t)B * tiles_per_cw), (unsigned)(cout_pad / CONV_TN));
-  conv1d_f32_kernel<K><<<grid, 32 * (TM / 8), smem, s>>>(in, out, packed, bias, L, cin, cout, cout_pad, tiles_per_cw,
-                                                         TM, AS, apply_elu);
+  conv1d_f32_kernel<K, BWD><<<grid, 32 * (TM / 8), smem, s>>>(in, yfwd, out, packed, bias, L, cin, cout, cout_pad,
+                                                              tiles_per_cw, TM, AS, apply_elu);
   return after_launch("conv1d_f32_kernel");
 }
 
@@ -306,15 +409,47 @@ int launch_conv_f32(const float* in, float* out, const float* packed, const floa
                     int cout, int k, int apply_elu, cudaStream_t s) {
   if (B == 0) return TAE_OK;
   switch (k) {
-    case 1: return launch_conv_k<1>(in, out, packed, bias, B, L, cin, cout, apply_elu, s);
-    case 3: return launch_conv_k<3>(in, out, packed, bias, B, L, cin, cout, apply_elu, s);
-    case 5: return launch_conv_k<5>(in, out, packed, bias, B, L, cin, cout, apply_elu, s);
-    case 7: return launch_conv_k<7>(in, out, packed, bias, B, L, cin, cout, apply_elu, s);
-    case 9: return launch_conv_k<9>(in, out, packed, bias, B, L, cin, cout, apply_elu, s);
+    case 1: return launch_conv_k<1, false>(in, nullptr, out, packed, bias, B, L, cin, cout, apply_elu, s);
+    case 3: return launch_conv_k<3, false>(in, nullptr, out, packed, bias, B, L, cin, cout, apply_elu, s);
+    case 5: return launch_conv_k<5, false>(in, nullptr, out, packed, bias, B, L, cin, cout, apply_elu, s);
+    case 7: return launch_conv_k<7, false>(in, nullptr, out, packed, bias, B, L, cin, cout, apply_elu, s);
+    case 9: return launch_conv_k<9, false>(in, nullptr, out, packed, bias, B, L, cin, cout, apply_elu, s);
     default:
       set_error("kernel_size %d unsupported (odd sizes 1..9 only: SameShapeConv1d pads K/2, cnn_utils.py:16)", k);
       return TAE_EUNSUPPORTED;
   }
+}
+
+
+size_t conv_bwd_packed_floats(int cin, int cout, int k) { return (size_t)cout * k * align_up(cin, CONV_TN); }
+
+int launch_conv_bwd_f32(const float* x, const float* y, const float* dy, const float* w, float* dx, float* dw, float* db, int B, int L,
+                        int cin, int cout, int k, int apply_elu, float* packed_ws, cudaStream_t s) {
+  if (B == 0) return TAE_OK;
+  if (dw) {
+    const int tiles = ((cout + 103) / 104) * ((cin + 103) / 104);
+    const long long n_chunks = (long long)B * ((L + WG_R - 1) / WG_R);
+    dim3 grid((unsigned)std::min<long long>(n_chunks, 148 * 2), (unsigned)k, (unsigned)tiles);
+    conv1d_wgrad_f32_kernel<<<grid, WG_T * WG_T, 0, s>>>(x, y, dy, dw, db, B, L, cin, cout, k, apply_elu);
+    int rc = after_launch("conv1d_wgrad_f32_kernel");
+    if (rc) return rc;
+  }
+  if (dx) {
+    const int cin_pad = (int)align_up(cin, CONV_TN);
+    const size_t n = (size_t)cout * k * cin_pad;
+    pack_conv_bwd_f32_kernel<<<grid_for(n, 256), 256, 0, s>>>(w, packed_ws, cin, cout, k, cin_pad);
+    int rc = after_launch("pack_conv_bwd_f32_kernel");
+    if (rc) return rc;
+    switch (k) {
+      case 1: return launch_conv_k<1, true>(dy, y, dx, packed_ws, nullptr, B, L, cout, cin, apply_elu, s);
+      case 3: return launch_conv_k<3, true>(dy, y, dx, packed_ws, nullptr, B, L, cout, cin, apply_elu, s);
+      case 5: return launch_conv_k<5, true>(dy, y, dx, packed_ws, nullptr, B, L, cout, cin, apply_elu, s);
+      case 7: return launch_conv_k<7, true>(dy, y, dx, packed_ws, nullptr, B, L, cout, cin, apply_elu, s);
+      case 9: return launch_conv_k<9, true>(dy, y, dx, packed_ws, nullptr, B, L, cout, cin, apply_elu, s);
+      default: set_error("kernel_size %d unsupported", k); return TAE_EUNSUPPORTED;
+    }
+  }
+  return TAE_OK;
 }
 
 int launch_interleave_f32(const float* in, float* out, const int32_t* perm, int B, int L, int F, cudaStream_t s) {

@@ -142,14 +142,37 @@ class DEC_LargeCNN(torch.nn.Module):
                                                 _lib.stream_ptr(dev)))
         return out_host
 
+    def _forward_train(self, received):
+        """Autograd path (reference trainer.py:64-76 backpropagates through decoders.py:219-269): the turbo schedule is
+        spelled out with this package's differentiable pieces -- SameShapeConv1d (fp32 conv + ELU kernels forward, weight- and
+        data-gradient kernels backward: ~98 % of the FLOPs), Interleaver / DeInterleaver (gather kernel both ways) -- and
+        torch glue for the concat, the 100->5 Linear and the subtractions."""
+        a = self.args
+        B, L, _ = received.shape
+        r_sys, r_par1, r_par2 = received[:, :, 0:1], received[:, :, 1:2], received[:, :, 2:3]
+        r_sys_int = self.interleaver(r_sys)
+        prior = torch.zeros((B, L, a.num_iter_ft), dtype=torch.float32, device=received.device)
+        x_plr = None
+        for idx in range(a.num_iteration):
+            last = idx == a.num_iteration - 1
+            x_plr = self.dec1_outputs[idx](self.dec1_cnns[idx](torch.cat([r_sys, r_par1, prior], dim=2)))
+            if a.extrinsic:
+                x_plr = x_plr - prior
+            x_plr_int = self.interleaver(x_plr)
+            x_plr = self.dec2_outputs[idx](self.dec2_cnns[idx](torch.cat([r_sys_int, r_par2, x_plr_int], dim=2)))
+            if not last:
+                if a.extrinsic:
+                    x_plr = x_plr - x_plr_int
+                prior = self.deinterleaver(x_plr)
+        return torch.sigmoid(self.deinterleaver(x_plr))
+
     def forward(self, received):
         if getattr(self.args, "is_variable_block_len", False):
             raise NotImplementedError("--is_variable_block_len is not supported by turboae_b200")
         if self.this_device.type != "cuda":
             raise _lib.TaeError("no CUDA device: turboae_b200 has no CPU fallback")
         if torch.is_grad_enabled() and (received.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("turboae_b200: decoder backward is not built yet (SURVEY.md 8(f) row 1); "
-                                      "use torch.no_grad()")
+            return self._forward_train(received.to(device=self.this_device, dtype=torch.float32))
         # reference decoders.py:219: received.type(torch.FloatTensor).to(self.this_device) -- here without the
         # device->host->device round trip when the tensor is already resident.
         x = received.to(device=self.this_device, dtype=torch.float32).contiguous()

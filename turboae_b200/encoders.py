@@ -133,14 +133,30 @@ class ENC_interCNN(ENCBase):
                                            _lib.ptr(stats), B, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
         return x_tx
 
+    def _forward_train(self, u):
+        """Autograd path (reference encoders.py:362-375 under trainer.py:74): conv stacks through this package's forward /
+        backward kernels, torch glue for the 100->1 Linear, ELU, concat and the power constraint (whose statistics and
+        gradient sums are all-reduced when the batch is sharded across ranks)."""
+        x = 2.0 * u - 1.0
+        outs = []
+        for i, inp in ((1, x), (2, x), (3, self.interleaver(x))):
+            h = getattr(self, "enc_cnn_%d" % i)(inp)
+            outs.append(torch.nn.functional.elu(getattr(self, "enc_linear_%d" % i)(h)))
+        x_tx = torch.cat(outs, dim=2)
+        if self.args.no_code_norm:
+            return x_tx
+        codes = shard.PowerNorm.apply(x_tx, self.shard_group)
+        if self.args.enc_truncate_limit > 0:
+            codes = torch.clamp(codes, -self.args.enc_truncate_limit, self.args.enc_truncate_limit)
+        return codes
+
     def forward(self, inputs):
         self._check_supported()
         if self.this_device.type != "cuda":
             raise _lib.TaeError("no CUDA device: turboae_b200 has no CPU fallback")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("turboae_b200: encoder backward is not built yet (SURVEY.md 8(f) row 1); "
-                                      "use torch.no_grad()")
         x = inputs.to(device=self.this_device, dtype=torch.float32).contiguous()
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return self._forward_train(x)
         if x.dim() != 3 or x.shape[2] != 1:
             raise _lib.TaeError("ENC_interCNN expects (B, L, 1) bits, got %s" % (tuple(x.shape),))
         lib = _lib.load()

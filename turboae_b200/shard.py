@@ -43,3 +43,59 @@ def max_over_ranks(value: float, device=None, group=None) -> float:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+class PowerNorm(torch.autograd.Function):
+    """ENCBase.power_constraint (reference encoders.py:107-116), differentiable and exact under sharding:
+    y = (x - mean) / std with mean / unbiased std over the WHOLE batch.  Forward all-reduces (sum x, sum x^2, count),
+    backward all-reduces (sum g, sum g*y):  dx = (g - mean(g) - y * sum(g*y) / (N - 1)) / std."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        xd = x.double()
+        stats = torch.stack([xd.sum(), (xd * xd).sum(), torch.tensor(float(x.numel()), dtype=torch.float64, device=x.device)])
+        merge_power_stats(stats, group)
+        n = stats[2]
+        mean = stats[0] / n
+        std = torch.sqrt(torch.clamp((stats[1] - n * mean * mean) / (n - 1.0), min=0.0))
+        y = (x - mean.float()) / std.float()
+        ctx.save_for_backward(y, std.float(), n)
+        ctx.group = group
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        y, std, n = ctx.saved_tensors
+        sums = torch.stack([g.double().sum(), (g.double() * y.double()).sum()])
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=ctx.group)
+        dx = (g - (sums[0] / n).float() - y * (sums[1] / (n - 1.0)).float()) / std
+        return dx, None
+
+
+def all_reduce_gradients(params, group=None) -> int:
+    """Data-parallel training (BASELINE config 4): ONE all-reduce (average) of the flat gradient of `params` -- the
+    replacement of nn.DataParallel's ReduceAddCoalesced.  Returns the number of floats reduced."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return sum(g.numel() for g in grads)
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+    return off
+
+
+def install_optimizer_hook(group=None):
+    """Registers a global optimizer pre-step hook that all-reduces the gradients of whatever the optimizer is about to
+    step: the reference's trainer.py (`loss.backward(); optimizer.step()`, :74-76) then trains data-parallel unchanged."""
+    from torch.optim.optimizer import register_optimizer_step_pre_hook
+
+    def hook(optimizer, args, kwargs):
+        params = [p for grp in optimizer.param_groups for p in grp["params"]]
+        all_reduce_gradients(params, group)
+
+    return register_optimizer_step_pre_hook(hook)

@@ -162,59 +162,64 @@ __global__ void pack_conv_bwd_f32_kernel(const float* __restrict__ w, float* __r
   }
 }
 
-constexpr int WG_T = 13;            // 13 x 13 threads, 8 x 8 accumulators each: up to 104 x 104 (Cout x Cin) per tap
-constexpr int WG_R = 32;            // rows staged per step
-constexpr int WG_LD = 104 + 4;      // padded row stride of the staged tiles (floats)
+constexpr int WG_TY = 26, WG_TX = 13;   // 26 x 13 threads, 4 x 8 accumulators each: up to 104 x 104 (Cout x Cin) per tap
+constexpr int WG_R = 50;                // rows staged per step (block_len 100 = 2 full steps)
+constexpr int WG_LD = 104 + 4;          // padded row stride of the staged tiles (floats)
 
-__global__ void __launch_bounds__(WG_T * WG_T)
+__global__ void __launch_bounds__(WG_TY * WG_TX, 2)
 conv1d_wgrad_f32_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
                         float* __restrict__ dw, float* __restrict__ db, int B, int L, int cin, int cout, int K, int apply_elu) {
   __shared__ __align__(16) float G_s[WG_R][WG_LD];
   __shared__ __align__(16) float X_s[WG_R][WG_LD];
   const int t = blockIdx.y, pad = K / 2;
   const int o0 = blockIdx.z / ((cin + 103) / 104) * 104, c0 = blockIdx.z % ((cin + 103) / 104) * 104;
-  const int ty = threadIdx.x / WG_T, tx = threadIdx.x % WG_T;
-  float acc[8][8];
+  const int ty = threadIdx.x / WG_TX, tx = threadIdx.x % WG_TX;
+  float acc[4][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  float gsum[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) gsum[i] = 0.f;
+  float gsum[4] = {0.f, 0.f, 0.f, 0.f};
 
   const int chunks_per_cw = (L + WG_R - 1) / WG_R;
   const long long n_chunks = (long long)B * chunks_per_cw;
   for (long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
     const int b = (int)(ch / chunks_per_cw), l0 = (int)(ch % chunks_per_cw) * WG_R;
-    __syncthreads();
-    for (int i = threadIdx.x; i < WG_R * 104; i += blockDim.x) {
+    // stage 48 rows of g = dy * ELU'(z) and of the tap-shifted input: all global loads of a thread are issued before the
+    // first use (15 x 3 loads in flight), otherwise this phase is latency-bound and dominates the kernel
+    constexpr int NT = WG_TY * WG_TX, NIT = (WG_R * 104 + NT - 1) / NT;
+    float vd[NIT], vy[NIT], vx[NIT];
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {
+      const int i = threadIdx.x + j * NT;
       const int r = i / 104, cc = i % 104, l = l0 + r;
-      float g = 0.f, xv = 0.f;
-      if (l < L) {
-        const int o = o0 + cc;
-        if (o < cout) {
-          g = dy[((size_t)b * L + l) * cout + o];
-          if (apply_elu) {
-            const float yy = y[((size_t)b * L + l) * cout + o];
-            g *= (yy > 0.f) ? 1.f : (yy + 1.f);
-          }
-        }
-        const int ls = l + t - pad, c = c0 + cc;
-        if (ls >= 0 && ls < L && c < cin) xv = x[((size_t)b * L + ls) * cin + c];
+      const int o = o0 + cc, ls = l + t - pad, c = c0 + cc;
+      const bool okg = (i < WG_R * 104) && (l < L) && (o < cout);
+      const bool okx = (i < WG_R * 104) && (l < L) && (ls >= 0) && (ls < L) && (c < cin);
+      vd[j] = okg ? __ldg(dy + ((size_t)b * L + l) * cout + o) : 0.f;
+      vy[j] = (okg && apply_elu) ? __ldg(y + ((size_t)b * L + l) * cout + o) : 1.f;
+      vx[j] = okx ? __ldg(x + ((size_t)b * L + ls) * cin + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {
+      const int i = threadIdx.x + j * NT;
+      if (i < WG_R * 104) {
+        const int r = i / 104, cc = i % 104;
+        G_s[r][cc] = vd[j] * ((vy[j] > 0.f) ? 1.f : (vy[j] + 1.f));
+        X_s[r][cc] = vx[j];
       }
-      G_s[r][cc] = g;
-      X_s[r][cc] = xv;
     }
     __syncthreads();
 #pragma unroll 4
     for (int r = 0; r < WG_R; ++r) {
-      const float4 g0 = *reinterpret_cast<const float4*>(&G_s[r][8 * ty]), g1 = *reinterpret_cast<const float4*>(&G_s[r][8 * ty + 4]);
-      const float4 x0 = *reinterpret_cast<const float4*>(&X_s[r][8 * tx]), x1 = *reinterpret_cast<const float4*>(&X_s[r][8 * tx + 4]);
-      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float4 g0 = *reinterpret_cast<const float4*>(&G_s[r][4 * ty]);
+      // a thread's 8 input channels are two groups of 4, 52 apart: consecutive lanes read consecutive 16-byte words
+      const float4 x0 = *reinterpret_cast<const float4*>(&X_s[r][4 * tx]), x1 = *reinterpret_cast<const float4*>(&X_s[r][52 + 4 * tx]);
+      const float gv[4] = {g0.x, g0.y, g0.z, g0.w};
       const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(gv[i], xv[j], acc[i][j]);
         if (tx == 0) gsum[i] += gv[i];
@@ -222,12 +227,12 @@ conv1d_wgrad_f32_kernel(const float* __restrict__ x, const float* __restrict__ y
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int o = o0 + 8 * ty + i;
+  for (int i = 0; i < 4; ++i) {
+    const int o = o0 + 4 * ty + i;
     if (o >= cout) continue;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = c0 + 8 * tx + j;
+      const int c = c0 + (j < 4 ? 4 * tx + j : 52 + 4 * tx + (j - 4));
       if (c < cin) atomicAdd(dw + ((size_t)o * cin + c) * K + t, acc[i][j]);
     }
     if (tx == 0 && t == pad && c0 == 0 && db) atomicAdd(db + o, gsum[i]);
@@ -430,7 +435,7 @@ int launch_conv_bwd_f32(const float* x, const float* y, const float* dy, const f
     const int tiles = ((cout + 103) / 104) * ((cin + 103) / 104);
     const long long n_chunks = (long long)B * ((L + WG_R - 1) / WG_R);
     dim3 grid((unsigned)std::min<long long>(n_chunks, 148 * 2), (unsigned)k, (unsigned)tiles);
-    conv1d_wgrad_f32_kernel<<<grid, WG_T * WG_T, 0, s>>>(x, y, dy, dw, db, B, L, cin, cout, k, apply_elu);
+    conv1d_wgrad_f32_kernel<<<grid, WG_TY * WG_TX, 0, s>>>(x, y, dy, dw, db, B, L, cin, cout, k, apply_elu);
     int rc = after_launch("conv1d_wgrad_f32_kernel");
     if (rc) return rc;
   }

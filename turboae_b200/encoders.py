@@ -58,7 +58,10 @@ class ENC_interCNN(ENCBase):
         self.interleaver = Interleaver(args, p_array)
         self._flat = FlatCache()
         self._ws = Workspace()
-        self.shard_group = None      # set to a torch.distributed group when the batch is sharded across ranks
+        # set to a torch.distributed group when the batch is sharded across ranks (the launcher does it under torchrun)
+        self.shard_group = None
+        if os.environ.get("TURBOAE_B200_SHARD") == "1" and torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.shard_group = torch.distributed.group.WORLD
         #: 'fp32' (CUDA-core path, elementwise parity <= 1e-4) or 'bf16' (the decoder's fused tcgen05 kernel with the three
         #: branches as three conv stacks: ~25x faster, codes within bf16 rounding of the reference's)
         self.precision = getattr(args, "tae_enc_precision", None) or os.environ.get("TURBOAE_B200_ENC_PRECISION", "fp32")

@@ -79,6 +79,17 @@ def main(argv=None):
     ap.add_argument("script_args", nargs=argparse.REMAINDER)
     a = ap.parse_args(argv)
     install(a.reference)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # data-parallel under torchrun: one process per GPU, whole codewords per rank; the reference's
+        # `loss.backward(); optimizer.step()` (trainer.py:74-76) is kept, gradients are averaged by an optimizer pre-step hook
+        import torch
+        import torch.distributed as dist
+        from . import shard
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+        os.environ["TURBOAE_B200_SHARD"] = "1"          # ENC_interCNN: batch-global power statistics across ranks
+        shard.install_optimizer_hook()
     script = a.script if os.path.isabs(a.script) else os.path.join(os.path.abspath(a.reference), a.script)
     for d in ("logs", "tmp"):
         os.makedirs(d, exist_ok=True)                            # main.py:106, 248 write there

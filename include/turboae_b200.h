@@ -151,6 +151,12 @@ int tae_enc_forward_bf16(const TaeEncConfig* cfg, const void* packed, const floa
 int tae_power_norm_f32(const float* x, float* codes, size_t n, const double* stats,
                        float* mean_std, void* stream);
 
+/* The same followed by STEQuantize.forward (reference encoders.py:20-37, applied at :118-120 when
+ * train_channel_mode == 'block_norm_ste'): clamp to +-value_limit, then sign() for quantize_level == 2 or
+ * quantize_level uniform levels otherwise.  (The straight-through backward is torch glue in the Python layer.)     */
+int tae_power_norm_ste_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std,
+                           float value_limit, float quantize_level, void* stream);
+
 /* ---- around the path: on-device channel and metrics -------------------------------------
  * AWGN channel, reference channel_ae.py:41-42 with channels.py:21-35: received = codes + sigma * N(0,1).
  * The reference draws torch.randn on the CPU (unseeded); this stream is Philox4x32-10 + Box-Muller, element i uses

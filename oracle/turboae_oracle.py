@@ -163,10 +163,20 @@ def power_constraint(x_tx: np.ndarray):
     return ((x_tx - mean32) * F32(1.0) / std32).astype(F32), mean32, std32
 
 
-def enc_forward(u: np.ndarray, weights, p: np.ndarray, prefix: str = "enc") -> np.ndarray:
-    """reference encoders.py:351-377 -> codes ``(B, L, 3)``."""
+def ste_quantize(x: np.ndarray, value_limit: float = 1.0, quantize_level: float = 2) -> np.ndarray:
+    """STEQuantize.forward, reference encoders.py:20-37."""
+    xc = np.clip(x.astype(F32), F32(-value_limit), F32(value_limit))
+    if quantize_level == 2:
+        return np.sign(xc).astype(F32)
+    q, rng = F32(quantize_level), F32(2.0 * value_limit)
+    return (np.round((xc + F32(value_limit)) * ((q - F32(1.0)) / rng)) * rng / (q - F32(1.0)) - F32(value_limit)).astype(F32)
+
+
+def enc_forward(u: np.ndarray, weights, p: np.ndarray, prefix: str = "enc", ste: bool = False, value_limit: float = 1.0,
+                quantize_level: float = 2) -> np.ndarray:
+    """reference encoders.py:351-377 -> codes ``(B, L, 3)``; ``ste`` = train_channel_mode 'block_norm_ste' (:118-120)."""
     codes, _, _ = power_constraint(enc_forward_unnormalised(u, weights, p, prefix))
-    return codes
+    return ste_quantize(codes, value_limit, quantize_level) if ste else codes
 
 
 # --------------------------------------------------------------------------- #

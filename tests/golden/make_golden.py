@@ -10,6 +10,7 @@ The reference cannot travel to the GPU box, so its outputs are committed here:
   kat_c1_b4.npz    SURVEY.md Appendix C known-answer run (torch.manual_seed(0), B=4)
   io_c1_b8.npz     B=8 @ 0 dB, numpy-RandomState inputs, with every dec Linear output (hooks)
   io_c3_b6.npz     same for the enc5/dec5 checkpoint, B=6 @ 1 dB
+  weights_c1s.npz / io_c1s_b8.npz   the binarised-code checkpoint dta_steq2_... (train_channel_mode block_norm_ste), B=8 @ 2 dB
   perm.npz         interleaver goldens (p, inverse, gather of arange through the reference modules)
   ber_c1.json      12-point BER/BLER sweep (reference trainer.py:157-178 loop restated with seeded
                    numpy inputs, batch 500) -- per-point bit/block error counts
@@ -37,12 +38,14 @@ C1_ARGS = ["-encoder", "TurboAE_rate3_cnn", "-decoder", "TurboAE_rate3_cnn", "-e
            "-dec_kernel_size", "5", "-channel", "awgn", "-num_train_dec", "5", "-num_train_enc", "1",
            "-code_rate_k", "1", "-code_rate_n", "3", "-block_len", "100", "--no-cuda"]
 C3_ARGS = [a if a != "2" or C1_ARGS[i - 1] != "-enc_num_layer" else "5" for i, a in enumerate(C1_ARGS)]
-CKPT = {"c1": "models/dta_cont_cnn2_cnn5_enctrain2_dectrainneg15_2.pt", "c3": "models/enc5_dec5_cont_1dBenc.pt"}
+C1S_ARGS = C1_ARGS + ["-train_channel_mode", "block_norm_ste", "-test_channel_mode", "block_norm_ste"]      # README.md:84-88
+CKPT = {"c1": "models/dta_cont_cnn2_cnn5_enctrain2_dectrainneg15_2.pt", "c3": "models/enc5_dec5_cont_1dBenc.pt",
+        "c1s": "models/dta_steq2_cnn2_cnn5_enctrain2_dectrainneg15_2.pt"}
 
 
 def build_reference_model(cfg, batch_size):
     compat.install()
-    args = compat.reference_args((C1_ARGS if cfg == "c1" else C3_ARGS) + ["-batch_size", str(batch_size)])
+    args = compat.reference_args({"c1": C1_ARGS, "c3": C3_ARGS, "c1s": C1S_ARGS}[cfg] + ["-batch_size", str(batch_size)])
     from numpy import arange
     from numpy.random import mtrand
     from encoders import ENC_interCNN          # reference main.py:35-36
@@ -151,11 +154,12 @@ if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     todo = a.only.split(",") if a.only else ["weights", "kat", "io", "perm", "ber"]
     if "weights" in todo:
-        dump_weights("c1"); dump_weights("c3")
+        dump_weights("c1"); dump_weights("c3"); dump_weights("c1s")
     if "kat" in todo:
         dump_kat()
     if "io" in todo:
         dump_io("c1", 8, 4242, 0.0, "io_c1_b8.npz"); dump_io("c3", 6, 777, 1.0, "io_c3_b6.npz")
+        dump_io("c1s", 8, 999, 2.0, "io_c1s_b8.npz")
     if "perm" in todo:
         dump_perm()
     if "ber" in todo:

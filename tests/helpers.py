@@ -18,7 +18,8 @@ def make_args(**over):
              extrinsic=1, code_rate_k=1, code_rate_n=3, block_len=100, batch_size=500, no_cuda=False,
              is_parallel=1, enc_act="elu", dec_act="linear", no_code_norm=False, enc_truncate_limit=0.0,
              precompute_norm_stats=False, is_variable_block_len=False, train_channel_mode="block_norm",
-             test_channel_mode="block_norm", is_interleave=1, dropout=0.0, tae_precision=None)
+             test_channel_mode="block_norm", is_interleave=1, dropout=0.0, tae_precision=None,
+             enc_quantize_level=2, enc_value_limit=1.0, enc_grad_limit=0.01, enc_clipping="both")
     a.update(over)
     return SimpleNamespace(**a)
 
@@ -43,7 +44,9 @@ class Codec(torch.nn.Module):
 def build_codec(cfg="c1", device="cuda", **over):
     from oracle import turboae_oracle as O
     w = load_npz("weights_%s.npz" % cfg)
-    args = make_args(enc_num_layer=2 if cfg == "c1" else 5, **over)
+    if cfg == "c1s":                                  # the binarised checkpoint (dta_steq2_...): README.md:84-88
+        over.setdefault("train_channel_mode", "block_norm_ste")
+    args = make_args(enc_num_layer=5 if cfg == "c3" else 2, **over)
     p = O.make_perm(args.block_len, 0)
     m = Codec(args, p)
     m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)

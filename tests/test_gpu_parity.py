@@ -129,6 +129,32 @@ def test_encoder_bf16_ragged_batches_and_ber():
     assert abs(be - ref["bit_errors"][3]) / (ref["blocks"] * 100) < 1e-4, (be, ref["bit_errors"][3])
 
 
+def test_binarised_code_path_vs_reference_fixture():
+    """Row f4: train_channel_mode 'block_norm_ste' with the shipped dta_steq2 checkpoint -- codes exactly +-1 and equal to the
+    reference's, decode within tolerance, STE backward = clipped pass-through (reference encoders.py:39-57)."""
+    g = load_npz("io_c1s_b8.npz")
+    m, w, p = build_codec("c1s", batch_size=8)
+    with torch.no_grad():
+        codes = m.enc(_t(g["u"]))
+        y = m.dec.decode(_t(g["received"]), precision="fp32").cpu().numpy()
+    assert np.array_equal(codes.cpu().numpy(), g["codes"])
+    np.testing.assert_allclose(y, g["y"], atol=2e-5, rtol=0)
+    # autograd path: same codes, gradient flows to the encoder through the straight-through estimator
+    m.train()
+    codes_t = m.enc(_t(g["u"]))
+    assert torch.equal(codes_t.detach(), codes)
+    codes_t.sum().backward()
+    gsum = sum(float(p_.grad.abs().sum()) for p_ in m.enc.parameters() if p_.grad is not None)
+    assert gsum > 0.0
+    # multi-level quantiser against the oracle
+    m.eval()
+    m.enc.args.enc_quantize_level = 4
+    with torch.no_grad():
+        c4 = m.enc(_t(g["u"])).cpu().numpy()
+    ref4 = O.enc_forward(g["u"], w, p, ste=True, quantize_level=4)
+    assert (c4 != ref4).mean() < 1e-3 and np.unique(c4).size == 4
+
+
 # ------------------------------------------------------------------------------------------------- a8 fp32
 @pytest.mark.parametrize("cfg,name", [("c1", "io_c1_b8.npz"), ("c3", "io_c3_b6.npz")])
 def test_decoder_fp32_vs_reference_fixture(cfg, name):

@@ -343,7 +343,15 @@ int tae_enc_forward_bf16(const TaeEncConfig* cfg, const void* packed, const floa
 int tae_power_norm_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std, void* stream) {
   if (n == 0) return TAE_OK;
   TAE_REQUIRE(x && codes && stats, "tae_power_norm_f32: NULL pointer");
-  return launch_power_norm_f32(x, codes, n, stats, mean_std, (cudaStream_t)stream);
+  return launch_power_norm_f32(x, codes, n, stats, mean_std, 1.f, 0.f, (cudaStream_t)stream);
+}
+
+int tae_power_norm_ste_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std, float value_limit,
+                           float quantize_level, void* stream) {
+  if (n == 0) return TAE_OK;
+  TAE_REQUIRE(x && codes && stats, "tae_power_norm_ste_f32: NULL pointer");
+  TAE_REQUIRE(value_limit > 0.f && quantize_level >= 2.f, "tae_power_norm_ste_f32: need value_limit > 0 and quantize_level >= 2");
+  return launch_power_norm_f32(x, codes, n, stats, mean_std, value_limit, quantize_level, (cudaStream_t)stream);
 }
 
 int tae_awgn_f32(const float* codes, float* received, size_t n, float sigma, uint64_t seed, uint64_t offset, void* stream) {

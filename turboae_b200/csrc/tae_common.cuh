@@ -96,7 +96,7 @@ int dec_forward_f32(const TaeDecConfig& c, const float* params, const float* rec
 size_t enc_workspace_bytes_f32(const TaeEncConfig& c, int B);
 int enc_forward_f32(const TaeEncConfig& c, const float* params, const float* u, const int32_t* perm, float* x_tx,
                     double* stats, int B, void* ws, size_t ws_bytes, cudaStream_t s);
-int launch_power_norm_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std,
+int launch_power_norm_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std, float limit, float q,
                           cudaStream_t s);
 
 // ---- bf16 tcgen05 path: fused CTA-pair kernel (tae_dec_pair.cu) -----------------------------

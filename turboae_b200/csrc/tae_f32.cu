@@ -358,16 +358,25 @@ __global__ void enc_tail_kernel(const float* __restrict__ h, const float* __rest
 __global__ void add_count_kernel(double* stats, double n) { stats[2] += n; }
 
 // codes = (x - mean) / std with unbiased std over everything counted in stats (encoders.py:107-116).
+// quantize_level 0: plain normalisation; 2: sign(clamp(.)) ; q > 2: q uniform levels on [-limit, limit]
+// (STEQuantize.forward, reference encoders.py:20-37, applied after the normalisation as in encoders.py:118-120)
 __global__ void power_norm_kernel(const float* __restrict__ x, float* __restrict__ codes, size_t n,
-                                  const double* __restrict__ stats, float* __restrict__ mean_std) {
+                                  const double* __restrict__ stats, float* __restrict__ mean_std, float limit, float q) {
   const double cnt = stats[2];
   const double mean = stats[0] / cnt;
   const double var = (stats[1] - cnt * mean * mean) / (cnt - 1.0);
   const float meanf = (float)mean;
   const float stdf = (float)sqrt(var > 0.0 ? var : 0.0);
   if (mean_std && blockIdx.x == 0 && threadIdx.x == 0) { mean_std[0] = meanf; mean_std[1] = stdf; }
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x)
-    codes[idx] = (x[idx] - meanf) / stdf;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    float v = (x[idx] - meanf) / stdf;
+    if (q >= 2.f) {
+      v = fminf(fmaxf(v, -limit), limit);
+      if (q == 2.f) v = (v > 0.f) ? 1.f : (v < 0.f ? -1.f : 0.f);                               // torch.sign
+      else v = rintf((v + limit) * ((q - 1.f) / (2.f * limit))) * (2.f * limit) / (q - 1.f) - limit;
+    }
+    codes[idx] = v;
+  }
 }
 
 inline int grid_for(size_t n, int block, int max_blocks = 148 * 16) {
@@ -636,10 +645,10 @@ int launch_add_count(double* stats, double n, cudaStream_t s) {
   return after_launch("add_count_kernel");
 }
 
-int launch_power_norm_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std,
+int launch_power_norm_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std, float limit, float q,
                           cudaStream_t s) {
   if (n == 0) return TAE_OK;
-  power_norm_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, codes, n, stats, mean_std);
+  power_norm_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, codes, n, stats, mean_std, limit, q);
   return after_launch("power_norm_kernel");
 }
 

@@ -15,6 +15,34 @@ from .cnn_utils import SameShapeConv1d
 from .interleavers import Interleaver
 
 
+class STEQuantize(torch.autograd.Function):
+    """reference encoders.py:20-57: quantised forward, clipped straight-through backward (torch glue: elementwise on (B,L,3)).
+    The experimental 'group_norm_noisy' gradient-noise branch (encoders.py:48-55) is not supported."""
+
+    @staticmethod
+    def forward(ctx, inputs, args):
+        ctx.save_for_backward(inputs)
+        ctx.args = args
+        lim = args.enc_value_limit
+        x = torch.clamp(inputs, -lim, lim)
+        if args.enc_quantize_level == 2:
+            return torch.sign(x)
+        q = args.enc_quantize_level
+        return torch.round((x + lim) * ((q - 1.0) / (2.0 * lim))) * (2.0 * lim) / (q - 1.0) - lim
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        a = ctx.args
+        g = grad_output.clone()
+        if a.enc_clipping in ("inputs", "both"):
+            inp, = ctx.saved_tensors
+            g[inp > a.enc_value_limit] = 0
+            g[inp < -a.enc_value_limit] = 0
+        if a.enc_clipping in ("gradient", "both"):
+            g = torch.clamp(g, -a.enc_grad_limit, a.enc_grad_limit)
+        return g, None
+
+
 class ENCBase(torch.nn.Module):
     """reference encoders.py:63-125."""
 
@@ -97,8 +125,8 @@ class ENC_interCNN(ENCBase):
             raise NotImplementedError("enc_act=%r: only 'elu' is built (get_args.py:100 'only elu works')" % a.enc_act)
         if getattr(a, "precompute_norm_stats", False):
             raise NotImplementedError("--precompute_norm_stats is not supported by turboae_b200")
-        if getattr(a, "train_channel_mode", "block_norm") == "block_norm_ste":
-            raise NotImplementedError("train_channel_mode=block_norm_ste (STEQuantize) is not built yet")
+        if getattr(a, "train_channel_mode", "block_norm") not in ("block_norm", "block_norm_ste"):
+            raise NotImplementedError("train_channel_mode=%r is not supported by turboae_b200" % a.train_channel_mode)
 
     def encode_unnormalised(self, inputs, stats):
         """x_tx (B, L, 3) before power_constraint; adds (sum, sumsq, count) into the 3 device doubles `stats`."""
@@ -148,7 +176,10 @@ class ENC_interCNN(ENCBase):
         x_tx = torch.cat(outs, dim=2)
         if self.args.no_code_norm:
             return x_tx
+        self._check_supported()
         codes = shard.PowerNorm.apply(x_tx, self.shard_group)
+        if getattr(self.args, "train_channel_mode", "block_norm") == "block_norm_ste":
+            codes = STEQuantize.apply(codes, self.args)
         if self.args.enc_truncate_limit > 0:
             codes = torch.clamp(codes, -self.args.enc_truncate_limit, self.args.enc_truncate_limit)
         return codes
@@ -172,8 +203,13 @@ class ENC_interCNN(ENCBase):
             shard.merge_power_stats(stats, self.shard_group)
         codes = torch.empty_like(x_tx)
         with torch.cuda.device(x.device):
-            _lib.check(lib.tae_power_norm_f32(_lib.ptr(x_tx), _lib.ptr(codes), x_tx.numel(), _lib.ptr(stats), None,
-                                              _lib.stream_ptr(x.device)))
+            if getattr(self.args, "train_channel_mode", "block_norm") == "block_norm_ste":      # encoders.py:118-120
+                _lib.check(lib.tae_power_norm_ste_f32(_lib.ptr(x_tx), _lib.ptr(codes), x_tx.numel(), _lib.ptr(stats), None,
+                                                      float(self.args.enc_value_limit), float(self.args.enc_quantize_level),
+                                                      _lib.stream_ptr(x.device)))
+            else:
+                _lib.check(lib.tae_power_norm_f32(_lib.ptr(x_tx), _lib.ptr(codes), x_tx.numel(), _lib.ptr(stats), None,
+                                                  _lib.stream_ptr(x.device)))
         if self.args.enc_truncate_limit > 0:
             codes = torch.clamp(codes, -self.args.enc_truncate_limit, self.args.enc_truncate_limit)
         return codes

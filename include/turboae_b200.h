@@ -157,6 +157,13 @@ int tae_power_norm_f32(const float* x, float* codes, size_t n, const double* sta
 int tae_power_norm_ste_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std,
                            float value_limit, float quantize_level, void* stream);
 
+/* ---- next row f2: DEC_LargeRNN (reference decoders.py:16-149, torch.nn.GRU 2 layers bidirectional) -----------------
+ * One direction of one GRU layer over a whole batch: xproj (B, L, 3H) = W_ih x + b_ih for every time step (gate order r,
+ * z, n; computed with tae_conv1d_elu_f32, K = 1), w_hh (3H, H), b_hh (3H); writes h_t into out[b, t, out_offset .. +H) of
+ * a (B, L, out_stride) tensor (out_offset = 0 forward, H reverse).  reverse != 0 runs t = L-1 .. 0.               */
+int tae_gru_direction_f32(const float* xproj, const float* w_hh, const float* b_hh, float* out,
+                          int32_t B, int32_t L, int32_t H, int32_t out_stride, int32_t out_offset, int32_t reverse, void* stream);
+
 /* ---- around the path: on-device channel and metrics -------------------------------------
  * AWGN channel, reference channel_ae.py:41-42 with channels.py:21-35: received = codes + sigma * N(0,1).
  * The reference draws torch.randn on the CPU (unseeded); this stream is Philox4x32-10 + Box-Muller, element i uses

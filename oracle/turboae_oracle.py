@@ -319,3 +319,65 @@ def error_counts(y_true: np.ndarray, y_pred: np.ndarray):
     q = np.round(y_pred.reshape(y_pred.shape[0], -1))
     wrong = t != q
     return int(wrong.sum()), int(wrong.any(axis=1).sum())
+
+
+# --------------------------------------------------------------------------- #
+# DEC_LargeRNN                                 #
+# --------------------------------------------------------------------------- #
+def gru_direction(x: np.ndarray, w_ih, w_hh, b_ih, b_hh, reverse: bool = False) -> np.ndarray:
+    """One direction of one torch.nn.GRU layer, batch_first (the reference calls torch.nn.GRU, decoders.py:43-52; this is
+    PyTorch's documented cell):  r = s(W_ir x + b_ir + W_hr h + b_hr), z = s(W_iz x + b_iz + W_hz h + b_hz),
+    n = tanh(W_in x + b_in + r * (W_hn h + b_hn)), h' = (1 - z) * n + z * h;  gate order in the weights is r, z, n."""
+    B, L, _ = x.shape
+    H = w_hh.shape[1]
+    xp = (x.reshape(B * L, -1).astype(F32) @ w_ih.T.astype(F32) + b_ih.astype(F32)).reshape(B, L, 3 * H)
+    h = np.zeros((B, H), dtype=F32)
+    out = np.zeros((B, L, H), dtype=F32)
+    steps = range(L - 1, -1, -1) if reverse else range(L)
+    for t in steps:
+        hp = h @ w_hh.T.astype(F32) + b_hh.astype(F32)
+        r = sigmoid(xp[:, t, :H] + hp[:, :H])
+        z = sigmoid(xp[:, t, H:2 * H] + hp[:, H:2 * H])
+        n = np.tanh(xp[:, t, 2 * H:] + r * hp[:, 2 * H:]).astype(F32)
+        h = ((F32(1.0) - z) * n + z * h).astype(F32)
+        out[:, t, :] = h
+    return out
+
+
+def gru_stack(x: np.ndarray, weights, prefix: str, num_layers: int = 2) -> np.ndarray:
+    """torch.nn.GRU(num_layers=2, bidirectional=True, batch_first=True) forward: (B, L, in) -> (B, L, 2H)."""
+    h = x
+    for layer in range(num_layers):
+        outs = []
+        for suffix, rev in (("", False), ("_reverse", True)):
+            k = "l%d%s" % (layer, suffix)
+            outs.append(gru_direction(h, _get(weights, "%s.module.weight_ih_%s" % (prefix, k)), _get(weights, "%s.module.weight_hh_%s" % (prefix, k)),
+                                      _get(weights, "%s.module.bias_ih_%s" % (prefix, k)), _get(weights, "%s.module.bias_hh_%s" % (prefix, k)), rev))
+        h = np.concatenate(outs, axis=2)
+    return h
+
+
+def dec_rnn_forward(received: np.ndarray, weights, p: np.ndarray, num_iteration: int = 6, num_iter_ft: int = 5,
+                    extrinsic: bool = True, prefix: str = "dec") -> np.ndarray:
+    """DEC_LargeRNN.forward, reference decoders.py:86-149 (dropout 0, dec_act 'linear'): the turbo schedule of dec_forward
+    with bi-GRU stacks instead of conv stacks."""
+    r = received.astype(F32, copy=False)
+    B, L, _ = r.shape
+    r_sys, r_par1, r_par2 = r[:, :, 0:1], r[:, :, 1:2], r[:, :, 2:3]
+    r_sys_int = interleave(r_sys, p)
+    prior = np.zeros((B, L, num_iter_ft), dtype=F32)
+    x_plr = None
+    for idx in range(num_iteration):
+        last = idx == num_iteration - 1
+        h = gru_stack(np.concatenate([r_sys, r_par1, prior], axis=2), weights, "%s.dec1_rnns.%d" % (prefix, idx))
+        x_plr = linear(h, _get(weights, "%s.dec1_outputs.%d.module.weight" % (prefix, idx)), _get(weights, "%s.dec1_outputs.%d.module.bias" % (prefix, idx)))
+        if extrinsic:
+            x_plr = x_plr - prior
+        x_plr_int = interleave(x_plr, p)
+        h = gru_stack(np.concatenate([r_sys_int, r_par2, x_plr_int], axis=2), weights, "%s.dec2_rnns.%d" % (prefix, idx))
+        x_plr = linear(h, _get(weights, "%s.dec2_outputs.%d.module.weight" % (prefix, idx)), _get(weights, "%s.dec2_outputs.%d.module.bias" % (prefix, idx)))
+        if not last:
+            if extrinsic:
+                x_plr = x_plr - x_plr_int
+            prior = deinterleave(x_plr, p)
+    return sigmoid(deinterleave(x_plr, p))

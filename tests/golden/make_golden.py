@@ -11,6 +11,7 @@ The reference cannot travel to the GPU box, so its outputs are committed here:
   io_c1_b8.npz     B=8 @ 0 dB, numpy-RandomState inputs, with every dec Linear output (hooks)
   io_c3_b6.npz     same for the enc5/dec5 checkpoint, B=6 @ 1 dB
   weights_c1s.npz / io_c1s_b8.npz   the binarised-code checkpoint dta_steq2_... (train_channel_mode block_norm_ste), B=8 @ 2 dB
+  rnn_*.npz        DEC_LargeRNN (bi-GRU decoder) runs with seeded default-init weights: weights, input, output
   perm.npz         interleaver goldens (p, inverse, gather of arange through the reference modules)
   ber_c1.json      12-point BER/BLER sweep (reference trainer.py:157-178 loop restated with seeded
                    numpy inputs, batch 500) -- per-point bit/block error counts
@@ -126,6 +127,30 @@ def dump_perm():
     print("perm.npz written")
 
 
+def dump_rnn(name, B, L, H, n_iter, seed):
+    """DEC_LargeRNN (reference decoders.py:16-149): no checkpoint is shipped, so weights are torch.manual_seed-ed default init."""
+    compat.install()
+    args = compat.reference_args(["-encoder", "TurboAE_rate3_cnn", "-decoder", "TurboAE_rate3_rnn", "-dec_rnn", "gru",
+                                  "-dec_num_unit", str(H), "-num_iteration", str(n_iter), "-block_len", str(L),
+                                  "-batch_size", str(B), "-code_rate_k", "1", "-code_rate_n", "3", "--no-cuda"])
+    from numpy import arange
+    from numpy.random import mtrand
+    from decoders import DEC_LargeRNN
+    p_array = mtrand.RandomState(0).permutation(arange(L))
+    torch.manual_seed(seed)
+    dec = DEC_LargeRNN(args, p_array)
+    dec.set_parallel()
+    dec.eval()
+    rs = np.random.mtrand.RandomState(seed)
+    received = (rs.randint(0, 2, size=(B, L, 3)) * 2.0 - 1.0 + 0.8 * rs.standard_normal((B, L, 3))).astype(np.float32)
+    with torch.no_grad():
+        y = dec(torch.from_numpy(received)).numpy()
+    out = {"dec." + k: v.detach().numpy().astype(np.float32) for k, v in dec.state_dict().items()}
+    out.update(received=received, y=y, p=np.asarray(p_array, dtype=np.int64), cfg=np.array([B, L, H, n_iter], dtype=np.int64))
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, "params", sum(v.size for k, v in out.items() if k.startswith("dec.")), "y range", float(y.min()), float(y.max()))
+
+
 def dump_ber(blocks, batch=500):
     model, args, p = build_reference_model("c1", batch)
     snrs = [-1.5 + 0.5 * i for i in range(12)]          # trainer.py:157-158 with the default flags
@@ -152,7 +177,7 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["weights", "kat", "io", "perm", "ber"]
+    todo = a.only.split(",") if a.only else ["weights", "kat", "io", "perm", "rnn", "ber"]
     if "weights" in todo:
         dump_weights("c1"); dump_weights("c3"); dump_weights("c1s")
     if "kat" in todo:
@@ -162,5 +187,7 @@ if __name__ == "__main__":
         dump_io("c1s", 8, 999, 2.0, "io_c1s_b8.npz")
     if "perm" in todo:
         dump_perm()
+    if "rnn" in todo:
+        dump_rnn("rnn_h32_i2_l40_b5.npz", 5, 40, 32, 2, 11); dump_rnn("rnn_h100_i1_l100_b3.npz", 3, 100, 100, 1, 12)
     if "ber" in todo:
         dump_ber(a.sweep_blocks)

@@ -19,7 +19,7 @@ def make_args(**over):
              is_parallel=1, enc_act="elu", dec_act="linear", no_code_norm=False, enc_truncate_limit=0.0,
              precompute_norm_stats=False, is_variable_block_len=False, train_channel_mode="block_norm",
              test_channel_mode="block_norm", is_interleave=1, dropout=0.0, tae_precision=None,
-             enc_quantize_level=2, enc_value_limit=1.0, enc_grad_limit=0.01, enc_clipping="both")
+             enc_quantize_level=2, enc_value_limit=1.0, enc_grad_limit=0.01, enc_clipping="both", dec_rnn="gru")
     a.update(over)
     return SimpleNamespace(**a)
 

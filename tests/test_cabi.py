@@ -76,6 +76,20 @@ def test_module_tree_matches_shipped_checkpoint_keys(cfg, n_enc_layer):
     assert "dec1_cnns.0.cnns.0.weight" in plain.state_dict()
 
 
+def test_rnn_decoder_module_tree_matches_reference_keys():
+    g = load_npz("rnn_h32_i2_l40_b5.npz")
+    B, L, H, n_iter = g["cfg"].tolist()
+    m = T.DEC_LargeRNN(make_args(no_cuda=True, num_iteration=n_iter, dec_num_unit=H, block_len=L), g["p"])
+    m.set_parallel()
+    sd = m.state_dict()
+    ref_keys = sorted(k[4:] for k in g if k.startswith("dec."))
+    assert sorted(sd.keys()) == ref_keys
+    for k, v in sd.items():
+        assert tuple(v.shape) == g["dec." + k].shape, k
+    with torch.no_grad(), pytest.raises(_lib.TaeError):
+        m(torch.zeros(B, L, 3))
+
+
 def test_interleaver_host_logic():
     p = O.make_perm(100, 0)
     args = make_args(no_cuda=True)

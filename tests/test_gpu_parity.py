@@ -504,6 +504,51 @@ def test_reference_training_loop_reduces_loss():
     assert losses[-1] < losses[0] - 0.02, losses
 
 
+# ------------------------------------------------------------------------------------------------- f2: DEC_LargeRNN
+def _rnn_module(g, scale=1.0):
+    import turboae_b200 as T
+    B, L, H, n_iter = g["cfg"].tolist()
+    m = T.DEC_LargeRNN(make_args(num_iteration=n_iter, dec_num_unit=H, block_len=L, batch_size=B), g["p"])
+    m.set_parallel()
+    m.load_state_dict({k[4:]: torch.from_numpy(v * np.float32(scale)) for k, v in g.items() if k.startswith("dec.")}, strict=True)
+    return m.to(DEV).eval()
+
+
+@pytest.mark.parametrize("name", ["rnn_h32_i2_l40_b5.npz", "rnn_h100_i1_l100_b3.npz"])
+def test_rnn_decoder_vs_reference_fixture(name):
+    g = load_npz(name)
+    m = _rnn_module(g)
+    with torch.no_grad():
+        y = m(_t(g["received"])).cpu().numpy()
+    np.testing.assert_allclose(y, g["y"], atol=1e-5, rtol=0)
+
+
+def test_rnn_decoder_amplified_weights_and_long_blocks_vs_oracle():
+    """Default-init weights barely move the outputs off 0.5, so the same network with 4x larger weights (saturating gates,
+    posteriors across (0,1)) and a block length of 1000 (BASELINE config 5) is checked against the pinned oracle."""
+    import turboae_b200 as T
+    g = load_npz("rnn_h32_i2_l40_b5.npz")
+    m = _rnn_module(g, scale=4.0)
+    w = {k: v * np.float32(4.0) for k, v in g.items() if k.startswith("dec.")}
+    rs = np.random.RandomState(5)
+    rec = (rs.randint(0, 2, size=(19, 40, 3)) * 2.0 - 1.0 + 0.8 * rs.standard_normal((19, 40, 3))).astype(np.float32)
+    with torch.no_grad():
+        y = m(_t(rec)).cpu().numpy()
+    ref = O.dec_rnn_forward(rec, w, g["p"], num_iteration=2)
+    assert ref.max() - ref.min() > 0.5
+    np.testing.assert_allclose(y, ref, atol=2e-4, rtol=0)
+    # block length 1000, H = 100
+    torch.manual_seed(4)
+    L = 1000
+    p = O.make_perm(L, 0)
+    big = T.DEC_LargeRNN(make_args(num_iteration=1, dec_num_unit=100, block_len=L, batch_size=2), p).to(DEV).eval()
+    wb = {"dec." + k: v.detach().cpu().numpy() for k, v in big.state_dict().items()}
+    rec = (rs.randint(0, 2, size=(2, L, 3)) * 2.0 - 1.0 + 0.8 * rs.standard_normal((2, L, 3))).astype(np.float32)
+    with torch.no_grad():
+        y = big(_t(rec)).cpu().numpy()
+    np.testing.assert_allclose(y, O.dec_rnn_forward(rec, wb, p, num_iteration=1), atol=2e-5, rtol=0)
+
+
 # ------------------------------------------------------------------------------------------------- full size
 def test_full_size_batch_properties():
     """BASELINE config 2 size (B = 50 000): size-independent properties -- finite posteriors in (0,1), agreement

@@ -9,7 +9,7 @@ the library or without a CUDA device every forward raises.
 from .interleavers import Interleaver, DeInterleaver          # noqa: F401
 from .cnn_utils import SameShapeConv1d                        # noqa: F401
 from .encoders import ENCBase, ENC_interCNN                   # noqa: F401
-from .decoders import DEC_LargeCNN                            # noqa: F401
+from .decoders import DEC_LargeCNN, DEC_LargeRNN              # noqa: F401
 from . import channel, shard                                  # noqa: F401
 
 __version__ = "0.1.0"

@@ -354,6 +354,15 @@ int tae_power_norm_ste_f32(const float* x, float* codes, size_t n, const double*
   return launch_power_norm_f32(x, codes, n, stats, mean_std, value_limit, quantize_level, (cudaStream_t)stream);
 }
 
+int tae_gru_direction_f32(const float* xproj, const float* w_hh, const float* b_hh, float* out, int32_t B, int32_t L, int32_t H,
+                          int32_t out_stride, int32_t out_offset, int32_t reverse, void* stream) {
+  TAE_REQUIRE(B >= 0 && L >= 1 && H >= 1, "tae_gru_direction_f32: bad shape B=%d L=%d H=%d", B, L, H);
+  TAE_REQUIRE(out_stride >= H && out_offset >= 0 && out_offset + H <= out_stride, "tae_gru_direction_f32: bad output window");
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(xproj && w_hh && b_hh && out, "tae_gru_direction_f32: NULL pointer");
+  return launch_gru_direction(xproj, w_hh, b_hh, out, B, L, H, out_stride, out_offset, reverse, (cudaStream_t)stream);
+}
+
 int tae_awgn_f32(const float* codes, float* received, size_t n, float sigma, uint64_t seed, uint64_t offset, void* stream) {
   if (n == 0) return TAE_OK;
   TAE_REQUIRE(codes && received, "tae_awgn_f32: NULL pointer");

@@ -112,6 +112,9 @@ int enc_pair_pack(const TaeEncConfig& c, const float* params, void* packed, cuda
 int enc_forward_pair(const TaeEncConfig& c, const void* packed, const float* u, const int32_t* perm, const int32_t* inv_perm,
                      float* x_tx, double* stats, int B, void* ws, size_t ws_bytes, cudaStream_t s);
 int launch_add_count(double* stats, double n, cudaStream_t s);
+// ---- DEC_LargeRNN recurrence (tae_gru.cu) ----------------------------------------------------
+int launch_gru_direction(const float* xproj, const float* w_hh, const float* b_hh, float* out, int B, int L, int H, int out_stride,
+                         int out_offset, int reverse, cudaStream_t s);
 // ---- channel + metrics (tae_channel.cu) ------------------------------------------------------
 int launch_awgn(const float* codes, float* received, size_t n, float sigma, uint64_t seed, uint64_t offset, cudaStream_t s);
 int launch_error_count(const float* y_true, const float* y_pred, int B, int L, unsigned long long* counts, cudaStream_t s);

@@ -177,3 +177,102 @@ class DEC_LargeCNN(torch.nn.Module):
         # device->host->device round trip when the tensor is already resident.
         x = received.to(device=self.this_device, dtype=torch.float32).contiguous()
         return self.decode(x)
+
+
+class DEC_LargeRNN(torch.nn.Module):
+    """DeepTurbo decoder with the reference's nn.Module surface (reference decoders.py:16-149): 2*num_iteration stacks of a
+    2-layer bidirectional GRU(2+F -> H) + Linear(2H -> F).  The ``torch.nn.GRU`` children only hold the parameters (same names
+    and shapes as the reference, so its checkpoints load); forward runs ``tae_conv1d_elu_f32`` (K = 1: all input projections
+    of a layer-direction as one pointwise GEMM), ``tae_gru_direction_f32`` (the recurrence, W_hh resident in shared memory)
+    and the interleaver gather.  Inference only (dropout is the identity in eval mode)."""
+
+    def __init__(self, args, p_array):
+        super().__init__()
+        self.args = args
+        use_cuda = not args.no_cuda and torch.cuda.is_available()
+        self.this_device = torch.device("cuda" if use_cuda else "cpu")
+        if getattr(args, "dec_rnn", "gru") != "gru":
+            raise NotImplementedError("turboae_b200.DEC_LargeRNN implements dec_rnn='gru' only (got %r)" % (args.dec_rnn,))
+        if getattr(args, "dec_act", "linear") != "linear":
+            raise NotImplementedError("dec_act=%r: only 'linear' is built" % (args.dec_act,))
+        self.interleaver = Interleaver(args, p_array)
+        self.deinterleaver = DeInterleaver(args, p_array)
+        self.dec1_rnns, self.dec2_rnns = torch.nn.ModuleList(), torch.nn.ModuleList()
+        self.dec1_outputs, self.dec2_outputs = torch.nn.ModuleList(), torch.nn.ModuleList()
+        for idx in range(args.num_iteration):
+            for lst in (self.dec1_rnns, self.dec2_rnns):
+                lst.append(torch.nn.GRU(2 + args.num_iter_ft, args.dec_num_unit, num_layers=2, bias=True, batch_first=True,
+                                        dropout=getattr(args, "dropout", 0.0), bidirectional=True))
+            self.dec1_outputs.append(torch.nn.Linear(2 * args.dec_num_unit, args.num_iter_ft))
+            self.dec2_outputs.append(torch.nn.Linear(2 * args.dec_num_unit, 1 if idx == args.num_iteration - 1 else args.num_iter_ft))
+
+    def set_parallel(self):
+        for lst in (self.dec1_rnns, self.dec2_rnns, self.dec1_outputs, self.dec2_outputs):
+            for idx in range(len(lst)):
+                if not isinstance(lst[idx], ParallelShim):
+                    lst[idx] = ParallelShim(lst[idx])
+
+    def set_interleaver(self, p_array):
+        self.interleaver.set_parray(p_array)
+        self.deinterleaver.set_parray(p_array)
+
+    @staticmethod
+    def _pointwise(x, w, b):
+        """(B, L, Cin) @ w(Cout, Cin)^T + b through the K = 1 case of the conv kernel."""
+        lib = _lib.load()
+        B, L, cin = x.shape
+        cout = w.shape[0]
+        ws_bytes = lib.tae_conv1d_workspace_bytes(cin, cout, 1)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        out = torch.empty((B, L, cout), dtype=torch.float32, device=x.device)
+        _lib.check(lib.tae_conv1d_elu_f32(_lib.ptr(x), _lib.ptr(out), _lib.ptr(w), _lib.ptr(b), B, L, cin, cout, 1, 0, _lib.ptr(ws),
+                                          ws_bytes, _lib.stream_ptr(x.device)))
+        return out
+
+    def _gru_stack(self, gru, x):
+        lib = _lib.load()
+        gru = unwrap(gru)
+        H = gru.hidden_size
+        B, L, _ = x.shape
+        h = x.contiguous()
+        for layer in range(gru.num_layers):
+            out = torch.empty((B, L, 2 * H), dtype=torch.float32, device=x.device)
+            for d, suffix in enumerate(("", "_reverse")):
+                k = "l%d%s" % (layer, suffix)
+                w_ih, w_hh = getattr(gru, "weight_ih_" + k).detach().contiguous(), getattr(gru, "weight_hh_" + k).detach().contiguous()
+                b_ih, b_hh = getattr(gru, "bias_ih_" + k).detach().contiguous(), getattr(gru, "bias_hh_" + k).detach().contiguous()
+                xproj = self._pointwise(h, w_ih, b_ih)
+                _lib.check(lib.tae_gru_direction_f32(_lib.ptr(xproj), _lib.ptr(w_hh), _lib.ptr(b_hh), _lib.ptr(out), B, L, H, 2 * H,
+                                                     d * H, d, _lib.stream_ptr(x.device)))
+            h = out
+        return h
+
+    def forward(self, received):
+        if self.this_device.type != "cuda":
+            raise _lib.TaeError("no CUDA device: turboae_b200 has no CPU fallback")
+        if torch.is_grad_enabled() and (received.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("turboae_b200.DEC_LargeRNN is inference-only so far; wrap the call in torch.no_grad()")
+        a = self.args
+        received = received.to(device=self.this_device, dtype=torch.float32).contiguous()
+        B, L, _ = received.shape
+        with torch.cuda.device(received.device):
+            r_sys, r_par1, r_par2 = received[:, :, 0:1], received[:, :, 1:2], received[:, :, 2:3]
+            r_sys_int = self.interleaver(r_sys.contiguous())
+            prior = torch.zeros((B, L, a.num_iter_ft), dtype=torch.float32, device=received.device)
+            x_plr = None
+            for idx in range(a.num_iteration):
+                last = idx == a.num_iteration - 1
+                lin = unwrap(self.dec1_outputs[idx])
+                x_plr = self._pointwise(self._gru_stack(self.dec1_rnns[idx], torch.cat([r_sys, r_par1, prior], dim=2)),
+                                        lin.weight.detach().contiguous(), lin.bias.detach().contiguous())
+                if a.extrinsic:
+                    x_plr = x_plr - prior
+                x_plr_int = self.interleaver(x_plr)
+                lin = unwrap(self.dec2_outputs[idx])
+                x_plr = self._pointwise(self._gru_stack(self.dec2_rnns[idx], torch.cat([r_sys_int, r_par2, x_plr_int], dim=2)),
+                                        lin.weight.detach().contiguous(), lin.bias.detach().contiguous())
+                if not last:
+                    if a.extrinsic:
+                        x_plr = x_plr - x_plr_int
+                    prior = self.deinterleaver(x_plr)
+            return torch.sigmoid(self.deinterleaver(x_plr))

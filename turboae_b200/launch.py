@@ -67,6 +67,7 @@ def install(reference_root: str) -> None:
     ref_interleavers.DeInterleaver = T.DeInterleaver
     ref_encoders.ENC_interCNN = T.ENC_interCNN
     ref_decoders.DEC_LargeCNN = T.DEC_LargeCNN
+    ref_decoders.DEC_LargeRNN = T.DEC_LargeRNN
     # SameShapeConv1d is imported by name into encoders/decoders at their import time; the replaced classes above
     # build this package's own conv stacks, so cnn_utils is left as is for the out-of-scope variants.
     del ref_cnn_utils

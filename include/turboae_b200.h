@@ -157,6 +157,65 @@ int tae_power_norm_f32(const float* x, float* codes, size_t n, const double* sta
 int tae_power_norm_ste_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std,
                            float value_limit, float quantize_level, void* stream);
 
+/* ---- next row f1 on the tensor cores: training of DEC_LargeCNN (reference trainer.py:33-76: forward, loss.backward()
+ * through decoders.py:219-269 and cnn_utils.py:36-46; bf16 operands, fp32 accumulation, fp32 gradients) ------------------
+ * Activations travel between the three kernels as "group images" in HBM: bf16 [group][chunk][516 rows][8 channels], the
+ * layout the fused kernel keeps in shared memory (rows: 2 halo rows, then per codeword L positions + 2 zero separator
+ * rows; a group holds floor(514 / (L + 2)) codewords).  All image buffers must be ZERO-INITIALISED once by the caller.
+ *   stash_y : [2I stacks][num_layer][groups][13 chunks]   forward output of every conv layer (after ELU)
+ *   stash_x : [2I stacks][groups][1 chunk]                 the 2+F input channels of every stack
+ *   stash_g : like stash_y                                  dL/dz (gradient at the pre-activation) of every conv layer
+ *   stash_d : [2I stacks][groups][1 chunk]                 gradient w.r.t. every Linear output
+ */
+#define TAE_IMG_CHUNK_BYTES 8256
+#define TAE_IMG_CHUNKS 13
+int32_t tae_train_groups(int32_t block_len, int32_t B);
+/* tae_dec_forward(TAE_PRECISION_BF16) that also writes stash_y / stash_x. */
+int tae_dec_forward_train_bf16(const TaeDecConfig* cfg, const void* packed, const float* received, const int32_t* perm,
+                               const int32_t* inv_perm, float* out, float* trace, int32_t B, void* stash_y, void* stash_x,
+                               void* workspace, size_t workspace_bytes, void* stream);
+/* Backward weight image (transposed, tap-flipped conv weights; transposed Linear).  Rebuild after every weight update. */
+size_t tae_dec_bwd_packed_bytes(const TaeDecConfig* cfg);
+int    tae_dec_pack_bwd_bf16(const TaeDecConfig* cfg, const float* params, void* packed_bwd, void* stream);
+/* Backward of conv stack + Linear number `stack` (0 .. 2I-1, order of the flat parameter buffer):
+ *   dlin (B, L, fin) = gradient w.r.t. the Linear output  ->  dxin (B, L, 8) = gradient w.r.t. the 2+F stack inputs
+ *   (columns 2+F.. are zero).  Reads stash_y, writes stash_g and stash_d (all indexed by `stack` internally).      */
+int tae_dec_stack_backward_bf16(const TaeDecConfig* cfg, const void* packed_bwd, int32_t stack, const float* dlin, int32_t fin,
+                                const void* stash_y, void* stash_g, void* stash_d, float* dxin, int32_t B,
+                                void* workspace, size_t workspace_bytes, void* stream);
+/* The same three steps for ENC_interCNN (reference encoders.py:362-373 under trainer.py:74): 3 branches = 3 stacks with one
+ * input channel and Linear(units, 1); x_tx / stats as tae_enc_forward_bf16; dlin (B, L, 1) = gradient w.r.t. the Linear
+ * output of the branch (i.e. d x_tx[:, :, branch] * ELU'), dxin (B, L, 8) = gradient w.r.t. the +-1 input in column 0.  */
+int tae_enc_forward_train_bf16(const TaeEncConfig* cfg, const void* packed, const float* u, const int32_t* perm,
+                               const int32_t* inv_perm, float* x_tx, double* stats, int32_t B, void* stash_y, void* stash_x,
+                               void* workspace, size_t workspace_bytes, void* stream);
+size_t tae_enc_bwd_packed_bytes(const TaeEncConfig* cfg);
+int    tae_enc_pack_bwd_bf16(const TaeEncConfig* cfg, const float* params, void* packed_bwd, void* stream);
+int tae_enc_stack_backward_bf16(const TaeEncConfig* cfg, const void* packed_bwd, int32_t branch, const float* dlin,
+                                const void* stash_y, void* stash_g, void* stash_d, float* dxin, int32_t B,
+                                void* workspace, size_t workspace_bytes, void* stream);
+/* Weight gradients as tensor-core GEMMs over group images (one CTA per job):
+ *   grad[m*s_m + (n0+n)*s_n + t*s_t] += sum_{group in [g0,g1)} sum_rows A[row, m] * B[row + t - taps/2, b_c0*8 + n]
+ * for m < m_valid, n < n_valid, t < taps; bias_grad[m] += sum_rows A[row, m] (NULL to skip; needs 8*b_nc < n_cols).
+ * a_img has 13 chunks per group, b_img has b_chunks; the job reads chunks [b_c0, b_c0 + b_nc) of B (b_nc <= 8).
+ * n_cols = UMMA N: a multiple of 16, 8*b_nc <= n_cols <= 8*(b_nc+1), taps * n_cols <= 512.
+ * Conv layer: A = stash_g layer, B = its input image (stash_y of the layer below, or stash_x), taps = 5, grad = dW
+ * (Cout, Cin, 5): s_m = 5*Cin, s_n = 5, s_t = 1.  Linear: A = last stash_y, B = stash_d, taps = 1, grad = dV (F, units):
+ * s_m = 1, s_n = units.  `jobs_host` is a HOST array; workspace (device) >= 256 + n_jobs * sizeof(TaeWgradJob).     */
+typedef struct TaeWgradJob {
+  const void* a_img;
+  const void* b_img;
+  float* grad;
+  float* bias_grad;
+  int32_t b_chunks, b_c0, b_nc;
+  int32_t taps, n_cols;
+  int32_t m_valid, n_valid, n0;
+  int32_t s_m, s_n, s_t;
+  int32_t g0, g1;
+  int32_t reserved;
+} TaeWgradJob;
+int tae_wgrad_bf16(const TaeWgradJob* jobs_host, int32_t n_jobs, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- next row f2: DEC_LargeRNN (reference decoders.py:16-149, torch.nn.GRU 2 layers bidirectional) -----------------
  * One direction of one GRU layer over a whole batch: xproj (B, L, 3H) = W_ih x + b_ih for every time step (gate order r,
  * z, n; computed with tae_conv1d_elu_f32, K = 1), w_hh (3H, H), b_hh (3H); writes h_t into out[b, t, out_offset .. +H) of

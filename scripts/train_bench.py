@@ -47,6 +47,6 @@ for mode, params in (("decoder", dec.parameters()), ("encoder", enc.parameters()
     ms = shard.max_over_ranks(e0.elapsed_time(e1) / steps, device=dev)
     res[mode] = {"ms_per_step": ms, "codewords_per_s": world * B / (ms * 1e-3), "loss": float(loss), "launches_per_step": (_lib.launch_count() - n0) / steps}
 if rank == 0:
-    print(json.dumps({"what": "training step (fwd+bwd+Adam), enc2/dec5, fp32 CUDA-core kernels", "n_gpus": world, "batch_per_gpu": B, **res}))
+    print(json.dumps({"what": "training step (fwd+bwd+Adam), enc2/dec5, decoder train_precision=%s" % dec.train_precision, "n_gpus": world, "batch_per_gpu": B, **res}))
 if world > 1:
     dist.barrier(); dist.destroy_process_group()

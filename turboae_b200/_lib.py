@@ -24,6 +24,16 @@ class TaeEncConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("block_len", "num_layer", "num_unit", "kernel_size")]
 
 
+class TaeWgradJob(C.Structure):
+    _fields_ = [("a_img", C.c_void_p), ("b_img", C.c_void_p), ("grad", C.c_void_p), ("bias_grad", C.c_void_p)] + \
+               [(n, C.c_int32) for n in ("b_chunks", "b_c0", "b_nc", "taps", "n_cols", "m_valid", "n_valid", "n0",
+                                         "s_m", "s_n", "s_t", "g0", "g1", "reserved")]
+
+
+IMG_CHUNK_BYTES = 8256
+IMG_CHUNKS = 13
+
+
 class TaeError(RuntimeError):
     pass
 
@@ -57,10 +67,22 @@ _SIGNATURES = {
     "tae_power_norm_f32": (C.c_int, [_P, _P, C.c_size_t, _P, _P, _P]),
     "tae_power_norm_ste_f32": (C.c_int, [_P, _P, C.c_size_t, _P, _P, C.c_float, C.c_float, _P]),
     "tae_gru_direction_f32": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "tae_train_groups": (C.c_int32, [C.c_int32, C.c_int32]),
+    "tae_dec_forward_train_bf16": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
+    "tae_dec_bwd_packed_bytes": (C.c_size_t, [C.POINTER(TaeDecConfig)]),
+    "tae_dec_pack_bwd_bf16": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P]),
+    "tae_dec_stack_backward_bf16": (C.c_int, [C.POINTER(TaeDecConfig), _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, C.c_int32, _P,
+                                              C.c_size_t, _P]),
+    "tae_enc_forward_train_bf16": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
+    "tae_enc_bwd_packed_bytes": (C.c_size_t, [C.POINTER(TaeEncConfig)]),
+    "tae_enc_pack_bwd_bf16": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P]),
+    "tae_enc_stack_backward_bf16": (C.c_int, [C.POINTER(TaeEncConfig), _P, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_size_t, _P]),
+    "tae_wgrad_bf16": (C.c_int, [C.POINTER(TaeWgradJob), C.c_int32, _P, C.c_size_t, _P]),
     "tae_awgn_f32": (C.c_int, [_P, _P, C.c_size_t, C.c_float, C.c_uint64, C.c_uint64, _P]),
     "tae_error_count_f32": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     # debug / self-test entry points
     "tae_debug_set_timeline": (None, [_P]),
+    "tae_debug_wgrad_swap": (None, [C.c_int]),
     "tae_debug_probe_rate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int32, _P]),
     "tae_debug_probe_lbo": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "tae_debug_probe_pair": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P]),

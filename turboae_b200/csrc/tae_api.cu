@@ -354,6 +354,112 @@ int tae_power_norm_ste_f32(const float* x, float* codes, size_t n, const double*
   return launch_power_norm_f32(x, codes, n, stats, mean_std, value_limit, quantize_level, (cudaStream_t)stream);
 }
 
+int32_t tae_train_groups(int32_t block_len, int32_t B) {
+  if (block_len < 1 || block_len > 512 || B < 0) return 0;
+  return train_groups(block_len, B);
+}
+
+int tae_dec_forward_train_bf16(const TaeDecConfig* cfg, const void* packed, const float* received, const int32_t* perm,
+                               const int32_t* inv_perm, float* out, float* trace, int32_t B, void* stash_y, void* stash_x,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_dec_config(cfg);
+  if (rc) return rc;
+  const char* why = nullptr;
+  if (!bf16_supported(*cfg, &why)) { set_error("bf16 path: %s", why); return TAE_EUNSUPPORTED; }
+  TAE_REQUIRE(B >= 0, "tae_dec_forward_train_bf16: negative batch %d", B);
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(packed && received && perm && inv_perm && out && workspace && stash_y && stash_x, "tae_dec_forward_train_bf16: NULL pointer");
+  return dec_forward_pair(*cfg, packed, received, perm, inv_perm, out, trace, B, workspace, workspace_bytes, (cudaStream_t)stream,
+                          stash_y, stash_x);
+}
+
+size_t tae_dec_bwd_packed_bytes(const TaeDecConfig* cfg) {
+  if (check_dec_config(cfg)) return 0;
+  const char* why = nullptr;
+  if (!bf16_supported(*cfg, &why)) { set_error("bf16 path: %s", why); return 0; }
+  return dec_pair_bwd_packed_bytes(*cfg);
+}
+
+int tae_dec_pack_bwd_bf16(const TaeDecConfig* cfg, const float* params, void* packed_bwd, void* stream) {
+  int rc = check_dec_config(cfg);
+  if (rc) return rc;
+  const char* why = nullptr;
+  if (!bf16_supported(*cfg, &why)) { set_error("bf16 path: %s", why); return TAE_EUNSUPPORTED; }
+  TAE_REQUIRE(params && packed_bwd, "tae_dec_pack_bwd_bf16: NULL pointer");
+  return dec_pair_pack_bwd(*cfg, params, packed_bwd, (cudaStream_t)stream);
+}
+
+int tae_dec_stack_backward_bf16(const TaeDecConfig* cfg, const void* packed_bwd, int32_t stack, const float* dlin, int32_t fin,
+                                const void* stash_y, void* stash_g, void* stash_d, float* dxin, int32_t B, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  int rc = check_dec_config(cfg);
+  if (rc) return rc;
+  const char* why = nullptr;
+  if (!bf16_supported(*cfg, &why)) { set_error("bf16 path: %s", why); return TAE_EUNSUPPORTED; }
+  TAE_REQUIRE(B >= 0, "tae_dec_stack_backward_bf16: negative batch %d", B);
+  TAE_REQUIRE(stack >= 0 && stack < 2 * cfg->num_iteration, "tae_dec_stack_backward_bf16: stack %d out of range", stack);
+  TAE_REQUIRE(fin >= 1 && fin <= 8, "tae_dec_stack_backward_bf16: fin %d out of range", fin);
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(packed_bwd && dlin && stash_y && stash_g && dxin && workspace, "tae_dec_stack_backward_bf16: NULL pointer");
+  return dec_stack_backward_pair(*cfg, packed_bwd, stack, dlin, fin, stash_y, stash_g, stash_d, dxin, B, workspace, workspace_bytes,
+                                 (cudaStream_t)stream);
+}
+
+int tae_enc_forward_train_bf16(const TaeEncConfig* cfg, const void* packed, const float* u, const int32_t* perm, const int32_t* inv_perm,
+                               float* x_tx, double* stats, int32_t B, void* stash_y, void* stash_x, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  int rc = check_enc_config(cfg);
+  if (rc) return rc;
+  const char* why = nullptr;
+  if (!enc_pair_supported(*cfg, &why)) { set_error("bf16 encoder path: %s", why); return TAE_EUNSUPPORTED; }
+  TAE_REQUIRE(B >= 0, "tae_enc_forward_train_bf16: negative batch %d", B);
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(packed && u && perm && inv_perm && x_tx && stats && workspace && stash_y && stash_x, "tae_enc_forward_train_bf16: NULL pointer");
+  rc = enc_forward_pair(*cfg, packed, u, perm, inv_perm, x_tx, stats, B, workspace, workspace_bytes, (cudaStream_t)stream, stash_y, stash_x);
+  if (rc) return rc;
+  return launch_add_count(stats, (double)B * cfg->block_len * 3, (cudaStream_t)stream);
+}
+
+size_t tae_enc_bwd_packed_bytes(const TaeEncConfig* cfg) {
+  if (check_enc_config(cfg)) return 0;
+  const char* why = nullptr;
+  if (!enc_pair_supported(*cfg, &why)) { set_error("bf16 encoder path: %s", why); return 0; }
+  return enc_pair_bwd_packed_bytes(*cfg);
+}
+
+int tae_enc_pack_bwd_bf16(const TaeEncConfig* cfg, const float* params, void* packed_bwd, void* stream) {
+  int rc = check_enc_config(cfg);
+  if (rc) return rc;
+  const char* why = nullptr;
+  if (!enc_pair_supported(*cfg, &why)) { set_error("bf16 encoder path: %s", why); return TAE_EUNSUPPORTED; }
+  TAE_REQUIRE(params && packed_bwd, "tae_enc_pack_bwd_bf16: NULL pointer");
+  return enc_pair_pack_bwd(*cfg, params, packed_bwd, (cudaStream_t)stream);
+}
+
+int tae_enc_stack_backward_bf16(const TaeEncConfig* cfg, const void* packed_bwd, int32_t branch, const float* dlin, const void* stash_y,
+                                void* stash_g, void* stash_d, float* dxin, int32_t B, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  int rc = check_enc_config(cfg);
+  if (rc) return rc;
+  const char* why = nullptr;
+  if (!enc_pair_supported(*cfg, &why)) { set_error("bf16 encoder path: %s", why); return TAE_EUNSUPPORTED; }
+  TAE_REQUIRE(B >= 0 && branch >= 0 && branch < 3, "tae_enc_stack_backward_bf16: bad batch %d / branch %d", B, branch);
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(packed_bwd && dlin && stash_y && stash_g && dxin && workspace, "tae_enc_stack_backward_bf16: NULL pointer");
+  return enc_stack_backward_pair(*cfg, packed_bwd, branch, dlin, stash_y, stash_g, stash_d, dxin, B, workspace, workspace_bytes,
+                                 (cudaStream_t)stream);
+}
+
+static int g_wgrad_swap = 0;
+void tae_debug_wgrad_swap(int v) { g_wgrad_swap = v; }
+
+int tae_wgrad_bf16(const TaeWgradJob* jobs_host, int32_t n_jobs, void* workspace, size_t workspace_bytes, void* stream) {
+  TAE_REQUIRE(n_jobs >= 0, "tae_wgrad_bf16: negative job count");
+  if (n_jobs == 0) return TAE_OK;
+  TAE_REQUIRE(jobs_host && workspace, "tae_wgrad_bf16: NULL pointer");
+  return launch_wgrad(jobs_host, n_jobs, workspace, workspace_bytes, g_wgrad_swap, (cudaStream_t)stream);
+}
+
 int tae_gru_direction_f32(const float* xproj, const float* w_hh, const float* b_hh, float* out, int32_t B, int32_t L, int32_t H,
                           int32_t out_stride, int32_t out_offset, int32_t reverse, void* stream) {
   TAE_REQUIRE(B >= 0 && L >= 1 && H >= 1, "tae_gru_direction_f32: bad shape B=%d L=%d H=%d", B, L, H);

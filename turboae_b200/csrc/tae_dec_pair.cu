@@ -31,6 +31,7 @@
 #include <cstdlib>
 
 #include "tae_common.cuh"
+#include "tae_umma.cuh"
 
 #ifndef TAE_TIMELINE
 #define TAE_TIMELINE 0      // 1: record clock64 stamps (scripts/dec_timeline.py); costs code size, keep off in production
@@ -65,6 +66,9 @@ constexpr uint32_t SLOT_B = KS_PER_SLOT * 2 * WCHUNK_B;         // 7168
 constexpr uint32_t L0_B = KS_L0 * 2 * WCHUNK_B;                 // 5376
 constexpr uint32_t LIN_WCHUNK_B = LIN_NHALF * ROW_B;            // 128
 constexpr uint32_t LIN_B = KS_LIN * 2 * LIN_WCHUNK_B;           // 1792
+constexpr int KS_FIN_SLOT = 16;                                 // backward: the units -> (2+F) transposed conv, 2 slots of 16 k-steps
+constexpr uint32_t FIN_B = KS_FIN_SLOT * 2 * LIN_WCHUNK_B;      // 4096
+constexpr int IMG_CHUNKS = 13;                                  // chunks of a stashed group image (channels 0..103)
 constexpr int NS = 12;                                          // weight ring slots (a layer uses 8; 4 are prefetch headroom)
 #ifndef TAE_EPI_WARPS
 #define TAE_EPI_WARPS 16
@@ -81,10 +85,6 @@ constexpr int N_THREADS = 32 * (1 + N_TILES + N_EPI_WARPS);      // 672
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TMEM_LIN_COL = N_TILES * NPAD;               // 448
 
-// instruction descriptor (kind::f16): D fp32, A/B bf16, both K-major
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
 
 struct Smem {
   uint32_t act, comb, xin[2], ones, wslot, perm, inv_perm, bars, tmem_ptr, total;
@@ -130,260 +130,23 @@ struct PairArgs {
   double* stats;               // enc: running (sum, sum of squares)
   uint32_t stack_bytes;        // bytes of one stack's image (both halves)
   unsigned long long* tl;      // optional timeline buffer (tae_debug_set_timeline): clock64 stamps of cluster 0, leader CTA
+  // training (group images in HBM, bf16 [group][chunk][516 rows][8 channels]; see tae_wgrad.cu)
+  uint8_t* stash_y;            // MODE 0: written, [stack][layer][group][13 chunks]; MODE 1: read, this stack's [layer][group][13]
+  uint8_t* stash_x;            // MODE 0: the stack inputs, [stack][group][1 chunk]; MODE 1: the dlin image of this stack, [group][1]
+  uint8_t* stash_g;            // MODE 1: written, gradients at the pre-activations, [layer][group][13 chunks]
+  const float* dlin;           // MODE 1: gradient w.r.t. the Linear output (B, L, fin)
+  float* dxin;                 // MODE 1: gradient w.r.t. the stack input (B, L, 8)
+  int fin;
 };
 
-// ------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
+// ELU'(z) from the bf16 forward output y packed two per word: y + 1 where y < 0, else 1 (cnn_utils.py:24-25 backward)
+__device__ __forceinline__ float elu_grad_lo(uint32_t ypair) {
+  const float y = __uint_as_float(ypair << 16);
+  return y < 0.f ? y + 1.f : 1.f;
 }
-__device__ __forceinline__ uint32_t cluster_id_x() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ uint32_t n_clusters_x() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// arrive (release at cluster scope) on the barrier at the same offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
-      "r"(rank)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// plain arrive on the barrier at the same offset in CTA `rank` (CTA-scope release: the data it publishes stays in
-// the arriving CTA's own shared memory and was already made visible to the async proxy by fence.proxy.async)
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
-      "r"(rank)
-      : "memory");
-}
-// arrive on the LEADER's barrier: a plain local arrive when executed in the leader CTA itself
-__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar, uint32_t my_rank) {
-  if (my_rank == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-  else mbar_arrive_remote(bar, 0);
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok;
-}
-__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok;
-}
-// Bounded waits: a protocol bug traps (context error) instead of hanging the GPU box.  The slow path lives in ONE
-// out-of-line function: the kernel must stay small enough for the instruction cache (rarely executed straight-line
-// code was measured at ~20 cycles per instruction when it did not).
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* err, int code) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      if (err) atomicExch(err, code);
-      __threadfence_system();
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
-  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, err, code);
-}
-__device__ __forceinline__ void mbar_wait_unused(uint32_t bar, uint32_t parity, int* err, int code) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      if (err) atomicExch(err, code);
-      __threadfence_system();
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* err, int code) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      if (err) atomicExch(err, code);
-      __threadfence_system();
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-template <int CG>
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  if (CG == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  } else {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-}
-template <int CG>
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  if (CG == 1)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-  else
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-
-// Shared-memory matrix descriptor, no swizzle, K-major: rows 16 bytes apart inside an 8-row core matrix,
-// SBO = byte distance between 8-row groups (128: rows are contiguous), LBO = byte distance between the two
-// 8-element K chunks of one UMMA_K = 16 slice.  Bits [46,48) = 1: Blackwell descriptor version.
-// low word (start address, LBO) and full descriptor (high word = SBO 128 B + version, a constant)
-__device__ __forceinline__ uint32_t dlo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); }
-__device__ __forceinline__ uint64_t dfull(uint32_t lo) { return ((uint64_t)((128u >> 4) | (1u << 14)) << 32) | lo; }
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)(128u >> 4) << 32) |
-         (1ull << 46);
-}
-
-template <int CG>
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  if (CG == 1) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-  }
-}
-// Arrives on the mbarrier (same offset in every CTA of `mask`) when all previously issued MMAs have completed.
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"(mask)
-               : "memory");
-}
-__device__ __forceinline__ void umma_commit_1(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// true in exactly one lane of a converged warp (ptxas keeps the surrounding values in uniform registers)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred px;\n\t"
-      "elect.sync _|px, 0xffffffff;\n\t"
-      "selp.b32 %0, 1, 0, px;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
-  uint32_t r;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-  return r;
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float fast_exp2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float elu_fast(float v) {
-  const float e = fast_exp2(v * 1.4426950408889634f) - 1.0f;
-  return v > 0.f ? v : e;
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
-  asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
-}
-__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
-  asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
-}
-__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint16_t ld_shared_u16(uint32_t addr) {
-  uint16_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ uint16_t bf16_bits(float v) {
-  __nv_bfloat16 t = __float2bfloat16_rn(v);
-  return *reinterpret_cast<uint16_t*>(&t);
+__device__ __forceinline__ float elu_grad_hi(uint32_t ypair) {
+  const float y = __uint_as_float(ypair & 0xFFFF0000u);
+  return y < 0.f ? y + 1.f : 1.f;
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_THREADS) : "memory"); }
 
@@ -477,10 +240,81 @@ __global__ void pack_pair_kernel(const float* __restrict__ params, __nv_bfloat16
   }
 }
 
+// K element e (0..15) of k-step ks of a units->units operand sequence -> (channel, tap); false: bias / padding element
+__device__ __forceinline__ bool conv_k_map(int ks, int e, int* c, int* t) {
+  if (ks < 30) { *t = ks / 6; *c = 16 * (ks % 6) + e; return true; }
+  if (ks == 30) { *t = e >> 2; *c = N_REG_CH + (e & 3); return true; }
+  if (e < 4) { *t = 4; *c = N_REG_CH + e; return true; }
+  return false;
+}
+
+// Backward weight image of one stack (MODE 1 of the fused kernel), same slot structure as the forward image:
+//   slot 0   : the transposed Linear as a "layer 0" (F -> units): only the centre tap is non-zero, no bias;
+//   8 slots per units->units layer, layers in REVERSE order, weights transposed and tap-flipped:
+//              dx[l, c] = sum_o sum_t W[o, c, 4 - t] g[l + t - 2, o]                     (backward of cnn_utils.py:42-44)
+//   2 slots  : the transposed first layer (units -> cin0), 16 k-steps each, N = 16 (8 columns per CTA half).
+__global__ void pack_bwd_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ img,
+                                const DecStackLayout* __restrict__ lay, int n_stacks, int n_layer, int units, int cin0,
+                                uint32_t stack_elems) {
+  const size_t total = (size_t)n_stacks * stack_elems;
+  const uint32_t l0_elems = 2 * L0_B / 2;
+  const uint32_t conv_elems = (uint32_t)(n_layer - 1) * SLOTS_CONV * (2 * SLOT_B / 2);
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int st = (int)(idx / stack_elems);
+    uint32_t r = (uint32_t)(idx % stack_elems);
+    const DecStackLayout& S = lay[st];
+    float v = 0.f;
+    if (r < l0_elems) {
+      const int half = r / (L0_B / 2);
+      r %= (L0_B / 2);
+      const int ks = r / (2 * NHALF * 8), ch = (r / (NHALF * 8)) & 1, n = (r / 8) % NHALF, e8 = r % 8;
+      const int o = half * NHALF + n, t = 2 * ks + ch, f = e8;
+      if (o < units && t == 2 && f < S.fout) v = params[S.lin_w_off + (size_t)f * units + o];
+    } else if (r < l0_elems + conv_elems) {
+      r -= l0_elems;
+      const uint32_t slot_elems = 2 * SLOT_B / 2;
+      const int sl = r / slot_elems;
+      r %= slot_elems;
+      const int half = r / (SLOT_B / 2);
+      r %= (SLOT_B / 2);
+      const int j = n_layer - 1 - sl / SLOTS_CONV;                     // forward layer whose gradient this step propagates
+      const int ks = (sl % SLOTS_CONV) * KS_PER_SLOT + r / (2 * NHALF * 8);
+      const int ch = (r / (NHALF * 8)) & 1, n = (r / 8) % NHALF, e8 = r % 8;
+      const int cdst = half * NHALF + n;                               // output channel of the backward step = input channel of layer j
+      int c, t;
+      if (cdst < units && conv_k_map(ks, ch * 8 + e8, &c, &t) && c < units)
+        v = params[S.conv[j].w_off + ((size_t)c * units + cdst) * TAPS + (TAPS - 1 - t)];
+    } else {
+      r -= l0_elems + conv_elems;
+      const uint32_t slot_elems = 2 * FIN_B / 2;
+      const int sl = r / slot_elems;
+      r %= slot_elems;
+      const int half = r / (FIN_B / 2);
+      r %= (FIN_B / 2);
+      const int ks = sl * KS_FIN_SLOT + r / (2 * LIN_NHALF * 8);
+      const int ch = (r / (LIN_NHALF * 8)) & 1, n = (r / 8) % LIN_NHALF, e8 = r % 8;
+      const int qdst = half * LIN_NHALF + n;                           // input channel of the first layer
+      int c, t;
+      if (qdst < cin0 && conv_k_map(ks, ch * 8 + e8, &c, &t) && c < units)
+        v = params[S.conv[0].w_off + ((size_t)c * cin0 + qdst) * TAPS + (TAPS - 1 - t)];
+    }
+    img[idx] = __float2bfloat16_rn(v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // the fused decoder kernel (cluster of 2)
 // ------------------------------------------------------------------------------------------
+// MODE 0: forward (DEC_LargeCNN / ENC_interCNN schedule; optionally stashes every layer's output for training).
+// MODE 1: backward of ONE conv stack + Linear: the same pipeline run on gradients -- "layer 0" is the transposed Linear
+//         (F -> units, centre tap only), the units -> units layers use the transposed, tap-flipped weights, every epilogue
+//         multiplies by ELU'(y) taken from the stashed forward output (ELU'(z) = y + 1 for y < 0, else 1) and writes the
+//         pre-activation gradient g to shared memory (next layer's operand) and to HBM (weight-gradient kernel); the last
+//         step is the transposed first layer (units -> 2+F, 5 taps, N = 16).
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pair_kernel(const PairArgs a) {
+  constexpr bool FWD = (MODE != 1);          // MODE 2 = MODE 0 + stash of every layer's output (training forward)
+  constexpr bool STASH = (MODE == 2);
   extern __shared__ __align__(1024) uint8_t smem[];
   const Smem S = make_smem(a.F);
   const uint32_t sbase = smem_u32(smem);
@@ -488,7 +322,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
   const uint32_t rank = cluster_ctarank();
   const int L = a.L, F = a.F, CW_ROWS = a.L + 2;
   const int n_stacks = a.n_stacks;
-  const int slots_per_stack = 2 + SLOTS_CONV * (a.n_layer - 1);    // weight transfers: layer 0, 8 per layer, Linear
+  // weight transfers of a stack: layer 0, 8 per units->units layer, then the Linear (MODE 0) or 2 slots of the transposed
+  // first layer (MODE 1)
+  const int slots_per_stack = (FWD ? 2 : 3) + SLOTS_CONV * (a.n_layer - 1);
 
   auto bar = [&](int i) { return sbase + S.bars + 8u * (uint32_t)i; };
 
@@ -500,7 +336,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
     for (int m = 0; m < N_TILES; ++m) { mbar_init(bar(B_ACC + m), 1); mbar_init(bar(B_ACT + m), 2 * N_EPI_WARPS); }
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < L; i += N_THREADS) {
+  for (int i = threadIdx.x; i < L && FWD; i += N_THREADS) {
     st_shared_u16(sbase + S.perm + 2 * i, (uint16_t)a.perm[i]);
     st_shared_u16(sbase + S.inv_perm + 2 * i, (uint16_t)a.inv_perm[i]);
   }
@@ -528,7 +364,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
         for (int st = 0; st < n_stacks; ++st) {
           const uint8_t* src = a.wimg + (size_t)st * a.stack_bytes;
           for (int i = 0; i < slots_per_stack; ++i) {
-            const uint32_t bytes = (i == 0) ? L0_B : (i == slots_per_stack - 1 ? LIN_B : SLOT_B);
+            const uint32_t bytes = (i == 0) ? L0_B : (i <= SLOTS_CONV * (a.n_layer - 1) ? SLOT_B : (FWD ? LIN_B : FIN_B));
             mbar_wait(bar(B_WEMPTY + pos), phase ^ 1, a.err, 1);
             mbar_arrive_expect_tx(bar(B_WFULL + pos), bytes);
             bulk_g2s(sbase + S.wslot + pos * SLOT_B, src + rank * bytes, bytes, bar(B_WFULL + pos));
@@ -622,6 +458,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
                   wlo += SLOT_B / 16;
                   if (++p == NS) { p = 0; ph ^= 1; wlo -= NS * SLOT_B / 16; }
                 }
+              } else if (MODE == 1) {
+                // transposed first layer: all 5 taps x units channels (the conv layers' A sequence) onto N = 16 columns
+                const uint32_t act_lo = dlo(act + rowoff, CHUNK_B);
+                const uint32_t c30_lo = dlo(comb + rowoff, 2 * ROW_B);
+                const uint32_t c31_lo = dlo(comb + rowoff + 4 * ROW_B, (ones + 2 * ROW_B) - (comb + 4 * ROW_B));
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                  mbar_wait(bar(B_WFULL + p), ph, a.err, 3);
+                  tc_fence_after();
+                  const uint32_t wl = dlo(sbase + S.wslot + p * SLOT_B, LIN_WCHUNK_B);
+                  if (elect_one()) {
+#pragma unroll
+                    for (int k16 = 0; k16 < KS_FIN_SLOT; ++k16) {
+                      const int ks = s * KS_FIN_SLOT + k16;
+                      const uint32_t alo = ks < 30 ? act_lo + ((uint32_t)(2 * (ks % 6)) * CHUNK_B + (uint32_t)(ks / 6) * ROW_B) / 16
+                                                   : (ks == 30 ? c30_lo : c31_lo);
+                      umma_bf16<2>(tmem_base + TMEM_LIN_COL + m * LIN_N, dfull(alo), dfull(wl + (uint32_t)(k16 * 2 * LIN_WCHUNK_B) / 16),
+                                   IDESC_LIN, ks > 0);
+                    }
+                    umma_commit_pair(bar(B_WEMPTY + p), 3);
+                    if (s == 1) umma_commit_pair(bar(B_ACC + m), 3);
+                  }
+                  __syncwarp();
+                  if (++p == NS) { p = 0; ph ^= 1; }
+                }
               } else {
                 mbar_wait(bar(B_WFULL + p), ph, a.err, 3);
                 tc_fence_after();
@@ -641,7 +502,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
               if (stamp) a.tl[(step * 4 + m) * 8 + 2] = clock64();
             }
             // advance the ring past this layer's slots
-            const int n_adv = conv ? SLOTS_CONV : 1;
+            const int n_adv = conv ? SLOTS_CONV : ((MODE == 1 && layer == a.n_layer) ? 2 : 1);
             for (int s = 0; s < n_adv; ++s)
               if (++pos == NS) { pos = 0; wphase ^= 1; }
           }
@@ -671,7 +532,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
       // ---- group start: stack inputs (prior channels = 0, decoders.py:227), ones chunk ----------------------------------------
       for (uint32_t i = tid * 16; i < 3 * CHUNK_B; i += N_EPI_THREADS * 16) st_shared_v4(sbase + S.xin[0] + i, 0u, 0u, 0u, 0u);
       epi_bar_sync();
-      if (a.enc) {
+      const bool grp_ok = grp < a.n_groups;               // the odd group of the last pair does not exist: no stash traffic
+      if (MODE == 1) {
+        // gradient w.r.t. the Linear output, as the 8-channel operand chunk of the first (transposed Linear) step
+        for (int i = tid; i < n_cw * L; i += N_EPI_THREADS) {
+          const int c = i / L, l = i % L;
+          const float* d = a.dlin + ((size_t)(cw0 + c) * L + l) * a.fin;
+          float v[8];
+#pragma unroll
+          for (int f = 0; f < 8; ++f) v[f] = f < a.fin ? d[f] : 0.f;
+          st_shared_v4(sbase + S.xin[0] + (uint32_t)(c * CW_ROWS + l + 2) * ROW_B, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                       pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+      } else if (a.enc) {
         for (int i = tid; i < n_cw * L; i += N_EPI_THREADS) {
           const int c = i / L, l = i % L;
           const uint16_t x = bf16_bits(2.0f * a.u[(size_t)(cw0 + c) * L + l] - 1.0f);                  // encoders.py:362
@@ -698,6 +571,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
       epi_bar_sync();
       if (lane == 0)
         for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_ACT + m), rank);
+      if (MODE == 1 && a.stash_x && grp_ok)
+        for (int i = tid; i < BUF_ROWS; i += N_EPI_THREADS) {
+          uint32_t x0, x1, x2, x3;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(sbase + S.xin[0] + (uint32_t)i * ROW_B) : "memory");
+          *reinterpret_cast<uint4*>(a.stash_x + ((size_t)grp * BUF_ROWS + i) * ROW_B) = make_uint4(x0, x1, x2, x3);
+        }
 
       // Deferred rows: the last two rows of tile m are still read by the MMAs of tile m+1 (taps 0, 1), so the two
       // lanes that own them keep their packed outputs in registers and store them at the start of the next tile.
@@ -709,7 +588,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
         for (int layer = 0; layer <= a.n_layer; ++layer, ++step) {
           const uint32_t par = step & 1;
           const bool last_step = (st == n_stacks - 1 && layer == a.n_layer);
-          if (layer == a.n_layer && a.enc) {
+          if (MODE == 1 && layer == a.n_layer) {
+            // -- gradient w.r.t. the stack input (transposed first layer): one (8-float) row per position -----------------
+#pragma unroll
+            for (int m = 0; m < N_TILES; ++m) mbar_wait(bar(B_ACC + m), par, a.err, 6);
+            tc_fence_after();
+            if (part == 0) {
+#pragma unroll 1
+              for (int m = 0; m < N_TILES; ++m) {
+                uint32_t r[8];
+                tmem_ld8(lane_addr + TMEM_LIN_COL + (uint32_t)(m * LIN_N), r);
+                tmem_ld_wait();
+                if (!((vmask >> m) & 1u)) continue;
+                const int g_row = 128 * m + 32 * q + lane;
+                const int g_cw = g_row / CW_ROWS, g_l = g_row - g_cw * CW_ROWS;
+                float4* dst = reinterpret_cast<float4*>(a.dxin + ((size_t)(cw0 + g_cw) * L + g_l) * 8);
+                dst[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
+                dst[1] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
+              }
+            }
+            if (!last_step) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0)
+                for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_ACT + m), rank);
+            }
+            continue;
+          }
+          if (FWD && layer == a.n_layer && a.enc) {
             // -- ENC_interCNN tail: x_tx[:, :, branch] = ELU(Linear(h)) (encoders.py:364,367,371) + the power sums ------
 #pragma unroll
             for (int m = 0; m < N_TILES; ++m) mbar_wait(bar(B_ACC + m), par, a.err, 6);
@@ -818,20 +724,48 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
             if (stamp) a.tl[(step * 4 + 0) * 8 + 5] = clock64();
             continue;
           }
+          // training: this layer's group image in HBM (MODE 0: stash of the outputs; MODE 1: forward outputs in, gradients out)
+          uint8_t* img_out = nullptr;
+          const uint8_t* img_y = nullptr;
+          if (FWD) {
+            if (STASH && a.stash_y && grp_ok) img_out = a.stash_y + ((size_t)(st * a.n_layer + layer) * a.n_groups + grp) * (IMG_CHUNKS * CHUNK_B);
+          } else if (grp_ok) {
+            const size_t off = ((size_t)(a.n_layer - 1 - layer) * a.n_groups + grp) * (IMG_CHUNKS * CHUNK_B);
+            img_y = a.stash_y + off;
+            img_out = a.stash_g + off;
+          }
 #pragma unroll 1
           for (int m = 0; m < N_TILES; ++m) {
             const bool stamp = TAE_TIMELINE && a.tl && pr == 0 && rank == 0 && lane == 0 && ew == 0;
             if (stamp && ew == 0) a.tl[(step * 4 + m) * 8 + 3] = clock64();
+            const int g_row = 128 * m + 32 * q + lane;
+            const uint32_t brow = (uint32_t)(g_row + 2);
+            const bool has_comb = (part == PARTS - 1);               // this part also owns channels 96..99
+            uint4 yv[CPP];
+            uint2 yc = make_uint2(0u, 0u);
+            if (MODE == 1) {
+              // forward outputs of this row (ELU' comes from them), requested before the accumulators are waited for
+#pragma unroll
+              for (int c = 0; c < CPP; ++c)
+                yv[c] = img_y ? __ldg(reinterpret_cast<const uint4*>(img_y + (size_t)(part * CPP + c) * CHUNK_B + brow * ROW_B)) : make_uint4(0u, 0u, 0u, 0u);
+              if (has_comb && img_y) yc = __ldg(reinterpret_cast<const uint2*>(img_y + (size_t)N_REG_CHUNKS * CHUNK_B + brow * ROW_B));
+            }
             mbar_wait(bar(B_ACC + m), par, a.err, 6);
             tc_fence_after();
             if (stamp) a.tl[(step * 4 + m) * 8 + (ew == 0 ? 4 : 6)] = clock64();
-            const int g_row = 128 * m + 32 * q + lane;
+            if (STASH && layer == 0 && m == 0 && a.stash_x && grp_ok) {
+              // the stack input (sys, parity, priors as the stack saw them): complete since the MMAs of layer 0 were released
+              const uint32_t xsrc = sbase + S.xin[a.enc ? (st == 2) : (st & 1)];
+              for (int i = tid; i < BUF_ROWS; i += N_EPI_THREADS) {
+                uint32_t x0, x1, x2, x3;
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(xsrc + (uint32_t)i * ROW_B) : "memory");
+                *reinterpret_cast<uint4*>(a.stash_x + (((size_t)st * a.n_groups + grp) * BUF_ROWS + i) * ROW_B) = make_uint4(x0, x1, x2, x3);
+              }
+            }
             const bool valid = (vmask >> m) & 1u;
             {
               const bool owns_tail = (q == 3) && (lane >= 30);
               const bool defer = owns_tail && (m < N_TILES - 1);
-              const bool has_comb = (part == PARTS - 1);               // this part also owns channels 96..99
-              const uint32_t brow = (uint32_t)(g_row + 2);
               const uint32_t col0 = (uint32_t)(m * NPAD + part * CPP * 8);
               const uint32_t act_part = sbase + S.act + (uint32_t)(part * CPP) * CHUNK_B;
               uint32_t r[CPP * 8 + 8];
@@ -856,9 +790,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
 #pragma unroll
               for (int c = 0; c < CPP; ++c) {
                 uint32_t p[4];
+                if (FWD) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  p[j] = pack_bf16x2(elu_fast(__uint_as_float(r[8 * c + 2 * j])), elu_fast(__uint_as_float(r[8 * c + 2 * j + 1]))) & keep;
+                  for (int j = 0; j < 4; ++j)
+                    p[j] = pack_bf16x2(elu_fast(__uint_as_float(r[8 * c + 2 * j])), elu_fast(__uint_as_float(r[8 * c + 2 * j + 1]))) & keep;
+                } else {
+                  const uint32_t yw[4] = {yv[c].x, yv[c].y, yv[c].z, yv[c].w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    p[j] = pack_bf16x2(__uint_as_float(r[8 * c + 2 * j]) * elu_grad_lo(yw[j]), __uint_as_float(r[8 * c + 2 * j + 1]) * elu_grad_hi(yw[j])) & keep;
+                }
+                if (img_out) *reinterpret_cast<uint4*>(img_out + (size_t)(part * CPP + c) * CHUNK_B + brow * ROW_B) = make_uint4(p[0], p[1], p[2], p[3]);
                 if (defer) {
                   dq[4 * c] = p[0]; dq[4 * c + 1] = p[1]; dq[4 * c + 2] = p[2]; dq[4 * c + 3] = p[3];
                 } else {
@@ -866,8 +808,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
                 }
               }
               if (has_comb) {
-                const uint32_t p0 = pack_bf16x2(elu_fast(__uint_as_float(r[8 * CPP])), elu_fast(__uint_as_float(r[8 * CPP + 1]))) & keep;
-                const uint32_t p1 = pack_bf16x2(elu_fast(__uint_as_float(r[8 * CPP + 2])), elu_fast(__uint_as_float(r[8 * CPP + 3]))) & keep;
+                uint32_t p0, p1;
+                if (FWD) {
+                  p0 = pack_bf16x2(elu_fast(__uint_as_float(r[8 * CPP])), elu_fast(__uint_as_float(r[8 * CPP + 1]))) & keep;
+                  p1 = pack_bf16x2(elu_fast(__uint_as_float(r[8 * CPP + 2])), elu_fast(__uint_as_float(r[8 * CPP + 3]))) & keep;
+                } else {
+                  p0 = pack_bf16x2(__uint_as_float(r[8 * CPP]) * elu_grad_lo(yc.x), __uint_as_float(r[8 * CPP + 1]) * elu_grad_hi(yc.x)) & keep;
+                  p1 = pack_bf16x2(__uint_as_float(r[8 * CPP + 2]) * elu_grad_lo(yc.y), __uint_as_float(r[8 * CPP + 3]) * elu_grad_hi(yc.y)) & keep;
+                }
+                if (img_out) *reinterpret_cast<uint4*>(img_out + (size_t)N_REG_CHUNKS * CHUNK_B + brow * ROW_B) = make_uint4(p0, p1, 0u, 0u);
                 if (defer) {
                   dq[4 * CPP] = p0; dq[4 * CPP + 1] = p1;
                 } else {
@@ -1104,6 +1053,9 @@ static unsigned long long* g_timeline = nullptr;
 static uint32_t stack_image_bytes(const TaeDecConfig& c) {
   return 2 * (L0_B + (uint32_t)(c.num_layer - 1) * SLOTS_CONV * SLOT_B + LIN_B);
 }
+static uint32_t stack_bwd_image_bytes(const TaeDecConfig& c) {
+  return 2 * (L0_B + (uint32_t)(c.num_layer - 1) * SLOTS_CONV * SLOT_B + 2 * FIN_B);
+}
 
 }  // namespace
 
@@ -1152,8 +1104,12 @@ static int pair_launch_setup(const TaeDecConfig&, int* n_sm_out) {
     if (e != cudaSuccess) { set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
     if (prop.major != 10) { set_error("bf16 path needs an sm_100a device (found sm_%d%d)", prop.major, prop.minor); return TAE_EUNSUPPORTED; }
     n_sm = prop.multiProcessorCount;
-    e = cudaFuncSetAttribute(dec_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)make_smem(5).total);
+    e = cudaFuncSetAttribute(dec_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)make_smem(5).total);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dec_pair_kernel): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+    e = cudaFuncSetAttribute(dec_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)make_smem(5).total);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dec_pair_kernel<1>): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+    e = cudaFuncSetAttribute(dec_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)make_smem(5).total);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dec_pair_kernel<2>): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
     attr_done = true;
   }
   *n_sm_out = n_sm;
@@ -1161,7 +1117,8 @@ static int pair_launch_setup(const TaeDecConfig&, int* n_sm_out) {
 }
 
 int dec_forward_pair(const TaeDecConfig& c, const void* packed, const float* received, const int32_t* perm,
-                     const int32_t* inv_perm, float* out, float* trace, int B, void* ws, size_t ws_bytes, cudaStream_t s) {
+                     const int32_t* inv_perm, float* out, float* trace, int B, void* ws, size_t ws_bytes, cudaStream_t s,
+                     void* stash_y, void* stash_x) {
   if (ws_bytes < 256) { set_error("tae_dec_forward(bf16): workspace %zu < 256 bytes", ws_bytes); return TAE_EWORKSPACE; }
   const Smem S = make_smem(c.num_iter_ft);
   int n_sm = 0;
@@ -1185,9 +1142,68 @@ int dec_forward_pair(const TaeDecConfig& c, const void* packed, const float* rec
   a.n_pairs = (a.n_groups + 1) / 2;
   a.stack_bytes = stack_image_bytes(c);
   a.tl = g_timeline;
+  a.stash_y = reinterpret_cast<uint8_t*>(stash_y);
+  a.stash_x = reinterpret_cast<uint8_t*>(stash_x);
   const int n_clusters = std::min(a.n_pairs, n_sm / 2);
-  dec_pair_kernel<<<2 * n_clusters, N_THREADS, S.total, s>>>(a);
+  if (stash_y) dec_pair_kernel<2><<<2 * n_clusters, N_THREADS, S.total, s>>>(a);
+  else dec_pair_kernel<0><<<2 * n_clusters, N_THREADS, S.total, s>>>(a);
   return after_launch("dec_pair_kernel");
+}
+
+// ---- training: group-image geometry, backward weight image, backward of one stack ---------------------------------
+int train_groups(int block_len, int B) {
+  const int cpg = (GROUP_ROWS + 2) / (block_len + 2);
+  return (B + cpg - 1) / cpg;
+}
+
+size_t dec_pair_bwd_packed_bytes(const TaeDecConfig& c) { return (size_t)2 * c.num_iteration * stack_bwd_image_bytes(c); }
+
+int dec_pair_pack_bwd(const TaeDecConfig& c, const float* params, void* packed, cudaStream_t s) {
+  DecStackLayout lay[64];
+  dec_layout(c, lay);
+  const int n_stacks = 2 * c.num_iteration;
+  DecStackLayout* d_lay = nullptr;
+  cudaError_t e = cudaMallocAsync(&d_lay, sizeof(DecStackLayout) * n_stacks, s);
+  if (e != cudaSuccess) { set_error("cudaMallocAsync: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+  e = cudaMemcpyAsync(d_lay, lay, sizeof(DecStackLayout) * n_stacks, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) { set_error("cudaMemcpyAsync: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+  const uint32_t stack_elems = stack_bwd_image_bytes(c) / 2;
+  const size_t total = (size_t)n_stacks * stack_elems;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  pack_bwd_kernel<<<blocks, 256, 0, s>>>(params, reinterpret_cast<__nv_bfloat16*>(packed), d_lay, n_stacks, c.num_layer,
+                                         c.num_unit, 2 + c.num_iter_ft, stack_elems);
+  int rc = after_launch("pack_bwd_kernel");
+  cudaFreeAsync(d_lay, s);
+  return rc;
+}
+
+// Backward of stack `stack` (0 .. 2I-1): dlin (B, L, fin) -> dxin (B, L, 8); reads the stack's stashed forward outputs,
+// writes the pre-activation gradients (stash_g, same indexing as stash_y) and the dlin image (stash_d: [stack][group][1]).
+int dec_stack_backward_pair(const TaeDecConfig& c, const void* packed_bwd, int stack, const float* dlin, int fin, const void* stash_y,
+                            void* stash_g, void* stash_d, float* dxin, int B, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (ws_bytes < 256) { set_error("tae_dec_stack_backward_bf16: workspace %zu < 256 bytes", ws_bytes); return TAE_EWORKSPACE; }
+  const Smem S = make_smem(c.num_iter_ft);
+  int n_sm = 0;
+  {
+    int rc = pair_launch_setup(c, &n_sm);
+    if (rc) return rc;
+  }
+  PairArgs a{};
+  a.B = B; a.L = c.block_len; a.F = c.num_iter_ft; a.n_stacks = 1; a.n_layer = c.num_layer;
+  a.cw_per_group = (GROUP_ROWS + 2) / (c.block_len + 2);
+  a.n_groups = (B + a.cw_per_group - 1) / a.cw_per_group;
+  a.n_pairs = (a.n_groups + 1) / 2;
+  a.stack_bytes = stack_bwd_image_bytes(c);
+  a.wimg = reinterpret_cast<const uint8_t*>(packed_bwd) + (size_t)stack * a.stack_bytes;
+  a.err = reinterpret_cast<int*>(align_up(reinterpret_cast<uintptr_t>(ws), 16));
+  const size_t layer_img = (size_t)a.n_groups * IMG_CHUNKS * CHUNK_B;
+  a.stash_y = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(stash_y)) + (size_t)stack * c.num_layer * layer_img;
+  a.stash_g = reinterpret_cast<uint8_t*>(stash_g) + (size_t)stack * c.num_layer * layer_img;
+  a.stash_x = stash_d ? reinterpret_cast<uint8_t*>(stash_d) + (size_t)stack * a.n_groups * CHUNK_B : nullptr;
+  a.dlin = dlin; a.dxin = dxin; a.fin = fin;
+  const int n_clusters = std::min(a.n_pairs, n_sm / 2);
+  dec_pair_kernel<1><<<2 * n_clusters, N_THREADS, S.total, s>>>(a);
+  return after_launch("dec_pair_kernel<1>");
 }
 
 
@@ -1236,8 +1252,40 @@ int enc_pair_pack(const TaeEncConfig& c, const float* params, void* packed, cuda
   return rc;
 }
 
+size_t enc_pair_bwd_packed_bytes(const TaeEncConfig& c) { return (size_t)3 * stack_bwd_image_bytes(enc_as_dec(c)); }
+
+int enc_pair_pack_bwd(const TaeEncConfig& c, const float* params, void* packed, cudaStream_t s) {
+  EncBranchLayout el[3];
+  enc_layout(c, el);
+  DecStackLayout lay[3];
+  for (int b = 0; b < 3; ++b) {
+    lay[b] = DecStackLayout{};
+    for (int j = 0; j < c.num_layer; ++j) lay[b].conv[j] = el[b].conv[j];
+    lay[b].lin_w_off = el[b].lin_w_off; lay[b].lin_b_off = el[b].lin_b_off; lay[b].fout = 1;
+  }
+  DecStackLayout* d_lay = nullptr;
+  cudaError_t e = cudaMallocAsync(&d_lay, sizeof(lay), s);
+  if (e != cudaSuccess) { set_error("cudaMallocAsync: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+  e = cudaMemcpyAsync(d_lay, lay, sizeof(lay), cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) { set_error("cudaMemcpyAsync: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+  const TaeDecConfig d = enc_as_dec(c);
+  const uint32_t stack_elems = stack_bwd_image_bytes(d) / 2;
+  const size_t total = (size_t)3 * stack_elems;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  pack_bwd_kernel<<<blocks, 256, 0, s>>>(params, reinterpret_cast<__nv_bfloat16*>(packed), d_lay, 3, c.num_layer, c.num_unit, 1, stack_elems);
+  int rc = after_launch("pack_bwd_kernel");
+  cudaFreeAsync(d_lay, s);
+  return rc;
+}
+
+// Backward of encoder branch `branch` (0..2): the decoder's stack backward with Linear(units, 1) and one input channel.
+int enc_stack_backward_pair(const TaeEncConfig& c, const void* packed_bwd, int branch, const float* dlin, const void* stash_y,
+                            void* stash_g, void* stash_d, float* dxin, int B, void* ws, size_t ws_bytes, cudaStream_t s) {
+  return dec_stack_backward_pair(enc_as_dec(c), packed_bwd, branch, dlin, 1, stash_y, stash_g, stash_d, dxin, B, ws, ws_bytes, s);
+}
+
 int enc_forward_pair(const TaeEncConfig& c, const void* packed, const float* u, const int32_t* perm, const int32_t* inv_perm,
-                     float* x_tx, double* stats, int B, void* ws, size_t ws_bytes, cudaStream_t s) {
+                     float* x_tx, double* stats, int B, void* ws, size_t ws_bytes, cudaStream_t s, void* stash_y, void* stash_x) {
   if (ws_bytes < 256) { set_error("tae_enc_forward_bf16: workspace %zu < 256 bytes", ws_bytes); return TAE_EWORKSPACE; }
   const TaeDecConfig d = enc_as_dec(c);
   // reuse the decoder launcher's one-time setup by going through the same code path
@@ -1255,8 +1303,11 @@ int enc_forward_pair(const TaeEncConfig& c, const void* packed, const float* u, 
   a.n_pairs = (a.n_groups + 1) / 2;
   a.stack_bytes = stack_image_bytes(d);
   a.tl = nullptr;
+  a.stash_y = reinterpret_cast<uint8_t*>(stash_y);
+  a.stash_x = reinterpret_cast<uint8_t*>(stash_x);
   const int n_clusters = std::min(a.n_pairs, n_sm / 2);
-  dec_pair_kernel<<<2 * n_clusters, N_THREADS, make_smem(1).total, s>>>(a);
+  if (stash_y) dec_pair_kernel<2><<<2 * n_clusters, N_THREADS, make_smem(1).total, s>>>(a);
+  else dec_pair_kernel<0><<<2 * n_clusters, N_THREADS, make_smem(1).total, s>>>(a);
   return after_launch("dec_pair_kernel(enc)");
 }
 

@@ -1,0 +1,151 @@
+// Weight gradients of the conv stacks on 5th-gen tensor cores (training path).
+//
+// Reference arithmetic restated: trainer.py:74 (loss.backward()) through cnn_utils.py:36-46, i.e. for one Conv1d layer
+//     dW[o, c, t] = sum_{b, l} g[b, l, o] * x[b, l + t - K/2, c]          db[o] = sum_{b, l} g[b, l, o]
+// with g = dL/dz (gradient at the pre-activation) and x the layer input, and for the Linear after the stack
+//     dV[f, o] = sum_{b, l} dlin[b, l, f] * h[b, l, o].
+//
+// Both operands are "group images": the bf16 activation layout the fused forward / backward kernels keep in shared
+// memory and stash in HBM, [group][chunk = C/8][516 rows][8 channels] (rows = 2 halo rows, then per codeword L positions
+// + 2 all-zero separator rows).  The reduction runs over ROWS, so both operands are MN-major for tcgen05.mma (8 channels
+// contiguous, consecutive rows 16 bytes apart, 8-row blocks 128 bytes apart = LBO, 8-channel blocks one chunk apart = SBO):
+// the images are consumed exactly as they were written, no transpose.  Tap t of the convolution is the B operand's start
+// address moved by 16*t bytes; the zero separator rows make the shifted products vanish across codeword borders.
+//     D_t[m = o][n = c]  +=  A[rows, o]^T  B[rows + t - 2, c]        (M = 128, N = 16..64, K = 16 rows per MMA)
+// One CTA = one job (a layer, a slab of input channels, a range of groups): accumulators of all taps stay in TMEM for
+// the whole range (5 x 64 columns), then go out as fp32 atomics.  A constant all-ones chunk appended to B yields db in
+// a spare column.
+#include <cuda_bf16.h>
+
+#include "tae_common.cuh"
+#include "tae_umma.cuh"
+
+namespace tae {
+
+namespace {
+
+constexpr uint32_t W_ROWS = 516, W_CHUNK_B = W_ROWS * 16, W_A_CHUNKS = 13, W_B_CHUNKS_MAX = 8;
+constexpr uint32_t W_A_OFF = 0, W_B_OFF = W_A_CHUNKS * W_CHUNK_B;
+constexpr uint32_t W_BAR_OFF = W_B_OFF + (W_B_CHUNKS_MAX + 1) * W_CHUNK_B;      // B slab + ones chunk
+constexpr uint32_t W_SMEM = W_BAR_OFF + 64;
+constexpr int W_KSTEPS = 32;                                                   // 512 rows / 16
+
+__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
+         (1ull << 46);
+}
+
+__global__ void __launch_bounds__(128, 1) wgrad_kernel(const TaeWgradJob* __restrict__ jobs, int* err, int swap_lbo_sbo) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const TaeWgradJob J = jobs[blockIdx.x];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = sbase + W_BAR_OFF, bar_done = sbase + W_BAR_OFF + 8, bar_final = sbase + W_BAR_OFF + 16, tptr = sbase + W_BAR_OFF + 24;
+  const int n_it = J.g1 - J.g0;
+
+  // B slab region: zeros, then the ones chunk right behind the slab (channel 0 of every row = 1.0)
+  for (uint32_t i = threadIdx.x * 16; i < (W_B_CHUNKS_MAX + 1) * W_CHUNK_B; i += blockDim.x * 16) st_shared_v4(sbase + W_B_OFF + i, 0u, 0u, 0u, 0u);
+  __syncthreads();
+  for (uint32_t r = threadIdx.x; r < W_ROWS; r += blockDim.x)
+    st_shared_v4(sbase + W_B_OFF + (uint32_t)J.b_nc * W_CHUNK_B + r * 16, 0x00003F80u, 0u, 0u, 0u);
+  if (threadIdx.x == 0) { mbar_init(bar_full, 1); mbar_init(bar_done, 1); mbar_init(bar_final, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc<1>(tptr, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tptr) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t bytes = (W_A_CHUNKS + (uint32_t)J.b_nc) * W_CHUNK_B;
+      for (int it = 0; it < n_it; ++it) {
+        const size_t g = (size_t)(J.g0 + it);
+        if (it > 0) mbar_wait(bar_done, (uint32_t)(it - 1) & 1u, err, 21);      // the MMAs of the previous group have read the buffers
+        mbar_arrive_expect_tx(bar_full, bytes);
+        const uint8_t* a = reinterpret_cast<const uint8_t*>(J.a_img) + g * W_A_CHUNKS * W_CHUNK_B;
+        for (uint32_t c = 0; c < W_A_CHUNKS; ++c) bulk_g2s(sbase + W_A_OFF + c * W_CHUNK_B, a + (size_t)c * W_CHUNK_B, W_CHUNK_B, bar_full);
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(J.b_img) + (g * (size_t)J.b_chunks + (size_t)J.b_c0) * W_CHUNK_B;
+        for (uint32_t c = 0; c < (uint32_t)J.b_nc; ++c) bulk_g2s(sbase + W_B_OFF + c * W_CHUNK_B, b + (size_t)c * W_CHUNK_B, W_CHUNK_B, bar_full);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(128, J.n_cols) | (1u << 15) | (1u << 16);     // A and B MN-major
+    const uint32_t lbo = swap_lbo_sbo ? W_CHUNK_B : 128u, sbo = swap_lbo_sbo ? 128u : W_CHUNK_B;
+    const uint64_t a0 = mn_desc(sbase + W_A_OFF + 2 * 16, lbo, sbo);
+    const int half = J.taps / 2;
+    for (int it = 0; it < n_it; ++it) {
+      mbar_wait(bar_full, (uint32_t)it & 1u, err, 22);
+      tc_fence_after();
+      if (elect_one()) {
+        for (int t = 0; t < J.taps; ++t) {
+          const uint64_t b0 = mn_desc(sbase + W_B_OFF + (uint32_t)(2 + t - half) * 16, lbo, sbo);
+          const uint32_t d = tmem_base + (uint32_t)(t * J.n_cols);
+#pragma unroll 8
+          for (int ks = 0; ks < W_KSTEPS; ++ks)
+            umma_bf16<1>(d, a0 + (uint64_t)(ks * 16), b0 + (uint64_t)(ks * 16), idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit_1(bar_done);
+        if (it == n_it - 1) umma_commit_1(bar_final);      // its own barrier: the drain threads do not follow the per-group phases
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  // ---- drain: every thread owns TMEM lane m = output row -------------------------------------------------------------
+  if (n_it > 0) {
+    mbar_wait(bar_final, 0u, err, 23);
+    tc_fence_after();
+    const int m = 32 * warp + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * warp) << 16);
+    for (int t = 0; t < J.taps; ++t)
+      for (int cb = 0; cb < J.n_cols / 16; ++cb) {
+        uint32_t r[16];
+        tmem_ld16(lane_addr + (uint32_t)(t * J.n_cols + cb * 16), r);
+        tmem_ld_wait();
+        if (m < J.m_valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = cb * 16 + j;
+            if (n < J.n_valid) atomicAdd(J.grad + (size_t)m * J.s_m + (size_t)(J.n0 + n) * J.s_n + (size_t)t * J.s_t, __uint_as_float(r[j]));
+            else if (J.bias_grad && t == 0 && n == 8 * J.b_nc) atomicAdd(J.bias_grad + m, __uint_as_float(r[j]));
+          }
+        }
+      }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<1>(tmem_base, 512); }
+}
+
+}  // namespace
+
+int launch_wgrad(const TaeWgradJob* jobs_host, int n_jobs, void* ws, size_t ws_bytes, int swap_lbo_sbo, cudaStream_t s) {
+  if (n_jobs == 0) return TAE_OK;
+  const size_t need = 256 + sizeof(TaeWgradJob) * (size_t)n_jobs;
+  if (ws_bytes < need) { set_error("tae_wgrad_bf16: workspace %zu < %zu bytes", ws_bytes, need); return TAE_EWORKSPACE; }
+  for (int i = 0; i < n_jobs; ++i) {
+    const TaeWgradJob& J = jobs_host[i];
+    if (!J.a_img || !J.b_img || !J.grad || J.b_nc < 1 || J.b_nc > (int)W_B_CHUNKS_MAX || J.b_c0 < 0 || J.b_c0 + J.b_nc > J.b_chunks ||
+        (J.taps != 1 && J.taps != 3 && J.taps != 5) || J.n_cols % 16 || J.n_cols < 16 || J.n_cols > 8 * (J.b_nc + 1) || J.taps * J.n_cols > 512 ||
+        J.m_valid < 1 || J.m_valid > 104 || J.n_valid < 0 || J.n_valid > 8 * J.b_nc || J.g1 < J.g0) {
+      set_error("tae_wgrad_bf16: job %d is malformed", i);
+      return TAE_EINVAL;
+    }
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_SMEM);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(wgrad_kernel): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+    attr_done = true;
+  }
+  int* err = reinterpret_cast<int*>(align_up(reinterpret_cast<uintptr_t>(ws), 16));
+  TaeWgradJob* d_jobs = reinterpret_cast<TaeWgradJob*>(reinterpret_cast<uint8_t*>(err) + 128);
+  cudaError_t e = cudaMemcpyAsync(d_jobs, jobs_host, sizeof(TaeWgradJob) * (size_t)n_jobs, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) { set_error("cudaMemcpyAsync(jobs): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+  wgrad_kernel<<<n_jobs, 128, W_SMEM, s>>>(d_jobs, err, swap_lbo_sbo);
+  return after_launch("wgrad_kernel");
+}
+
+}  // namespace tae

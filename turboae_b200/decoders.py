@@ -43,6 +43,9 @@ class DEC_LargeCNN(torch.nn.Module):
         self._ws_host = Workspace()
         #: 'bf16' (fused tcgen05 kernel) or 'fp32' (CUDA-core parity path)
         self.precision = getattr(args, "tae_precision", None) or os.environ.get("TURBOAE_B200_PRECISION", "bf16")
+        #: training (autograd) path: 'fp32' = CUDA-core kernels layer by layer (gradients within 2e-3 of the reference's),
+        #: 'bf16' = tensor cores (train_tc.py: fused forward with stash, fused backward per stack, weight-gradient GEMMs)
+        self.train_precision = getattr(args, "tae_train_precision", None) or os.environ.get("TURBOAE_B200_TRAIN_PRECISION", "fp32")
 
     def set_parallel(self):
         for lst in (self.dec1_cnns, self.dec2_cnns, self.dec1_outputs, self.dec2_outputs):
@@ -172,7 +175,13 @@ class DEC_LargeCNN(torch.nn.Module):
         if self.this_device.type != "cuda":
             raise _lib.TaeError("no CUDA device: turboae_b200 has no CPU fallback")
         if torch.is_grad_enabled() and (received.requires_grad or any(p.requires_grad for p in self.parameters())):
-            return self._forward_train(received.to(device=self.this_device, dtype=torch.float32))
+            x = received.to(device=self.this_device, dtype=torch.float32)
+            if self.train_precision == "bf16":
+                from . import train_tc
+                return train_tc.decoder_forward_train(self, x)
+            if self.train_precision != "fp32":
+                raise _lib.TaeError("train_precision must be 'bf16' or 'fp32', got %r" % (self.train_precision,))
+            return self._forward_train(x)
         # reference decoders.py:219: received.type(torch.FloatTensor).to(self.this_device) -- here without the
         # device->host->device round trip when the tensor is already resident.
         x = received.to(device=self.this_device, dtype=torch.float32).contiguous()

@@ -93,6 +93,8 @@ class ENC_interCNN(ENCBase):
         #: 'fp32' (CUDA-core path, elementwise parity <= 1e-4) or 'bf16' (the decoder's fused tcgen05 kernel with the three
         #: branches as three conv stacks: ~25x faster, codes within bf16 rounding of the reference's)
         self.precision = getattr(args, "tae_enc_precision", None) or os.environ.get("TURBOAE_B200_ENC_PRECISION", "fp32")
+        #: training (autograd) path: 'fp32' (CUDA-core kernels) or 'bf16' (tensor cores, train_tc.py)
+        self.train_precision = getattr(args, "tae_train_precision", None) or os.environ.get("TURBOAE_B200_TRAIN_PRECISION", "fp32")
 
     def set_interleaver(self, p_array):
         self.interleaver.set_parray(p_array)
@@ -168,12 +170,18 @@ class ENC_interCNN(ENCBase):
         """Autograd path (reference encoders.py:362-375 under trainer.py:74): conv stacks through this package's forward /
         backward kernels, torch glue for the 100->1 Linear, ELU, concat and the power constraint (whose statistics and
         gradient sums are all-reduced when the batch is sharded across ranks)."""
-        x = 2.0 * u - 1.0
-        outs = []
-        for i, inp in ((1, x), (2, x), (3, self.interleaver(x))):
-            h = getattr(self, "enc_cnn_%d" % i)(inp)
-            outs.append(torch.nn.functional.elu(getattr(self, "enc_linear_%d" % i)(h)))
-        x_tx = torch.cat(outs, dim=2)
+        if self.train_precision == "bf16":
+            from . import train_tc
+            x_tx = train_tc.encoder_branches_train(self, u)
+        elif self.train_precision == "fp32":
+            x = 2.0 * u - 1.0
+            outs = []
+            for i, inp in ((1, x), (2, x), (3, self.interleaver(x))):
+                h = getattr(self, "enc_cnn_%d" % i)(inp)
+                outs.append(torch.nn.functional.elu(getattr(self, "enc_linear_%d" % i)(h)))
+            x_tx = torch.cat(outs, dim=2)
+        else:
+            raise _lib.TaeError("train_precision must be 'bf16' or 'fp32', got %r" % (self.train_precision,))
         if self.args.no_code_norm:
             return x_tx
         self._check_supported()

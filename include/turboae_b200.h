@@ -179,10 +179,24 @@ size_t tae_dec_bwd_packed_bytes(const TaeDecConfig* cfg);
 int    tae_dec_pack_bwd_bf16(const TaeDecConfig* cfg, const float* params, void* packed_bwd, void* stream);
 /* Backward of conv stack + Linear number `stack` (0 .. 2I-1, order of the flat parameter buffer):
  *   dlin (B, L, fin) = gradient w.r.t. the Linear output  ->  dxin (B, L, 8) = gradient w.r.t. the 2+F stack inputs
- *   (columns 2+F.. are zero).  Reads stash_y, writes stash_g and stash_d (all indexed by `stack` internally).      */
+ *   (columns 2+F.. are zero).  Reads stash_y, writes stash_g and stash_d (all indexed by `stack` internally).
+ * `chain` (may be NULL) fuses the glue between two stacks of the turbo schedule into this launch: with dlin == NULL,
+ *   dlin[b,l,f] = prev_dxin[b, idx[l], 2+f] - (subtract ? prev_dlin[b, idx[l], f] : 0)
+ * is the backward of the extrinsic subtraction + (de)interleaver (reference decoders.py:235-249) applied to the outputs of
+ * the launch for the NEXT stack; dlin_out (NULL or (B, L, fin)) receives the dlin used; lin_bias_grad (NULL or fin floats)
+ * is incremented by sum_{b,l} dlin (the Linear's bias gradient).                                                      */
+typedef struct TaeStackBwdChain {
+  const float* prev_dxin;      /* (B, L, 8)        */
+  const float* prev_dlin;      /* (B, L, prev_fin) */
+  const int32_t* idx;          /* int32[L]         */
+  int32_t prev_fin;
+  int32_t subtract;
+  float* dlin_out;
+  float* lin_bias_grad;
+} TaeStackBwdChain;
 int tae_dec_stack_backward_bf16(const TaeDecConfig* cfg, const void* packed_bwd, int32_t stack, const float* dlin, int32_t fin,
                                 const void* stash_y, void* stash_g, void* stash_d, float* dxin, int32_t B,
-                                void* workspace, size_t workspace_bytes, void* stream);
+                                const TaeStackBwdChain* chain, void* workspace, size_t workspace_bytes, void* stream);
 /* The same three steps for ENC_interCNN (reference encoders.py:362-373 under trainer.py:74): 3 branches = 3 stacks with one
  * input channel and Linear(units, 1); x_tx / stats as tae_enc_forward_bf16; dlin (B, L, 1) = gradient w.r.t. the Linear
  * output of the branch (i.e. d x_tx[:, :, branch] * ELU'), dxin (B, L, 8) = gradient w.r.t. the +-1 input in column 0.  */
@@ -193,7 +207,7 @@ size_t tae_enc_bwd_packed_bytes(const TaeEncConfig* cfg);
 int    tae_enc_pack_bwd_bf16(const TaeEncConfig* cfg, const float* params, void* packed_bwd, void* stream);
 int tae_enc_stack_backward_bf16(const TaeEncConfig* cfg, const void* packed_bwd, int32_t branch, const float* dlin,
                                 const void* stash_y, void* stash_g, void* stash_d, float* dxin, int32_t B,
-                                void* workspace, size_t workspace_bytes, void* stream);
+                                const TaeStackBwdChain* chain, void* workspace, size_t workspace_bytes, void* stream);
 /* Weight gradients as tensor-core GEMMs over group images (one CTA per job):
  *   grad[m*s_m + (n0+n)*s_n + t*s_t] += sum_{group in [g0,g1)} sum_rows A[row, m] * B[row + t - taps/2, b_c0*8 + n]
  * for m < m_valid, n < n_valid, t < taps; bias_grad[m] += sum_rows A[row, m] (NULL to skip; needs 8*b_nc < n_cols).
@@ -201,7 +215,9 @@ int tae_enc_stack_backward_bf16(const TaeEncConfig* cfg, const void* packed_bwd,
  * n_cols = UMMA N: a multiple of 16, 8*b_nc <= n_cols <= 8*(b_nc+1), taps * n_cols <= 512.
  * Conv layer: A = stash_g layer, B = its input image (stash_y of the layer below, or stash_x), taps = 5, grad = dW
  * (Cout, Cin, 5): s_m = 5*Cin, s_n = 5, s_t = 1.  Linear: A = last stash_y, B = stash_d, taps = 1, grad = dV (F, units):
- * s_m = 1, s_n = units.  `jobs_host` is a HOST array; workspace (device) >= 256 + n_jobs * sizeof(TaeWgradJob).     */
+ * s_m = 1, s_n = units.  `jobs_host` is a HOST array (validated on every call); `jobs_dev` is NULL or a device copy of it
+ * the caller uploaded once (job lists are reused from step to step: no per-call copy, no host synchronisation);
+ * workspace (device) >= 256 bytes, + n_jobs * sizeof(TaeWgradJob) when jobs_dev is NULL.                             */
 typedef struct TaeWgradJob {
   const void* a_img;
   const void* b_img;
@@ -214,7 +230,8 @@ typedef struct TaeWgradJob {
   int32_t g0, g1;
   int32_t reserved;
 } TaeWgradJob;
-int tae_wgrad_bf16(const TaeWgradJob* jobs_host, int32_t n_jobs, void* workspace, size_t workspace_bytes, void* stream);
+int tae_wgrad_bf16(const TaeWgradJob* jobs_host, int32_t n_jobs, const void* jobs_dev, void* workspace, size_t workspace_bytes,
+                   void* stream);
 
 /* ---- next row f2: DEC_LargeRNN (reference decoders.py:16-149, torch.nn.GRU 2 layers bidirectional) -----------------
  * One direction of one GRU layer over a whole batch: xproj (B, L, 3H) = W_ih x + b_ih for every time step (gate order r,

@@ -44,3 +44,28 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         step()
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+
+# ---- per-launch times of the training kernels (CUDA events around single launches) ----
+from turboae_b200 import train_tc, _lib
+def timed(fn, n=5):
+    fn(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+for name, mod in (("dec", dec), ("enc", enc)):
+    bufs = list(mod.__dict__.get("_tc_buffers", {}).values())
+    if not bufs or bufs[0].jobs is None:
+        continue
+    buf = bufs[0]
+    arr, n = buf.jobs[0], buf.jobs[1]
+    print("%s wgrad: %d jobs, %.3f ms" % (name, n, timed(lambda: train_tc.run_packed(buf.jobs, dev))))
+    kinds = {}
+    for j in arr:
+        kinds.setdefault((j.b_chunks, j.b_nc, j.n_cols, j.taps), []).append(j)
+    for k, js in kinds.items():
+        sub = train_tc.pack_jobs(js, dev)
+        print("   kind (b_chunks,nc,N,taps)=%s: %d jobs x %d groups: %.3f ms" % (k, len(js), js[0].g1 - js[0].g0, timed(lambda: train_tc.run_packed(sub, dev))))
+        one = train_tc.pack_jobs(js[:1], dev)
+        print("      one job alone: %.3f ms" % timed(lambda: train_tc.run_packed(one, dev)))

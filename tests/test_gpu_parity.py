@@ -141,6 +141,7 @@ def test_binarised_code_path_vs_reference_fixture():
     np.testing.assert_allclose(y, g["y"], atol=2e-5, rtol=0)
     # autograd path: same codes, gradient flows to the encoder through the straight-through estimator
     m.train()
+    m.enc.train_precision = "fp32"          # same arithmetic as the fp32 inference path above
     codes_t = m.enc(_t(g["u"]))
     assert torch.equal(codes_t.detach(), codes)
     codes_t.sum().backward()
@@ -459,6 +460,7 @@ def test_training_step_gradients_vs_reference_autograd():
     B = 6
     m, w, p = build_codec("c1", batch_size=B)
     m.train()
+    m.enc.train_precision = m.dec.train_precision = "fp32"        # the elementwise-parity training path (bf16: test_gpu_train_tc.py)
     u, noise = gen_inputs(2718, B, 100, 0.0)
     ud, nd = _t(u), _t(noise)
     codes = m.enc(ud)
@@ -491,6 +493,7 @@ def test_reference_training_loop_reduces_loss():
     args = make_args(batch_size=200)
     p = O.make_perm(100, 0)
     enc, dec = T.ENC_interCNN(args, p).to(DEV), T.DEC_LargeCNN(args, p).to(DEV)
+    enc.train_precision = dec.train_precision = "fp32"
     opt = torch.optim.Adam(dec.parameters(), lr=1e-3)
     losses = []
     for it in range(12):

@@ -390,8 +390,8 @@ int tae_dec_pack_bwd_bf16(const TaeDecConfig* cfg, const float* params, void* pa
 }
 
 int tae_dec_stack_backward_bf16(const TaeDecConfig* cfg, const void* packed_bwd, int32_t stack, const float* dlin, int32_t fin,
-                                const void* stash_y, void* stash_g, void* stash_d, float* dxin, int32_t B, void* workspace,
-                                size_t workspace_bytes, void* stream) {
+                                const void* stash_y, void* stash_g, void* stash_d, float* dxin, int32_t B, const TaeStackBwdChain* chain,
+                                void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_dec_config(cfg);
   if (rc) return rc;
   const char* why = nullptr;
@@ -400,9 +400,9 @@ int tae_dec_stack_backward_bf16(const TaeDecConfig* cfg, const void* packed_bwd,
   TAE_REQUIRE(stack >= 0 && stack < 2 * cfg->num_iteration, "tae_dec_stack_backward_bf16: stack %d out of range", stack);
   TAE_REQUIRE(fin >= 1 && fin <= 8, "tae_dec_stack_backward_bf16: fin %d out of range", fin);
   if (B == 0) return TAE_OK;
-  TAE_REQUIRE(packed_bwd && dlin && stash_y && stash_g && dxin && workspace, "tae_dec_stack_backward_bf16: NULL pointer");
+  TAE_REQUIRE(packed_bwd && (dlin || chain) && stash_y && stash_g && dxin && workspace, "tae_dec_stack_backward_bf16: NULL pointer");
   return dec_stack_backward_pair(*cfg, packed_bwd, stack, dlin, fin, stash_y, stash_g, stash_d, dxin, B, workspace, workspace_bytes,
-                                 (cudaStream_t)stream);
+                                 (cudaStream_t)stream, chain);
 }
 
 int tae_enc_forward_train_bf16(const TaeEncConfig* cfg, const void* packed, const float* u, const int32_t* perm, const int32_t* inv_perm,
@@ -437,8 +437,8 @@ int tae_enc_pack_bwd_bf16(const TaeEncConfig* cfg, const float* params, void* pa
 }
 
 int tae_enc_stack_backward_bf16(const TaeEncConfig* cfg, const void* packed_bwd, int32_t branch, const float* dlin, const void* stash_y,
-                                void* stash_g, void* stash_d, float* dxin, int32_t B, void* workspace, size_t workspace_bytes,
-                                void* stream) {
+                                void* stash_g, void* stash_d, float* dxin, int32_t B, const TaeStackBwdChain* chain, void* workspace,
+                                size_t workspace_bytes, void* stream) {
   int rc = check_enc_config(cfg);
   if (rc) return rc;
   const char* why = nullptr;
@@ -447,17 +447,14 @@ int tae_enc_stack_backward_bf16(const TaeEncConfig* cfg, const void* packed_bwd,
   if (B == 0) return TAE_OK;
   TAE_REQUIRE(packed_bwd && dlin && stash_y && stash_g && dxin && workspace, "tae_enc_stack_backward_bf16: NULL pointer");
   return enc_stack_backward_pair(*cfg, packed_bwd, branch, dlin, stash_y, stash_g, stash_d, dxin, B, workspace, workspace_bytes,
-                                 (cudaStream_t)stream);
+                                 (cudaStream_t)stream, chain);
 }
 
-static int g_wgrad_swap = 0;
-void tae_debug_wgrad_swap(int v) { g_wgrad_swap = v; }
-
-int tae_wgrad_bf16(const TaeWgradJob* jobs_host, int32_t n_jobs, void* workspace, size_t workspace_bytes, void* stream) {
+int tae_wgrad_bf16(const TaeWgradJob* jobs_host, int32_t n_jobs, const void* jobs_dev, void* workspace, size_t workspace_bytes, void* stream) {
   TAE_REQUIRE(n_jobs >= 0, "tae_wgrad_bf16: negative job count");
   if (n_jobs == 0) return TAE_OK;
   TAE_REQUIRE(jobs_host && workspace, "tae_wgrad_bf16: NULL pointer");
-  return launch_wgrad(jobs_host, n_jobs, workspace, workspace_bytes, g_wgrad_swap, (cudaStream_t)stream);
+  return launch_wgrad(jobs_host, n_jobs, jobs_dev, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int tae_gru_direction_f32(const float* xproj, const float* w_hh, const float* b_hh, float* out, int32_t B, int32_t L, int32_t H,

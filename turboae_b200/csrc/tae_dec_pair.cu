@@ -137,6 +137,14 @@ struct PairArgs {
   const float* dlin;           // MODE 1: gradient w.r.t. the Linear output (B, L, fin)
   float* dxin;                 // MODE 1: gradient w.r.t. the stack input (B, L, 8)
   int fin;
+  // MODE 1, chained form (dlin == nullptr): dlin[b, l, f] = prev_dxin[b, idx[l], 2 + f] - (sub ? prev_dlin[b, idx[l], f] : 0),
+  // i.e. the extrinsic subtraction and the (de)interleaver between two stacks, backwards (decoders.py:235-249)
+  const float* prev_dxin;      // (B, L, 8) gradient w.r.t. the input of the NEXT stack of the schedule
+  const float* prev_dlin;      // (B, L, prev_fin) gradient w.r.t. that stack's Linear output
+  const int32_t* idx;          // int32[L]
+  int prev_fin, sub;
+  float* dlin_out;             // nullptr or (B, L, fin): the dlin this launch used
+  float* lin_bias_grad;        // nullptr or fin floats: += sum over (b, l) of dlin
 };
 
 // ELU'(z) from the bf16 forward output y packed two per word: y + 1 where y < 0, else 1 (cnn_utils.py:24-25 backward)
@@ -202,8 +210,22 @@ __device__ __forceinline__ float lin_w_elem(const float* __restrict__ w, const f
   return 0.f;
 }
 
+// Flat-parameter layout of a sequence of conv stacks + Linear (dec_layout / enc_layout of tae_common.cuh), passed BY VALUE:
+// only the last stack's Linear may have a different width, so every offset is arithmetic (no device table, no copy).
+struct PackLayout {
+  int n_stacks, n_layer, units, cin0, f_regular, f_last;
+  __host__ __device__ size_t l0() const { return (size_t)units * cin0 * TAPS + units; }
+  __host__ __device__ size_t lj() const { return (size_t)units * units * TAPS + units; }
+  __host__ __device__ size_t base(int st) const { return (size_t)st * (l0() + (size_t)(n_layer - 1) * lj() + (size_t)f_regular * units + f_regular); }
+  __host__ __device__ int fout(int st) const { return st == n_stacks - 1 ? f_last : f_regular; }
+  __host__ __device__ size_t conv_w(int st, int j) const { return base(st) + (j == 0 ? 0 : l0() + (size_t)(j - 1) * lj()); }
+  __host__ __device__ size_t conv_b(int st, int j) const { return conv_w(st, j) + (size_t)units * (j == 0 ? cin0 : units) * TAPS; }
+  __host__ __device__ size_t lin_w(int st) const { return base(st) + l0() + (size_t)(n_layer - 1) * lj(); }
+  __host__ __device__ size_t lin_b(int st) const { return lin_w(st) + (size_t)fout(st) * units; }
+};
+
 __global__ void pack_pair_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ img,
-                                 const DecStackLayout* __restrict__ lay, int n_stacks, int n_layer, int units, int cin0,
+                                 const PackLayout lay, int n_stacks, int n_layer, int units, int cin0,
                                  uint32_t stack_elems) {
   const size_t total = (size_t)n_stacks * stack_elems;
   const uint32_t l0_elems = 2 * L0_B / 2;
@@ -211,13 +233,12 @@ __global__ void pack_pair_kernel(const float* __restrict__ params, __nv_bfloat16
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int st = (int)(idx / stack_elems);
     uint32_t r = (uint32_t)(idx % stack_elems);
-    const DecStackLayout& S = lay[st];
     float v;
     if (r < l0_elems) {
       const int half = r / (L0_B / 2);
       r %= (L0_B / 2);
       const int ks = r / (2 * NHALF * 8), ch = (r / (NHALF * 8)) & 1, n = (r / 8) % NHALF, e8 = r % 8;
-      v = l0_w_elem(params + S.conv[0].w_off, params + S.conv[0].b_off, units, cin0, half * NHALF + n, ks, ch * 8 + e8);
+      v = l0_w_elem(params + lay.conv_w(st, 0), params + lay.conv_b(st, 0), units, cin0, half * NHALF + n, ks, ch * 8 + e8);
     } else if (r < l0_elems + conv_elems) {
       r -= l0_elems;
       const uint32_t slot_elems = 2 * SLOT_B / 2;      // both halves of one slot
@@ -228,13 +249,13 @@ __global__ void pack_pair_kernel(const float* __restrict__ params, __nv_bfloat16
       const int j = 1 + sl / SLOTS_CONV;
       const int ks = (sl % SLOTS_CONV) * KS_PER_SLOT + r / (2 * NHALF * 8);
       const int ch = (r / (NHALF * 8)) & 1, n = (r / 8) % NHALF, e8 = r % 8;
-      v = conv_w_elem(params + S.conv[j].w_off, params + S.conv[j].b_off, units, half * NHALF + n, ks, ch * 8 + e8);
+      v = conv_w_elem(params + lay.conv_w(st, j), params + lay.conv_b(st, j), units, half * NHALF + n, ks, ch * 8 + e8);
     } else {
       r -= l0_elems + conv_elems;
       const int half = r / (LIN_B / 2);
       r %= (LIN_B / 2);
       const int ks = r / (2 * LIN_NHALF * 8), ch = (r / (LIN_NHALF * 8)) & 1, n = (r / 8) % LIN_NHALF, e8 = r % 8;
-      v = lin_w_elem(params + S.lin_w_off, params + S.lin_b_off, units, S.fout, half * LIN_NHALF + n, ks, ch * 8 + e8);
+      v = lin_w_elem(params + lay.lin_w(st), params + lay.lin_b(st), units, lay.fout(st), half * LIN_NHALF + n, ks, ch * 8 + e8);
     }
     img[idx] = __float2bfloat16_rn(v);
   }
@@ -254,7 +275,7 @@ __device__ __forceinline__ bool conv_k_map(int ks, int e, int* c, int* t) {
 //              dx[l, c] = sum_o sum_t W[o, c, 4 - t] g[l + t - 2, o]                     (backward of cnn_utils.py:42-44)
 //   2 slots  : the transposed first layer (units -> cin0), 16 k-steps each, N = 16 (8 columns per CTA half).
 __global__ void pack_bwd_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ img,
-                                const DecStackLayout* __restrict__ lay, int n_stacks, int n_layer, int units, int cin0,
+                                const PackLayout lay, int n_stacks, int n_layer, int units, int cin0,
                                 uint32_t stack_elems) {
   const size_t total = (size_t)n_stacks * stack_elems;
   const uint32_t l0_elems = 2 * L0_B / 2;
@@ -262,14 +283,13 @@ __global__ void pack_bwd_kernel(const float* __restrict__ params, __nv_bfloat16*
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int st = (int)(idx / stack_elems);
     uint32_t r = (uint32_t)(idx % stack_elems);
-    const DecStackLayout& S = lay[st];
     float v = 0.f;
     if (r < l0_elems) {
       const int half = r / (L0_B / 2);
       r %= (L0_B / 2);
       const int ks = r / (2 * NHALF * 8), ch = (r / (NHALF * 8)) & 1, n = (r / 8) % NHALF, e8 = r % 8;
       const int o = half * NHALF + n, t = 2 * ks + ch, f = e8;
-      if (o < units && t == 2 && f < S.fout) v = params[S.lin_w_off + (size_t)f * units + o];
+      if (o < units && t == 2 && f < lay.fout(st)) v = params[lay.lin_w(st) + (size_t)f * units + o];
     } else if (r < l0_elems + conv_elems) {
       r -= l0_elems;
       const uint32_t slot_elems = 2 * SLOT_B / 2;
@@ -283,7 +303,7 @@ __global__ void pack_bwd_kernel(const float* __restrict__ params, __nv_bfloat16*
       const int cdst = half * NHALF + n;                               // output channel of the backward step = input channel of layer j
       int c, t;
       if (cdst < units && conv_k_map(ks, ch * 8 + e8, &c, &t) && c < units)
-        v = params[S.conv[j].w_off + ((size_t)c * units + cdst) * TAPS + (TAPS - 1 - t)];
+        v = params[lay.conv_w(st, j) + ((size_t)c * units + cdst) * TAPS + (TAPS - 1 - t)];
     } else {
       r -= l0_elems + conv_elems;
       const uint32_t slot_elems = 2 * FIN_B / 2;
@@ -296,7 +316,7 @@ __global__ void pack_bwd_kernel(const float* __restrict__ params, __nv_bfloat16*
       const int qdst = half * LIN_NHALF + n;                           // input channel of the first layer
       int c, t;
       if (qdst < cin0 && conv_k_map(ks, ch * 8 + e8, &c, &t) && c < units)
-        v = params[S.conv[0].w_off + ((size_t)c * cin0 + qdst) * TAPS + (TAPS - 1 - t)];
+        v = params[lay.conv_w(st, 0) + ((size_t)c * cin0 + qdst) * TAPS + (TAPS - 1 - t)];
     }
     img[idx] = __float2bfloat16_rn(v);
   }
@@ -535,14 +555,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
       const bool grp_ok = grp < a.n_groups;               // the odd group of the last pair does not exist: no stash traffic
       if (MODE == 1) {
         // gradient w.r.t. the Linear output, as the 8-channel operand chunk of the first (transposed Linear) step
+        float bsum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         for (int i = tid; i < n_cw * L; i += N_EPI_THREADS) {
           const int c = i / L, l = i % L;
-          const float* d = a.dlin + ((size_t)(cw0 + c) * L + l) * a.fin;
           float v[8];
+          if (a.dlin) {
+            const float* d = a.dlin + ((size_t)(cw0 + c) * L + l) * a.fin;
 #pragma unroll
-          for (int f = 0; f < 8; ++f) v[f] = f < a.fin ? d[f] : 0.f;
+            for (int f = 0; f < 8; ++f) v[f] = f < a.fin ? d[f] : 0.f;
+          } else {
+            const size_t src = (size_t)(cw0 + c) * L + a.idx[l];
+            const float* px = a.prev_dxin + src * 8 + 2;
+            const float* pd = a.prev_dlin + src * a.prev_fin;
+#pragma unroll
+            for (int f = 0; f < 8; ++f) v[f] = f < a.fin ? px[f] - (a.sub ? pd[f] : 0.f) : 0.f;
+          }
+          if (a.dlin_out) {
+            float* o = a.dlin_out + ((size_t)(cw0 + c) * L + l) * a.fin;
+#pragma unroll
+            for (int f = 0; f < 5; ++f)
+              if (f < a.fin) o[f] = v[f];
+          }
+#pragma unroll
+          for (int f = 0; f < 5; ++f) bsum[f] += v[f];
           st_shared_v4(sbase + S.xin[0] + (uint32_t)(c * CW_ROWS + l + 2) * ROW_B, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                        pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        }
+        if (a.lin_bias_grad) {
+#pragma unroll
+          for (int f = 0; f < 5; ++f) {
+            float t = bsum[f];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+            if (lane == 0 && f < a.fin && t != 0.f) atomicAdd(a.lin_bias_grad + f, t);
+          }
         }
       } else if (a.enc) {
         for (int i = tid; i < n_cw * L; i += N_EPI_THREADS) {
@@ -1075,22 +1121,14 @@ bool dec_pair_supported(const TaeDecConfig& c, const char** why) {
 size_t dec_pair_packed_bytes(const TaeDecConfig& c) { return (size_t)2 * c.num_iteration * stack_image_bytes(c); }
 
 int dec_pair_pack(const TaeDecConfig& c, const float* params, void* packed, cudaStream_t s) {
-  DecStackLayout lay[64];
-  dec_layout(c, lay);
   const int n_stacks = 2 * c.num_iteration;
-  DecStackLayout* d_lay = nullptr;
-  cudaError_t e = cudaMallocAsync(&d_lay, sizeof(DecStackLayout) * n_stacks, s);
-  if (e != cudaSuccess) { set_error("cudaMallocAsync: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
-  e = cudaMemcpyAsync(d_lay, lay, sizeof(DecStackLayout) * n_stacks, cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) { set_error("cudaMemcpyAsync: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+  const PackLayout lay{n_stacks, c.num_layer, c.num_unit, 2 + c.num_iter_ft, c.num_iter_ft, 1};
   const uint32_t stack_elems = stack_image_bytes(c) / 2;
   const size_t total = (size_t)n_stacks * stack_elems;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-  pack_pair_kernel<<<blocks, 256, 0, s>>>(params, reinterpret_cast<__nv_bfloat16*>(packed), d_lay, n_stacks, c.num_layer,
+  pack_pair_kernel<<<blocks, 256, 0, s>>>(params, reinterpret_cast<__nv_bfloat16*>(packed), lay, n_stacks, c.num_layer,
                                           c.num_unit, 2 + c.num_iter_ft, stack_elems);
-  int rc = after_launch("pack_pair_kernel");
-  cudaFreeAsync(d_lay, s);
-  return rc;
+  return after_launch("pack_pair_kernel");
 }
 
 static int pair_launch_setup(const TaeDecConfig&, int* n_sm_out) {
@@ -1159,28 +1197,21 @@ int train_groups(int block_len, int B) {
 size_t dec_pair_bwd_packed_bytes(const TaeDecConfig& c) { return (size_t)2 * c.num_iteration * stack_bwd_image_bytes(c); }
 
 int dec_pair_pack_bwd(const TaeDecConfig& c, const float* params, void* packed, cudaStream_t s) {
-  DecStackLayout lay[64];
-  dec_layout(c, lay);
   const int n_stacks = 2 * c.num_iteration;
-  DecStackLayout* d_lay = nullptr;
-  cudaError_t e = cudaMallocAsync(&d_lay, sizeof(DecStackLayout) * n_stacks, s);
-  if (e != cudaSuccess) { set_error("cudaMallocAsync: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
-  e = cudaMemcpyAsync(d_lay, lay, sizeof(DecStackLayout) * n_stacks, cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) { set_error("cudaMemcpyAsync: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+  const PackLayout lay{n_stacks, c.num_layer, c.num_unit, 2 + c.num_iter_ft, c.num_iter_ft, 1};
   const uint32_t stack_elems = stack_bwd_image_bytes(c) / 2;
   const size_t total = (size_t)n_stacks * stack_elems;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-  pack_bwd_kernel<<<blocks, 256, 0, s>>>(params, reinterpret_cast<__nv_bfloat16*>(packed), d_lay, n_stacks, c.num_layer,
+  pack_bwd_kernel<<<blocks, 256, 0, s>>>(params, reinterpret_cast<__nv_bfloat16*>(packed), lay, n_stacks, c.num_layer,
                                          c.num_unit, 2 + c.num_iter_ft, stack_elems);
-  int rc = after_launch("pack_bwd_kernel");
-  cudaFreeAsync(d_lay, s);
-  return rc;
+  return after_launch("pack_bwd_kernel");
 }
 
 // Backward of stack `stack` (0 .. 2I-1): dlin (B, L, fin) -> dxin (B, L, 8); reads the stack's stashed forward outputs,
 // writes the pre-activation gradients (stash_g, same indexing as stash_y) and the dlin image (stash_d: [stack][group][1]).
 int dec_stack_backward_pair(const TaeDecConfig& c, const void* packed_bwd, int stack, const float* dlin, int fin, const void* stash_y,
-                            void* stash_g, void* stash_d, float* dxin, int B, void* ws, size_t ws_bytes, cudaStream_t s) {
+                            void* stash_g, void* stash_d, float* dxin, int B, void* ws, size_t ws_bytes, cudaStream_t s,
+                            const TaeStackBwdChain* chain) {
   if (ws_bytes < 256) { set_error("tae_dec_stack_backward_bf16: workspace %zu < 256 bytes", ws_bytes); return TAE_EWORKSPACE; }
   const Smem S = make_smem(c.num_iter_ft);
   int n_sm = 0;
@@ -1201,6 +1232,15 @@ int dec_stack_backward_pair(const TaeDecConfig& c, const void* packed_bwd, int s
   a.stash_g = reinterpret_cast<uint8_t*>(stash_g) + (size_t)stack * c.num_layer * layer_img;
   a.stash_x = stash_d ? reinterpret_cast<uint8_t*>(stash_d) + (size_t)stack * a.n_groups * CHUNK_B : nullptr;
   a.dlin = dlin; a.dxin = dxin; a.fin = fin;
+  if (chain) {
+    a.prev_dxin = chain->prev_dxin; a.prev_dlin = chain->prev_dlin; a.idx = chain->idx; a.prev_fin = chain->prev_fin;
+    a.sub = chain->subtract; a.dlin_out = chain->dlin_out; a.lin_bias_grad = chain->lin_bias_grad;
+  }
+  if (!a.dlin && !(a.prev_dxin && a.idx && (!a.sub || a.prev_dlin))) {
+    set_error("tae_dec_stack_backward_bf16: dlin is NULL and the chained form is incomplete");
+    return TAE_EINVAL;
+  }
+  if (fin > 5 && a.lin_bias_grad) { set_error("tae_dec_stack_backward_bf16: lin_bias_grad supports fin <= 5"); return TAE_EINVAL; }
   const int n_clusters = std::min(a.n_pairs, n_sm / 2);
   dec_pair_kernel<1><<<2 * n_clusters, N_THREADS, S.total, s>>>(a);
   return after_launch("dec_pair_kernel<1>");
@@ -1228,60 +1268,33 @@ bool enc_pair_supported(const TaeEncConfig& c, const char** why) {
 size_t enc_pair_packed_bytes(const TaeEncConfig& c) { return (size_t)3 * stack_image_bytes(enc_as_dec(c)); }
 
 int enc_pair_pack(const TaeEncConfig& c, const float* params, void* packed, cudaStream_t s) {
-  EncBranchLayout el[3];
-  enc_layout(c, el);
-  DecStackLayout lay[3];
-  for (int b = 0; b < 3; ++b) {
-    lay[b] = DecStackLayout{};
-    for (int j = 0; j < c.num_layer; ++j) lay[b].conv[j] = el[b].conv[j];
-    lay[b].lin_w_off = el[b].lin_w_off; lay[b].lin_b_off = el[b].lin_b_off; lay[b].fout = 1;
-  }
-  DecStackLayout* d_lay = nullptr;
-  cudaError_t e = cudaMallocAsync(&d_lay, sizeof(lay), s);
-  if (e != cudaSuccess) { set_error("cudaMallocAsync: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
-  e = cudaMemcpyAsync(d_lay, lay, sizeof(lay), cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) { set_error("cudaMemcpyAsync: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+  const PackLayout lay{3, c.num_layer, c.num_unit, 1, 1, 1};
   const TaeDecConfig d = enc_as_dec(c);
   const uint32_t stack_elems = stack_image_bytes(d) / 2;
   const size_t total = (size_t)3 * stack_elems;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-  pack_pair_kernel<<<blocks, 256, 0, s>>>(params, reinterpret_cast<__nv_bfloat16*>(packed), d_lay, 3, c.num_layer, c.num_unit, 1,
+  pack_pair_kernel<<<blocks, 256, 0, s>>>(params, reinterpret_cast<__nv_bfloat16*>(packed), lay, 3, c.num_layer, c.num_unit, 1,
                                           stack_elems);
-  int rc = after_launch("pack_pair_kernel");
-  cudaFreeAsync(d_lay, s);
-  return rc;
+  return after_launch("pack_pair_kernel");
 }
 
 size_t enc_pair_bwd_packed_bytes(const TaeEncConfig& c) { return (size_t)3 * stack_bwd_image_bytes(enc_as_dec(c)); }
 
 int enc_pair_pack_bwd(const TaeEncConfig& c, const float* params, void* packed, cudaStream_t s) {
-  EncBranchLayout el[3];
-  enc_layout(c, el);
-  DecStackLayout lay[3];
-  for (int b = 0; b < 3; ++b) {
-    lay[b] = DecStackLayout{};
-    for (int j = 0; j < c.num_layer; ++j) lay[b].conv[j] = el[b].conv[j];
-    lay[b].lin_w_off = el[b].lin_w_off; lay[b].lin_b_off = el[b].lin_b_off; lay[b].fout = 1;
-  }
-  DecStackLayout* d_lay = nullptr;
-  cudaError_t e = cudaMallocAsync(&d_lay, sizeof(lay), s);
-  if (e != cudaSuccess) { set_error("cudaMallocAsync: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
-  e = cudaMemcpyAsync(d_lay, lay, sizeof(lay), cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) { set_error("cudaMemcpyAsync: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+  const PackLayout lay{3, c.num_layer, c.num_unit, 1, 1, 1};
   const TaeDecConfig d = enc_as_dec(c);
   const uint32_t stack_elems = stack_bwd_image_bytes(d) / 2;
   const size_t total = (size_t)3 * stack_elems;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-  pack_bwd_kernel<<<blocks, 256, 0, s>>>(params, reinterpret_cast<__nv_bfloat16*>(packed), d_lay, 3, c.num_layer, c.num_unit, 1, stack_elems);
-  int rc = after_launch("pack_bwd_kernel");
-  cudaFreeAsync(d_lay, s);
-  return rc;
+  pack_bwd_kernel<<<blocks, 256, 0, s>>>(params, reinterpret_cast<__nv_bfloat16*>(packed), lay, 3, c.num_layer, c.num_unit, 1, stack_elems);
+  return after_launch("pack_bwd_kernel");
 }
 
 // Backward of encoder branch `branch` (0..2): the decoder's stack backward with Linear(units, 1) and one input channel.
 int enc_stack_backward_pair(const TaeEncConfig& c, const void* packed_bwd, int branch, const float* dlin, const void* stash_y,
-                            void* stash_g, void* stash_d, float* dxin, int B, void* ws, size_t ws_bytes, cudaStream_t s) {
-  return dec_stack_backward_pair(enc_as_dec(c), packed_bwd, branch, dlin, 1, stash_y, stash_g, stash_d, dxin, B, ws, ws_bytes, s);
+                            void* stash_g, void* stash_d, float* dxin, int B, void* ws, size_t ws_bytes, cudaStream_t s,
+                            const TaeStackBwdChain* chain) {
+  return dec_stack_backward_pair(enc_as_dec(c), packed_bwd, branch, dlin, 1, stash_y, stash_g, stash_d, dxin, B, ws, ws_bytes, s, chain);
 }
 
 int enc_forward_pair(const TaeEncConfig& c, const void* packed, const float* u, const int32_t* perm, const int32_t* inv_perm,

@@ -13,7 +13,8 @@
 // address moved by 16*t bytes; the zero separator rows make the shifted products vanish across codeword borders.
 //     D_t[m = o][n = c]  +=  A[rows, o]^T  B[rows + t - 2, c]        (M = 128, N = 16..64, K = 16 rows per MMA)
 // One CTA = one job (a layer, a slab of input channels, a range of groups): accumulators of all taps stay in TMEM for
-// the whole range (5 x 64 columns), then go out as fp32 atomics.  A constant all-ones chunk appended to B yields db in
+// the whole range (5 x 64 columns), then go out as fp32 atomics.  Half groups stream through a 2-stage bulk-copy pipeline
+// (the copies of half i+1 overlap the 80 MMAs of half i).  A constant all-ones chunk appended to B yields db in
 // a spare column.
 #include <cuda_bf16.h>
 
@@ -25,30 +26,44 @@ namespace tae {
 namespace {
 
 constexpr uint32_t W_ROWS = 516, W_CHUNK_B = W_ROWS * 16, W_A_CHUNKS = 13, W_B_CHUNKS_MAX = 8;
-constexpr uint32_t W_A_OFF = 0, W_B_OFF = W_A_CHUNKS * W_CHUNK_B;
-constexpr uint32_t W_BAR_OFF = W_B_OFF + (W_B_CHUNKS_MAX + 1) * W_CHUNK_B;      // B slab + ones chunk
+// One pipeline stage holds HALF a group: a 260-row window (256 reduction rows + 2 halo rows each side for the taps) of the
+// 13 A chunks and of up to 8 B chunks, followed by the constant ones chunk; chunks are W_WIN_B apart (= SBO).  The three
+// A chunks that M = 128 reads past channel 103 fall into the stage's own B region (their output rows are never stored).
+constexpr uint32_t W_WIN_ROWS = 260, W_WIN_B = W_WIN_ROWS * 16;                 // 4160
+constexpr uint32_t W_STAGE_B = (W_A_CHUNKS + W_B_CHUNKS_MAX + 1) * W_WIN_B;     // 91 520
+constexpr uint32_t W_BAR_OFF = 2 * W_STAGE_B;
 constexpr uint32_t W_SMEM = W_BAR_OFF + 64;
-constexpr int W_KSTEPS = 32;                                                   // 512 rows / 16
+constexpr int W_KSTEPS = 16;                                                   // 256 rows / 16 per half
 
 __device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
          (1ull << 46);
 }
 
-__global__ void __launch_bounds__(128, 1) wgrad_kernel(const TaeWgradJob* __restrict__ jobs, int* err, int swap_lbo_sbo) {
+__global__ void __launch_bounds__(128, 1) wgrad_kernel(const TaeWgradJob* __restrict__ jobs, int* err) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const TaeWgradJob J = jobs[blockIdx.x];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar_full = sbase + W_BAR_OFF, bar_done = sbase + W_BAR_OFF + 8, bar_final = sbase + W_BAR_OFF + 16, tptr = sbase + W_BAR_OFF + 24;
-  const int n_it = J.g1 - J.g0;
+  auto bar_full = [&](int s) { return sbase + W_BAR_OFF + 8u * (uint32_t)s; };
+  auto bar_empty = [&](int s) { return sbase + W_BAR_OFF + 16u + 8u * (uint32_t)s; };
+  const uint32_t bar_final = sbase + W_BAR_OFF + 32, tptr = sbase + W_BAR_OFF + 40;
+  const int n_it = 2 * (J.g1 - J.g0);                   // half groups
 
-  // B slab region: zeros, then the ones chunk right behind the slab (channel 0 of every row = 1.0)
-  for (uint32_t i = threadIdx.x * 16; i < (W_B_CHUNKS_MAX + 1) * W_CHUNK_B; i += blockDim.x * 16) st_shared_v4(sbase + W_B_OFF + i, 0u, 0u, 0u, 0u);
+  // B regions of both stages: zeros, then the ones chunk right behind the slab (channel 0 of every row = 1.0)
+  for (int st = 0; st < 2; ++st) {
+    const uint32_t b_off = sbase + (uint32_t)st * W_STAGE_B + W_A_CHUNKS * W_WIN_B;
+    for (uint32_t i = threadIdx.x * 16; i < (W_B_CHUNKS_MAX + 1) * W_WIN_B; i += blockDim.x * 16) st_shared_v4(b_off + i, 0u, 0u, 0u, 0u);
+  }
   __syncthreads();
-  for (uint32_t r = threadIdx.x; r < W_ROWS; r += blockDim.x)
-    st_shared_v4(sbase + W_B_OFF + (uint32_t)J.b_nc * W_CHUNK_B + r * 16, 0x00003F80u, 0u, 0u, 0u);
-  if (threadIdx.x == 0) { mbar_init(bar_full, 1); mbar_init(bar_done, 1); mbar_init(bar_final, 1); fence_barrier_init(); }
+  for (int st = 0; st < 2; ++st)
+    for (uint32_t r = threadIdx.x; r < W_WIN_ROWS; r += blockDim.x)
+      st_shared_v4(sbase + (uint32_t)st * W_STAGE_B + (W_A_CHUNKS + (uint32_t)J.b_nc) * W_WIN_B + r * 16, 0x00003F80u, 0u, 0u, 0u);
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < 2; ++st) { mbar_init(bar_full(st), 1); mbar_init(bar_empty(st), 1); }
+    mbar_init(bar_final, 1);
+    fence_barrier_init();
+  }
   if (warp == 0) tmem_alloc<1>(tptr, 512);
   fence_proxy_async();
   tc_fence_before();
@@ -59,35 +74,42 @@ __global__ void __launch_bounds__(128, 1) wgrad_kernel(const TaeWgradJob* __rest
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t bytes = (W_A_CHUNKS + (uint32_t)J.b_nc) * W_CHUNK_B;
+      // producer: half h of group g = rows [256 h, 256 h + 260) of every chunk
+      const uint32_t bytes = (W_A_CHUNKS + (uint32_t)J.b_nc) * W_WIN_B;
       for (int it = 0; it < n_it; ++it) {
-        const size_t g = (size_t)(J.g0 + it);
-        if (it > 0) mbar_wait(bar_done, (uint32_t)(it - 1) & 1u, err, 21);      // the MMAs of the previous group have read the buffers
-        mbar_arrive_expect_tx(bar_full, bytes);
-        const uint8_t* a = reinterpret_cast<const uint8_t*>(J.a_img) + g * W_A_CHUNKS * W_CHUNK_B;
-        for (uint32_t c = 0; c < W_A_CHUNKS; ++c) bulk_g2s(sbase + W_A_OFF + c * W_CHUNK_B, a + (size_t)c * W_CHUNK_B, W_CHUNK_B, bar_full);
-        const uint8_t* b = reinterpret_cast<const uint8_t*>(J.b_img) + (g * (size_t)J.b_chunks + (size_t)J.b_c0) * W_CHUNK_B;
-        for (uint32_t c = 0; c < (uint32_t)J.b_nc; ++c) bulk_g2s(sbase + W_B_OFF + c * W_CHUNK_B, b + (size_t)c * W_CHUNK_B, W_CHUNK_B, bar_full);
+        const int st = it & 1;
+        const size_t g = (size_t)(J.g0 + (it >> 1));
+        const uint32_t row_off = (uint32_t)(it & 1) * 256u * 16u;
+        if (it >= 2) mbar_wait(bar_empty(st), (uint32_t)((it >> 1) - 1) & 1u, err, 21);    // the MMAs that read this stage are done
+        mbar_arrive_expect_tx(bar_full(st), bytes);
+        const uint32_t dst = sbase + (uint32_t)st * W_STAGE_B;
+        const uint8_t* a = reinterpret_cast<const uint8_t*>(J.a_img) + g * W_A_CHUNKS * W_CHUNK_B + row_off;
+        for (uint32_t c = 0; c < W_A_CHUNKS; ++c) bulk_g2s(dst + c * W_WIN_B, a + (size_t)c * W_CHUNK_B, W_WIN_B, bar_full(st));
+        const uint8_t* b = reinterpret_cast<const uint8_t*>(J.b_img) + (g * (size_t)J.b_chunks + (size_t)J.b_c0) * W_CHUNK_B + row_off;
+        for (uint32_t c = 0; c < (uint32_t)J.b_nc; ++c)
+          bulk_g2s(dst + (W_A_CHUNKS + c) * W_WIN_B, b + (size_t)c * W_CHUNK_B, W_WIN_B, bar_full(st));
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc(128, J.n_cols) | (1u << 15) | (1u << 16);     // A and B MN-major
-    const uint32_t lbo = swap_lbo_sbo ? W_CHUNK_B : 128u, sbo = swap_lbo_sbo ? 128u : W_CHUNK_B;
-    const uint64_t a0 = mn_desc(sbase + W_A_OFF + 2 * 16, lbo, sbo);
+    // MMA issuer.  Both operands MN-major: LBO = 128 B between 8-row blocks of the reduction, SBO = one chunk window.
+    const uint32_t idesc = make_idesc(128, J.n_cols) | (1u << 15) | (1u << 16);
     const int half = J.taps / 2;
     for (int it = 0; it < n_it; ++it) {
-      mbar_wait(bar_full, (uint32_t)it & 1u, err, 22);
+      const int st = it & 1;
+      mbar_wait(bar_full(st), (uint32_t)(it >> 1) & 1u, err, 22);
       tc_fence_after();
       if (elect_one()) {
+        const uint32_t stage = sbase + (uint32_t)st * W_STAGE_B;
+        const uint64_t a0 = mn_desc(stage + 2 * 16, 128u, W_WIN_B);
         for (int t = 0; t < J.taps; ++t) {
-          const uint64_t b0 = mn_desc(sbase + W_B_OFF + (uint32_t)(2 + t - half) * 16, lbo, sbo);
+          const uint64_t b0 = mn_desc(stage + W_A_CHUNKS * W_WIN_B + (uint32_t)(2 + t - half) * 16, 128u, W_WIN_B);
           const uint32_t d = tmem_base + (uint32_t)(t * J.n_cols);
-#pragma unroll 8
+#pragma unroll
           for (int ks = 0; ks < W_KSTEPS; ++ks)
             umma_bf16<1>(d, a0 + (uint64_t)(ks * 16), b0 + (uint64_t)(ks * 16), idesc, (it > 0 || ks > 0) ? 1u : 0u);
         }
-        umma_commit_1(bar_done);
-        if (it == n_it - 1) umma_commit_1(bar_final);      // its own barrier: the drain threads do not follow the per-group phases
+        umma_commit_1(bar_empty(st));
+        if (it == n_it - 1) umma_commit_1(bar_final);      // its own barrier: the drain threads do not follow the per-stage phases
       }
       __syncwarp();
     }
@@ -121,9 +143,9 @@ __global__ void __launch_bounds__(128, 1) wgrad_kernel(const TaeWgradJob* __rest
 
 }  // namespace
 
-int launch_wgrad(const TaeWgradJob* jobs_host, int n_jobs, void* ws, size_t ws_bytes, int swap_lbo_sbo, cudaStream_t s) {
+int launch_wgrad(const TaeWgradJob* jobs_host, int n_jobs, const void* jobs_dev, void* ws, size_t ws_bytes, cudaStream_t s) {
   if (n_jobs == 0) return TAE_OK;
-  const size_t need = 256 + sizeof(TaeWgradJob) * (size_t)n_jobs;
+  const size_t need = 256 + (jobs_dev ? 0 : sizeof(TaeWgradJob) * (size_t)n_jobs);
   if (ws_bytes < need) { set_error("tae_wgrad_bf16: workspace %zu < %zu bytes", ws_bytes, need); return TAE_EWORKSPACE; }
   for (int i = 0; i < n_jobs; ++i) {
     const TaeWgradJob& J = jobs_host[i];
@@ -141,10 +163,14 @@ int launch_wgrad(const TaeWgradJob* jobs_host, int n_jobs, void* ws, size_t ws_b
     attr_done = true;
   }
   int* err = reinterpret_cast<int*>(align_up(reinterpret_cast<uintptr_t>(ws), 16));
-  TaeWgradJob* d_jobs = reinterpret_cast<TaeWgradJob*>(reinterpret_cast<uint8_t*>(err) + 128);
-  cudaError_t e = cudaMemcpyAsync(d_jobs, jobs_host, sizeof(TaeWgradJob) * (size_t)n_jobs, cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) { set_error("cudaMemcpyAsync(jobs): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
-  wgrad_kernel<<<n_jobs, 128, W_SMEM, s>>>(d_jobs, err, swap_lbo_sbo);
+  const TaeWgradJob* d_jobs = reinterpret_cast<const TaeWgradJob*>(jobs_dev);
+  if (!d_jobs) {      // no resident copy: upload (a pageable source makes this call wait for the copy)
+    TaeWgradJob* up = reinterpret_cast<TaeWgradJob*>(reinterpret_cast<uint8_t*>(err) + 128);
+    cudaError_t e = cudaMemcpyAsync(up, jobs_host, sizeof(TaeWgradJob) * (size_t)n_jobs, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { set_error("cudaMemcpyAsync(jobs): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+    d_jobs = up;
+  }
+  wgrad_kernel<<<n_jobs, 128, W_SMEM, s>>>(d_jobs, err);
   return after_launch("wgrad_kernel");
 }
 

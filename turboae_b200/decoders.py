@@ -45,7 +45,10 @@ class DEC_LargeCNN(torch.nn.Module):
         self.precision = getattr(args, "tae_precision", None) or os.environ.get("TURBOAE_B200_PRECISION", "bf16")
         #: training (autograd) path: 'fp32' = CUDA-core kernels layer by layer (gradients within 2e-3 of the reference's),
         #: 'bf16' = tensor cores (train_tc.py: fused forward with stash, fused backward per stack, weight-gradient GEMMs)
-        self.train_precision = getattr(args, "tae_train_precision", None) or os.environ.get("TURBOAE_B200_TRAIN_PRECISION", "fp32")
+        #: default: 'bf16' whenever the tensor path covers the configuration (decided here, once, from args)
+        from . import train_tc
+        self.train_precision = (getattr(args, "tae_train_precision", None) or os.environ.get("TURBOAE_B200_TRAIN_PRECISION")
+                                or ("bf16" if train_tc.supported(args, "dec") else "fp32"))
 
     def set_parallel(self):
         for lst in (self.dec1_cnns, self.dec2_cnns, self.dec1_outputs, self.dec2_outputs):

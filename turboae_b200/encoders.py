@@ -94,7 +94,9 @@ class ENC_interCNN(ENCBase):
         #: branches as three conv stacks: ~25x faster, codes within bf16 rounding of the reference's)
         self.precision = getattr(args, "tae_enc_precision", None) or os.environ.get("TURBOAE_B200_ENC_PRECISION", "fp32")
         #: training (autograd) path: 'fp32' (CUDA-core kernels) or 'bf16' (tensor cores, train_tc.py)
-        self.train_precision = getattr(args, "tae_train_precision", None) or os.environ.get("TURBOAE_B200_TRAIN_PRECISION", "fp32")
+        from . import train_tc
+        self.train_precision = (getattr(args, "tae_train_precision", None) or os.environ.get("TURBOAE_B200_TRAIN_PRECISION")
+                                or ("bf16" if train_tc.supported(args, "enc") else "fp32"))
 
     def set_interleaver(self, p_array):
         self.interleaver.set_parray(p_array)

@@ -53,7 +53,8 @@ class PowerNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, group):
         xd = x.double()
-        stats = torch.stack([xd.sum(), (xd * xd).sum(), torch.tensor(float(x.numel()), dtype=torch.float64, device=x.device)])
+        # (torch.full, not torch.tensor: a host scalar copied to the device would make the host wait for the stream)
+        stats = torch.stack([xd.sum(), (xd * xd).sum(), torch.full((), float(x.numel()), dtype=torch.float64, device=x.device)])
         merge_power_stats(stats, group)
         n = stats[2]
         mean = stats[0] / n

@@ -30,9 +30,11 @@ def _odd_chunks(n_ch: int, c0: int) -> int:
 
 
 class _Buffers:
-    """Zero-initialised group-image buffers of one (batch, block length) shape, reused across steps."""
+    """Zero-initialised group-image buffers (and the small fp32 chain buffers) of one (batch, block length) shape, reused
+    across steps; also caches everything whose device pointers are stable: the flat gradient buffer, the weight-gradient
+    job array and the per-stack chain descriptors."""
 
-    def __init__(self, n_stacks, n_layer, groups, device):
+    def __init__(self, n_stacks, n_layer, groups, B, L, F, device):
         cb = _lib.IMG_CHUNK_BYTES
         z = lambda n: torch.zeros(n, dtype=torch.uint8, device=device)
         self.groups = groups
@@ -40,30 +42,56 @@ class _Buffers:
         self.stash_g = z(n_stacks * n_layer * groups * _lib.IMG_CHUNKS * cb)
         self.stash_x = z(n_stacks * groups * cb)
         self.stash_d = z(n_stacks * groups * cb)
+        self.dxin = torch.zeros((n_stacks, B, L, 8), dtype=torch.float32, device=device)
+        self.dlin = torch.zeros((n_stacks, B, L, F), dtype=torch.float32, device=device)
+        self.gflat = None
+        self.jobs = None          # (ctypes array, n, device workspace)
+        self.chains = None
 
 
-def _buffers(dec, n_stacks, n_layer, groups, device):
-    key = (n_stacks, n_layer, groups, str(device))
-    cache = dec.__dict__.setdefault("_tc_buffers", {})
+def _buffers(mod, n_stacks, n_layer, groups, B, L, F, device):
+    key = (n_stacks, n_layer, groups, B, L, F, str(device))
+    cache = mod.__dict__.setdefault("_tc_buffers", {})
     if key not in cache:
         cache.clear()                      # one live shape at a time: the images are large
-        cache[key] = _Buffers(n_stacks, n_layer, groups, device)
+        cache[key] = _Buffers(n_stacks, n_layer, groups, B, L, F, device)
     return cache[key]
 
 
-def wgrad_jobs(n_layer, units, cin0, fouts, groups, stash_y, stash_x, stash_g, stash_d, gflat, offsets, splits=1):
+def _flat_grad(buf, flat, params):
+    """The persistent flat gradient buffer, zeroed -- or a fresh one when some .grad still aliases it (gradient accumulation
+    without zero_grad: the views handed out by the previous backward were adopted by autograd as the .grad tensors)."""
+    g = buf.gflat
+    if g is not None and g.numel() == flat.numel():
+        base = g.untyped_storage().data_ptr()
+        if not any(p.grad is not None and p.grad.untyped_storage().data_ptr() == base for p in params):
+            g.zero_()
+            return g, False
+    buf.gflat = torch.zeros_like(flat)
+    buf.jobs = None
+    buf.chains = None
+    return buf.gflat, True
+
+
+def _job_cost_us(b_chunks, n_cols, taps):
+    """Measured cost of one group in one job (B200, microseconds): the MMAs are operand-fetch bound."""
+    if b_chunks > 1:
+        return 5.0 if n_cols > 48 else 4.4
+    return 3.9 if taps > 1 else 1.1
+
+
+def wgrad_jobs(n_layer, units, cin0, fouts, groups, stash_y, stash_x, stash_g, stash_d, gflat, offsets, splits=None):
     """Job list of ``tae_wgrad_bf16`` for conv stacks laid out like a DEC_LargeCNN: ``offsets[st]`` = (per layer (w_off, b_off),
-    lin_w_off) in floats into ``gflat``; ``fouts[st]`` = features of the stack's Linear."""
+    lin_w_off) in floats into ``gflat``; ``fouts[st]`` = features of the stack's Linear.  One job = one CTA.  Every
+    (layer, channel slab) is cut into group ranges of about equal estimated duration (3-4 CTAs per SM in total, at least
+    ~60 us each so that the TMEM drain stays a small share) and the list is sorted longest first: the hardware dispatches
+    CTAs in order, which then balances the SMs.  ``splits`` forces the number of ranges instead."""
     cb = _lib.IMG_CHUNK_BYTES
     layer_img = groups * _lib.IMG_CHUNKS * cb
-    jobs = []
+    protos = []
 
-    def add(a, b, grad, bias, b_chunks, c0, nc, taps, n_cols, m_valid, n_valid, n0, s_m, s_n, s_t):
-        for sp in range(splits):
-            g0, g1 = groups * sp // splits, groups * (sp + 1) // splits
-            if g1 > g0:
-                jobs.append(_lib.TaeWgradJob(a, b, grad, bias, b_chunks, c0, nc, taps, n_cols, m_valid, n_valid, n0,
-                                             s_m, s_n, s_t, g0, g1, 0))
+    def add(*f):
+        protos.append(f)
 
     gp = gflat.data_ptr()
     for st, (layers, lin_w_off) in enumerate(offsets):
@@ -71,7 +99,7 @@ def wgrad_jobs(n_layer, units, cin0, fouts, groups, stash_y, stash_x, stash_g, s
         g = stash_g.data_ptr() + st * n_layer * layer_img
         x = stash_x.data_ptr() + st * groups * cb
         d = stash_d.data_ptr() + st * groups * cb
-        for j in range(n_layer - 1, 0, -1):          # the big jobs first
+        for j in range(n_layer - 1, 0, -1):
             w_off, b_off = layers[j]
             a_img, b_img = g + j * layer_img, y + (j - 1) * layer_img
             c0 = 0
@@ -91,15 +119,54 @@ def wgrad_jobs(n_layer, units, cin0, fouts, groups, stash_y, stash_x, stash_g, s
         w_off, b_off = layers[0]
         add(g, x, gp + 4 * w_off, gp + 4 * b_off, 1, 0, 1, 5, 16, units, cin0, 0, 5 * cin0, 5, 1)
         add(y + (n_layer - 1) * layer_img, d, gp + 4 * lin_w_off, None, 1, 0, 1, 1, 16, units, fouts[st], 0, 1, units, 0)
-    return jobs
+    costs = [_job_cost_us(f[4], f[8], f[7]) * groups for f in protos]
+    target = max(sum(costs) / (3.5 * N_SM), 60.0)
+    jobs = []
+    for f, c in zip(protos, costs):
+        n_split = splits if splits is not None else max(1, min(groups, int(round(c / target))))
+        for sp in range(n_split):
+            g0, g1 = groups * sp // n_split, groups * (sp + 1) // n_split
+            if g1 > g0:
+                jobs.append((c * (g1 - g0) / groups, _lib.TaeWgradJob(*f, g0, g1, 0)))
+    jobs.sort(key=lambda t: -t[0])
+    return [j for _, j in jobs]
+
+
+def pack_jobs(jobs, device):
+    """(host array, count, device copy, device workspace): uploaded once, reused by every later launch."""
+    arr = (_lib.TaeWgradJob * len(jobs))(*jobs)
+    dev_copy = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+    ws = torch.empty(512, dtype=torch.uint8, device=device)
+    return arr, len(jobs), dev_copy, ws
+
+
+def run_packed(packed, device):
+    arr, n, dev_copy, ws = packed
+    lib = _lib.load()
+    _lib.check(lib.tae_wgrad_bf16(arr, n, _lib.ptr(dev_copy), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(device)))
 
 
 def run_wgrad(jobs, device):
-    lib = _lib.load()
-    arr = (_lib.TaeWgradJob * len(jobs))(*jobs)
-    ws = torch.empty(256 + C.sizeof(_lib.TaeWgradJob) * len(jobs) + 64, dtype=torch.uint8, device=device)
-    _lib.check(lib.tae_wgrad_bf16(arr, len(jobs), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(device)))
-    return ws
+    packed = pack_jobs(jobs, device)
+    run_packed(packed, device)
+    return packed[3]
+
+
+def _dec_offsets(a):
+    F, units, n_layer, I = a.num_iter_ft, a.dec_num_unit, a.dec_num_layer, a.num_iteration
+    offsets, fouts, off = [], [], 0
+    for idx in range(I):
+        for s_ in range(2):
+            layers = []
+            for j in range(n_layer):
+                cin = (2 + F) if j == 0 else units
+                layers.append((off, off + units * cin * 5))
+                off += units * cin * 5 + units
+            fout = 1 if (s_ == 1 and idx == I - 1) else F
+            offsets.append((layers, off))
+            fouts.append(fout)
+            off += fout * units + fout
+    return offsets, fouts
 
 
 class DecoderTrainFn(torch.autograd.Function):
@@ -113,7 +180,7 @@ class DecoderTrainFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             _, cfg, flat, packed, _ = dec._prepare(L, dev, "bf16")
             groups = lib.tae_train_groups(L, B)
-            buf = _buffers(dec, n_stacks, n_layer, groups, dev)
+            buf = _buffers(dec, n_stacks, n_layer, groups, B, L, a.num_iter_ft, dev)
             perm, inv = dec.interleaver.device_index(dev)
             out = torch.empty((B, L, 1), dtype=torch.float32, device=dev)
             ws = dec._ws.get(256, dev)
@@ -137,6 +204,7 @@ class DecoderTrainFn(torch.autograd.Function):
         dev = d_out.device
         F, units, n_layer, I = a.num_iter_ft, a.dec_num_unit, a.dec_num_layer, a.num_iteration
         n_stacks = 2 * I
+        params = dec.ordered_parameters()
         with torch.cuda.device(dev):
             packed_bwd = dec._flat.derived.get("bf16_bwd")
             if packed_bwd is None:
@@ -144,61 +212,59 @@ class DecoderTrainFn(torch.autograd.Function):
                 _lib.check(lib.tae_dec_pack_bwd_bf16(cfg, _lib.ptr(flat), _lib.ptr(packed_bwd), _lib.stream_ptr(dev)))
                 dec._flat.derived["bf16_bwd"] = packed_bwd
             perm, inv = dec.interleaver.device_index(dev)
-            perm_l, inv_l = perm.long(), inv.long()
             ws = dec._ws.get(256, dev)
-            d_rec = torch.zeros((B, L, 3), dtype=torch.float32, device=dev)
-            gflat = torch.zeros_like(flat)
+            gflat, _ = _flat_grad(buf, flat, params)
+            offsets, fouts = _dec_offsets(a)
+            if buf.chains is None or buf.chains[0] != (perm.data_ptr(), inv.data_ptr()):
+                chains = []
+                for st in range(n_stacks):
+                    bias = gflat.data_ptr() + 4 * (offsets[st][1] + fouts[st] * units)
+                    if st == n_stacks - 1:
+                        chains.append(_lib.TaeStackBwdChain(None, None, None, 0, 0, None, bias))
+                    else:
+                        nxt = st + 1
+                        last = nxt == n_stacks - 1
+                        chains.append(_lib.TaeStackBwdChain(
+                            buf.dxin[nxt].data_ptr(), None if last else buf.dlin[nxt].data_ptr(),
+                            (inv if nxt % 2 == 1 else perm).data_ptr(), F, 1 if (a.extrinsic and not last) else 0,
+                            buf.dlin[st].data_ptr(), bias))
+                buf.chains = ((perm.data_ptr(), inv.data_ptr()), chains)
+            chains = buf.chains[1]
             # out = sigmoid(deinterleave(o_last))  (decoders.py:267)  =>  d o_last = interleave(d_out * out * (1 - out))
-            d_o = (d_out.to(torch.float32) * out * (1.0 - out)).index_select(1, perm_l).contiguous()
-            dxin = torch.empty((B, L, 8), dtype=torch.float32, device=dev)
-            lin_bias_grads = []
+            d_o = (d_out.to(torch.float32) * out * (1.0 - out)).index_select(1, perm.long()).contiguous()
+            stream = _lib.stream_ptr(dev)
             for st in range(n_stacks - 1, -1, -1):
-                fin = d_o.shape[2]
-                lin_bias_grads.append((st, d_o.sum(dim=(0, 1))))
-                _lib.check(lib.tae_dec_stack_backward_bf16(cfg, _lib.ptr(packed_bwd), st, _lib.ptr(d_o), fin, _lib.ptr(buf.stash_y),
-                                                           _lib.ptr(buf.stash_g), _lib.ptr(buf.stash_d), _lib.ptr(dxin), B,
-                                                           _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
-                if st % 2 == 0:      # [r_sys, r_par1, prior]                                 (decoders.py:230)
-                    d_rec[:, :, 0] += dxin[:, :, 0]
-                    d_rec[:, :, 1] += dxin[:, :, 1]
-                else:                # [interleave(r_sys), r_par2, interleave(x_plr)]          (decoders.py:240)
-                    d_rec[:, :, 0] += dxin[:, :, 0].index_select(1, inv_l)
-                    d_rec[:, :, 2] += dxin[:, :, 1]
-                if st == 0:
-                    break
-                d_prior = dxin[:, :, 2:2 + F]
-                if a.extrinsic and st != n_stacks - 1:
-                    d_prior = d_prior - d_o            # x_plr = Linear(...) - prior            (decoders.py:235-236, 246-247)
-                # the prior of stack st is interleave (st odd) / deinterleave (st even) of the previous stack's extrinsic output
-                d_o = d_prior.index_select(1, inv_l if st % 2 == 1 else perm_l).contiguous()
-            grads = [None] * len(dec.ordered_parameters())
+                last = st == n_stacks - 1
+                _lib.check(lib.tae_dec_stack_backward_bf16(cfg, _lib.ptr(packed_bwd), st, _lib.ptr(d_o) if last else None, 1 if last else F,
+                                                           _lib.ptr(buf.stash_y), _lib.ptr(buf.stash_g), _lib.ptr(buf.stash_d),
+                                                           _lib.ptr(buf.dxin[st]), B, C.byref(chains[st]), _lib.ptr(ws), ws.numel(), stream))
+            d_rec = None
+            if ctx.need_input:
+                # stack inputs: even [r_sys, r_par1, prior] (decoders.py:230), odd [interleave(r_sys), r_par2, ...] (:240)
+                ev, od = buf.dxin[0::2].sum(0), buf.dxin[1::2].sum(0)
+                d_rec = torch.stack([ev[:, :, 0] + od[:, :, 0].index_select(1, inv.long()), ev[:, :, 1], od[:, :, 1]], dim=2)
+            grads = [None] * len(params)
             if ctx.need_params:
-                offsets, fouts, off = [], [], 0
-                for idx in range(I):
-                    for s in range(2):
-                        layers = []
-                        for j in range(n_layer):
-                            cin = (2 + F) if j == 0 else units
-                            layers.append((off, off + units * cin * 5))
-                            off += units * cin * 5 + units
-                        fout = 1 if (s == 1 and idx == I - 1) else F
-                        offsets.append((layers, off))
-                        fouts.append(fout)
-                        off += fout * units + fout
-                jobs = wgrad_jobs(n_layer, units, 2 + F, fouts, buf.groups, buf.stash_y, buf.stash_x, buf.stash_g, buf.stash_d,
-                                  gflat, offsets, splits=getattr(dec, "wgrad_splits", 1))
-                keep = run_wgrad(jobs, dev)
-                for st, gb in lin_bias_grads:
-                    lin_w_off = offsets[st][1]
-                    gflat[lin_w_off + fouts[st] * units: lin_w_off + fouts[st] * units + fouts[st]] = gb
+                if buf.jobs is None:
+                    jobs = wgrad_jobs(n_layer, units, 2 + F, fouts, buf.groups, buf.stash_y, buf.stash_x, buf.stash_g, buf.stash_d,
+                                      gflat, offsets, splits=getattr(dec, "wgrad_splits", None))
+                    buf.jobs = pack_jobs(jobs, dev)
+                run_packed(buf.jobs, dev)
                 off = 0
-                for i, p in enumerate(dec.ordered_parameters()):
+                for i, p in enumerate(params):
                     n = p.numel()
                     if p.requires_grad:
                         grads[i] = gflat[off:off + n].view_as(p)
                     off += n
-                del keep
-        return (None, d_rec if ctx.need_input else None, *grads)
+        return (None, d_rec, *grads)
+
+
+def supported(args, which):
+    """Static check (at module construction) whether the tensor-core training path covers this configuration."""
+    if which == "dec":
+        return (args.dec_kernel_size == 5 and 1 <= args.dec_num_unit <= 100 and args.dec_num_layer >= 2 and args.num_iter_ft <= 5
+                and args.block_len <= 512)
+    return args.enc_kernel_size == 5 and 1 <= args.enc_num_unit <= 100 and args.enc_num_layer >= 2 and args.block_len <= 512
 
 
 def decoder_forward_train(dec, received):
@@ -232,7 +298,7 @@ class EncoderTrainFn(torch.autograd.Function):
                 _lib.check(lib.tae_enc_pack_bf16(cfg, _lib.ptr(flat), _lib.ptr(packed), _lib.stream_ptr(dev)))
                 enc._flat.derived["bf16"] = packed
             groups = lib.tae_train_groups(L, B)
-            buf = _buffers(enc, 3, n_layer, groups, dev)
+            buf = _buffers(enc, 3, n_layer, groups, B, L, 1, dev)
             perm, inv = enc.interleaver.device_index(dev)
             x_tx = torch.empty((B, L, 3), dtype=torch.float32, device=dev)
             stats = torch.zeros(3, dtype=torch.float64, device=dev)
@@ -260,10 +326,10 @@ class EncoderTrainFn(torch.autograd.Function):
                 _lib.check(lib.tae_enc_pack_bwd_bf16(cfg, _lib.ptr(flat), _lib.ptr(packed_bwd), _lib.stream_ptr(dev)))
                 enc._flat.derived["bf16_bwd"] = packed_bwd
             ws = enc._ws.get(256, dev)
-            gflat = torch.zeros_like(flat)
-            # x_tx = ELU(Linear(h))  =>  d lin = d x_tx * ELU'   (ELU' = x_tx + 1 where x_tx < 0)
-            d_lin = (d_x.to(torch.float32) * torch.where(x_tx > 0, torch.ones_like(x_tx), x_tx + 1.0))
-            dxin = torch.empty((B, L, 8), dtype=torch.float32, device=dev)
+            params = enc.ordered_parameters()
+            gflat, _ = _flat_grad(buf, flat, params)
+            # x_tx = ELU(Linear(h))  =>  d lin = d x_tx * ELU'   (ELU' = x_tx + 1 where x_tx < 0); one (B, L, 1) slab per branch
+            d_lin = (d_x.to(torch.float32) * torch.where(x_tx > 0, torch.ones_like(x_tx), x_tx + 1.0)).permute(2, 0, 1).contiguous()
             offsets, off = [], 0
             for br in range(3):
                 layers = []
@@ -273,21 +339,24 @@ class EncoderTrainFn(torch.autograd.Function):
                     off += units * cin * 5 + units
                 offsets.append((layers, off))
                 off += units + 1
+            if buf.chains is None:
+                buf.chains = (None, [_lib.TaeStackBwdChain(None, None, None, 0, 0, None, gflat.data_ptr() + 4 * (offsets[br][1] + units))
+                                     for br in range(3)])
+            stream = _lib.stream_ptr(dev)
             for br in range(3):
-                d_br = d_lin[:, :, br:br + 1].contiguous()
-                _lib.check(lib.tae_enc_stack_backward_bf16(cfg, _lib.ptr(packed_bwd), br, _lib.ptr(d_br), _lib.ptr(buf.stash_y),
-                                                           _lib.ptr(buf.stash_g), _lib.ptr(buf.stash_d), _lib.ptr(dxin), B, _lib.ptr(ws),
-                                                           ws.numel(), _lib.stream_ptr(dev)))
-                gflat[offsets[br][1] + units] = d_br.sum()
-            jobs = wgrad_jobs(n_layer, units, 1, [1, 1, 1], buf.groups, buf.stash_y, buf.stash_x, buf.stash_g, buf.stash_d, gflat,
-                              offsets, splits=getattr(enc, "wgrad_splits", 1))
-            keep = run_wgrad(jobs, dev)
+                _lib.check(lib.tae_enc_stack_backward_bf16(cfg, _lib.ptr(packed_bwd), br, _lib.ptr(d_lin[br]), _lib.ptr(buf.stash_y),
+                                                           _lib.ptr(buf.stash_g), _lib.ptr(buf.stash_d), _lib.ptr(buf.dxin[br]), B,
+                                                           C.byref(buf.chains[1][br]), _lib.ptr(ws), ws.numel(), stream))
+            if buf.jobs is None:
+                jobs = wgrad_jobs(n_layer, units, 1, [1, 1, 1], buf.groups, buf.stash_y, buf.stash_x, buf.stash_g, buf.stash_d, gflat,
+                                  offsets, splits=getattr(enc, "wgrad_splits", None))
+                buf.jobs = pack_jobs(jobs, dev)
+            run_packed(buf.jobs, dev)
             grads, off = [], 0
-            for p in enc.ordered_parameters():
+            for p in params:
                 n = p.numel()
                 grads.append(gflat[off:off + n].view_as(p) if p.requires_grad else None)
                 off += n
-            del keep
         return (None, None, *grads)
 
 

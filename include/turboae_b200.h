@@ -240,6 +240,34 @@ int tae_wgrad_bf16(const TaeWgradJob* jobs_host, int32_t n_jobs, const void* job
 int tae_gru_direction_f32(const float* xproj, const float* w_hh, const float* b_hh, float* out,
                           int32_t B, int32_t L, int32_t H, int32_t out_stride, int32_t out_offset, int32_t reverse, void* stream);
 
+/* The same recurrence on the tensor cores (bf16 operands, fp32 accumulation, fp32 hidden state): the input projection is
+ * part of the per-step MMA chain, so no (B, L, 3H) projection tensor exists.  Activations travel between the launches as
+ * TIME-MAJOR TILES: bf16 [block of R codewords][t][chunk of 8 channels][R][8] -- the operand chunks of one time step are
+ * contiguous (bulk copies in, coalesced stores out).  R = tae_gru_rows_per_block(B): 16, 32, 64, 96 or 128 (small
+ * batches use fewer rows per CTA so that every SM gets a block); a tile buffer holds an even number of blocks
+ * (tae_gru_tile_bytes).  Channels are stored in groups of grp_valid real channels padded to a multiple of 8: the stack
+ * input is one group (2 + F channels in 8), a layer's output is two groups (forward | reverse, H channels each in 13
+ * chunks), which is the next layer's input (in_ch = 2H, grp_valid = H).
+ *   tae_gru_tiles_from_f32 : (B, L, C) fp32 -> tiles with ceil(C/8) chunks
+ *   tae_gru_pack_bf16      : weight_ih (3H, in_ch), weight_hh (3H, H), bias_ih, bias_hh of one layer-direction -> `packed`
+ *                            (rebuild after a weight update)
+ *   tae_gru_direction_bf16 : x_tiles -> h_t for all t into chunks [out_chunk0, out_chunk0 + 13) of out_tiles (out_chunks
+ *                            chunks per time step: 26 for a bidirectional layer); reverse != 0 runs t = L-1 .. 0
+ *   tae_gru_linear_f32     : the dec*_outputs Linear (reference decoders.py:104-105, 118-119) straight from tiles:
+ *                            out (B, L, F) fp32 = weight (F, in_ch) . h + bias, F <= 8
+ * H: multiple of 4, <= 104; at most 26 input chunks; workspace >= 256 bytes.                                          */
+int32_t tae_gru_rows_per_block(int32_t B);
+size_t tae_gru_tile_bytes(int32_t B, int32_t L, int32_t n_chunks, int32_t R);
+size_t tae_gru_packed_bytes(int32_t H, int32_t in_ch, int32_t grp_valid);
+int    tae_gru_pack_bf16(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, void* packed,
+                         int32_t H, int32_t in_ch, int32_t grp_valid, void* stream);
+int tae_gru_direction_bf16(const void* packed, const void* x_tiles, void* out_tiles, int32_t B, int32_t L, int32_t H,
+                           int32_t in_ch, int32_t grp_valid, int32_t R, int32_t out_chunks, int32_t out_chunk0,
+                           int32_t reverse, void* workspace, size_t workspace_bytes, void* stream);
+int tae_gru_tiles_from_f32(const float* x, void* tiles, int32_t B, int32_t L, int32_t C, int32_t R, void* stream);
+int tae_gru_linear_f32(const void* tiles, const float* weight, const float* bias, float* out, int32_t B, int32_t L,
+                       int32_t in_ch, int32_t grp_valid, int32_t F, int32_t R, void* stream);
+
 /* ---- around the path: on-device channel and metrics -------------------------------------
  * AWGN channel, reference channel_ae.py:41-42 with channels.py:21-35: received = codes + sigma * N(0,1).
  * The reference draws torch.randn on the CPU (unseeded); this stream is Philox4x32-10 + Box-Muller, element i uses

@@ -13,6 +13,7 @@ L = int(os.environ.get("RNN_L", "1000")); B = int(os.environ.get("RNN_B", "2368"
 torch.manual_seed(0)
 args = make_args(num_iteration=6, dec_num_unit=100, block_len=L, batch_size=B)
 dec = T.DEC_LargeRNN(args, O.make_perm(L, 0)).cuda().eval()
+if os.environ.get("RNN_PRECISION"): dec.precision = os.environ["RNN_PRECISION"]
 rec = torch.randn(B, L, 3, device="cuda")
 with torch.no_grad():
     dec(rec); torch.cuda.synchronize()
@@ -27,7 +28,12 @@ x = torch.randn(Bc, L, 7)
 torch.set_num_threads(os.cpu_count())
 with torch.no_grad():
     gru(x); t0 = time.perf_counter(); gru(x); dt = time.perf_counter() - t0
-print(json.dumps({"what": "DEC_LargeRNN decode, block_len %d, num_iteration 6, H 100, fp32" % L, "batch": B, "ms": ms,
+if os.environ.get("RNN_PROFILE"):
+    from torch.profiler import profile, ProfilerActivity
+    with torch.no_grad(), profile(activities=[ProfilerActivity.CUDA]) as prof:
+        dec(rec); torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=8, max_name_column_width=50), file=sys.stderr)
+print(json.dumps({"what": "DEC_LargeRNN decode, block_len %d, num_iteration 6, H 100, precision %s" % (L, dec.precision), "batch": B, "ms": ms,
                   "codewords_per_s": B / (ms * 1e-3), "own_launches": _lib.launch_count() - n0,
                   "cpu_torch_gru_cw_per_s_est": Bc / (12 * dt), "cpu_cores": os.cpu_count(),
                   "finite": bool(torch.isfinite(y).all())}))

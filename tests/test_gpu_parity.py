@@ -508,12 +508,13 @@ def test_reference_training_loop_reduces_loss():
 
 
 # ------------------------------------------------------------------------------------------------- f2: DEC_LargeRNN
-def _rnn_module(g, scale=1.0):
+def _rnn_module(g, scale=1.0, precision="fp32"):
     import turboae_b200 as T
     B, L, H, n_iter = g["cfg"].tolist()
     m = T.DEC_LargeRNN(make_args(num_iteration=n_iter, dec_num_unit=H, block_len=L, batch_size=B), g["p"])
     m.set_parallel()
     m.load_state_dict({k[4:]: torch.from_numpy(v * np.float32(scale)) for k, v in g.items() if k.startswith("dec.")}, strict=True)
+    m.precision = precision
     return m.to(DEV).eval()
 
 
@@ -545,11 +546,91 @@ def test_rnn_decoder_amplified_weights_and_long_blocks_vs_oracle():
     L = 1000
     p = O.make_perm(L, 0)
     big = T.DEC_LargeRNN(make_args(num_iteration=1, dec_num_unit=100, block_len=L, batch_size=2), p).to(DEV).eval()
+    big.precision = "fp32"
     wb = {"dec." + k: v.detach().cpu().numpy() for k, v in big.state_dict().items()}
     rec = (rs.randint(0, 2, size=(2, L, 3)) * 2.0 - 1.0 + 0.8 * rs.standard_normal((2, L, 3))).astype(np.float32)
     with torch.no_grad():
         y = big(_t(rec)).cpu().numpy()
     np.testing.assert_allclose(y, O.dec_rnn_forward(rec, wb, p, num_iteration=1), atol=2e-5, rtol=0)
+
+
+@pytest.mark.parametrize("B,L,H,cin,reverse", [(300, 50, 100, 7, 0), (300, 50, 100, 7, 1), (37, 64, 100, 200, 0), (513, 24, 100, 200, 1),
+                                                 (5, 30, 32, 7, 1), (260, 20, 32, 64, 0)])
+def test_gru_direction_bf16_vs_oracle(B, L, H, cin, reverse):
+    """tae_gru_direction_bf16 (tcgen05 recurrence, input projection inside the MMA chain) against the pinned numpy GRU on the
+    same bf16-rounded inputs and weights: what remains is bf16 rounding of h as the next step's operand and the approximate
+    tanh -- |dh| <= 2e-2 at every step (measured ~5e-3), no drift with sequence position."""
+    from turboae_b200 import _lib
+    lib = _lib.load()
+    rs = np.random.RandomState(B + L + H + cin)
+    q = lambda a: torch.from_numpy(a).to(torch.bfloat16).float().numpy()
+    sc = 1.0 / np.sqrt(H)
+    w_ih, w_hh = q((rs.uniform(-1, 1, (3 * H, cin)) * 2 * sc).astype(np.float32)), q((rs.uniform(-1, 1, (3 * H, H)) * 2 * sc).astype(np.float32))
+    b_ih, b_hh = (rs.uniform(-1, 1, 3 * H) * sc).astype(np.float32), (rs.uniform(-1, 1, 3 * H) * sc).astype(np.float32)
+    x = q(rs.standard_normal((B, L, cin)).astype(np.float32))
+    ref = O.gru_direction(x, w_ih, w_hh, b_ih, b_hh, reverse=bool(reverse))
+    # inputs as ONE group of cin channels (layer-0 form) or as two groups of cin/2 (the form a bidirectional layer below produces)
+    grp = cin if cin <= 8 or cin % 2 else cin // 2
+    R = lib.tae_gru_rows_per_block(B)
+    gp = 8 * ((grp + 7) // 8)
+    n_in = (cin // grp) * gp // 8
+    xpad = np.zeros((B, L, n_in * 8), np.float32)
+    for gi in range(cin // grp):
+        xpad[:, :, gi * gp:gi * gp + grp] = x[:, :, gi * grp:(gi + 1) * grp]
+    xt = torch.empty(lib.tae_gru_tile_bytes(B, L, n_in, R), dtype=torch.uint8, device=DEV)
+    xpad_d = _t(xpad)
+    _lib.check(lib.tae_gru_tiles_from_f32(_lib.ptr(xpad_d), _lib.ptr(xt), B, L, n_in * 8, R, _lib.stream_ptr()))
+    packed = torch.empty(lib.tae_gru_packed_bytes(H, cin, grp), dtype=torch.uint8, device=DEV)
+    wd = [_t(w_ih), _t(w_hh), _t(b_ih), _t(b_hh)]          # keep the device copies alive until the pack kernel has run
+    _lib.check(lib.tae_gru_pack_bf16(_lib.ptr(wd[0]), _lib.ptr(wd[1]), _lib.ptr(wd[2]), _lib.ptr(wd[3]), _lib.ptr(packed), H, cin, grp,
+                                     _lib.stream_ptr()))
+    n_out = 2 * ((H + 7) // 8)
+    out = torch.zeros(lib.tae_gru_tile_bytes(B, L, n_out, R), dtype=torch.uint8, device=DEV)
+    ws = torch.zeros(256, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.tae_gru_direction_bf16(_lib.ptr(packed), _lib.ptr(xt), _lib.ptr(out), B, L, H, cin, grp, R, n_out, reverse * (n_out // 2),
+                                          reverse, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    # read the hidden states back through the tile Linear with an identity weight (8 output features at a time)
+    got = np.zeros((B, L, 2 * H), np.float32)
+    for f0 in range(0, 2 * H, 8):
+        wsel = torch.zeros(8, 2 * H, device=DEV)
+        for f in range(8):
+            if f0 + f < 2 * H:
+                wsel[f, f0 + f] = 1.0
+        y8 = torch.empty(B, L, 8, device=DEV)
+        _lib.check(lib.tae_gru_linear_f32(_lib.ptr(out), _lib.ptr(wsel), _lib.ptr(torch.zeros(8, device=DEV)), _lib.ptr(y8), B, L, 2 * H, H, 8, R,
+                                          _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        got[:, :, f0:f0 + 8] = y8.cpu().numpy()[:, :, :min(8, 2 * H - f0)]
+    off = H if reverse else 0
+    assert np.all(got[:, :, (0 if reverse else H):(H if reverse else 2 * H)] == 0.0)        # the other direction's half is untouched
+    err = np.abs(got[:, :, off:off + H] - ref)
+    assert ref.std() > 0.1
+    assert err.max() < 2e-2, (err.max(), err.mean())
+    first, last = (err[:, -4:], err[:, :4]) if reverse else (err[:, :4], err[:, -4:])
+    assert last.mean() < 4 * first.mean() + 2e-3
+
+
+@pytest.mark.parametrize("name", ["rnn_h32_i2_l40_b5.npz", "rnn_h100_i1_l100_b3.npz"])
+def test_rnn_decoder_bf16_vs_reference_fixture(name):
+    g = load_npz(name)
+    m = _rnn_module(g, precision="bf16")
+    with torch.no_grad():
+        y = m(_t(g["received"])).cpu().numpy()
+    np.testing.assert_allclose(y, g["y"], atol=3e-3, rtol=0)
+
+
+def test_rnn_decoder_bf16_amplified_weights_vs_oracle():
+    g = load_npz("rnn_h32_i2_l40_b5.npz")
+    m = _rnn_module(g, scale=4.0, precision="bf16")
+    w = {k: v * np.float32(4.0) for k, v in g.items() if k.startswith("dec.")}
+    rs = np.random.RandomState(5)
+    rec = (rs.randint(0, 2, size=(19, 40, 3)) * 2.0 - 1.0 + 0.8 * rs.standard_normal((19, 40, 3))).astype(np.float32)
+    with torch.no_grad():
+        y = m(_t(rec)).cpu().numpy()
+    ref = O.dec_rnn_forward(rec, w, g["p"], num_iteration=2)
+    d = np.abs(y - ref)
+    assert ref.max() - ref.min() > 0.5
+    assert d.mean() < 1.5e-2 and d.max() < 0.12, (d.mean(), d.max())      # 4x weights amplify the bf16 rounding; measured 7e-3 / 6.5e-2
 
 
 # ------------------------------------------------------------------------------------------------- full size

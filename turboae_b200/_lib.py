@@ -72,6 +72,14 @@ _SIGNATURES = {
     "tae_power_norm_f32": (C.c_int, [_P, _P, C.c_size_t, _P, _P, _P]),
     "tae_power_norm_ste_f32": (C.c_int, [_P, _P, C.c_size_t, _P, _P, C.c_float, C.c_float, _P]),
     "tae_gru_direction_f32": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "tae_gru_rows_per_block": (C.c_int32, [C.c_int32]),
+    "tae_gru_tile_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "tae_gru_packed_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "tae_gru_pack_bf16": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "tae_gru_direction_bf16": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, C.c_int32, _P, C.c_size_t, _P]),
+    "tae_gru_tiles_from_f32": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "tae_gru_linear_f32": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "tae_train_groups": (C.c_int32, [C.c_int32, C.c_int32]),
     "tae_dec_forward_train_bf16": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "tae_dec_bwd_packed_bytes": (C.c_size_t, [C.POINTER(TaeDecConfig)]),
@@ -88,6 +96,7 @@ _SIGNATURES = {
     "tae_error_count_f32": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     # debug / self-test entry points
     "tae_debug_set_timeline": (None, [_P]),
+    "tae_debug_gru_timeline": (None, [_P]),
     "tae_debug_probe_rate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int32, _P]),
     "tae_debug_probe_lbo": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "tae_debug_probe_pair": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P]),

@@ -466,6 +466,59 @@ int tae_gru_direction_f32(const float* xproj, const float* w_hh, const float* b_
   return launch_gru_direction(xproj, w_hh, b_hh, out, B, L, H, out_stride, out_offset, reverse, (cudaStream_t)stream);
 }
 
+void tae_debug_gru_timeline(long long* dev) { gru_tc_set_timeline(dev); }
+
+int32_t tae_gru_rows_per_block(int32_t B) { return gru_tc_rows_per_block(B < 0 ? 0 : B); }
+
+size_t tae_gru_tile_bytes(int32_t B, int32_t L, int32_t n_chunks, int32_t R) {
+  if (B < 0 || L < 1 || n_chunks < 1 || !(R == 16 || (R >= 32 && R <= 128 && R % 32 == 0))) return 0;
+  const size_t n_blk = 2 * ((((size_t)B + R - 1) / R + 1) / 2);
+  return n_blk * (size_t)L * n_chunks * R * 16;
+}
+
+size_t tae_gru_packed_bytes(int32_t H, int32_t in_ch, int32_t grp_valid) {
+  const char* why = nullptr;
+  if (!gru_tc_supported(H, in_ch, grp_valid, &why)) { set_error("bf16 GRU path: %s", why); return 0; }
+  return gru_tc_packed_bytes(H, in_ch, grp_valid);
+}
+
+int tae_gru_pack_bf16(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, void* packed, int32_t H, int32_t in_ch,
+                      int32_t grp_valid, void* stream) {
+  const char* why = nullptr;
+  if (!gru_tc_supported(H, in_ch, grp_valid, &why)) { set_error("bf16 GRU path: %s", why); return TAE_EUNSUPPORTED; }
+  TAE_REQUIRE(w_ih && w_hh && b_ih && b_hh && packed, "tae_gru_pack_bf16: NULL pointer");
+  return gru_tc_pack(w_ih, w_hh, b_ih, b_hh, packed, H, in_ch, grp_valid, (cudaStream_t)stream);
+}
+
+int tae_gru_direction_bf16(const void* packed, const void* x_tiles, void* out_tiles, int32_t B, int32_t L, int32_t H, int32_t in_ch,
+                           int32_t grp_valid, int32_t R, int32_t out_chunks, int32_t out_chunk0, int32_t reverse, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  const char* why = nullptr;
+  if (!gru_tc_supported(H, in_ch, grp_valid, &why)) { set_error("bf16 GRU path: %s", why); return TAE_EUNSUPPORTED; }
+  TAE_REQUIRE(B >= 0 && L >= 1, "tae_gru_direction_bf16: bad shape B=%d L=%d", B, L);
+  TAE_REQUIRE(R == 16 || (R >= 32 && R <= 128 && R % 32 == 0), "tae_gru_direction_bf16: rows per block %d (16, 32, 64, 96 or 128)", R);
+  TAE_REQUIRE(out_chunk0 >= 0 && out_chunk0 + (H + 7) / 8 <= out_chunks, "tae_gru_direction_bf16: bad output chunk window");
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(packed && x_tiles && out_tiles && workspace, "tae_gru_direction_bf16: NULL pointer");
+  return gru_tc_direction(packed, x_tiles, out_tiles, B, L, H, in_ch, grp_valid, R, out_chunks, out_chunk0, reverse, workspace,
+                          workspace_bytes, (cudaStream_t)stream);
+}
+
+int tae_gru_tiles_from_f32(const float* x, void* tiles, int32_t B, int32_t L, int32_t C, int32_t R, void* stream) {
+  TAE_REQUIRE(B >= 0 && L >= 1 && C >= 1 && (R == 16 || (R >= 32 && R <= 128 && R % 32 == 0)), "tae_gru_tiles_from_f32: bad shape");
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(x && tiles, "tae_gru_tiles_from_f32: NULL pointer");
+  return gru_tc_tiles_from_f32(x, tiles, B, L, C, R, (cudaStream_t)stream);
+}
+
+int tae_gru_linear_f32(const void* tiles, const float* weight, const float* bias, float* out, int32_t B, int32_t L, int32_t in_ch,
+                       int32_t grp_valid, int32_t F, int32_t R, void* stream) {
+  TAE_REQUIRE(B >= 0 && L >= 1 && F >= 1 && F <= 8 && (R == 16 || (R >= 32 && R <= 128 && R % 32 == 0)), "tae_gru_linear_f32: bad shape (F <= 8)");
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(tiles && weight && bias && out, "tae_gru_linear_f32: NULL pointer");
+  return gru_tc_linear(tiles, weight, bias, out, B, L, in_ch, grp_valid, F, R, (cudaStream_t)stream);
+}
+
 int tae_awgn_f32(const float* codes, float* received, size_t n, float sigma, uint64_t seed, uint64_t offset, void* stream) {
   if (n == 0) return TAE_OK;
   TAE_REQUIRE(codes && received, "tae_awgn_f32: NULL pointer");

@@ -130,6 +130,18 @@ int launch_add_count(double* stats, double n, cudaStream_t s);
 // ---- DEC_LargeRNN recurrence (tae_gru.cu) ----------------------------------------------------
 int launch_gru_direction(const float* xproj, const float* w_hh, const float* b_hh, float* out, int B, int L, int H, int out_stride,
                          int out_offset, int reverse, cudaStream_t s);
+// tensor-core recurrence (tae_gru_tc.cu)
+bool gru_tc_supported(int H, int in_ch, int grp_valid, const char** why);
+void gru_tc_set_timeline(long long* dev);
+int gru_tc_rows_per_block(int B);
+size_t gru_tc_packed_bytes(int H, int in_ch, int grp_valid);
+int gru_tc_pack(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, void* packed, int H, int in_ch, int grp_valid,
+                cudaStream_t s);
+int gru_tc_direction(const void* packed, const void* x_tiles, void* out_tiles, int B, int L, int H, int in_ch, int grp_valid, int R,
+                     int out_chunks, int out_c0, int reverse, void* ws, size_t ws_bytes, cudaStream_t s);
+int gru_tc_tiles_from_f32(const float* x, void* tiles, int B, int L, int C, int R, cudaStream_t s);
+int gru_tc_linear(const void* tiles, const float* w, const float* bias, float* out, int B, int L, int in_ch, int grp_valid, int F, int R,
+                  cudaStream_t s);
 // ---- channel + metrics (tae_channel.cu) ------------------------------------------------------
 int launch_awgn(const float* codes, float* received, size_t n, float sigma, uint64_t seed, uint64_t offset, cudaStream_t s);
 int launch_error_count(const float* y_true, const float* y_pred, int B, int L, unsigned long long* counts, cudaStream_t s);

@@ -217,6 +217,14 @@ class DEC_LargeRNN(torch.nn.Module):
                                         dropout=getattr(args, "dropout", 0.0), bidirectional=True))
             self.dec1_outputs.append(torch.nn.Linear(2 * args.dec_num_unit, args.num_iter_ft))
             self.dec2_outputs.append(torch.nn.Linear(2 * args.dec_num_unit, 1 if idx == args.num_iteration - 1 else args.num_iter_ft))
+        H = args.dec_num_unit
+        tc_ok = H % 4 == 0 and 4 <= H <= 100 and 2 + args.num_iter_ft <= 200
+        #: 'bf16' = tensor-core recurrence (tae_gru_direction_bf16: bf16 operands, fp32 accumulation and state), 'fp32' = CUDA-core
+        #: recurrence (elementwise parity with torch.nn.GRU); the default is decided here, once, from the configuration
+        self.precision = (getattr(args, "tae_rnn_precision", None) or os.environ.get("TURBOAE_B200_RNN_PRECISION")
+                          or ("bf16" if tc_ok else "fp32"))
+        self._packed = {}
+        self._ws = Workspace()
 
     def set_parallel(self):
         for lst in (self.dec1_rnns, self.dec2_rnns, self.dec1_outputs, self.dec2_outputs):
@@ -240,6 +248,56 @@ class DEC_LargeRNN(torch.nn.Module):
         _lib.check(lib.tae_conv1d_elu_f32(_lib.ptr(x), _lib.ptr(out), _lib.ptr(w), _lib.ptr(b), B, L, cin, cout, 1, 0, _lib.ptr(ws),
                                           ws_bytes, _lib.stream_ptr(x.device)))
         return out
+
+    def _stack_tc(self, gru, lin, x):
+        """One decoder stack on the tensor cores: 2-layer bidirectional GRU + its Linear, (B, L, 2+F) fp32 -> (B, L, Fout) fp32.
+        Activations stay in time-major bf16 tiles between the launches (include/turboae_b200.h)."""
+        lib = _lib.load()
+        gru, lin = unwrap(gru), unwrap(lin)
+        H = gru.hidden_size
+        B, L, cin = x.shape
+        dev = x.device
+        R = lib.tae_gru_rows_per_block(B)
+        ws = self._ws.get(256, dev)
+        stream = _lib.stream_ptr(dev)
+        tiles = torch.empty(lib.tae_gru_tile_bytes(B, L, (cin + 7) // 8, R), dtype=torch.uint8, device=dev)
+        _lib.check(lib.tae_gru_tiles_from_f32(_lib.ptr(x.contiguous()), _lib.ptr(tiles), B, L, cin, R, stream))
+        in_ch, grp = cin, cin
+        n_out = 2 * ((H + 7) // 8)
+        for layer in range(gru.num_layers):
+            out = torch.empty(lib.tae_gru_tile_bytes(B, L, n_out, R), dtype=torch.uint8, device=dev)
+            for d, suffix in enumerate(("", "_reverse")):
+                k = "l%d%s" % (layer, suffix)
+                ps = [getattr(gru, n + k) for n in ("weight_ih_", "weight_hh_", "bias_ih_", "bias_hh_")]
+                key = (id(gru), k)
+                ver = tuple((p.data_ptr(), p._version) for p in ps)
+                ent = self._packed.get(key)
+                if ent is None or ent[0] != ver:
+                    nbytes = lib.tae_gru_packed_bytes(H, in_ch, grp)
+                    if nbytes == 0:
+                        raise _lib.TaeError("bf16 GRU path unavailable (%s); set precision='fp32'" % lib.tae_last_error().decode())
+                    packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                    w = [p.detach().to(torch.float32).contiguous() for p in ps]
+                    _lib.check(lib.tae_gru_pack_bf16(_lib.ptr(w[0]), _lib.ptr(w[1]), _lib.ptr(w[2]), _lib.ptr(w[3]), _lib.ptr(packed), H, in_ch,
+                                                     grp, stream))
+                    ent = (ver, packed, w)
+                    self._packed[key] = ent
+                _lib.check(lib.tae_gru_direction_bf16(_lib.ptr(ent[1]), _lib.ptr(tiles), _lib.ptr(out), B, L, H, in_ch, grp, R, n_out,
+                                                      d * (n_out // 2), d, _lib.ptr(ws), ws.numel(), stream))
+            tiles, in_ch, grp = out, 2 * H, H
+        F = lin.out_features
+        y = torch.empty((B, L, F), dtype=torch.float32, device=dev)
+        _lib.check(lib.tae_gru_linear_f32(_lib.ptr(tiles), _lib.ptr(lin.weight.detach().contiguous()), _lib.ptr(lin.bias.detach().contiguous()),
+                                          _lib.ptr(y), B, L, 2 * H, H, F, R, stream))
+        return y
+
+    def _stack(self, gru, lin, x):
+        if self.precision == "bf16":
+            return self._stack_tc(gru, lin, x)
+        if self.precision != "fp32":
+            raise _lib.TaeError("precision must be 'bf16' or 'fp32', got %r" % (self.precision,))
+        lin = unwrap(lin)
+        return self._pointwise(self._gru_stack(gru, x), lin.weight.detach().contiguous(), lin.bias.detach().contiguous())
 
     def _gru_stack(self, gru, x):
         lib = _lib.load()
@@ -274,15 +332,11 @@ class DEC_LargeRNN(torch.nn.Module):
             x_plr = None
             for idx in range(a.num_iteration):
                 last = idx == a.num_iteration - 1
-                lin = unwrap(self.dec1_outputs[idx])
-                x_plr = self._pointwise(self._gru_stack(self.dec1_rnns[idx], torch.cat([r_sys, r_par1, prior], dim=2)),
-                                        lin.weight.detach().contiguous(), lin.bias.detach().contiguous())
+                x_plr = self._stack(self.dec1_rnns[idx], self.dec1_outputs[idx], torch.cat([r_sys, r_par1, prior], dim=2))
                 if a.extrinsic:
                     x_plr = x_plr - prior
                 x_plr_int = self.interleaver(x_plr)
-                lin = unwrap(self.dec2_outputs[idx])
-                x_plr = self._pointwise(self._gru_stack(self.dec2_rnns[idx], torch.cat([r_sys_int, r_par2, x_plr_int], dim=2)),
-                                        lin.weight.detach().contiguous(), lin.bias.detach().contiguous())
+                x_plr = self._stack(self.dec2_rnns[idx], self.dec2_outputs[idx], torch.cat([r_sys_int, r_par2, x_plr_int], dim=2))
                 if not last:
                     if a.extrinsic:
                         x_plr = x_plr - x_plr_int

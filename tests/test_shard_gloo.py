@@ -101,7 +101,15 @@ def _grad_worker(rank, world, port, out_dir):
     opt = torch.optim.SGD(lin.parameters(), lr=0.0)
     opt.step()
     handle.remove()
-    torch.save({"y": y.detach(), "dx": x.grad, "lo": lo, "hi": hi, "local": local, "avg": [p.grad.clone() for p in lin.parameters()]},
+    # gradients handed out as consecutive views of one flat buffer (the tensor-core training path): reduced in place, one collective
+    torch.manual_seed(200 + rank)
+    flat = torch.randn(2 + 12 + 5)                          # leading padding, then a (3, 4) and a (5,) view
+    pa, pb = torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5))
+    flat_local = flat.clone()
+    pa.grad, pb.grad = flat[2:14].view(3, 4), flat[14:19]
+    n_red = shard.all_reduce_gradients([pa, pb])
+    torch.save({"y": y.detach(), "dx": x.grad, "lo": lo, "hi": hi, "local": local, "avg": [p.grad.clone() for p in lin.parameters()],
+                "flat_local": flat_local, "flat_after": flat.clone(), "n_red": n_red, "pa": pa.grad.clone()},
                os.path.join(out_dir, "g%d.pt" % rank))
     dist.barrier()
     dist.destroy_process_group()
@@ -123,6 +131,12 @@ def test_two_rank_power_norm_backward_and_gradient_all_reduce(tmp_path):
         mean = (parts[0]["local"][i] + parts[1]["local"][i]) / 2
         for z in parts:
             np.testing.assert_allclose(z["avg"][i].numpy(), mean.numpy(), atol=1e-7)
+    mean_flat = (parts[0]["flat_local"] + parts[1]["flat_local"]) / 2
+    for z in parts:
+        assert z["n_red"] == 17
+        np.testing.assert_allclose(z["flat_after"][2:].numpy(), mean_flat[2:].numpy(), atol=1e-7)
+        np.testing.assert_array_equal(z["flat_after"][:2].numpy(), z["flat_local"][:2].numpy())      # outside the views: untouched
+        np.testing.assert_allclose(z["pa"].numpy(), mean_flat[2:14].view(3, 4).numpy(), atol=1e-7)
 
 
 def test_single_process_is_a_no_op():

@@ -80,6 +80,17 @@ def all_reduce_gradients(params, group=None) -> int:
     grads = [p.grad for p in params if p.grad is not None]
     if not grads or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return sum(g.numel() for g in grads)
+    # The tensor-core training path hands out gradients as consecutive views of ONE flat buffer (train_tc.py): reduce it in
+    # place -- one collective, no gather / scatter copies.
+    base = grads[0].untyped_storage()
+    if all(g.is_contiguous() and g.untyped_storage().data_ptr() == base.data_ptr() for g in grads):
+        offs = [g.storage_offset() for g in grads]
+        if all(offs[i] + grads[i].numel() == offs[i + 1] for i in range(len(grads) - 1)):
+            n = offs[-1] + grads[-1].numel() - offs[0]
+            flat = torch.empty(0, dtype=grads[0].dtype, device=grads[0].device).set_(base, offs[0], (n,), (1,))
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+            flat /= dist.get_world_size(group)
+            return n
     flat = torch.cat([g.reshape(-1) for g in grads])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     flat /= dist.get_world_size(group)

@@ -261,6 +261,9 @@ def run_b200(a):
             torch.cuda.synchronize()
             return t0e.elapsed_time(t1e) / reps
 
+        def O_make_perm(L_):
+            return np.random.mtrand.RandomState(0).permutation(np.arange(L_))      # the reference's permutation (main.py:124-126)
+
         with torch.no_grad():
             sec = {}
             noise = torch.randn(B, 100, 3, device=dev)
@@ -273,6 +276,40 @@ def run_b200(a):
             sec["channel_ae_forward_bf16_cw_per_s"] = B / (ms * 1e-3)
             m.enc.precision = "fp32"
             sec["encoder_flop_per_cw"] = 30_360_000
+        # training step (SURVEY.md 8(f) row 1 / BASELINE config 4: enc2/dec5, batch 1000, forward + backward + Adam) and the
+        # bi-GRU decoder (row 2 / config 5: block length 1000) on the tensor cores; single-GPU figures measured on rank 0
+        try:
+            import torch.nn.functional as Fn
+            import turboae_b200 as T
+            from helpers import make_args
+            TB = 1000
+            targs = make_args(batch_size=TB)
+            tenc, tdec = T.ENC_interCNN(targs, p).to(dev), T.DEC_LargeCNN(targs, p).to(dev)
+            opt = torch.optim.Adam(tdec.parameters(), lr=1e-4)
+
+            def train_step():
+                opt.zero_grad()
+                u = torch.randint(0, 2, (TB, 100, 1), device=dev).float()
+                out = tdec(tenc(u) + torch.randn(TB, 100, 3, device=dev))
+                Fn.binary_cross_entropy(torch.clamp(out, 0.0, 1.0), u).backward()
+                opt.step()
+
+            train_step()
+            ms = timed(train_step, 5)
+            sec["train_step_decoder_mode_cw_per_s"] = TB / (ms * 1e-3)
+            sec["train_step"] = "enc2/dec5, batch %d, fwd+bwd+Adam, train_precision=%s, %.2f ms/step" % (TB, tdec.train_precision, ms)
+            del tenc, tdec, opt
+            RB, RL = 4736, 1000
+            rdec = T.DEC_LargeRNN(make_args(num_iteration=6, dec_num_unit=100, block_len=RL, batch_size=RB),
+                                  O_make_perm(RL)).to(dev).eval()
+            rrec = torch.randn(RB, RL, 3, device=dev)
+            with torch.no_grad():
+                ms = timed(lambda: rdec(rrec), 1)
+            sec["rnn_decoder_cw_per_s"] = RB / (ms * 1e-3)
+            sec["rnn_decoder"] = "DEC_LargeRNN block_len %d, 6 iterations, H 100, batch %d, precision=%s, %.1f ms" % (RL, RB, rdec.precision, ms)
+            del rdec, rrec
+        except Exception as e:  # pragma: no cover -- secondary figures must never cost the headline line
+            sec["secondary_error"] = str(e)[:200]
         line["secondary"] = sec
         if world == 1 and not a.no_cpu_baseline:
             v, times, cores = cpu_reference_rate(a.cpu_sample, 10.0, 30)

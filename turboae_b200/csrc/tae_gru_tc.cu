@@ -39,10 +39,14 @@ constexpr uint32_t G_CHUNK_B = G_ROWS * 16;          // one 8-channel chunk of t
 constexpr int G_HCH = 13;                            // hidden chunks (H <= 104)
 constexpr int G_HKS = 7;                             // k-steps of the hidden part: (h0,h1) .. (h10,h11), (h12, ones)
 constexpr int G_XCH_MAX = 26;                        // input chunks (two directions of 13 chunks)
-constexpr int G_NG = 112;                            // columns per gate
-constexpr uint32_t G_RZ_KS_B = 2 * G_NG * 16;        // bytes of one k-step of W_rz per CTA (2 chunks x 112 columns x 16 B)
-constexpr uint32_t G_N_KS_B = 2 * (G_NG / 2) * 16;   // bytes of one k-step of W_nx / W_nh per CTA (56 columns)
-constexpr uint32_t G_TM_RZ = 0, G_TM_NX = 224, G_TM_NH = 336;
+// The hidden units are processed in two halves, U0 = units [0, 64) and U1 = units [64, 112), each with its own accumulators
+// and its own commit: the epilogue of U0 overlaps the MMAs of U1 (the epilogue is MUFU-bound, the MMAs use the tensor pipe).
+constexpr int G_NU0 = 64, G_NU1 = 48;                // units per half (UMMA N: 2*NU for r|z, NU for n; all multiples of 16)
+constexpr int G_NG = G_NU0 + G_NU1;                  // 112 columns per gate
+constexpr int G_CH0 = G_NU0 / 8;                     // chunks of U0 (8); U1 = chunks 8..12
+constexpr uint32_t G_RZ_KS_B = 2 * G_NG * 16;        // bytes of one k-step of W_rz per CTA, both halves (2 chunks x 112 columns x 16 B)
+constexpr uint32_t G_N_KS_B = 2 * (G_NG / 2) * 16;   // bytes of one k-step of W_nx / W_nh per CTA, both halves (56 columns)
+constexpr uint32_t G_TM_RZ0 = 0, G_TM_NX0 = 128, G_TM_NH0 = 192, G_TM_RZ1 = 256, G_TM_NX1 = 352, G_TM_NH1 = 400;
 constexpr int G_EPI_WARP0 = 4, G_EPI_WARPS = 16, G_LOAD_WARP = 1;
 constexpr int G_THREADS = 32 * (G_EPI_WARP0 + G_EPI_WARPS);      // 640
 constexpr int G_RDY_COUNT = 2 * (G_EPI_WARPS + 1);
@@ -56,7 +60,7 @@ __host__ __device__ inline GruGeom gru_geom(int n_xch) {
   GruGeom g{};
   g.n_xch = n_xch;
   g.xks = (g.n_xch + 2) / 2;                         // chunks x0..x_{n-1}, ones (+ a repeat of ones with zero weights if needed)
-  g.off_x = G_HCH * G_CHUNK_B;
+  g.off_x = 2 * G_HCH * G_CHUNK_B;                   // two hidden-state buffers (step parity): see the epilogue
   g.off_ones = g.off_x + (uint32_t)g.n_xch * G_CHUNK_B;
   g.off_w = g.off_ones + G_CHUNK_B;
   g.w_rz_b = (uint32_t)(g.xks + G_HKS) * G_RZ_KS_B;
@@ -118,36 +122,37 @@ __device__ __forceinline__ float gru_h_elem(const float* w_hh, const float* bias
 
 __global__ void gru_pack_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b_ih,
                                 const float* __restrict__ b_hh, __nv_bfloat16* __restrict__ img, int H, const InMap im, int n_xch) {
+  // per CTA half: [RZ of U0 | RZ of U1 | NX of U0 | NX of U1 | NH of U0 | NH of U1]; every section is [k-step][2 chunks][columns][8]
   const GruGeom g = gru_geom(n_xch);
   const uint32_t half_elems = (g.w_rz_b + g.w_nx_b + g.w_nh_b) / 2;
+  const int ks_rz = g.xks + G_HKS;
+  const uint32_t sec[6] = {(uint32_t)ks_rz * 2 * G_NU0 * 8,       (uint32_t)ks_rz * 2 * G_NU1 * 8,
+                           (uint32_t)g.xks * 2 * (G_NU0 / 2) * 8, (uint32_t)g.xks * 2 * (G_NU1 / 2) * 8,
+                           (uint32_t)G_HKS * 2 * (G_NU0 / 2) * 8, (uint32_t)G_HKS * 2 * (G_NU1 / 2) * 8};
   for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 2 * half_elems; idx += gridDim.x * blockDim.x) {
     const int hf = idx / half_elems;
     uint32_t r = idx % half_elems;
+    int sc = 0;
+    while (r >= sec[sc]) { r -= sec[sc]; ++sc; }
+    const int hu = sc & 1, kind = sc >> 1;                 // kind 0: r|z, 1: n (input part), 2: n (hidden part)
+    const int NU = hu ? G_NU1 : G_NU0, u0 = hu ? G_NU0 : 0;
+    const int cols = kind == 0 ? NU : NU / 2;              // columns this CTA stages
+    const int ks = r / (2 * cols * 8), ch = (r / (cols * 8)) & 1, n = (r / 8) % cols, e8 = r % 8;
     float v;
-    if (r < g.w_rz_b / 2) {
-      const int ks = r / (2 * G_NG * 8), ch = (r / (G_NG * 8)) & 1, n = (r / 8) % G_NG, e8 = r % 8;
-      const int row = hf * H + n;                     // half 0 = r gate, half 1 = z gate
-      const bool valid = n < H;
+    if (kind == 0) {
+      const int u = u0 + n, row = hf * H + u;              // CTA 0 = r gate, CTA 1 = z gate
+      const bool valid = u < H;
       if (ks < g.xks) {
         const float bsum = valid ? b_ih[row] + b_hh[row] : 0.f;
         v = gru_x_elem(w_ih, &bsum, im, g.n_xch, row, valid, ks, ch, e8);
       } else {
         v = gru_h_elem(w_hh, nullptr, H, row, valid, ks - g.xks, ch, e8);
       }
-    } else if (r < (g.w_rz_b + g.w_nx_b) / 2) {
-      r -= g.w_rz_b / 2;
-      const int NH_ = G_NG / 2;
-      const int ks = r / (2 * NH_ * 8), ch = (r / (NH_ * 8)) & 1, n = (r / 8) % NH_, e8 = r % 8;
-      const int u = hf * NH_ + n;
-      const bool valid = u < H;
-      v = gru_x_elem(w_ih, valid ? b_ih + 2 * H + u : nullptr, im, g.n_xch, 2 * H + u, valid, ks, ch, e8);
     } else {
-      r -= (g.w_rz_b + g.w_nx_b) / 2;
-      const int NH_ = G_NG / 2;
-      const int hk = r / (2 * NH_ * 8), ch = (r / (NH_ * 8)) & 1, n = (r / 8) % NH_, e8 = r % 8;
-      const int u = hf * NH_ + n;
+      const int u = u0 + hf * (NU / 2) + n;
       const bool valid = u < H;
-      v = gru_h_elem(w_hh, valid ? b_hh + 2 * H + u : nullptr, H, 2 * H + u, valid, hk, ch, e8);
+      if (kind == 1) v = gru_x_elem(w_ih, valid ? b_ih + 2 * H + u : nullptr, im, g.n_xch, 2 * H + u, valid, ks, ch, e8);
+      else v = gru_h_elem(w_hh, valid ? b_hh + 2 * H + u : nullptr, H, 2 * H + u, valid, ks, ch, e8);
     }
     img[idx] = __float2bfloat16_rn(v);
   }
@@ -174,7 +179,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1) gru_pa
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const uint32_t bar_w = sbase + g.off_bars, bar_rdy = bar_w + 8, bar_acc = bar_w + 16, bar_x = bar_w + 24, tptr = bar_w + 32;
+  const uint32_t bar_w = sbase + g.off_bars, bar_rdy = bar_w + 8, bar_acc = bar_w + 16, bar_x = bar_w + 24, tptr = bar_w + 32, bar_acc1 = bar_w + 40,
+                 bar_xfree = bar_w + 48;
   const int L = a.L;
 
   // ---- setup: zero the operand region, ones chunk, barriers, TMEM, weights ------------------------------------------
@@ -185,6 +191,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1) gru_pa
     mbar_init(bar_w, 1);
     mbar_init(bar_rdy, rank == 0 ? G_RDY_COUNT : 1);
     mbar_init(bar_acc, 1);
+    mbar_init(bar_acc1, 1);
+    mbar_init(bar_xfree, 1);
     mbar_init(bar_x, 1);
     fence_barrier_init();
   }
@@ -209,9 +217,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1) gru_pa
   if (warp == 0) {
     // ================= MMA issuer (leader CTA) ========================================================================
     if (rank == 0) {
-      constexpr uint32_t IDESC_RZ = make_idesc(256, 2 * G_NG), IDESC_N = make_idesc(256, G_NG);
       const uint32_t h0 = sbase, x0 = sbase + g.off_x, ones = sbase + g.off_ones;
-      const uint32_t w_rz = sbase + g.off_w, w_nx = w_rz + g.w_rz_b, w_nh = w_nx + g.w_nx_b;
+      const int ks_rz = g.xks + G_HKS;
+      // weight sections of this CTA (gru_pack_kernel): [RZ0 | RZ1 | NX0 | NX1 | NH0 | NH1]
+      uint32_t w_sec[6];
+      {
+        uint32_t o = sbase + g.off_w;
+        const uint32_t bytes[6] = {(uint32_t)ks_rz * 2 * G_NU0 * 16,       (uint32_t)ks_rz * 2 * G_NU1 * 16,
+                                   (uint32_t)g.xks * 2 * (G_NU0 / 2) * 16, (uint32_t)g.xks * 2 * (G_NU1 / 2) * 16,
+                                   (uint32_t)G_HKS * 2 * (G_NU0 / 2) * 16, (uint32_t)G_HKS * 2 * (G_NU1 / 2) * 16};
+        for (int i = 0; i < 6; ++i) { w_sec[i] = o; o += bytes[i]; }
+      }
       uint32_t step = 0;
       for (int pr = pair0; pr < a.n_pairs; pr += pair_stride)
         for (int s = 0; s < L; ++s, ++step) {
@@ -221,24 +237,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1) gru_pa
           tc_fence_after();
           if (stamp) a.tl[step * 8 + 1] = clock64();
           if (elect_one()) {
-            // input part: chunk pairs (x0,x1) .. ; the last pair ends on the ones chunk (LBO = distance to it)
-            for (int ks = 0; ks < g.xks; ++ks) {
-              const int c0 = 2 * ks;
-              const uint32_t a_addr = c0 < g.n_xch ? x0 + (uint32_t)c0 * G_CHUNK_B : ones;
-              const uint32_t a_lbo = (c0 + 1 < g.n_xch) ? G_CHUNK_B : (c0 < g.n_xch ? ones - a_addr : 0u);
-              const uint64_t ad = make_desc(a_addr, a_lbo);
-              umma_bf16<2>(tmem_base + G_TM_RZ, ad, make_desc(w_rz + (uint32_t)ks * G_RZ_KS_B, G_NG * 16), IDESC_RZ, ks > 0);
-              umma_bf16<2>(tmem_base + G_TM_NX, ad, make_desc(w_nx + (uint32_t)ks * G_N_KS_B, (G_NG / 2) * 16), IDESC_N, ks > 0);
-            }
-            // hidden part: (h0,h1) .. (h10,h11), (h12, ones)
+            const uint32_t hbuf = h0 + (step & 1u) * (uint32_t)(G_HCH * G_CHUNK_B);      // h_{t-1}: the buffer of this step's parity
+            // per half: input part, hidden part, commit -- so U0's accumulators complete while U1's MMAs still run and the
+            // (MUFU-bound) epilogue of U0 overlaps them.  The x chunks are free once U1's input part has been read.
 #pragma unroll
-            for (int hk = 0; hk < G_HKS; ++hk) {
-              const uint32_t a_addr = h0 + (uint32_t)(2 * hk) * G_CHUNK_B;
-              const uint64_t ad = make_desc(a_addr, hk < G_HKS - 1 ? G_CHUNK_B : ones - a_addr);
-              umma_bf16<2>(tmem_base + G_TM_RZ, ad, make_desc(w_rz + (uint32_t)(g.xks + hk) * G_RZ_KS_B, G_NG * 16), IDESC_RZ, 1);
-              umma_bf16<2>(tmem_base + G_TM_NH, ad, make_desc(w_nh + (uint32_t)hk * G_N_KS_B, (G_NG / 2) * 16), IDESC_N, hk > 0);
+            for (int hu = 0; hu < 2; ++hu) {
+              const uint32_t NU = hu ? G_NU1 : G_NU0;
+              const uint32_t idesc_rz = make_idesc(256, 2 * (int)NU), idesc_n = make_idesc(256, (int)NU);
+              const uint32_t d_rz = tmem_base + (hu ? G_TM_RZ1 : G_TM_RZ0), d_nx = tmem_base + (hu ? G_TM_NX1 : G_TM_NX0),
+                             d_nh = tmem_base + (hu ? G_TM_NH1 : G_TM_NH0);
+              const uint32_t w_rz = w_sec[hu], w_nx = w_sec[2 + hu], w_nh = w_sec[4 + hu];
+              const uint32_t rz_ks_b = 2 * NU * 16, n_ks_b = NU * 16;         // bytes per k-step (2 chunks x columns x 16 B)
+              for (int ks = 0; ks < g.xks; ++ks) {      // chunk pairs (x0,x1) ..; the last pair ends on the ones chunk
+                const int c0 = 2 * ks;
+                const uint32_t a_addr = c0 < g.n_xch ? x0 + (uint32_t)c0 * G_CHUNK_B : ones;
+                const uint32_t a_lbo = (c0 + 1 < g.n_xch) ? G_CHUNK_B : (c0 < g.n_xch ? ones - a_addr : 0u);
+                const uint64_t ad = make_desc(a_addr, a_lbo);
+                umma_bf16<2>(d_rz, ad, make_desc(w_rz + (uint32_t)ks * rz_ks_b, NU * 16), idesc_rz, ks > 0);
+                umma_bf16<2>(d_nx, ad, make_desc(w_nx + (uint32_t)ks * n_ks_b, (NU / 2) * 16), idesc_n, ks > 0);
+              }
+              if (hu == 1) umma_commit_pair(bar_xfree, 3);
+#pragma unroll
+              for (int hk = 0; hk < G_HKS; ++hk) {       // (h0,h1) .. (h10,h11), (h12, ones)
+                const uint32_t a_addr = hbuf + (uint32_t)(2 * hk) * G_CHUNK_B;
+                const uint64_t ad = make_desc(a_addr, hk < G_HKS - 1 ? G_CHUNK_B : ones - a_addr);
+                umma_bf16<2>(d_rz, ad, make_desc(w_rz + (uint32_t)(g.xks + hk) * rz_ks_b, NU * 16), idesc_rz, 1);
+                umma_bf16<2>(d_nh, ad, make_desc(w_nh + (uint32_t)hk * n_ks_b, (NU / 2) * 16), idesc_n, hk > 0);
+              }
+              umma_commit_pair(hu ? bar_acc1 : bar_acc, 3);
             }
-            umma_commit_pair(bar_acc, 3);
           }
           __syncwarp();
           if (stamp) a.tl[step * 8 + 2] = clock64();
@@ -253,12 +280,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1) gru_pa
         const size_t blk = (size_t)(2 * pr + (int)rank);
         for (int s = 0; s < L; ++s, ++step) {
           const int t = a.reverse ? L - 1 - s : s;
-          if (step > 0) mbar_wait(bar_acc, (step - 1) & 1u, a.err, 33);       // the MMAs of the previous step have read the x chunks
+          if (step > 0) mbar_wait(bar_xfree, (step - 1) & 1u, a.err, 33);     // the input-part MMAs of the previous step have read the x chunks
           const bool stamp = a.tl && pair0 == 0 && rank == 0 && step < 64;
           if (stamp) a.tl[step * 8 + 3] = clock64();
           const uint8_t* src = a.x + ((blk * L + t) * a.n_xch) * chunk_bytes;
           mbar_arrive_expect_tx(bar_x, (uint32_t)a.n_xch * chunk_bytes);
-          for (int c = 0; c < a.n_xch; ++c) bulk_g2s(sbase + g.off_x + (uint32_t)c * G_CHUNK_B, src + (size_t)c * chunk_bytes, chunk_bytes, bar_x);
+          if (a.R == G_ROWS) bulk_g2s(sbase + g.off_x, src, (uint32_t)a.n_xch * chunk_bytes, bar_x);      // a full tile is contiguous on both sides
+          else for (int c = 0; c < a.n_xch; ++c) bulk_g2s(sbase + g.off_x + (uint32_t)c * G_CHUNK_B, src + (size_t)c * chunk_bytes, chunk_bytes, bar_x);
           if (s + 1 < L) {            // next step's tile towards L2 while this one lands and the step computes
             const int tn = a.reverse ? t - 1 : t + 1;
             const uint8_t* nsrc = a.x + ((blk * L + tn) * a.n_xch) * chunk_bytes;
@@ -273,7 +301,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1) gru_pa
   } else if (warp >= G_EPI_WARP0) {
     // ================= epilogue: gates, new hidden state =============================================================
     const int ew = warp - G_EPI_WARP0, q = warp & 3, part = ew >> 2;
-    const int c_begin = part == 0 ? 0 : 1 + 3 * part, n_ch = part == 0 ? 4 : 3;     // chunks [0,4) [4,7) [7,10) [10,13)
+    // chunks of this thread: U0 -> {part, part + 4}; U1 -> {8 + part} and, for part 0, chunk 12.  Slot i of hp[] <-> chunk_of[i].
+    const int chunk_of[4] = {part, part + 4, 8 + part, 12};
+    const int n_slots = part == 0 ? 4 : 3;
     const int row = 32 * q + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
     uint32_t step = 0;
@@ -284,27 +314,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1) gru_pa
       float hp[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) hp[i] = 0.f;
-      // h_0 = 0 (the previous pair's last epilogue has been consumed: every MMA that read it completed before bar_acc)
-      for (int c = 0; c < n_ch; ++c) st_shared_v4(sbase + (uint32_t)(c_begin + c) * G_CHUNK_B + (uint32_t)row * 16, 0u, 0u, 0u, 0u);
+      // h_0 = 0 in the buffer the first step of this pair reads (its previous readers completed before bar_acc1 of that step)
+      for (int i = 0; i < n_slots; ++i)
+        st_shared_v4(sbase + (step & 1u) * (uint32_t)(G_HCH * G_CHUNK_B) + (uint32_t)chunk_of[i] * G_CHUNK_B + (uint32_t)row * 16, 0u, 0u, 0u, 0u);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(bar_rdy, rank);
       for (int s = 0; s < L; ++s, ++step) {
         const int t = a.reverse ? L - 1 - s : s;
         uint8_t* otile = a.out + (((blk * L + t) * a.out_chunks + a.out_c0) * a.R + row) * 16;
-        mbar_wait(bar_acc, step & 1u, a.err, 34);
-        tc_fence_after();
         const bool stamp = a.tl && pair0 == 0 && rank == 0 && step < 64 && ew == 0 && lane == 0;
-        if (stamp) a.tl[step * 8 + 5] = clock64();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < n_ch && warp_ok && c_begin + c < a.hch) {
-            const uint32_t col = (uint32_t)(8 * (c_begin + c));
+        for (int i = 0; i < 4; ++i) {
+          if (i == 0) {
+            mbar_wait(bar_acc, step & 1u, a.err, 34);       // accumulators of U0 complete (the MMAs of U1 are still running)
+            tc_fence_after();
+            if (stamp) a.tl[step * 8 + 5] = clock64();
+          }
+          if (i == 2) {
+            mbar_wait(bar_acc1, step & 1u, a.err, 36);      // accumulators of U1 complete
+            tc_fence_after();
+            if (stamp) a.tl[step * 8 + 7] = clock64();
+          }
+          const int cidx = chunk_of[i];
+          if (i < n_slots && warp_ok && cidx < a.hch) {
+            const bool u1 = i >= 2;
+            const uint32_t NU = u1 ? G_NU1 : G_NU0;
+            const uint32_t col = (uint32_t)(8 * (cidx - (u1 ? G_CH0 : 0)));
             uint32_t dr[8], dz[8], dx[8], dh[8];
-            tmem_ld8(lane_addr + G_TM_RZ + col, dr);
-            tmem_ld8(lane_addr + G_TM_RZ + G_NG + col, dz);
-            tmem_ld8(lane_addr + G_TM_NX + col, dx);
-            tmem_ld8(lane_addr + G_TM_NH + col, dh);
+            tmem_ld8(lane_addr + (u1 ? G_TM_RZ1 : G_TM_RZ0) + col, dr);
+            tmem_ld8(lane_addr + (u1 ? G_TM_RZ1 : G_TM_RZ0) + NU + col, dz);
+            tmem_ld8(lane_addr + (u1 ? G_TM_NX1 : G_TM_NX0) + col, dx);
+            tmem_ld8(lane_addr + (u1 ? G_TM_NH1 : G_TM_NH0) + col, dh);
             tmem_ld_wait();
             uint32_t pk[4];
 #pragma unroll
@@ -314,13 +355,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G_THREADS, 1) gru_pa
               for (int k = 0; k < 2; ++k) {
                 const float2 rz = sigmoid2_fast(__uint_as_float(dr[j + k]), __uint_as_float(dz[j + k]));
                 const float n = tanh_fast(fmaf(rz.x, __uint_as_float(dh[j + k]), __uint_as_float(dx[j + k])));
-                hn[k] = fmaf(rz.y, hp[8 * c + j + k] - n, n);                     // (1 - z) n + z h
-                hp[8 * c + j + k] = hn[k];
+                hn[k] = fmaf(rz.y, hp[8 * i + j + k] - n, n);                     // (1 - z) n + z h
+                hp[8 * i + j + k] = hn[k];
               }
               pk[j >> 1] = pack_bf16x2(hn[0], hn[1]);
             }
-            st_shared_v4(sbase + (uint32_t)(c_begin + c) * G_CHUNK_B + (uint32_t)row * 16, pk[0], pk[1], pk[2], pk[3]);
-            if (ok) *reinterpret_cast<uint4*>(otile + (size_t)(c_begin + c) * a.R * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            // h_t goes to the OTHER buffer: the hidden-part MMAs of U1 may still be reading h_{t-1} while U0's epilogue runs
+            st_shared_v4(sbase + ((step + 1) & 1u) * (uint32_t)(G_HCH * G_CHUNK_B) + (uint32_t)cidx * G_CHUNK_B + (uint32_t)row * 16, pk[0], pk[1],
+                         pk[2], pk[3]);
+            if (ok) *reinterpret_cast<uint4*>(otile + (size_t)cidx * a.R * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
         if (stamp) a.tl[step * 8 + 6] = clock64();

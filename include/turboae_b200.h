@@ -177,37 +177,27 @@ int tae_dec_forward_train_bf16(const TaeDecConfig* cfg, const void* packed, cons
 /* Backward weight image (transposed, tap-flipped conv weights; transposed Linear).  Rebuild after every weight update. */
 size_t tae_dec_bwd_packed_bytes(const TaeDecConfig* cfg);
 int    tae_dec_pack_bwd_bf16(const TaeDecConfig* cfg, const float* params, void* packed_bwd, void* stream);
-/* Backward of conv stack + Linear number `stack` (0 .. 2I-1, order of the flat parameter buffer):
- *   dlin (B, L, fin) = gradient w.r.t. the Linear output  ->  dxin (B, L, 8) = gradient w.r.t. the 2+F stack inputs
- *   (columns 2+F.. are zero).  Reads stash_y, writes stash_g and stash_d (all indexed by `stack` internally).
- * `chain` (may be NULL) fuses the glue between two stacks of the turbo schedule into this launch: with dlin == NULL,
- *   dlin[b,l,f] = prev_dxin[b, idx[l], 2+f] - (subtract ? prev_dlin[b, idx[l], f] : 0)
- * is the backward of the extrinsic subtraction + (de)interleaver (reference decoders.py:235-249) applied to the outputs of
- * the launch for the NEXT stack; dlin_out (NULL or (B, L, fin)) receives the dlin used; lin_bias_grad (NULL or fin floats)
- * is incremented by sum_{b,l} dlin (the Linear's bias gradient).                                                      */
-typedef struct TaeStackBwdChain {
-  const float* prev_dxin;      /* (B, L, 8)        */
-  const float* prev_dlin;      /* (B, L, prev_fin) */
-  const int32_t* idx;          /* int32[L]         */
-  int32_t prev_fin;
-  int32_t subtract;
-  float* dlin_out;
-  float* lin_bias_grad;
-} TaeStackBwdChain;
-int tae_dec_stack_backward_bf16(const TaeDecConfig* cfg, const void* packed_bwd, int32_t stack, const float* dlin, int32_t fin,
-                                const void* stash_y, void* stash_g, void* stash_d, float* dxin, int32_t B,
-                                const TaeStackBwdChain* chain, void* workspace, size_t workspace_bytes, void* stream);
-/* The same three steps for ENC_interCNN (reference encoders.py:362-373 under trainer.py:74): 3 branches = 3 stacks with one
- * input channel and Linear(units, 1); x_tx / stats as tae_enc_forward_bf16; dlin (B, L, 1) = gradient w.r.t. the Linear
- * output of the branch (i.e. d x_tx[:, :, branch] * ELU'), dxin (B, L, 8) = gradient w.r.t. the +-1 input in column 0.  */
+/* Backward of all 2I conv stacks + Linears in ONE launch, the turbo schedule walked backwards:
+ *   d_out_last (B, L, 1) = gradient w.r.t. the last stack's Linear output (before deinterleave + sigmoid)
+ *   dxin_all (2I, B, L, 8) receives the gradient w.r.t. every stack's 2+F inputs (columns 2+F.. are zero); the caller sums the
+ *   sys / parity columns into d received.  Between stacks the kernel itself applies the backward of the extrinsic subtraction
+ *   and the (de)interleaver (reference decoders.py:235-249): dlin_s[b,l,f] = dxin_{s+1}[b, idx[l], 2+f] - dlin_{s+1}[b, idx[l], f];
+ *   dlin_all (2I, B, L, F) is scratch for that chain.  Reads stash_y, writes stash_g and stash_d.  grad_flat: NULL, or the flat
+ *   gradient buffer (layout of the flat parameter buffer) into which the Linear bias gradients (sums of dlin) are ADDED.      */
+int tae_dec_backward_bf16(const TaeDecConfig* cfg, const void* packed_bwd, const float* d_out_last, const int32_t* perm,
+                          const int32_t* inv_perm, const void* stash_y, void* stash_g, void* stash_d, float* dxin_all,
+                          float* dlin_all, float* grad_flat, int32_t B, void* workspace, size_t workspace_bytes, void* stream);
+/* The same three steps for ENC_interCNN (reference encoders.py:362-373 under trainer.py:74): 3 branches = 3 independent stacks
+ * with one input channel and Linear(units, 1); x_tx / stats as tae_enc_forward_bf16; dlin (3, B, L, 1) = gradient w.r.t. each
+ * branch's Linear output (i.e. d x_tx[:, :, branch] * ELU'), dxin_all (3, B, L, 8) = gradient w.r.t. the +-1 input in column 0. */
 int tae_enc_forward_train_bf16(const TaeEncConfig* cfg, const void* packed, const float* u, const int32_t* perm,
                                const int32_t* inv_perm, float* x_tx, double* stats, int32_t B, void* stash_y, void* stash_x,
                                void* workspace, size_t workspace_bytes, void* stream);
 size_t tae_enc_bwd_packed_bytes(const TaeEncConfig* cfg);
 int    tae_enc_pack_bwd_bf16(const TaeEncConfig* cfg, const float* params, void* packed_bwd, void* stream);
-int tae_enc_stack_backward_bf16(const TaeEncConfig* cfg, const void* packed_bwd, int32_t branch, const float* dlin,
-                                const void* stash_y, void* stash_g, void* stash_d, float* dxin, int32_t B,
-                                const TaeStackBwdChain* chain, void* workspace, size_t workspace_bytes, void* stream);
+int tae_enc_backward_bf16(const TaeEncConfig* cfg, const void* packed_bwd, const float* dlin, const void* stash_y, void* stash_g,
+                          void* stash_d, float* dxin_all, float* grad_flat, int32_t B, void* workspace, size_t workspace_bytes,
+                          void* stream);
 /* Weight gradients as tensor-core GEMMs over group images (one CTA per job):
  *   grad[m*s_m + (n0+n)*s_n + t*s_t] += sum_{group in [g0,g1)} sum_rows A[row, m] * B[row + t - taps/2, b_c0*8 + n]
  * for m < m_valid, n < n_valid, t < taps; bias_grad[m] += sum_rows A[row, m] (NULL to skip; needs 8*b_nc < n_cols).

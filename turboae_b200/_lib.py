@@ -30,11 +30,6 @@ class TaeWgradJob(C.Structure):
                                          "s_m", "s_n", "s_t", "g0", "g1", "reserved")]
 
 
-class TaeStackBwdChain(C.Structure):
-    _fields_ = [("prev_dxin", C.c_void_p), ("prev_dlin", C.c_void_p), ("idx", C.c_void_p), ("prev_fin", C.c_int32),
-                ("subtract", C.c_int32), ("dlin_out", C.c_void_p), ("lin_bias_grad", C.c_void_p)]
-
-
 IMG_CHUNK_BYTES = 8256
 IMG_CHUNKS = 13
 
@@ -84,13 +79,11 @@ _SIGNATURES = {
     "tae_dec_forward_train_bf16": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "tae_dec_bwd_packed_bytes": (C.c_size_t, [C.POINTER(TaeDecConfig)]),
     "tae_dec_pack_bwd_bf16": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P]),
-    "tae_dec_stack_backward_bf16": (C.c_int, [C.POINTER(TaeDecConfig), _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P, C.c_int32,
-                                              C.POINTER(TaeStackBwdChain), _P, C.c_size_t, _P]),
+    "tae_dec_backward_bf16": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_size_t, _P]),
     "tae_enc_forward_train_bf16": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "tae_enc_bwd_packed_bytes": (C.c_size_t, [C.POINTER(TaeEncConfig)]),
     "tae_enc_pack_bwd_bf16": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P]),
-    "tae_enc_stack_backward_bf16": (C.c_int, [C.POINTER(TaeEncConfig), _P, C.c_int32, _P, _P, _P, _P, _P, C.c_int32,
-                                              C.POINTER(TaeStackBwdChain), _P, C.c_size_t, _P]),
+    "tae_enc_backward_bf16": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_size_t, _P]),
     "tae_wgrad_bf16": (C.c_int, [C.POINTER(TaeWgradJob), C.c_int32, _P, _P, C.c_size_t, _P]),
     "tae_awgn_f32": (C.c_int, [_P, _P, C.c_size_t, C.c_float, C.c_uint64, C.c_uint64, _P]),
     "tae_error_count_f32": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),

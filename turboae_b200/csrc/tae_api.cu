@@ -389,20 +389,19 @@ int tae_dec_pack_bwd_bf16(const TaeDecConfig* cfg, const float* params, void* pa
   return dec_pair_pack_bwd(*cfg, params, packed_bwd, (cudaStream_t)stream);
 }
 
-int tae_dec_stack_backward_bf16(const TaeDecConfig* cfg, const void* packed_bwd, int32_t stack, const float* dlin, int32_t fin,
-                                const void* stash_y, void* stash_g, void* stash_d, float* dxin, int32_t B, const TaeStackBwdChain* chain,
-                                void* workspace, size_t workspace_bytes, void* stream) {
+int tae_dec_backward_bf16(const TaeDecConfig* cfg, const void* packed_bwd, const float* d_out_last, const int32_t* perm,
+                          const int32_t* inv_perm, const void* stash_y, void* stash_g, void* stash_d, float* dxin_all, float* dlin_all,
+                          float* grad_flat, int32_t B, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_dec_config(cfg);
   if (rc) return rc;
   const char* why = nullptr;
   if (!bf16_supported(*cfg, &why)) { set_error("bf16 path: %s", why); return TAE_EUNSUPPORTED; }
-  TAE_REQUIRE(B >= 0, "tae_dec_stack_backward_bf16: negative batch %d", B);
-  TAE_REQUIRE(stack >= 0 && stack < 2 * cfg->num_iteration, "tae_dec_stack_backward_bf16: stack %d out of range", stack);
-  TAE_REQUIRE(fin >= 1 && fin <= 8, "tae_dec_stack_backward_bf16: fin %d out of range", fin);
+  TAE_REQUIRE(B >= 0, "tae_dec_backward_bf16: negative batch %d", B);
   if (B == 0) return TAE_OK;
-  TAE_REQUIRE(packed_bwd && (dlin || chain) && stash_y && stash_g && dxin && workspace, "tae_dec_stack_backward_bf16: NULL pointer");
-  return dec_stack_backward_pair(*cfg, packed_bwd, stack, dlin, fin, stash_y, stash_g, stash_d, dxin, B, workspace, workspace_bytes,
-                                 (cudaStream_t)stream, chain);
+  TAE_REQUIRE(packed_bwd && d_out_last && perm && inv_perm && stash_y && stash_g && stash_d && dxin_all && dlin_all && workspace,
+              "tae_dec_backward_bf16: NULL pointer");
+  return dec_backward_pair(*cfg, packed_bwd, d_out_last, perm, inv_perm, stash_y, stash_g, stash_d, dxin_all, dlin_all, grad_flat, B, workspace,
+                           workspace_bytes, (cudaStream_t)stream);
 }
 
 int tae_enc_forward_train_bf16(const TaeEncConfig* cfg, const void* packed, const float* u, const int32_t* perm, const int32_t* inv_perm,
@@ -436,18 +435,17 @@ int tae_enc_pack_bwd_bf16(const TaeEncConfig* cfg, const float* params, void* pa
   return enc_pair_pack_bwd(*cfg, params, packed_bwd, (cudaStream_t)stream);
 }
 
-int tae_enc_stack_backward_bf16(const TaeEncConfig* cfg, const void* packed_bwd, int32_t branch, const float* dlin, const void* stash_y,
-                                void* stash_g, void* stash_d, float* dxin, int32_t B, const TaeStackBwdChain* chain, void* workspace,
-                                size_t workspace_bytes, void* stream) {
+int tae_enc_backward_bf16(const TaeEncConfig* cfg, const void* packed_bwd, const float* dlin, const void* stash_y, void* stash_g, void* stash_d,
+                          float* dxin_all, float* grad_flat, int32_t B, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_enc_config(cfg);
   if (rc) return rc;
   const char* why = nullptr;
   if (!enc_pair_supported(*cfg, &why)) { set_error("bf16 encoder path: %s", why); return TAE_EUNSUPPORTED; }
-  TAE_REQUIRE(B >= 0 && branch >= 0 && branch < 3, "tae_enc_stack_backward_bf16: bad batch %d / branch %d", B, branch);
+  TAE_REQUIRE(B >= 0, "tae_enc_backward_bf16: negative batch %d", B);
   if (B == 0) return TAE_OK;
-  TAE_REQUIRE(packed_bwd && dlin && stash_y && stash_g && dxin && workspace, "tae_enc_stack_backward_bf16: NULL pointer");
-  return enc_stack_backward_pair(*cfg, packed_bwd, branch, dlin, stash_y, stash_g, stash_d, dxin, B, workspace, workspace_bytes,
-                                 (cudaStream_t)stream, chain);
+  TAE_REQUIRE(packed_bwd && dlin && stash_y && stash_g && stash_d && dxin_all && workspace, "tae_enc_backward_bf16: NULL pointer");
+  return enc_backward_pair(*cfg, packed_bwd, dlin, stash_y, stash_g, stash_d, dxin_all, grad_flat, B, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
 }
 
 int tae_wgrad_bf16(const TaeWgradJob* jobs_host, int32_t n_jobs, const void* jobs_dev, void* workspace, size_t workspace_bytes, void* stream) {

@@ -110,9 +110,9 @@ int dec_forward_pair(const TaeDecConfig& c, const void* packed, const float* rec
 int train_groups(int block_len, int B);
 size_t dec_pair_bwd_packed_bytes(const TaeDecConfig& c);
 int dec_pair_pack_bwd(const TaeDecConfig& c, const float* params, void* packed, cudaStream_t s);
-int dec_stack_backward_pair(const TaeDecConfig& c, const void* packed_bwd, int stack, const float* dlin, int fin, const void* stash_y,
-                            void* stash_g, void* stash_d, float* dxin, int B, void* ws, size_t ws_bytes, cudaStream_t s,
-                            const TaeStackBwdChain* chain = nullptr);
+int dec_backward_pair(const TaeDecConfig& c, const void* packed_bwd, const float* d_out_last, const int32_t* perm, const int32_t* inv_perm,
+                      const void* stash_y, void* stash_g, void* stash_d, float* dxin_all, float* dlin_all, float* grad_flat, int B, void* ws,
+                      size_t ws_bytes, cudaStream_t s);
 int launch_wgrad(const TaeWgradJob* jobs_host, int n_jobs, const void* jobs_dev, void* ws, size_t ws_bytes, cudaStream_t s);
 // ENC_interCNN on the same CTA-pair kernel (three branches as three stacks)
 bool enc_pair_supported(const TaeEncConfig& c, const char** why);
@@ -123,9 +123,8 @@ int enc_forward_pair(const TaeEncConfig& c, const void* packed, const float* u, 
                      void* stash_y = nullptr, void* stash_x = nullptr);
 size_t enc_pair_bwd_packed_bytes(const TaeEncConfig& c);
 int enc_pair_pack_bwd(const TaeEncConfig& c, const float* params, void* packed, cudaStream_t s);
-int enc_stack_backward_pair(const TaeEncConfig& c, const void* packed_bwd, int branch, const float* dlin, const void* stash_y,
-                            void* stash_g, void* stash_d, float* dxin, int B, void* ws, size_t ws_bytes, cudaStream_t s,
-                            const TaeStackBwdChain* chain = nullptr);
+int enc_backward_pair(const TaeEncConfig& c, const void* packed_bwd, const float* dlin, const void* stash_y, void* stash_g, void* stash_d,
+                      float* dxin_all, float* grad_flat, int B, void* ws, size_t ws_bytes, cudaStream_t s);
 int launch_add_count(double* stats, double n, cudaStream_t s);
 // ---- DEC_LargeRNN recurrence (tae_gru.cu) ----------------------------------------------------
 int launch_gru_direction(const float* xproj, const float* w_hh, const float* b_hh, float* out, int B, int L, int H, int out_stride,

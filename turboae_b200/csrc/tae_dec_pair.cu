@@ -115,6 +115,20 @@ __host__ __device__ inline Smem make_smem(int F) {
   return s;
 }
 
+// Flat-parameter layout of a sequence of conv stacks + Linear (dec_layout / enc_layout of tae_common.cuh), passed BY VALUE:
+// only the last stack's Linear may have a different width, so every offset is arithmetic (no device table, no copy).
+struct PackLayout {
+  int n_stacks, n_layer, units, cin0, f_regular, f_last;
+  __host__ __device__ size_t l0() const { return (size_t)units * cin0 * TAPS + units; }
+  __host__ __device__ size_t lj() const { return (size_t)units * units * TAPS + units; }
+  __host__ __device__ size_t base(int st) const { return (size_t)st * (l0() + (size_t)(n_layer - 1) * lj() + (size_t)f_regular * units + f_regular); }
+  __host__ __device__ int fout(int st) const { return st == n_stacks - 1 ? f_last : f_regular; }
+  __host__ __device__ size_t conv_w(int st, int j) const { return base(st) + (j == 0 ? 0 : l0() + (size_t)(j - 1) * lj()); }
+  __host__ __device__ size_t conv_b(int st, int j) const { return conv_w(st, j) + (size_t)units * (j == 0 ? cin0 : units) * TAPS; }
+  __host__ __device__ size_t lin_w(int st) const { return base(st) + l0() + (size_t)(n_layer - 1) * lj(); }
+  __host__ __device__ size_t lin_b(int st) const { return lin_w(st) + (size_t)fout(st) * units; }
+};
+
 struct PairArgs {
   const uint8_t* wimg;
   const float* received;
@@ -135,16 +149,16 @@ struct PairArgs {
   uint8_t* stash_x;            // MODE 0: the stack inputs, [stack][group][1 chunk]; MODE 1: the dlin image of this stack, [group][1]
   uint8_t* stash_g;            // MODE 1: written, gradients at the pre-activations, [layer][group][13 chunks]
   const float* dlin;           // MODE 1: gradient w.r.t. the Linear output (B, L, fin)
-  float* dxin;                 // MODE 1: gradient w.r.t. the stack input (B, L, 8)
-  int fin;
-  // MODE 1, chained form (dlin == nullptr): dlin[b, l, f] = prev_dxin[b, idx[l], 2 + f] - (sub ? prev_dlin[b, idx[l], f] : 0),
-  // i.e. the extrinsic subtraction and the (de)interleaver between two stacks, backwards (decoders.py:235-249)
-  const float* prev_dxin;      // (B, L, 8) gradient w.r.t. the input of the NEXT stack of the schedule
-  const float* prev_dlin;      // (B, L, prev_fin) gradient w.r.t. that stack's Linear output
-  const int32_t* idx;          // int32[L]
-  int prev_fin, sub;
-  float* dlin_out;             // nullptr or (B, L, fin): the dlin this launch used
-  float* lin_bias_grad;        // nullptr or fin floats: += sum over (b, l) of dlin
+  float* dxin;                 // MODE 1: gradient w.r.t. every stack's input, (n_stacks, B, L, 8)
+  // MODE 1 runs the stacks n_stacks-1 .. 0 in one launch.  chain == 0 (encoder branches): stack s reads dlin + s*B*L*fout(s).
+  // chain == 1 (turbo schedule): the last stack reads dlin (B, L, fout); every other stack s derives its dlin from the outputs of
+  // stack s+1 -- dlin_s[b, l, f] = dxin_{s+1}[b, idx[l], 2 + f] - (sub ? dlin_{s+1}[b, idx[l], f] : 0), the extrinsic subtraction
+  // and the (de)interleaver backwards (decoders.py:235-249; idx = inv_perm for odd s+1, perm for even; sub = extrinsic and s+1
+  // not the last stack) -- and records it in dlin_all (n_stacks, B, L, F) for stack s-1.
+  int chain;
+  float* dlin_all;
+  float* grad_flat;            // nullptr or the flat gradient buffer: the Linear bias gradients (sum of dlin) are added at lay.lin_b(s)
+  PackLayout lay;              // flat-parameter layout (fout per stack, bias offsets)
 };
 
 // ELU'(z) from the bf16 forward output y packed two per word: y + 1 where y < 0, else 1 (cnn_utils.py:24-25 backward)
@@ -209,20 +223,6 @@ __device__ __forceinline__ float lin_w_elem(const float* __restrict__ w, const f
   if (e == 9) return b[o] - bf16_round(b[o]);
   return 0.f;
 }
-
-// Flat-parameter layout of a sequence of conv stacks + Linear (dec_layout / enc_layout of tae_common.cuh), passed BY VALUE:
-// only the last stack's Linear may have a different width, so every offset is arithmetic (no device table, no copy).
-struct PackLayout {
-  int n_stacks, n_layer, units, cin0, f_regular, f_last;
-  __host__ __device__ size_t l0() const { return (size_t)units * cin0 * TAPS + units; }
-  __host__ __device__ size_t lj() const { return (size_t)units * units * TAPS + units; }
-  __host__ __device__ size_t base(int st) const { return (size_t)st * (l0() + (size_t)(n_layer - 1) * lj() + (size_t)f_regular * units + f_regular); }
-  __host__ __device__ int fout(int st) const { return st == n_stacks - 1 ? f_last : f_regular; }
-  __host__ __device__ size_t conv_w(int st, int j) const { return base(st) + (j == 0 ? 0 : l0() + (size_t)(j - 1) * lj()); }
-  __host__ __device__ size_t conv_b(int st, int j) const { return conv_w(st, j) + (size_t)units * (j == 0 ? cin0 : units) * TAPS; }
-  __host__ __device__ size_t lin_w(int st) const { return base(st) + l0() + (size_t)(n_layer - 1) * lj(); }
-  __host__ __device__ size_t lin_b(int st) const { return lin_w(st) + (size_t)fout(st) * units; }
-};
 
 __global__ void pack_pair_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ img,
                                  const PackLayout lay, int n_stacks, int n_layer, int units, int cin0,
@@ -382,7 +382,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
       uint32_t pos = 0, phase = 0;
       for (int pr = pair0; pr < a.n_pairs; pr += pair_stride) {
         for (int st = 0; st < n_stacks; ++st) {
-          const uint8_t* src = a.wimg + (size_t)st * a.stack_bytes;
+          const uint8_t* src = a.wimg + (size_t)(MODE == 1 ? n_stacks - 1 - st : st) * a.stack_bytes;
           for (int i = 0; i < slots_per_stack; ++i) {
             const uint32_t bytes = (i == 0) ? L0_B : (i <= SLOTS_CONV * (a.n_layer - 1) ? SLOT_B : (FWD ? LIN_B : FIN_B));
             mbar_wait(bar(B_WEMPTY + pos), phase ^ 1, a.err, 1);
@@ -419,7 +419,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
       const uint32_t act = sbase + S.act, comb = sbase + S.comb, ones = sbase + S.ones;
       for (int pr = pair0; pr < a.n_pairs; pr += pair_stride) {
         for (int st = 0; st < n_stacks; ++st) {
-          const uint32_t xin = sbase + S.xin[a.enc ? (st == 2) : (st & 1)];   // enc: branch 3 reads the interleaved bits
+          const uint32_t xin = sbase + S.xin[MODE == 1 ? 0 : (a.enc ? (st == 2) : (st & 1))];   // enc: branch 3 reads the interleaved bits; backward: one operand chunk
           for (int layer = 0; layer <= a.n_layer; ++layer, ++step) {
             const uint32_t par = step & 1;
             const bool conv = (layer > 0 && layer < a.n_layer);
@@ -554,42 +554,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
       epi_bar_sync();
       const bool grp_ok = grp < a.n_groups;               // the odd group of the last pair does not exist: no stash traffic
       if (MODE == 1) {
-        // gradient w.r.t. the Linear output, as the 8-channel operand chunk of the first (transposed Linear) step
-        float bsum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int i = tid; i < n_cw * L; i += N_EPI_THREADS) {
-          const int c = i / L, l = i % L;
-          float v[8];
-          if (a.dlin) {
-            const float* d = a.dlin + ((size_t)(cw0 + c) * L + l) * a.fin;
-#pragma unroll
-            for (int f = 0; f < 8; ++f) v[f] = f < a.fin ? d[f] : 0.f;
-          } else {
-            const size_t src = (size_t)(cw0 + c) * L + a.idx[l];
-            const float* px = a.prev_dxin + src * 8 + 2;
-            const float* pd = a.prev_dlin + src * a.prev_fin;
-#pragma unroll
-            for (int f = 0; f < 8; ++f) v[f] = f < a.fin ? px[f] - (a.sub ? pd[f] : 0.f) : 0.f;
-          }
-          if (a.dlin_out) {
-            float* o = a.dlin_out + ((size_t)(cw0 + c) * L + l) * a.fin;
-#pragma unroll
-            for (int f = 0; f < 5; ++f)
-              if (f < a.fin) o[f] = v[f];
-          }
-#pragma unroll
-          for (int f = 0; f < 5; ++f) bsum[f] += v[f];
-          st_shared_v4(sbase + S.xin[0] + (uint32_t)(c * CW_ROWS + l + 2) * ROW_B, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                       pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-        }
-        if (a.lin_bias_grad) {
-#pragma unroll
-          for (int f = 0; f < 5; ++f) {
-            float t = bsum[f];
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
-            if (lane == 0 && f < a.fin && t != 0.f) atomicAdd(a.lin_bias_grad + f, t);
-          }
-        }
+        // the stack loop below fills the operand chunk of each stack's first step
       } else if (a.enc) {
         for (int i = tid; i < n_cw * L; i += N_EPI_THREADS) {
           const int c = i / L, l = i % L;
@@ -613,16 +578,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
         st_shared_u16(sbase + S.xin[1] + row + 2, bf16_bits(r2));        // r_par2         (decoders.py:224)
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + S.ones + row), "r"(0x3F803F80u) : "memory");   // bias inputs
       }
-      fence_proxy_async();
-      epi_bar_sync();
-      if (lane == 0)
-        for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_ACT + m), rank);
-      if (MODE == 1 && a.stash_x && grp_ok)
-        for (int i = tid; i < BUF_ROWS; i += N_EPI_THREADS) {
-          uint32_t x0, x1, x2, x3;
-          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(sbase + S.xin[0] + (uint32_t)i * ROW_B) : "memory");
-          *reinterpret_cast<uint4*>(a.stash_x + ((size_t)grp * BUF_ROWS + i) * ROW_B) = make_uint4(x0, x1, x2, x3);
-        }
+      if (FWD) {
+        fence_proxy_async();
+        epi_bar_sync();
+        if (lane == 0)
+          for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_ACT + m), rank);
+      }
 
       // Deferred rows: the last two rows of tile m are still read by the MMAs of tile m+1 (taps 0, 1), so the two
       // lanes that own them keep their packed outputs in registers and store them at the start of the next tile.
@@ -631,6 +592,68 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
       for (int i = 0; i < NDQ; ++i) dq[i] = 0u;
 
       for (int st = 0; st < n_stacks; ++st) {
+        const int sr = MODE == 1 ? n_stacks - 1 - st : st;          // MODE 1 walks the schedule backwards
+        float* dxin_s = nullptr;
+        if (MODE == 1) {
+          // ---- gradient w.r.t. this stack's Linear output -> the 8-channel operand chunk of its first (transposed Linear) step ------
+          const int fin = a.lay.fout(sr);
+          const size_t BL = (size_t)a.B * L;
+          dxin_s = a.dxin + (size_t)sr * BL * 8;
+          const bool direct = a.chain == 0 || sr == n_stacks - 1;
+          const float* src_d = a.dlin + (a.chain == 0 ? (size_t)sr * BL * fin : 0);
+          const float* px_b = a.dxin + (size_t)(sr + 1) * BL * 8 + 2;
+          const float* pd_b = a.dlin_all + (size_t)(sr + 1) * BL * F;
+          const int32_t* idx = ((sr + 1) & 1) ? a.inv_perm : a.perm;
+          const bool sub = a.extrinsic && (sr + 1 != n_stacks - 1);
+          float* out_d = (a.chain && a.dlin_all) ? a.dlin_all + (size_t)sr * BL * F : nullptr;
+          if (st > 0) epi_bar_sync();          // the previous stack's dxin rows (written by this CTA) are visible to every thread
+          float bsum[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int i = tid; i < n_cw * L; i += N_EPI_THREADS) {
+            const int c = i / L, l = i % L;
+            float v[8];
+            if (direct) {
+              const float* d = src_d + ((size_t)(cw0 + c) * L + l) * fin;
+#pragma unroll
+              for (int f = 0; f < 8; ++f) v[f] = f < fin ? d[f] : 0.f;
+            } else {
+              const size_t src = (size_t)(cw0 + c) * L + idx[l];
+              const float* px = px_b + src * 8;
+              const float* pd = pd_b + src * F;
+#pragma unroll
+              for (int f = 0; f < 8; ++f) v[f] = f < fin ? px[f] - (sub ? pd[f] : 0.f) : 0.f;
+            }
+            if (out_d) {
+              float* o = out_d + ((size_t)(cw0 + c) * L + l) * F;
+#pragma unroll
+              for (int f = 0; f < 5; ++f)
+                if (f < fin) o[f] = v[f];
+            }
+#pragma unroll
+            for (int f = 0; f < 5; ++f) bsum[f] += v[f];
+            st_shared_v4(sbase + S.xin[0] + (uint32_t)(c * CW_ROWS + l + 2) * ROW_B, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                         pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+          }
+          if (a.grad_flat) {
+            float* bg = a.grad_flat + a.lay.lin_b(sr);
+#pragma unroll
+            for (int f = 0; f < 5; ++f) {
+              float t = bsum[f];
+#pragma unroll
+              for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+              if (lane == 0 && f < fin && t != 0.f) atomicAdd(bg + f, t);
+            }
+          }
+          fence_proxy_async();
+          epi_bar_sync();
+          if (lane == 0)
+            for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_ACT + m), rank);
+          if (a.stash_x && grp_ok)          // the dlin image of this stack (B operand of the Linear's weight gradient)
+            for (int i = tid; i < BUF_ROWS; i += N_EPI_THREADS) {
+              uint32_t x0, x1, x2, x3;
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(sbase + S.xin[0] + (uint32_t)i * ROW_B) : "memory");
+              *reinterpret_cast<uint4*>(a.stash_x + (((size_t)sr * a.n_groups + grp) * BUF_ROWS + i) * ROW_B) = make_uint4(x0, x1, x2, x3);
+            }
+        }
         for (int layer = 0; layer <= a.n_layer; ++layer, ++step) {
           const uint32_t par = step & 1;
           const bool last_step = (st == n_stacks - 1 && layer == a.n_layer);
@@ -648,17 +671,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
                 if (!((vmask >> m) & 1u)) continue;
                 const int g_row = 128 * m + 32 * q + lane;
                 const int g_cw = g_row / CW_ROWS, g_l = g_row - g_cw * CW_ROWS;
-                float4* dst = reinterpret_cast<float4*>(a.dxin + ((size_t)(cw0 + g_cw) * L + g_l) * 8);
+                float4* dst = reinterpret_cast<float4*>(dxin_s + ((size_t)(cw0 + g_cw) * L + g_l) * 8);
                 dst[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
                 dst[1] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
               }
             }
-            if (!last_step) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0)
-                for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_ACT + m), rank);
-            }
+            tc_fence_before();              // (the next stack's prologue, or the next group's, arrives on B_ACT)
+            __syncwarp();
             continue;
           }
           if (FWD && layer == a.n_layer && a.enc) {
@@ -776,7 +795,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
           if (FWD) {
             if (STASH && a.stash_y && grp_ok) img_out = a.stash_y + ((size_t)(st * a.n_layer + layer) * a.n_groups + grp) * (IMG_CHUNKS * CHUNK_B);
           } else if (grp_ok) {
-            const size_t off = ((size_t)(a.n_layer - 1 - layer) * a.n_groups + grp) * (IMG_CHUNKS * CHUNK_B);
+            const size_t off = ((size_t)(sr * a.n_layer + a.n_layer - 1 - layer) * a.n_groups + grp) * (IMG_CHUNKS * CHUNK_B);
             img_y = a.stash_y + off;
             img_out = a.stash_g + off;
           }
@@ -1207,12 +1226,13 @@ int dec_pair_pack_bwd(const TaeDecConfig& c, const float* params, void* packed, 
   return after_launch("pack_bwd_kernel");
 }
 
-// Backward of stack `stack` (0 .. 2I-1): dlin (B, L, fin) -> dxin (B, L, 8); reads the stack's stashed forward outputs,
-// writes the pre-activation gradients (stash_g, same indexing as stash_y) and the dlin image (stash_d: [stack][group][1]).
-int dec_stack_backward_pair(const TaeDecConfig& c, const void* packed_bwd, int stack, const float* dlin, int fin, const void* stash_y,
-                            void* stash_g, void* stash_d, float* dxin, int B, void* ws, size_t ws_bytes, cudaStream_t s,
-                            const TaeStackBwdChain* chain) {
-  if (ws_bytes < 256) { set_error("tae_dec_stack_backward_bf16: workspace %zu < 256 bytes", ws_bytes); return TAE_EWORKSPACE; }
+// Backward of all 2I stacks in ONE launch (schedule walked backwards; the glue between stacks runs in the kernel's per-stack
+// prologue): d_out_last (B, L, fout of the last stack) -> dxin_all (2I, B, L, 8); dlin_all (2I, B, L, F) is scratch for the chain;
+// the Linear bias gradients are added into grad_flat (flat parameter layout) when it is not NULL.
+static int backward_pair(const TaeDecConfig& c, const PackLayout& lay, int n_stacks, int chain, const void* packed_bwd, const float* dlin,
+                         const int32_t* perm, const int32_t* inv_perm, const void* stash_y, void* stash_g, void* stash_d, float* dxin_all,
+                         float* dlin_all, float* grad_flat, int B, void* ws, size_t ws_bytes, cudaStream_t s, const char* who) {
+  if (ws_bytes < 256) { set_error("%s: workspace %zu < 256 bytes", who, ws_bytes); return TAE_EWORKSPACE; }
   const Smem S = make_smem(c.num_iter_ft);
   int n_sm = 0;
   {
@@ -1220,32 +1240,31 @@ int dec_stack_backward_pair(const TaeDecConfig& c, const void* packed_bwd, int s
     if (rc) return rc;
   }
   PairArgs a{};
-  a.B = B; a.L = c.block_len; a.F = c.num_iter_ft; a.n_stacks = 1; a.n_layer = c.num_layer;
+  a.B = B; a.L = c.block_len; a.F = c.num_iter_ft; a.n_stacks = n_stacks; a.n_layer = c.num_layer; a.extrinsic = c.extrinsic;
   a.cw_per_group = (GROUP_ROWS + 2) / (c.block_len + 2);
   a.n_groups = (B + a.cw_per_group - 1) / a.cw_per_group;
   a.n_pairs = (a.n_groups + 1) / 2;
   a.stack_bytes = stack_bwd_image_bytes(c);
-  a.wimg = reinterpret_cast<const uint8_t*>(packed_bwd) + (size_t)stack * a.stack_bytes;
+  a.wimg = reinterpret_cast<const uint8_t*>(packed_bwd);
   a.err = reinterpret_cast<int*>(align_up(reinterpret_cast<uintptr_t>(ws), 16));
-  const size_t layer_img = (size_t)a.n_groups * IMG_CHUNKS * CHUNK_B;
-  a.stash_y = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(stash_y)) + (size_t)stack * c.num_layer * layer_img;
-  a.stash_g = reinterpret_cast<uint8_t*>(stash_g) + (size_t)stack * c.num_layer * layer_img;
-  a.stash_x = stash_d ? reinterpret_cast<uint8_t*>(stash_d) + (size_t)stack * a.n_groups * CHUNK_B : nullptr;
-  a.dlin = dlin; a.dxin = dxin; a.fin = fin;
-  if (chain) {
-    a.prev_dxin = chain->prev_dxin; a.prev_dlin = chain->prev_dlin; a.idx = chain->idx; a.prev_fin = chain->prev_fin;
-    a.sub = chain->subtract; a.dlin_out = chain->dlin_out; a.lin_bias_grad = chain->lin_bias_grad;
-  }
-  if (!a.dlin && !(a.prev_dxin && a.idx && (!a.sub || a.prev_dlin))) {
-    set_error("tae_dec_stack_backward_bf16: dlin is NULL and the chained form is incomplete");
-    return TAE_EINVAL;
-  }
-  if (fin > 5 && a.lin_bias_grad) { set_error("tae_dec_stack_backward_bf16: lin_bias_grad supports fin <= 5"); return TAE_EINVAL; }
+  a.stash_y = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(stash_y));
+  a.stash_g = reinterpret_cast<uint8_t*>(stash_g);
+  a.stash_x = reinterpret_cast<uint8_t*>(stash_d);
+  a.dlin = dlin; a.dxin = dxin_all; a.dlin_all = dlin_all; a.grad_flat = grad_flat; a.chain = chain; a.lay = lay;
+  a.perm = perm; a.inv_perm = inv_perm;
   const int n_clusters = std::min(a.n_pairs, n_sm / 2);
   dec_pair_kernel<1><<<2 * n_clusters, N_THREADS, S.total, s>>>(a);
   return after_launch("dec_pair_kernel<1>");
 }
 
+int dec_backward_pair(const TaeDecConfig& c, const void* packed_bwd, const float* d_out_last, const int32_t* perm, const int32_t* inv_perm,
+                      const void* stash_y, void* stash_g, void* stash_d, float* dxin_all, float* dlin_all, float* grad_flat, int B, void* ws,
+                      size_t ws_bytes, cudaStream_t s) {
+  const int n_stacks = 2 * c.num_iteration;
+  const PackLayout lay{n_stacks, c.num_layer, c.num_unit, 2 + c.num_iter_ft, c.num_iter_ft, 1};
+  return backward_pair(c, lay, n_stacks, 1, packed_bwd, d_out_last, perm, inv_perm, stash_y, stash_g, stash_d, dxin_all, dlin_all, grad_flat, B,
+                       ws, ws_bytes, s, "tae_dec_backward_bf16");
+}
 
 // ---- ENC_interCNN on the same kernel ----------------------------------------------------------------------------
 static TaeDecConfig enc_as_dec(const TaeEncConfig& c) {
@@ -1290,11 +1309,12 @@ int enc_pair_pack_bwd(const TaeEncConfig& c, const float* params, void* packed, 
   return after_launch("pack_bwd_kernel");
 }
 
-// Backward of encoder branch `branch` (0..2): the decoder's stack backward with Linear(units, 1) and one input channel.
-int enc_stack_backward_pair(const TaeEncConfig& c, const void* packed_bwd, int branch, const float* dlin, const void* stash_y,
-                            void* stash_g, void* stash_d, float* dxin, int B, void* ws, size_t ws_bytes, cudaStream_t s,
-                            const TaeStackBwdChain* chain) {
-  return dec_stack_backward_pair(enc_as_dec(c), packed_bwd, branch, dlin, 1, stash_y, stash_g, stash_d, dxin, B, ws, ws_bytes, s, chain);
+// Backward of the three encoder branches in one launch: dlin (3, B, L, 1) -> dxin_all (3, B, L, 8); independent stacks (no chain).
+int enc_backward_pair(const TaeEncConfig& c, const void* packed_bwd, const float* dlin, const void* stash_y, void* stash_g, void* stash_d,
+                      float* dxin_all, float* grad_flat, int B, void* ws, size_t ws_bytes, cudaStream_t s) {
+  const PackLayout lay{3, c.num_layer, c.num_unit, 1, 1, 1};
+  return backward_pair(enc_as_dec(c), lay, 3, 0, packed_bwd, dlin, nullptr, nullptr, stash_y, stash_g, stash_d, dxin_all, nullptr, grad_flat, B,
+                       ws, ws_bytes, s, "tae_enc_backward_bf16");
 }
 
 int enc_forward_pair(const TaeEncConfig& c, const void* packed, const float* u, const int32_t* perm, const int32_t* inv_perm,

@@ -32,7 +32,7 @@ def _odd_chunks(n_ch: int, c0: int) -> int:
 class _Buffers:
     """Zero-initialised group-image buffers (and the small fp32 chain buffers) of one (batch, block length) shape, reused
     across steps; also caches everything whose device pointers are stable: the flat gradient buffer, the weight-gradient
-    job array and the per-stack chain descriptors."""
+    job array."""
 
     def __init__(self, n_stacks, n_layer, groups, B, L, F, device):
         cb = _lib.IMG_CHUNK_BYTES
@@ -46,7 +46,6 @@ class _Buffers:
         self.dlin = torch.zeros((n_stacks, B, L, F), dtype=torch.float32, device=device)
         self.gflat = None
         self.jobs = None          # (ctypes array, n, device workspace)
-        self.chains = None
 
 
 def _buffers(mod, n_stacks, n_layer, groups, B, L, F, device):
@@ -69,7 +68,6 @@ def _flat_grad(buf, flat, params):
             return g, False
     buf.gflat = torch.zeros_like(flat)
     buf.jobs = None
-    buf.chains = None
     return buf.gflat, True
 
 
@@ -215,29 +213,13 @@ class DecoderTrainFn(torch.autograd.Function):
             ws = dec._ws.get(256, dev)
             gflat, _ = _flat_grad(buf, flat, params)
             offsets, fouts = _dec_offsets(a)
-            if buf.chains is None or buf.chains[0] != (perm.data_ptr(), inv.data_ptr()):
-                chains = []
-                for st in range(n_stacks):
-                    bias = gflat.data_ptr() + 4 * (offsets[st][1] + fouts[st] * units)
-                    if st == n_stacks - 1:
-                        chains.append(_lib.TaeStackBwdChain(None, None, None, 0, 0, None, bias))
-                    else:
-                        nxt = st + 1
-                        last = nxt == n_stacks - 1
-                        chains.append(_lib.TaeStackBwdChain(
-                            buf.dxin[nxt].data_ptr(), None if last else buf.dlin[nxt].data_ptr(),
-                            (inv if nxt % 2 == 1 else perm).data_ptr(), F, 1 if (a.extrinsic and not last) else 0,
-                            buf.dlin[st].data_ptr(), bias))
-                buf.chains = ((perm.data_ptr(), inv.data_ptr()), chains)
-            chains = buf.chains[1]
             # out = sigmoid(deinterleave(o_last))  (decoders.py:267)  =>  d o_last = interleave(d_out * out * (1 - out))
             d_o = (d_out.to(torch.float32) * out * (1.0 - out)).index_select(1, perm.long()).contiguous()
-            stream = _lib.stream_ptr(dev)
-            for st in range(n_stacks - 1, -1, -1):
-                last = st == n_stacks - 1
-                _lib.check(lib.tae_dec_stack_backward_bf16(cfg, _lib.ptr(packed_bwd), st, _lib.ptr(d_o) if last else None, 1 if last else F,
-                                                           _lib.ptr(buf.stash_y), _lib.ptr(buf.stash_g), _lib.ptr(buf.stash_d),
-                                                           _lib.ptr(buf.dxin[st]), B, C.byref(chains[st]), _lib.ptr(ws), ws.numel(), stream))
+            # all 2I stacks in one launch, schedule walked backwards (the glue between stacks runs inside the kernel)
+            _lib.check(lib.tae_dec_backward_bf16(cfg, _lib.ptr(packed_bwd), _lib.ptr(d_o), _lib.ptr(perm), _lib.ptr(inv), _lib.ptr(buf.stash_y),
+                                                 _lib.ptr(buf.stash_g), _lib.ptr(buf.stash_d), _lib.ptr(buf.dxin), _lib.ptr(buf.dlin),
+                                                 _lib.ptr(gflat) if ctx.need_params else None, B, _lib.ptr(ws), ws.numel(),
+                                                 _lib.stream_ptr(dev)))
             d_rec = None
             if ctx.need_input:
                 # stack inputs: even [r_sys, r_par1, prior] (decoders.py:230), odd [interleave(r_sys), r_par2, ...] (:240)
@@ -339,14 +321,9 @@ class EncoderTrainFn(torch.autograd.Function):
                     off += units * cin * 5 + units
                 offsets.append((layers, off))
                 off += units + 1
-            if buf.chains is None:
-                buf.chains = (None, [_lib.TaeStackBwdChain(None, None, None, 0, 0, None, gflat.data_ptr() + 4 * (offsets[br][1] + units))
-                                     for br in range(3)])
-            stream = _lib.stream_ptr(dev)
-            for br in range(3):
-                _lib.check(lib.tae_enc_stack_backward_bf16(cfg, _lib.ptr(packed_bwd), br, _lib.ptr(d_lin[br]), _lib.ptr(buf.stash_y),
-                                                           _lib.ptr(buf.stash_g), _lib.ptr(buf.stash_d), _lib.ptr(buf.dxin[br]), B,
-                                                           C.byref(buf.chains[1][br]), _lib.ptr(ws), ws.numel(), stream))
+            _lib.check(lib.tae_enc_backward_bf16(cfg, _lib.ptr(packed_bwd), _lib.ptr(d_lin), _lib.ptr(buf.stash_y), _lib.ptr(buf.stash_g),
+                                                 _lib.ptr(buf.stash_d), _lib.ptr(buf.dxin), _lib.ptr(gflat), B, _lib.ptr(ws), ws.numel(),
+                                                 _lib.stream_ptr(dev)))
             if buf.jobs is None:
                 jobs = wgrad_jobs(n_layer, units, 1, [1, 1, 1], buf.groups, buf.stash_y, buf.stash_x, buf.stash_g, buf.stash_d, gflat,
                                   offsets, splits=getattr(enc, "wgrad_splits", None))

@@ -107,7 +107,7 @@ def _grad_worker(rank, world, port, out_dir):
     pa, pb = torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5))
     flat_local = flat.clone()
     pa.grad, pb.grad = flat[2:14].view(3, 4), flat[14:19]
-    n_red = shard.all_reduce_gradients([pa, pb])
+    n_red = shard.all_reduce_gradients([pb, pa])               # any order: the views tile one range of the buffer
     torch.save({"y": y.detach(), "dx": x.grad, "lo": lo, "hi": hi, "local": local, "avg": [p.grad.clone() for p in lin.parameters()],
                 "flat_local": flat_local, "flat_after": flat.clone(), "n_red": n_red, "pa": pa.grad.clone()},
                os.path.join(out_dir, "g%d.pt" % rank))

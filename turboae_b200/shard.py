@@ -84,9 +84,10 @@ def all_reduce_gradients(params, group=None) -> int:
     # place -- one collective, no gather / scatter copies.
     base = grads[0].untyped_storage()
     if all(g.is_contiguous() and g.untyped_storage().data_ptr() == base.data_ptr() for g in grads):
-        offs = [g.storage_offset() for g in grads]
-        if all(offs[i] + grads[i].numel() == offs[i + 1] for i in range(len(grads) - 1)):
-            n = offs[-1] + grads[-1].numel() - offs[0]
+        spans = sorted((g.storage_offset(), g.numel()) for g in grads)      # any parameter order: the views must tile one range
+        offs = [o for o, _ in spans]
+        if all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1)):
+            n = spans[-1][0] + spans[-1][1] - offs[0]
             flat = torch.empty(0, dtype=grads[0].dtype, device=grads[0].device).set_(base, offs[0], (n,), (1,))
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
             flat /= dist.get_world_size(group)

@@ -279,6 +279,8 @@ def run_b200(a):
         # training step (SURVEY.md 8(f) row 1 / BASELINE config 4: enc2/dec5, batch 1000, forward + backward + Adam) and the
         # bi-GRU decoder (row 2 / config 5: block length 1000) on the tensor cores; single-GPU figures measured on rank 0
         try:
+            if world > 1:
+                raise RuntimeError("single-GPU legs: measured when n_gpus == 1 (scripts/train_bench.py covers N > 1)")
             import torch.nn.functional as Fn
             import turboae_b200 as T
             from helpers import make_args

@@ -101,6 +101,14 @@ def _grad_worker(rank, world, port, out_dir):
     opt = torch.optim.SGD(lin.parameters(), lr=0.0)
     opt.step()
     handle.remove()
+    # an UN-sharded call inside a multi-rank job (only this rank makes it, e.g. bench.py's rank-0 legs): must not enter a collective
+    y_local = None
+    if rank == 0:
+        xl = full.clone().requires_grad_(True)
+        y_local = shard.PowerNorm.apply(xl, shard.LOCAL)
+        y_local.backward(g_full)
+        y_local = (y_local.detach(), xl.grad.clone(),
+                   shard.merge_power_stats(torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64), shard.LOCAL).tolist())
     # gradients handed out as consecutive views of one flat buffer (the tensor-core training path): reduced in place, one collective
     torch.manual_seed(200 + rank)
     flat = torch.randn(2 + 12 + 5)                          # leading padding, then a (3, 4) and a (5,) view
@@ -109,7 +117,7 @@ def _grad_worker(rank, world, port, out_dir):
     pa.grad, pb.grad = flat[2:14].view(3, 4), flat[14:19]
     n_red = shard.all_reduce_gradients([pb, pa])               # any order: the views tile one range of the buffer
     torch.save({"y": y.detach(), "dx": x.grad, "lo": lo, "hi": hi, "local": local, "avg": [p.grad.clone() for p in lin.parameters()],
-                "flat_local": flat_local, "flat_after": flat.clone(), "n_red": n_red, "pa": pa.grad.clone()},
+                "flat_local": flat_local, "flat_after": flat.clone(), "n_red": n_red, "pa": pa.grad.clone(), "y_local": y_local},
                os.path.join(out_dir, "g%d.pt" % rank))
     dist.barrier()
     dist.destroy_process_group()
@@ -131,6 +139,10 @@ def test_two_rank_power_norm_backward_and_gradient_all_reduce(tmp_path):
         mean = (parts[0]["local"][i] + parts[1]["local"][i]) / 2
         for z in parts:
             np.testing.assert_allclose(z["avg"][i].numpy(), mean.numpy(), atol=1e-7)
+    yl, dxl, st = parts[0]["y_local"]
+    np.testing.assert_allclose(yl.numpy(), y.detach().numpy(), atol=1e-6)
+    np.testing.assert_allclose(dxl.numpy(), full.grad.numpy(), atol=1e-6)
+    assert st == [1.0, 2.0, 3.0] and parts[1]["y_local"] is None
     mean_flat = (parts[0]["flat_local"] + parts[1]["flat_local"]) / 2
     for z in parts:
         assert z["n_red"] == 17

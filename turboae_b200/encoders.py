@@ -187,7 +187,8 @@ class ENC_interCNN(ENCBase):
         if self.args.no_code_norm:
             return x_tx
         self._check_supported()
-        codes = shard.PowerNorm.apply(x_tx, self.shard_group)
+        # statistics are merged across ranks only when the batch is sharded (shard_group set); otherwise this call stays local
+        codes = shard.PowerNorm.apply(x_tx, self.shard_group if self.shard_group is not None else shard.LOCAL)
         if getattr(self.args, "train_channel_mode", "block_norm") == "block_norm_ste":
             codes = STEQuantize.apply(codes, self.args)
         if self.args.enc_truncate_limit > 0:

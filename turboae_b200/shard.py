@@ -11,6 +11,11 @@ import torch
 import torch.distributed as dist
 
 
+#: pass as `group` to keep a reduction local to this rank even though torch.distributed is initialised (an un-sharded module
+#: inside a multi-rank job: only some ranks call it, so it must not enter a collective)
+LOCAL = False
+
+
 def shard_range(n_codewords: int, rank: int, world_size: int) -> tuple[int, int]:
     """Contiguous [begin, end) of the batch owned by `rank`; sizes differ by at most one codeword."""
     if world_size < 1 or not (0 <= rank < world_size):
@@ -24,6 +29,8 @@ def merge_power_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
     """In-place sum over ranks of the float64 triple (sum x, sum x^2, count) produced by `tae_enc_forward`."""
     if stats.dtype != torch.float64 or stats.numel() != 3:
         raise ValueError("power statistics must be 3 float64 values (sum, sum of squares, count)")
+    if group is LOCAL:
+        return stats
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
     return stats
@@ -68,7 +75,7 @@ class PowerNorm(torch.autograd.Function):
     def backward(ctx, g):
         y, std, n = ctx.saved_tensors
         sums = torch.stack([g.double().sum(), (g.double() * y.double()).sum()])
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
+        if ctx.group is not LOCAL and dist.is_available() and dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=ctx.group)
         dx = (g - (sums[0] / n).float() - y * (sums[1] / (n - 1.0)).float()) / std
         return dx, None

@@ -1,0 +1,133 @@
+"""CPU tests (`-m "not gpu"`) of the host-side logic behind the tensor-core training and GRU paths: weight-gradient job
+construction, flat-gradient buffer reuse, the C ABI's argument validation and geometry helpers (no kernel is launched)."""
+import ctypes as C
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+from helpers import make_args
+from turboae_b200 import _lib, train_tc
+
+
+def _jobs(units, n_layer, cin0, fouts, groups, splits=None):
+    n_stacks = len(fouts)
+    img = lambda n: torch.zeros(max(n, 1), dtype=torch.uint8)
+    cb = _lib.IMG_CHUNK_BYTES
+    stash_y = img(n_stacks * n_layer * groups * 13 * cb // 1024)       # only the base addresses matter here
+    stash_g, stash_x, stash_d = img(64), img(64), img(64)
+    offsets, off = [], 0
+    for st in range(n_stacks):
+        layers = []
+        for j in range(n_layer):
+            cin = cin0 if j == 0 else units
+            layers.append((off, off + units * cin * 5))
+            off += units * cin * 5 + units
+        offsets.append((layers, off))
+        off += fouts[st] * units + fouts[st]
+    gflat = torch.zeros(off)
+    jobs = train_tc.wgrad_jobs(n_layer, units, cin0, fouts, groups, stash_y, stash_x, stash_g, stash_d, gflat, offsets, splits=splits)
+    return jobs, offsets, gflat
+
+
+@pytest.mark.parametrize("units,n_layer,cin0,fouts,groups", [(100, 5, 7, [5] * 11 + [1], 200), (64, 3, 5, [3, 3], 7), (60, 2, 1, [1, 1, 1], 40),
+                                                              (30, 4, 7, [5, 1], 1), (8, 2, 4, [2], 3), (96, 5, 7, [5, 1], 1000)])
+def test_wgrad_jobs_cover_every_parameter_exactly_once(units, n_layer, cin0, fouts, groups):
+    jobs, offsets, gflat = _jobs(units, n_layer, cin0, fouts, groups)
+    base = gflat.data_ptr()
+    seen = {}                      # (grad offset in floats, channel, group) -> count
+    bias_jobs = {}
+    last_cost = None
+    for j in jobs:
+        # constraints of tae_wgrad_bf16 (include/turboae_b200.h)
+        assert j.n_cols % 16 == 0 and 8 * j.b_nc <= j.n_cols <= 8 * (j.b_nc + 1) and j.taps * j.n_cols <= 512
+        assert 1 <= j.b_nc <= 8 and 0 <= j.b_c0 and j.b_c0 + j.b_nc <= j.b_chunks and j.taps in (1, 5)
+        assert 0 <= j.n_valid <= 8 * j.b_nc and 1 <= j.m_valid <= 104 and 0 <= j.g0 < j.g1 <= groups
+        if j.bias_grad:
+            assert 8 * j.b_nc < j.n_cols                                  # the spare column that carries the bias gradient exists
+            for g in range(j.g0, j.g1):
+                bias_jobs[(j.bias_grad, g)] = bias_jobs.get((j.bias_grad, g), 0) + 1
+        goff = (j.grad - base) // 4
+        for n in range(j.n_valid):
+            for g in range(j.g0, j.g1):
+                k = (goff, j.n0 + n, g)
+                seen[k] = seen.get(k, 0) + 1
+        cost = train_tc._job_cost_us(j.b_chunks, j.n_cols, j.taps) * (j.g1 - j.g0)
+        assert last_cost is None or cost <= last_cost + 1e-9              # longest first
+        last_cost = cost
+    assert all(v == 1 for v in seen.values()) and all(v == 1 for v in bias_jobs.values())
+    for st, (layers, lin_w_off) in enumerate(offsets):
+        for jl, (w_off, b_off) in enumerate(layers):
+            cin = cin0 if jl == 0 else units
+            for c in range(cin):
+                for g in (0, groups - 1):
+                    assert seen.get((w_off, c, g)) == 1, (st, jl, c, g)
+            assert bias_jobs.get((base + 4 * b_off, 0)) == 1 and bias_jobs.get((base + 4 * b_off, groups - 1)) == 1
+        for f in range(fouts[st]):
+            assert seen.get((lin_w_off, f, 0)) == 1
+
+
+def test_wgrad_jobs_forced_splits_partition_the_groups():
+    jobs, _, _ = _jobs(100, 5, 7, [5, 1], 10, splits=3)
+    ranges = sorted({(j.g0, j.g1) for j in jobs})
+    assert ranges == [(0, 3), (3, 6), (6, 10)]
+
+
+def test_flat_gradient_buffer_is_reused_unless_a_grad_still_aliases_it():
+    buf = SimpleNamespace(gflat=None, jobs="cached")
+    params = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5))]
+    flat = torch.zeros(17)
+    g1, fresh = train_tc._flat_grad(buf, flat, params)
+    assert fresh and buf.jobs is None and g1.numel() == 17
+    buf.jobs = "cached"
+    g1.fill_(3.0)
+    g2, fresh = train_tc._flat_grad(buf, flat, params)                    # zero_grad(set_to_none=True) case: same buffer, zeroed
+    assert not fresh and g2.data_ptr() == g1.data_ptr() and float(g2.abs().sum()) == 0.0 and buf.jobs == "cached"
+    params[0].grad = g2[:12].view(3, 4)                                    # autograd adopted a view as .grad: accumulation in progress
+    g3, fresh = train_tc._flat_grad(buf, flat, params)
+    assert fresh and g3.data_ptr() != g2.data_ptr() and buf.jobs is None   # a new buffer: the live gradient is not clobbered
+
+
+def test_supported_configurations():
+    assert train_tc.supported(make_args(), "dec") and train_tc.supported(make_args(), "enc")
+    assert not train_tc.supported(make_args(dec_kernel_size=3), "dec")
+    assert not train_tc.supported(make_args(dec_num_unit=128), "dec")
+    assert not train_tc.supported(make_args(block_len=1000), "dec") and not train_tc.supported(make_args(block_len=1000), "enc")
+    assert not train_tc.supported(make_args(enc_num_layer=1), "enc")
+
+
+def test_cabi_geometry_and_validation_without_a_gpu():
+    lib = _lib.load()
+    assert lib.tae_train_groups(100, 1000) == 200 and lib.tae_train_groups(100, 1) == 1 and lib.tae_train_groups(100, 0) == 0
+    assert lib.tae_train_groups(37, 29) == 3                               # 13 codewords of 37 + 2 rows per 512-row group
+    assert lib.tae_train_groups(512, 3) == 3 and lib.tae_train_groups(513, 3) == 0
+    assert [lib.tae_gru_rows_per_block(b) for b in (1, 2368, 4736, 5000, 9472, 18944, 10 ** 6)] == [32, 32, 32, 64, 64, 128, 128]
+    assert lib.tae_gru_tile_bytes(300, 50, 26, 96) == 4 * 50 * 26 * 96 * 16   # 4 blocks: an even number (whole CTA pairs)
+    assert lib.tae_gru_tile_bytes(300, 50, 26, 48) == 0                     # rows per block: 32, 64, 96 or 128
+    # weight image of one layer-direction: (input k-steps + 7) x 3584 + input k-steps x 1792 + 7 x 1792 bytes per CTA
+    assert lib.tae_gru_packed_bytes(100, 7, 7) == 2 * ((1 + 7) * 3584 + 1 * 1792 + 7 * 1792)
+    assert lib.tae_gru_packed_bytes(100, 200, 100) == 2 * ((14 + 7) * 3584 + 14 * 1792 + 7 * 1792)
+    assert lib.tae_gru_packed_bytes(33, 7, 7) == 0 and b"hidden size" in lib.tae_last_error()
+    assert lib.tae_gru_packed_bytes(100, 300, 100) == 0                     # 39 input chunks > 26
+    # malformed weight-gradient jobs are rejected before anything touches the device
+    good = dict(a_img=8, b_img=8, grad=8, bias_grad=None, b_chunks=13, b_c0=0, b_nc=8, taps=5, n_cols=64, m_valid=100, n_valid=64, n0=0,
+                s_m=500, s_n=5, s_t=1, g0=0, g1=4, reserved=0)
+    for bad in (dict(n_cols=72), dict(b_nc=9), dict(b_c0=6), dict(taps=4), dict(n_cols=112), dict(m_valid=105), dict(g1=-1), dict(grad=None)):
+        job = _lib.TaeWgradJob(**{**good, **bad})
+        arr = (_lib.TaeWgradJob * 1)(job)
+        assert lib.tae_wgrad_bf16(arr, 1, None, C.c_void_p(8), 4096, None) == -1, bad
+        assert b"malformed" in lib.tae_last_error()
+    assert lib.tae_wgrad_bf16(None, 0, None, None, 0, None) == 0             # an empty job list is a no-op
+
+
+def test_local_power_normalisation_without_process_group():
+    from turboae_b200 import shard
+    x = torch.randn(4, 10, 3, dtype=torch.float32, requires_grad=True)
+    y = shard.PowerNorm.apply(x, shard.LOCAL)
+    ref = (x - x.mean()) / x.std()
+    assert torch.allclose(y, ref, atol=1e-6)
+    g = torch.randn_like(x)
+    y.backward(g)
+    xr = x.detach().clone().requires_grad_(True)
+    ((xr - xr.mean()) / xr.std()).backward(g)
+    assert torch.allclose(x.grad, xr.grad, atol=1e-6)

@@ -301,7 +301,7 @@ def run_b200(a):
             sec["train_step_decoder_mode_cw_per_s"] = TB / (ms * 1e-3)
             sec["train_step"] = "enc2/dec5, batch %d, fwd+bwd+Adam, train_precision=%s, %.2f ms/step" % (TB, tdec.train_precision, ms)
             del tenc, tdec, opt
-            RB, RL = 4736, 1000
+            RB, RL = 18944, 1000                # one 128-codeword block per CTA on all 148 SMs (profiles/r01_rnn_bench.json)
             rdec = T.DEC_LargeRNN(make_args(num_iteration=6, dec_num_unit=100, block_len=RL, batch_size=RB),
                                   O_make_perm(RL)).to(dev).eval()
             rrec = torch.randn(RB, RL, 3, device=dev)

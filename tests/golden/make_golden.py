@@ -13,6 +13,8 @@ The reference cannot travel to the GPU box, so its outputs are committed here:
   weights_c1s.npz / io_c1s_b8.npz   the binarised-code checkpoint dta_steq2_... (train_channel_mode block_norm_ste), B=8 @ 2 dB
   rnn_*.npz        DEC_LargeRNN (bi-GRU decoder) runs with seeded default-init weights: weights, input, output
   perm.npz         interleaver goldens (p, inverse, gather of arange through the reference modules)
+  grad_c1_b6.npz   one training step (forward, clamp, BCE, backward) of the reference with checkpoint c1, B=6 @ -1.5 dB:
+                   loss, per-parameter gradient norms / first values, six gradients in full
   ber_c1.json      12-point BER/BLER sweep (reference trainer.py:157-178 loop restated with seeded
                    numpy inputs, batch 500) -- per-point bit/block error counts
 
@@ -171,13 +173,39 @@ def dump_ber(blocks, batch=500):
     json.dump(res, open(os.path.join(HERE, "ber_c1.json"), "w"), indent=1)
 
 
+def dump_grad(cfg, B, seed, snr_db, name):
+    """One trainer.train step of the UNMODIFIED reference on CPU (reference trainer.py:53-74: forward through Channel_AE, clamp,
+    BCE (loss.py:32-35), loss.backward()) with the shipped checkpoint and seeded inputs: loss, every parameter gradient's
+    L2 norm and first 16 values, and a few gradients in full.  Pins the training arithmetic of the oracle (row f1)."""
+    import torch.nn.functional as F
+    model, args, p_array = build_reference_model(cfg, B)
+    model.train()
+    u, noise = gen_inputs(seed, B, args.block_len, snr_db)
+    out, codes = model(torch.from_numpy(u), torch.from_numpy(noise))
+    loss = F.binary_cross_entropy(torch.clamp(out, 0.0, 1.0), torch.from_numpy(u))
+    loss.backward()
+    d = {"u": u, "noise": noise, "p": np.asarray(p_array), "loss": np.float64(float(loss)), "snr_db": np.float64(snr_db)}
+    full = ("enc.enc_cnn_1.module.cnns.0.weight", "enc.enc_linear_3.module.weight", "dec.dec1_cnns.0.module.cnns.0.weight",
+            "dec.dec2_cnns.3.module.cnns.2.bias", "dec.dec1_outputs.5.module.weight", "dec.dec2_outputs.5.module.weight")
+    names = []
+    for k, v in model.named_parameters():
+        g = v.grad.detach().numpy().astype(np.float32)
+        names.append(k)
+        d["norm/" + k] = np.float64(np.sqrt((g.astype(np.float64) ** 2).sum()))
+        d["head/" + k] = g.reshape(-1)[:16].copy()
+        if k in full:
+            d["full/" + k] = g
+    np.savez_compressed(os.path.join(HERE, name), **d)
+    print("%s: loss %.6f, %d parameter gradients" % (name, float(loss), len(names)))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--sweep-blocks", type=int, default=10000)
     ap.add_argument("--only", default="")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["weights", "kat", "io", "perm", "rnn", "ber"]
+    todo = a.only.split(",") if a.only else ["weights", "kat", "io", "perm", "rnn", "ber", "grad"]
     if "weights" in todo:
         dump_weights("c1"); dump_weights("c3"); dump_weights("c1s")
     if "kat" in todo:
@@ -191,3 +219,5 @@ if __name__ == "__main__":
         dump_rnn("rnn_h32_i2_l40_b5.npz", 5, 40, 32, 2, 11); dump_rnn("rnn_h100_i1_l100_b3.npz", 3, 100, 100, 1, 12)
     if "ber" in todo:
         dump_ber(a.sweep_blocks)
+    if "grad" in todo:
+        dump_grad("c1", 6, 2718, -1.5, "grad_c1_b6.npz")

@@ -233,7 +233,7 @@ int tae_gru_direction_f32(const float* xproj, const float* w_hh, const float* b_
 /* The same recurrence on the tensor cores (bf16 operands, fp32 accumulation, fp32 hidden state): the input projection is
  * part of the per-step MMA chain, so no (B, L, 3H) projection tensor exists.  Activations travel between the launches as
  * TIME-MAJOR TILES: bf16 [block of R codewords][t][chunk of 8 channels][R][8] -- the operand chunks of one time step are
- * contiguous (bulk copies in, coalesced stores out).  R = tae_gru_rows_per_block(B): 16, 32, 64, 96 or 128 (small
+ * contiguous (bulk copies in, coalesced stores out).  R = rows per block: 16, 32, 64, 96 or 128; tae_gru_rows_per_block(B) picks 32 .. 128 (small
  * batches use fewer rows per CTA so that every SM gets a block); a tile buffer holds an even number of blocks
  * (tae_gru_tile_bytes).  Channels are stored in groups of grp_valid real channels padded to a multiple of 8: the stack
  * input is one group (2 + F channels in 8), a layer's output is two groups (forward | reverse, H channels each in 13

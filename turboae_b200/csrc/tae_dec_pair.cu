@@ -370,6 +370,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sbase + S.tmem_ptr) : "memory");
 
   const int pair0 = (int)cluster_id_x(), pair_stride = (int)n_clusters_x();
+  // timeline: the third group of cluster 0 (steady state: weights in L2, clocks settled), else its first
+  const int tl_pr = (a.n_pairs > 2 * pair_stride) ? 2 * pair_stride : 0;
+  (void)tl_pr;
   unsigned long long t_start_ns = 0, t_start_clk = 0;
   if (TAE_TIMELINE && a.tl && threadIdx.x == 0) {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start_ns));
@@ -424,8 +427,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
             const uint32_t par = step & 1;
             const bool conv = (layer > 0 && layer < a.n_layer);
             {
-              const bool stamp = TAE_TIMELINE && a.tl && pr == 0 && lane == 0;
-              if (stamp) a.tl[(step * 4 + m) * 8 + 0] = clock64();
+              const bool stamp = TAE_TIMELINE && a.tl && pr == tl_pr && lane == 0;
+              const uint32_t sidx = (uint32_t)(st * (a.n_layer + 1) + layer);
+              (void)sidx;
+              if (stamp) a.tl[(sidx * 4 + m) * 8 + 0] = clock64();
               // inputs of tile m: its own rows and the last rows of tile m-1 (both covered by B_ACT[m]), the first rows of
               // tile m+1 and the deferred last two rows of tile m, stored by the epilogue of tile m+1 (B_ACT[m+1]).  Layer 0 reads the stack input, which the
               // previous Linear epilogue scatters across the whole group.
@@ -436,7 +441,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
                 if (m < N_TILES - 1) mbar_wait(bar(B_ACT + m + 1), par, a.err, 5);
               }
               tc_fence_after();
-              if (stamp) a.tl[(step * 4 + m) * 8 + 1] = clock64();
+              if (stamp) a.tl[(sidx * 4 + m) * 8 + 1] = clock64();
               const uint32_t rowoff = (uint32_t)(128 * m) * ROW_B;
               uint32_t p = pos, ph = wphase;
               // descriptors = per-tile base words + compile-time constants (everything below is fully unrolled)
@@ -519,7 +524,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
                 }
                 __syncwarp();
               }
-              if (stamp) a.tl[(step * 4 + m) * 8 + 2] = clock64();
+              if (stamp) a.tl[(sidx * 4 + m) * 8 + 2] = clock64();
             }
             // advance the ring past this layer's slots
             const int n_adv = conv ? SLOTS_CONV : ((MODE == 1 && layer == a.n_layer) ? 2 : 1);
@@ -656,6 +661,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
         }
         for (int layer = 0; layer <= a.n_layer; ++layer, ++step) {
           const uint32_t par = step & 1;
+          const uint32_t sidx = (uint32_t)(st * (a.n_layer + 1) + layer);      // timeline row
+          (void)sidx;
           const bool last_step = (st == n_stacks - 1 && layer == a.n_layer);
           if (MODE == 1 && layer == a.n_layer) {
             // -- gradient w.r.t. the stack input (transposed first layer): one (8-float) row per position -----------------
@@ -722,12 +729,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
             const bool last = (st == n_stacks - 1);
             const uint32_t xin_cur = sbase + S.xin[st & 1], xin_nxt = sbase + S.xin[(st & 1) ^ 1];
             const uint32_t map = sbase + (last ? S.perm : ((st & 1) ? S.perm : S.inv_perm));   // where position l lands
-            const bool stamp = TAE_TIMELINE && a.tl && pr == 0 && rank == 0 && lane == 0 && ew == 0;
-            if (stamp) a.tl[(step * 4 + 0) * 8 + 3] = clock64();
+            const bool stamp = TAE_TIMELINE && a.tl && pr == tl_pr && rank == 0 && lane == 0 && ew == 0;
+            if (stamp) a.tl[(sidx * 4 + 0) * 8 + 3] = clock64();
 #pragma unroll
             for (int m = 0; m < N_TILES; ++m) mbar_wait(bar(B_ACC + m), par, a.err, 6);
             tc_fence_after();
-            if (stamp) a.tl[(step * 4 + 0) * 8 + 4] = clock64();
+            if (stamp) a.tl[(sidx * 4 + 0) * 8 + 4] = clock64();
             // One warp per lane quadrant (part 0) does the whole row: the prior that is subtracted is the bf16 value the
             // stack actually saw (channels 2.. of its own input row), so no separate fp32 prior buffer exists, and the
             // extrinsic values of a row go out as one 4-byte and one 8-byte store (scattered rows => bank conflicts,
@@ -786,7 +793,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
               if (lane == 0)
                 for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_ACT + m), rank);
             }
-            if (stamp) a.tl[(step * 4 + 0) * 8 + 5] = clock64();
+            if (stamp) a.tl[(sidx * 4 + 0) * 8 + 5] = clock64();
             continue;
           }
           // training: this layer's group image in HBM (MODE 0: stash of the outputs; MODE 1: forward outputs in, gradients out)
@@ -801,8 +808,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
           }
 #pragma unroll 1
           for (int m = 0; m < N_TILES; ++m) {
-            const bool stamp = TAE_TIMELINE && a.tl && pr == 0 && rank == 0 && lane == 0 && ew == 0;
-            if (stamp && ew == 0) a.tl[(step * 4 + m) * 8 + 3] = clock64();
+            const bool stamp = TAE_TIMELINE && a.tl && pr == tl_pr && rank == 0 && lane == 0 && ew == 0;
+            if (stamp && ew == 0) a.tl[(sidx * 4 + m) * 8 + 3] = clock64();
             const int g_row = 128 * m + 32 * q + lane;
             const uint32_t brow = (uint32_t)(g_row + 2);
             const bool has_comb = (part == PARTS - 1);               // this part also owns channels 96..99
@@ -817,7 +824,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
             }
             mbar_wait(bar(B_ACC + m), par, a.err, 6);
             tc_fence_after();
-            if (stamp) a.tl[(step * 4 + m) * 8 + (ew == 0 ? 4 : 6)] = clock64();
+            if (stamp) a.tl[(sidx * 4 + m) * 8 + 4] = clock64();
             if (STASH && layer == 0 && m == 0 && a.stash_x && grp_ok) {
               // the stack input (sys, parity, priors as the stack saw them): complete since the MMAs of layer 0 were released
               const uint32_t xsrc = sbase + S.xin[a.enc ? (st == 2) : (st & 1)];
@@ -850,7 +857,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
                 }
               }
               tmem_ld_wait();
-              if (stamp && ew == 0) a.tl[(step * 4 + m) * 8 + 6] = clock64();
+              if (stamp && ew == 0) a.tl[(sidx * 4 + m) * 8 + 6] = clock64();
               const uint32_t keep = valid ? 0xFFFFFFFFu : 0u;
 #pragma unroll
               for (int c = 0; c < CPP; ++c) {
@@ -892,13 +899,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
             }
             {
               // every warp reports on its own: no CTA-wide barrier on the tile-to-tile critical path
-              if (stamp && ew == 0) a.tl[(step * 4 + m) * 8 + 7] = clock64();
+              if (stamp && ew == 0) a.tl[(sidx * 4 + m) * 8 + 7] = clock64();
               fence_proxy_async();
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive_leader(bar(B_ACT + m), rank);
             }
-            if (stamp) a.tl[(step * 4 + m) * 8 + (ew == 0 ? 5 : 7)] = clock64();
+            if (stamp) a.tl[(sidx * 4 + m) * 8 + 5] = clock64();
           }
         }
       }

@@ -76,12 +76,25 @@ def install(reference_root: str) -> None:
 def main(argv=None):
     ap = argparse.ArgumentParser(prog="python -m turboae_b200.launch", add_help=True)
     ap.add_argument("--reference", default=os.environ.get("TURBOAE_REF", "."), help="path of the turboae checkout")
+    ap.add_argument("--seed", type=int, default=None, help="seed numpy / torch before the script starts (the reference sets "
+                    "no seed; with one, two runs draw identical bits and noise)")
+    ap.add_argument("--stock", action="store_true", help="do NOT swap the hot-path classes: run the reference's own modules "
+                    "(only the library-compatibility shim is applied); the comparison arm of scripts/run_reference_dropin.py")
     ap.add_argument("script", help="reference script to run, e.g. main.py")
     ap.add_argument("script_args", nargs=argparse.REMAINDER)
     a = ap.parse_args(argv)
-    install(a.reference)
+    if a.stock:
+        sys.path.insert(0, os.path.abspath(a.reference))
+        _modernise()
+    else:
+        install(a.reference)
+    if a.seed is not None:
+        import numpy as np
+        import torch
+        np.random.seed(a.seed)
+        torch.manual_seed(a.seed)
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world > 1:
+    if world > 1 and not a.stock:
         # data-parallel under torchrun: one process per GPU, whole codewords per rank; the reference's
         # `loss.backward(); optimizer.step()` (trainer.py:74-76) is kept, gradients are averaged by an optimizer pre-step hook
         import torch

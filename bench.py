@@ -85,27 +85,64 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_reference_rate(sample_b, min_seconds, max_reps, warmup=1):
-    """The reference's operator sequence on torch CPU kernels (oracle/turboae_torch.py), all host threads."""
-    import numpy as np
+    """CPU baseline on the box's host cores, all threads: the reference's OWN DEC_LargeCNN.forward when baseline/_ref is
+    staged (kind "reference"), else its operator sequence on torch CPU kernels (oracle/turboae_torch.py, kind "port")."""
     import torch
-    from helpers import load_npz
-    from oracle import turboae_oracle as O
-    from oracle import turboae_torch as TT
     torch.set_num_threads(os.cpu_count())
-    w = TT.to_torch(load_npz("weights_c1.npz"))
-    p = O.make_perm(100, 0)
     g = torch.Generator().manual_seed(1)
     rec = torch.randn(sample_b, 100, 3, generator=g) + (2.0 * torch.randint(0, 2, (sample_b, 100, 3), generator=g) - 1.0)
+    if staged_reference() is not None:
+        dec = reference_cpu_decoder(sample_b)
+        fwd, kind = (lambda: dec(rec)), "reference"
+    else:
+        from helpers import load_npz
+        from oracle import turboae_oracle as O
+        from oracle import turboae_torch as TT
+        w = TT.to_torch(load_npz("weights_c1.npz"))
+        p = O.make_perm(100, 0)
+        fwd, kind = (lambda: TT.dec_forward(rec, w, p)), "port"
     times = []
     with torch.no_grad():
         for _ in range(warmup):
-            TT.dec_forward(rec, w, p)
+            fwd()
         t_all = time.perf_counter()
         while len(times) < max_reps and (len(times) < 3 or time.perf_counter() - t_all < min_seconds):
             t0 = time.perf_counter()
-            TT.dec_forward(rec, w, p)
+            fwd()
             times.append(time.perf_counter() - t0)
-    return sample_b / statistics.median(times), times, torch.get_num_threads()
+    return sample_b / statistics.median(times), times, torch.get_num_threads(), kind
+
+
+def staged_reference():
+    """Path of the UNMODIFIED reference staged by scripts/stage_reference.py (git-ignored, ships with gpurun), or None."""
+    d = os.path.join(ROOT, "baseline", "_ref")
+    return d if os.path.isfile(os.path.join(d, "decoders.py")) else None
+
+
+def reference_cpu_decoder(sample_b):
+    """The reference's OWN DEC_LargeCNN (baseline/_ref/decoders.py:157-269) on the host cores, weights of the shipped
+    checkpoint, built exactly as main.py does with -no_cuda.  Returns a callable received -> posteriors."""
+    import torch
+    ref = staged_reference()
+    os.environ["TURBOAE_REF"] = ref
+    from oracle import compat                       # library-compatibility shim only (numpy aliases, matplotlib stub)
+    compat.REFERENCE_ROOT = ref
+    compat.install()
+    import decoders as ref_decoders                 # the reference module itself
+    from helpers import load_npz, make_args
+    from oracle import turboae_oracle as O
+    args = make_args(batch_size=sample_b, no_cuda=True)
+    dec = ref_decoders.DEC_LargeCNN(args, O.make_perm(100, 0))
+    w = load_npz("weights_c1.npz")
+    sd = {k[len("dec."):]: torch.from_numpy(v) for k, v in w.items() if k.startswith("dec.")}
+    if torch.cuda.is_available():
+        # same process as the CUDA arm: nn.DataParallel (main.py:158-159, -is_parallel 1) would move the batch to the GPUs, so the
+        # sub-modules stay unwrapped (the checkpoint's '.module.' level is dropped from the keys); the arithmetic is the same
+        sd = {k.replace(".module.", "."): v for k, v in sd.items()}
+    else:
+        dec.set_parallel()                          # on a CPU-only process DataParallel is a pass-through
+    dec.load_state_dict(sd, strict=True)
+    return dec.eval()
 
 
 def run_reference(a):
@@ -113,30 +150,42 @@ def run_reference(a):
     if rank != 0:
         return 0
     sample_b = a.cpu_sample
+    real = staged_reference() is not None
+    if real:
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""     # the reference's CPU path (what main.py -no_cuda runs); set before torch initialises CUDA
     import torch
-    from helpers import load_npz
-    from oracle import turboae_oracle as O
-    from oracle import turboae_torch as TT
     torch.set_num_threads(os.cpu_count())
-    w = TT.to_torch(load_npz("weights_c1.npz"))
-    p = O.make_perm(100, 0)
     g = torch.Generator().manual_seed(1)
     rec = torch.randn(sample_b, 100, 3, generator=g) + (2.0 * torch.randint(0, 2, (sample_b, 100, 3), generator=g) - 1.0)
+    if real:
+        dec = reference_cpu_decoder(sample_b)
+        fwd = lambda: dec(rec)
+        kind = "reference"
+        what = "the reference's own DEC_LargeCNN.forward (baseline/_ref/decoders.py, unmodified) on the host cores"
+    else:
+        from helpers import load_npz
+        from oracle import turboae_oracle as O
+        from oracle import turboae_torch as TT
+        w = TT.to_torch(load_npz("weights_c1.npz"))
+        p = O.make_perm(100, 0)
+        fwd = lambda: TT.dec_forward(rec, w, p)
+        kind = "port"
+        what = "torch CPU operators of the reference's decode path (oracle/turboae_torch.py; baseline/_ref not staged)"
     with torch.no_grad():
         for _ in range(a.warmup):
-            TT.dec_forward(rec, w, p)
+            fwd()
         t0 = time.perf_counter()
         for _ in range(a.steps):
-            TT.dec_forward(rec, w, p)
+            fwd()
         dt = time.perf_counter() - t0
     val = sample_b * a.steps / dt
-    sample = "%d of the %d codewords of one batch per step (same decoder, same checkpoint, torch CPU operators, " \
-             "%d threads)" % (sample_b, a.batch, torch.get_num_threads())
+    sample = "%d of the %d codewords of one batch per step (same decoder, same checkpoint; %s, %d threads)" % (
+        sample_b, a.batch, what, torch.get_num_threads())
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a.batch), "sample": sample},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
     return 0
@@ -279,6 +328,8 @@ def run_b200(a):
         # training step (SURVEY.md 8(f) row 1 / BASELINE config 4: enc2/dec5, batch 1000, forward + backward + Adam) and the
         # bi-GRU decoder (row 2 / config 5: block length 1000) on the tensor cores; single-GPU figures measured on rank 0
         try:
+            if os.environ.get("BENCH_SKIP_SECONDARY"):
+                raise RuntimeError("skipped (BENCH_SKIP_SECONDARY)")
             if world > 1:
                 raise RuntimeError("single-GPU legs: measured when n_gpus == 1 (scripts/train_bench.py covers N > 1)")
             import torch.nn.functional as Fn
@@ -314,10 +365,12 @@ def run_b200(a):
             sec["secondary_error"] = str(e)[:200]
         line["secondary"] = sec
         if world == 1 and not a.no_cpu_baseline:
-            v, times, cores = cpu_reference_rate(a.cpu_sample, 10.0, 30)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d codewords x %d repetitions (median), torch CPU operators of the "
-                                              "reference's decode path" % (a.cpu_sample, len(times))}
+            v, times, cores, kind = cpu_reference_rate(a.cpu_sample, 10.0, 30)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": "%d codewords x %d repetitions (median), %s" % (
+                                        a.cpu_sample, len(times),
+                                        "the reference's own DEC_LargeCNN.forward (baseline/_ref, unmodified)" if kind == "reference"
+                                        else "torch CPU operators of the reference's decode path (oracle/turboae_torch.py)")}
             # the reference's operator sequence executed by torch eager ON THIS GPU (cuDNN/cuBLAS): "what you get today"
             try:
                 from oracle import turboae_oracle as O

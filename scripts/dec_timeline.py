@@ -20,7 +20,7 @@ args = make_args(batch_size=B)
 dec = T.DEC_LargeCNN(args, O.make_perm(100, 0)).cuda().eval()
 rec = torch.randn(B, 100, 3, device="cuda")
 N_STEP = 72
-tl = torch.zeros(N_STEP * 4 * 8 + 148 * 4 + 128, dtype=torch.int64, device="cuda")
+tl = torch.zeros(N_STEP * 4 * 8 + 148 * 4 + 128 + 5 * 4 * 2 * 16 * 2, dtype=torch.int64, device="cuda")
 lib = _lib.load()
 with torch.no_grad():
     dec(rec); torch.cuda.synchronize()
@@ -30,7 +30,8 @@ with torch.no_grad():
 full = tl.cpu().numpy()
 t = full[:N_STEP * 4 * 8].reshape(N_STEP, 4, 8).astype(np.int64)
 cta = full[N_STEP * 4 * 8:N_STEP * 4 * 8 + 148 * 4].reshape(148, 4)
-gs = full[N_STEP * 4 * 8 + 148 * 4:]
+gs = full[N_STEP * 4 * 8 + 148 * 4:N_STEP * 4 * 8 + 148 * 4 + 128]
+wt = full[N_STEP * 4 * 8 + 148 * 4 + 128:].reshape(5, 4, 2, 16, 2).astype(np.int64)
 out = []
 P = out.append
 n_groups = int((gs > 0).sum())
@@ -97,8 +98,24 @@ for s in range(N_STEP):
             g.append(acc[s, m + 1] - acc[s, m] - 32 * 56)
 g = np.array(g)
 P("mean %.0f, p50 %d, p90 %d, max %d cycles (x %d tile transitions per group = %d cycles)" % (g.mean(), np.percentile(g, 50), np.percentile(g, 90), g.max(), len(g), g.sum()))
+P("")
+P("## per-warp epilogue of stack 6 (leader CTA / peer CTA; each SM has its own clock64): duration acc-seen -> reported, per column part (mean over the 4 lane quadrants), and spread of the report times")
+P("")
+P("| layer | tile | leader: part 0 / 1 / 2 / 3 duration | leader: last report - first report | leader: last report - warp 0 report | peer: part 0 / 1 / 2 / 3 duration | peer spread |")
+P("|---|---|---|---|---|---|---|")
+for layer in range(5):
+    for m in range(4):
+        row = []
+        for cta in range(2):
+            w = wt[layer, m, cta]
+            d = (w[:, 1] - w[:, 0]).reshape(4, 4)          # ew = part * 4 + quadrant-ish (warp & 3)
+            row.append(" / ".join("%d" % x for x in d.mean(axis=1)))
+            row.append("%d" % (w[:, 1].max() - w[:, 1].min()))
+            if cta == 0:
+                row.append("%d" % (w[:, 1].max() - w[0, 1]))
+        P("| %d | %d | %s |" % (layer, m, " | ".join(row)))
 text = "\n".join(out)
 print(text)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 open(os.path.join(ROOT, "gpurun_out", TAG + ".md"), "w").write(text + "\n")
-np.save(os.path.join(ROOT, "gpurun_out", TAG + ".npy"), t)
+np.save(os.path.join(ROOT, "gpurun_out", TAG + ".npy"), full)

@@ -103,7 +103,7 @@ def _fresh_codec(B, seed=0, **over):
 @pytest.mark.parametrize("B", [1, 23, 203])
 def test_decoder_tc_gradients_vs_fp32_path(B):
     """DEC_LargeCNN autograd on the tensor cores against the fp32 CUDA-core training path: same output as the inference
-    kernel (bitwise), every parameter gradient and the input gradient within bf16 rounding."""
+    kernel (within bf16 noise), every parameter gradient and the input gradient within bf16 rounding."""
     enc, dec, p = _fresh_codec(B)
     u, noise = gen_inputs(99, B, 100, 0.0)
     ud, nd = torch.from_numpy(u).to(DEV), torch.from_numpy(noise).to(DEV)
@@ -118,7 +118,9 @@ def test_decoder_tc_gradients_vs_fp32_path(B):
         out = dec(r)
         Fn.binary_cross_entropy(torch.clamp(out, 0.0, 1.0), ud).backward()
         got[prec] = ({k: v.grad.clone() for k, v in dec.named_parameters()}, r.grad.clone(), out.detach())
-    assert torch.equal(got["bf16"][2], y_inf)
+    # the training forward uses the plain weight image, inference the log2(e)-scaled one (same arithmetic, different bf16
+    # roundings): equal within bf16 noise on the posteriors, not bitwise
+    assert float((got["bf16"][2] - y_inf).abs().max()) < 5e-3
     rel, cos = _rel_cos(got["bf16"][1], got["fp32"][1])
     assert rel < 3e-2 and cos > 0.999, (rel, cos)
     lim = 5e-2 if B >= 23 else 1.5e-1            # a single codeword: few terms per sum, bf16 noise averages less

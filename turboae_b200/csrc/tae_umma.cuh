@@ -78,6 +78,18 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// non-blocking probe (try_wait may suspend the thread for a system-dependent time when the phase is not complete)
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
 __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -89,39 +101,53 @@ __device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t
       : "memory");
   return ok;
 }
-// Bounded waits: a protocol bug traps (context error) instead of hanging the GPU box.  The slow path lives in ONE
-// out-of-line function: the kernel must stay small enough for the instruction cache (rarely executed straight-line
-// code was measured at ~20 cycles per instruction when it did not).
+// Bounded waits: a protocol bug traps (context error) instead of hanging the GPU box.  The bound is wall time (%globaltimer,
+// TAE_WAIT_TIMEOUT_NS, default 4 s), not a spin count: a legitimate wait under preemption, MPS, a debugger or heavy throttling
+// is not mistaken for a hang.  The code written to `err` (the first int of the call's workspace) is read back by the host side
+// after a failed synchronisation (tae_last_error reports it).  The slow path lives in ONE out-of-line function: the kernel must
+// stay small enough for the instruction cache (rarely executed straight-line code was measured at ~20 cycles per instruction
+// when it did not).
+#ifndef TAE_WAIT_TIMEOUT_NS
+#define TAE_WAIT_TIMEOUT_NS 4000000000ull
+#endif
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// (%globaltimer is slow to read: it is consulted once per 256 failed try_waits, each of which already suspends the thread
+// for the hardware's time slice, so the wake-up latency of a wait is never the timer's)
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* err, int code) {
+  unsigned long long t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      if (err) atomicExch(err, code);
-      __threadfence_system();
-      __trap();
+    if ((++spins & 255u) == 0u) {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > TAE_WAIT_TIMEOUT_NS) {
+        if (err) atomicExch(err, code);
+        __threadfence_system();
+        __trap();
+      }
     }
   }
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
   if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, err, code);
 }
-__device__ __forceinline__ void mbar_wait_unused(uint32_t bar, uint32_t parity, int* err, int code) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      if (err) atomicExch(err, code);
-      __threadfence_system();
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* err, int code) {
+// cluster-scope acquire: the waiter reads data another CTA of the cluster wrote with plain stores (tae_gru_tc.cu)
+__device__ __noinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int* err, int code) {
+  unsigned long long t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      if (err) atomicExch(err, code);
-      __threadfence_system();
-      __trap();
+    if ((++spins & 255u) == 0u) {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > TAE_WAIT_TIMEOUT_NS) {
+        if (err) atomicExch(err, code);
+        __threadfence_system();
+        __trap();
+      }
     }
   }
 }

@@ -151,6 +151,11 @@ int tae_enc_forward_bf16(const TaeEncConfig* cfg, const void* packed, const floa
 int tae_power_norm_f32(const float* x, float* codes, size_t n, const double* stats,
                        float* mean_std, void* stream);
 
+/* ENCBase.power_constraint with precompute_norm_stats, reference encoders.py:110-114: codes = (x - mean) / std with the
+ * GIVEN running (mean, std) -- 2 device floats the caller keeps up to date -- followed, when quantize_level >= 2, by the
+ * STE quantiser's forward (encoders.py:118-120).  quantize_level 0: no quantiser.  x may alias codes.                  */
+int tae_power_norm_given_f32(const float* x, float* codes, size_t n, const float* mean_std, float value_limit,
+                             float quantize_level, void* stream);
 /* The same followed by STEQuantize.forward (reference encoders.py:20-37, applied at :118-120 when
  * train_channel_mode == 'block_norm_ste'): clamp to +-value_limit, then sign() for quantize_level == 2 or
  * quantize_level uniform levels otherwise.  (The straight-through backward is torch glue in the Python layer.)     */

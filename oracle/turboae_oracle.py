@@ -163,6 +163,19 @@ def power_constraint(x_tx: np.ndarray):
     return ((x_tx - mean32) * F32(1.0) / std32).astype(F32), mean32, std32
 
 
+def power_constraint_running(x_tx: np.ndarray, state):
+    """reference encoders.py:107-116 with -precompute_norm_stats (:110-114): running averages of the batch mean and
+    unbiased std over the calls so far.  `state` = [mean_scalar, std_scalar, num_test_block] (float32, float32, float),
+    updated in place like the module attributes (:76-84 start them at 0, 1, 0)."""
+    this_mean = np.float32(x_tx.astype(np.float64).mean())
+    this_std = np.float32(x_tx.astype(np.float64).std(ddof=1))
+    state[2] += 1.0
+    k = np.float32(state[2])
+    state[0] = np.float32((np.float32(state[0]) * (k - np.float32(1.0)) + this_mean) / k)
+    state[1] = np.float32((np.float32(state[1]) * (k - np.float32(1.0)) + this_std) / k)
+    return ((x_tx - state[0]) / state[1]).astype(np.float32)
+
+
 def ste_quantize(x: np.ndarray, value_limit: float = 1.0, quantize_level: float = 2) -> np.ndarray:
     """STEQuantize.forward, reference encoders.py:20-37."""
     xc = np.clip(x.astype(F32), F32(-value_limit), F32(value_limit))

@@ -15,6 +15,7 @@ The reference cannot travel to the GPU box, so its outputs are committed here:
   perm.npz         interleaver goldens (p, inverse, gather of arange through the reference modules)
   grad_c1_b6.npz   one training step (forward, clamp, BCE, backward) of the reference with checkpoint c1, B=6 @ -1.5 dB:
                    loss, per-parameter gradient norms / first values, six gradients in full
+  flags_c1_b8.npz  -precompute_norm_stats (three successive batches, running scalars) and -is_variable_block_len (block length 40)
   ber_c1.json      12-point BER/BLER sweep (reference trainer.py:157-178 loop restated with seeded
                    numpy inputs, batch 500) -- per-point bit/block error counts
 
@@ -199,13 +200,41 @@ def dump_grad(cfg, B, seed, snr_db, name):
     print("%s: loss %.6f, %d parameter gradients" % (name, float(loss), len(names)))
 
 
+def dump_flags(name):
+    """Two non-default branches of the hot path, executed on the UNMODIFIED reference with checkpoint c1:
+    -precompute_norm_stats (encoders.py:110-114): codes of three successive batches + the running scalars after each;
+    -is_variable_block_len (encoders.py:353-360, decoders.py:208-215): a batch of block length 40 through enc + dec."""
+    B = 8
+    model, args, p = build_reference_model("c1", B)
+    out = {}
+    args.precompute_norm_stats = True
+    model.enc.reset_precomp()
+    with torch.no_grad():
+        for i, seed in enumerate((11, 12, 13)):
+            u, _ = gen_inputs(seed, B, args.block_len, 0.0)
+            out["run_codes_%d" % i] = model.enc(torch.from_numpy(u)).numpy().astype(np.float32)
+            out["run_scalars_%d" % i] = np.array([float(model.enc.mean_scalar), float(model.enc.std_scalar), model.enc.num_test_block], np.float64)
+    args.precompute_norm_stats = False
+    args.is_variable_block_len = True
+    L = 40
+    u, noise = gen_inputs(77, B, L, 1.0)
+    with torch.no_grad():
+        codes = model.enc(torch.from_numpy(u))
+        y = model.dec(codes + torch.from_numpy(noise))
+    out.update(var_u=u, var_noise=noise, var_codes=codes.numpy().astype(np.float32), var_y=y.numpy().astype(np.float32),
+               var_p=np.asarray(model.dec.interleaver.p_array.numpy(), np.int64))
+    args.is_variable_block_len = False
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--sweep-blocks", type=int, default=10000)
     ap.add_argument("--only", default="")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["weights", "kat", "io", "perm", "rnn", "ber", "grad"]
+    todo = a.only.split(",") if a.only else ["weights", "kat", "io", "perm", "rnn", "ber", "grad", "flags"]
     if "weights" in todo:
         dump_weights("c1"); dump_weights("c3"); dump_weights("c1s")
     if "kat" in todo:
@@ -221,3 +250,5 @@ if __name__ == "__main__":
         dump_ber(a.sweep_blocks)
     if "grad" in todo:
         dump_grad("c1", 6, 2718, -1.5, "grad_c1_b6.npz")
+    if "flags" in todo:
+        dump_flags("flags_c1_b8.npz")

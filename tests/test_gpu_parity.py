@@ -652,3 +652,46 @@ def test_full_size_batch_properties():
         sl = slice(49000, 50000)
         y32 = m.dec.decode(rec[sl].contiguous(), precision="fp32")
         assert int((torch.round(y32) != torch.round(y[sl])).sum()) <= 40
+
+
+@pytest.mark.gpu
+def test_precompute_norm_stats_running_average():
+    """-precompute_norm_stats (reference encoders.py:110-114): codes are normalised with the running averages of the batch
+    statistics; mean_scalar / std_scalar / num_test_block evolve like the reference's attributes."""
+    B = 16
+    m, w, p = build_codec("c1", device=DEV, batch_size=B, precompute_norm_stats=True)
+    state = [np.float32(0.0), np.float32(1.0), 0.0]
+    for seed in (11, 12, 13):
+        u, _ = gen_inputs(seed, B, 100, 0.0)
+        with torch.no_grad():
+            codes = m.enc(_t(u))
+        ref = O.power_constraint_running(O.enc_forward_unnormalised(u, w, p), state)
+        np.testing.assert_allclose(codes.cpu().numpy(), ref, atol=2e-5, rtol=0)
+        assert abs(float(m.enc.mean_scalar) - float(state[0])) < 1e-6 and abs(float(m.enc.std_scalar) - float(state[1])) < 1e-5
+        assert m.enc.num_test_block == state[2]
+    m.enc.reset_precomp()
+    assert float(m.enc.mean_scalar) == 0.0 and float(m.enc.std_scalar) == 1.0 and m.enc.num_test_block == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L", [40, 100, 133])
+def test_variable_block_len_redraws_the_interleaver(L):
+    """-is_variable_block_len (reference encoders.py:353-360, decoders.py:208-215): block length taken from the batch, the
+    interleaver re-drawn for it (numpy RandomState(randint(0, is_interleave)); is_interleave = 1 -> seed 0)."""
+    B = 6
+    m, w, _ = build_codec("c1", device=DEV, batch_size=B, is_variable_block_len=True)     # built for block_len 100
+    u, noise = gen_inputs(77, B, L, 1.0)
+    p = O.make_perm(L, 0)
+    with torch.no_grad():
+        codes = m.enc(_t(u))
+        rec = (codes + _t(noise)).contiguous()
+        m.dec.precision = "fp32"
+        y32 = m.dec(rec)
+        m.dec.precision = "bf16"
+        y16 = m.dec(rec)
+    ref_codes = O.enc_forward(u, w, p)
+    np.testing.assert_allclose(codes.cpu().numpy(), ref_codes, atol=2e-5, rtol=0)
+    ref_y = O.dec_forward(rec.cpu().numpy(), w, p)
+    np.testing.assert_allclose(y32.cpu().numpy(), ref_y, atol=1e-4, rtol=0)
+    assert float(np.abs(y16.cpu().numpy() - ref_y).mean()) < 5e-3
+    assert np.array_equal(m.dec.interleaver.p_array.numpy(), p) and np.array_equal(m.enc.interleaver.p_array.numpy(), p)

@@ -257,3 +257,28 @@ def test_tc_training_other_configurations_vs_fp32_path(over):
             continue                                   # scalar biases: judged with their weights in the reference-autograd test
         rel, cos = _rel_cos(a, b)
         assert rel < 0.12 and cos > 0.995, (k, rel, cos, float(b.norm()))
+
+
+def test_two_forwards_before_backward_keep_separate_stashes():
+    """gradient accumulation over two micro-batches with ONE summed loss: the second forward must not overwrite
+    the first one's activation stash.  Reference: the same two losses back-propagated one after the other."""
+    B = 23
+    enc, dec, p = _fresh_codec(B)
+    dec.train_precision = "bf16"
+    recs, bits = [], []
+    for seed in (5, 6):
+        u, noise = gen_inputs(seed, B, 100, 0.0)
+        ud, nd = torch.from_numpy(u).to(DEV), torch.from_numpy(noise).to(DEV)
+        with torch.no_grad():
+            recs.append((enc(ud) + nd).contiguous())
+        bits.append(ud)
+    loss_of = lambda i: Fn.binary_cross_entropy(torch.clamp(dec(recs[i]), 0.0, 1.0), bits[i])
+    dec.zero_grad()
+    (loss_of(0) + loss_of(1)).backward()                     # two live graphs of the same module and shape
+    both = {k: v.grad.clone() for k, v in dec.named_parameters()}
+    dec.zero_grad()
+    loss_of(0).backward()
+    loss_of(1).backward()                                    # accumulates into .grad
+    for k, v in dec.named_parameters():
+        rel, cos = _rel_cos(both[k], v.grad)
+        assert rel < 1e-4, (k, rel, cos)            # fp32 atomics in the weight-gradient kernel: order-dependent rounding

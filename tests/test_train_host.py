@@ -131,3 +131,56 @@ def test_local_power_normalisation_without_process_group():
     xr = x.detach().clone().requires_grad_(True)
     ((xr - xr.mean()) / xr.std()).backward(g)
     assert torch.allclose(x.grad, xr.grad, atol=1e-6)
+
+
+def test_flat_cache_follows_writes_through_data():
+    """`p.data.copy_()` (the reference's Lookahead, optimizers.py:29) bumps no version counter; the cache is told
+    by the optimizer post-step hook / launch.py's Lookahead wrapper through invalidate_all()."""
+    import torch
+    import turboae_b200 as T
+    from turboae_b200._flat import FlatCache
+    p = [torch.nn.Parameter(torch.ones(4)), torch.nn.Parameter(torch.zeros(3))]
+    c = FlatCache()
+    f0 = c.get(p)
+    c.derived["bf16"] = "image"
+    assert c.get(p) is f0 and c.derived                     # unchanged parameters: cached
+    p[0].data.copy_(torch.full((4,), 2.0))                  # invisible to p._version
+    T.invalidate_all()
+    f1 = c.get(p)
+    assert f1 is not f0 and float(f1[0]) == 2.0 and not c.derived
+    # an optimizer step invalidates on its own (post-step hook registered at import)
+    opt = torch.optim.SGD(p, lr=1.0)
+    f2 = c.get(p)
+    p[1].grad = torch.ones(3)
+    opt.step()
+    f3 = c.get(p)
+    assert f3 is not f2 and float(f3[-1]) == -1.0
+
+
+def test_stash_is_not_shared_between_two_live_forwards():
+    """two forwards of one module before backward must not share the activation stash."""
+    import gc
+    import torch
+    from turboae_b200 import train_tc, _lib
+
+    class Mod:
+        pass
+    m = Mod()
+    b1 = train_tc._buffers(m, 2, 2, 1, 1, 10, 5, "cpu")
+    tok1, gen1 = b1.claim()
+    assert b1.busy()
+    b2 = train_tc._buffers(m, 2, 2, 1, 1, 10, 5, "cpu")      # second forward while the first graph is alive
+    assert b2 is not b1
+    tok1.done = True                                        # backward of the first graph ran
+    assert train_tc._buffers(m, 2, 2, 1, 1, 10, 5, "cpu") is b1
+    tok3, gen3 = b1.claim()
+    del tok3                                                # the graph was dropped without backward
+    gc.collect()
+    assert not b1.busy()
+
+    class Ctx:
+        pass
+    ctx = Ctx()
+    ctx.buf, ctx.gen = b1, gen1                             # stale generation (retain_graph + a later forward)
+    with pytest.raises(_lib.TaeError):
+        train_tc._check_stash(ctx)

@@ -11,5 +11,18 @@ from .cnn_utils import SameShapeConv1d                        # noqa: F401
 from .encoders import ENCBase, ENC_interCNN                   # noqa: F401
 from .decoders import DEC_LargeCNN, DEC_LargeRNN              # noqa: F401
 from . import channel, shard                                  # noqa: F401
+from ._flat import invalidate_all                             # noqa: F401
+
+
+def _register_step_hook():
+    # weight caches follow every optimizer step, including in-place writes through ``.data`` that bump no version counter
+    try:
+        from torch.optim.optimizer import register_optimizer_step_post_hook
+        register_optimizer_step_post_hook(lambda opt, args, kwargs: invalidate_all())
+    except Exception:  # pragma: no cover -- very old torch: FlatCache still follows the version counters
+        pass
+
+
+_register_step_hook()
 
 __version__ = "0.1.0"

@@ -5,6 +5,17 @@ from __future__ import annotations
 
 import torch
 
+# Parameter mutations that autograd's version counter does not see (``p.data.copy_(...)``: the reference's own Lookahead
+# optimizer, optimizers.py:29, writes the slow weights back that way) are caught by a process-wide epoch that every
+# optimizer step bumps (post-step hook registered in turboae_b200/__init__.py; launch.py also wraps Lookahead.step, which does
+# not go through torch's hook machinery).  Anything else that writes through ``.data`` must call ``invalidate_all()``.
+_EPOCH = [0]
+
+
+def invalidate_all() -> None:
+    """Force every FlatCache to rebuild its flat copy (and the derived bf16 images) at the next forward."""
+    _EPOCH[0] += 1
+
 
 class FlatCache:
     def __init__(self):
@@ -12,8 +23,12 @@ class FlatCache:
         self.flat = None
         self.derived = {}
 
+    def invalidate(self) -> None:
+        self._key = None
+        self.derived = {}
+
     def get(self, params):
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = (_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in params)
         if key != self._key:
             with torch.no_grad():
                 self.flat = torch.cat([p.detach().reshape(-1).to(torch.float32) for p in params]).contiguous()

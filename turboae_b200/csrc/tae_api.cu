@@ -1,11 +1,12 @@
 // C ABI of libturboae_b200.so (see include/turboae_b200.h): argument validation, the error
-// convention and dispatch to the fp32 (tae_f32.cu) and bf16 tcgen05 (tae_dec_bf16.cu) paths.
+// convention and dispatch to the fp32 (tae_f32.cu) and bf16 tcgen05 (tae_dec_pair.cu) paths.
 #include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "tae_common.cuh"
 
@@ -23,11 +24,51 @@ void set_error(const char* fmt, ...) {
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// ---- device-mapped host slots for the barrier-wait codes (one per device) --------------------------------------
+static std::mutex g_slot_mu;
+static int* g_slot_host[TAE_MAX_DEVICES] = {};
+static int* g_slot_dev[TAE_MAX_DEVICES] = {};
+
+int* wait_code_slot(void* fallback) {
+  int* fb = reinterpret_cast<int*>(align_up(reinterpret_cast<uintptr_t>(fallback), 16));
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= TAE_MAX_DEVICES) return fb;
+  std::lock_guard<std::mutex> lk(g_slot_mu);
+  if (!g_slot_dev[dev]) {
+    void* h = nullptr;
+    void* d = nullptr;
+    if (cudaHostAlloc(&h, 64, cudaHostAllocMapped) != cudaSuccess) { (void)cudaGetLastError(); return fb; }
+    memset(h, 0, 64);
+    if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { (void)cudaGetLastError(); cudaFreeHost(h); return fb; }
+    g_slot_host[dev] = reinterpret_cast<int*>(h);
+    g_slot_dev[dev] = reinterpret_cast<int*>(d);
+  }
+  return g_slot_dev[dev];
+}
+
+static int pending_wait_code() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= TAE_MAX_DEVICES) return 0;
+  std::lock_guard<std::mutex> lk(g_slot_mu);
+  return g_slot_host[dev] ? *reinterpret_cast<volatile int*>(g_slot_host[dev]) : 0;
+}
+
+int require_sm100(int dev, const char* who) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) { set_error("%s: cudaGetDeviceProperties: %s", who, cudaGetErrorString(e)); return TAE_ECUDA; }
+  if (prop.major != 10) { set_error("%s needs an sm_100a device (found sm_%d%d)", who, prop.major, prop.minor); return TAE_EUNSUPPORTED; }
+  return TAE_OK;
+}
+
 int after_launch(const char* kernel_name) {
   count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
-    set_error("%s launch failed: %s", kernel_name, cudaGetErrorString(e));
+    const int code = pending_wait_code();
+    if (code) set_error("%s launch failed: %s (an earlier kernel trapped in a bounded barrier wait, code %d: see tae_umma.cuh)",
+                        kernel_name, cudaGetErrorString(e), code);
+    else set_error("%s launch failed: %s", kernel_name, cudaGetErrorString(e));
     return TAE_ECUDA;
   }
   return TAE_OK;
@@ -232,11 +273,13 @@ int tae_dec_forward_host(const TaeDecConfig* cfg, const float* params, const voi
   }
   // per-device copy streams and events, created once
   struct Pipe { cudaStream_t in = nullptr, out = nullptr; cudaEvent_t h2d[2], dec[2], d2h[2], start; bool ok = false; };
-  static Pipe pipes[64];
+  static Pipe pipes[TAE_MAX_DEVICES];
+  static std::mutex pipes_mu;
   int dev = 0;
   cudaGetDevice(&dev);
-  TAE_REQUIRE(dev >= 0 && dev < 64, "tae_dec_forward_host: device index %d out of range", dev);
+  TAE_REQUIRE(dev >= 0 && dev < TAE_MAX_DEVICES, "tae_dec_forward_host: device index %d out of range", dev);
   Pipe& P = pipes[dev];
+  std::unique_lock<std::mutex> pipes_lk(pipes_mu);      // lazy creation is serialised; the streams are then used unlocked
   if (!P.ok) {
     cudaError_t e = cudaStreamCreateWithFlags(&P.in, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&P.out, cudaStreamNonBlocking);
@@ -249,6 +292,7 @@ int tae_dec_forward_host(const TaeDecConfig* cfg, const float* params, const voi
     if (e != cudaSuccess) { set_error("tae_dec_forward_host: stream/event setup: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
     P.ok = true;
   }
+  pipes_lk.unlock();
   cudaStream_t s = (cudaStream_t)stream;
   const int L = cfg->block_len;
   const size_t chunk = (size_t)host_chunk(B);
@@ -344,6 +388,16 @@ int tae_power_norm_f32(const float* x, float* codes, size_t n, const double* sta
   if (n == 0) return TAE_OK;
   TAE_REQUIRE(x && codes && stats, "tae_power_norm_f32: NULL pointer");
   return launch_power_norm_f32(x, codes, n, stats, mean_std, 1.f, 0.f, (cudaStream_t)stream);
+}
+
+int tae_power_norm_given_f32(const float* x, float* codes, size_t n, const float* mean_std, float value_limit, float quantize_level,
+                             void* stream) {
+  if (n == 0) return TAE_OK;
+  TAE_REQUIRE(x && codes && mean_std, "tae_power_norm_given_f32: NULL pointer");
+  TAE_REQUIRE(quantize_level == 0.f || (value_limit > 0.f && quantize_level >= 2.f),
+              "tae_power_norm_given_f32: quantize_level must be 0 (no quantiser) or >= 2 with value_limit > 0");
+  return launch_power_norm_f32(x, codes, n, nullptr, const_cast<float*>(mean_std), quantize_level == 0.f ? 1.f : value_limit,
+                               quantize_level, (cudaStream_t)stream);
 }
 
 int tae_power_norm_ste_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std, float value_limit,

@@ -6,6 +6,7 @@
 #include <stddef.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "turboae_b200.h"
 
@@ -18,6 +19,42 @@ int after_launch(const char* kernel_name);
 void count_launch();
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// One-time setup PER DEVICE (cudaFuncSetAttribute, capability check and SM count are properties of a device, and one
+// process may drive several devices from several threads): `fn(dev)` runs once for each device under the mutex.
+constexpr int TAE_MAX_DEVICES = 64;
+struct DeviceOnce {
+  std::mutex mu;
+  bool done[TAE_MAX_DEVICES] = {};
+  int n_sm[TAE_MAX_DEVICES] = {};
+};
+template <class F>
+int device_once(DeviceOnce& st, const char* who, F&& fn, int* n_sm_out = nullptr) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= TAE_MAX_DEVICES) {
+    set_error("%s: cudaGetDevice: %s (device %d)", who, cudaGetErrorString(e), dev);
+    return TAE_ECUDA;
+  }
+  std::lock_guard<std::mutex> lk(st.mu);
+  if (!st.done[dev]) {
+    int n_sm = 0;
+    e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) { set_error("%s: cudaDeviceGetAttribute: %s", who, cudaGetErrorString(e)); return TAE_ECUDA; }
+    int rc = fn(dev);
+    if (rc) return rc;
+    st.n_sm[dev] = n_sm;
+    st.done[dev] = true;
+  }
+  if (n_sm_out) *n_sm_out = st.n_sm[dev];
+  return TAE_OK;
+}
+// sm_100 check shared by the tcgen05 paths
+int require_sm100(int dev, const char* who);
+// Where a kernel's bounded barrier wait records its code before it traps: a page of pinned, device-mapped HOST memory per
+// device, so that the code survives the context error (tae_last_error() reports it).  Falls back to `fallback` (the caller's
+// workspace) when the mapping cannot be had.
+int* wait_code_slot(void* fallback);
 
 // ---- canonical flat-parameter layouts (see include/turboae_b200.h) ---------------------
 struct ConvLayer {

@@ -9,21 +9,30 @@
 //     buffer holding floor(514/(L+2)) codewords, each followed by 2 all-zero separator rows (= the zero
 //     padding of cnn_utils.py:16 for free).  4 MMA tiles of 128 rows per CTA.
 //   * every conv layer is tcgen05.mma.cta_group::2, M = 256 (tile m of both CTAs), N = 112 (100 output
-//     channels, padded), issued by ONE thread of the leader CTA.  Each CTA stages only ITS half of the weight
-//     columns (56 of 112), so a whole layer (57 KB per CTA) is resident while the four tiles run through it:
-//     tile-outer order => the epilogue of tile m overlaps the MMAs of tile m+1, and the next layer's tile 0 can
-//     start as soon as tiles 0 and 1 of this layer are written back.
+//     channels, padded).  Each CTA stages only ITS half of the weight columns (56 of 112), so a whole layer
+//     (57 KB per CTA) is resident while the four tiles run through it.  One issuer warp per tile (leader CTA); the
+//     units->units tiles are issued in program order with two in flight (B_ISS chain: one issuing thread alone reaches
+//     ~67 cycles per MMA, two interleaved streams the nominal 56), so the epilogue of tile m overlaps the MMAs of tiles
+//     m+1, m+2 and the next layer's tile 0 starts as soon as tiles 0 and 1 of this layer are written back.
 //   * K is packed to exactly 32 k-steps of 16: 5 taps x 96 channels = 30 k-steps from the canonical
 //     no-swizzle K-major activation layout [C/8][rows][8] (tap t = descriptor start address + 16*t bytes), and
 //     channels 96..99 live in a "combined" chunk whose row r holds [x[r][96..99], x[r+1][96..99]], so that one
 //     16-byte chunk carries two taps; the last k-step pairs tap 4 of those channels with a constant-one chunk
 //     that injects the bias (bf16 hi + lo split) -- no output channel, no epilogue add.
 //   * activations are updated IN PLACE: the epilogue of tile m may not touch the two rows that tile m+1's MMAs
-//     still read (its last two), so the two lanes owning them keep their packed outputs in registers and store
-//     them at the start of the next tile's epilogue.  Epilogue warps report per warp (no CTA-wide barrier).
-//   * priors stay in shared memory (fp32) for all 2*I half-iterations; (de)interleave is the row index of the
-//     Linear epilogue's store.  HBM sees `received` once and `out` once; weights stream from L2 once per CTA
-//     pair and layer through a bulk-copy (UBLKCP) ring.
+//     still read (its last two), so the two lanes owning them park their packed outputs in a 416-byte shared-memory
+//     scratch and move them into place at the start of the next tile's epilogue (B_DEF tells the Linear of tile m
+//     that they are there).  Epilogue warps report per warp (no CTA-wide barrier).
+//   * inference (MODE 0) keeps every activation scaled by log2(e) (the weight image absorbs the factor), so the ELU of
+//     the epilogue is max(z', fma(ex2(-|z'|), log2e, -log2e)): MUFU + FFMA + FMNMX.
+//   * priors stay in shared memory as the bf16 channels 2.. of the stack inputs for all 2*I half-iterations;
+//     (de)interleave is the row index of the Linear epilogue's store (one tile per 4 warps: column part t owns tile t),
+//     and the first layer of the next stack starts on the tiles whose codewords are complete.  HBM sees `received` once
+//     (pulled into L2 one stack ahead) and `out` once; weights stream from L2 once per CTA pair and layer through a
+//     bulk-copy (UBLKCP) ring.
+//   * what bounds it (profiles/r02_dec_schedule_variants.md): inside a layer both the tensor pipe (7 168 cycles) and the
+//     shared-memory port (105 B/clk of MMA operands + weight ring + epilogue stores = 7 056 cycles at 128 B/clk) are
+//     saturated; the stack boundary (Linear -> scatter -> first layer) is a chain of barrier hops of ~9 k cycles.
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -660,7 +669,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
       }
 
       // Deferred rows: the last two rows of tile m are still read by the MMAs of tile m+1 (taps 0, 1), so the two
-      // lanes that own them keep their packed outputs in registers and store them at the start of the next tile.
+      // lanes that own them park their packed outputs in shared memory (S.defer) and store them at the start of the next tile.
       bool le_pending = false;       // this warp's Linear epilogue (tile == part) of stack le_stack (step le_step) is due
       int le_stack = 0;
       uint32_t le_step = 0;
@@ -1272,26 +1281,17 @@ int dec_pair_pack(const TaeDecConfig& c, const float* params, void* packed, cuda
 }
 
 static int pair_launch_setup(const TaeDecConfig&, int* n_sm_out) {
-  static int n_sm = 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceProp prop;
-    cudaError_t e = cudaGetDeviceProperties(&prop, dev);
-    if (e != cudaSuccess) { set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
-    if (prop.major != 10) { set_error("bf16 path needs an sm_100a device (found sm_%d%d)", prop.major, prop.minor); return TAE_EUNSUPPORTED; }
-    n_sm = prop.multiProcessorCount;
-    e = cudaFuncSetAttribute(dec_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)make_smem(5).total);
+  static DeviceOnce once;
+  return device_once(once, "dec_pair_kernel", [](int dev) -> int {
+    int rc = require_sm100(dev, "the bf16 tensor path");
+    if (rc) return rc;
+    const int smem = (int)make_smem(5).total;
+    cudaError_t e = cudaFuncSetAttribute(dec_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dec_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dec_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dec_pair_kernel): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
-    e = cudaFuncSetAttribute(dec_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)make_smem(5).total);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dec_pair_kernel<1>): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
-    e = cudaFuncSetAttribute(dec_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)make_smem(5).total);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(dec_pair_kernel<2>): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
-    attr_done = true;
-  }
-  *n_sm_out = n_sm;
-  return TAE_OK;
+    return TAE_OK;
+  }, n_sm_out);
 }
 
 int dec_forward_pair(const TaeDecConfig& c, const void* packed, const float* received, const int32_t* perm,
@@ -1309,7 +1309,7 @@ int dec_forward_pair(const TaeDecConfig& c, const void* packed, const float* rec
   a.received = received;
   a.out = out;
   a.trace = trace;
-  a.err = reinterpret_cast<int*>(align_up(reinterpret_cast<uintptr_t>(ws), 16));
+  a.err = wait_code_slot(ws);
   a.perm = perm;
   a.inv_perm = inv_perm;
   a.B = B; a.L = c.block_len; a.F = c.num_iter_ft; a.n_stacks = 2 * c.num_iteration; a.n_layer = c.num_layer;
@@ -1367,7 +1367,7 @@ static int backward_pair(const TaeDecConfig& c, const PackLayout& lay, int n_sta
   a.n_pairs = (a.n_groups + 1) / 2;
   a.stack_bytes = stack_bwd_image_bytes(c);
   a.wimg = reinterpret_cast<const uint8_t*>(packed_bwd);
-  a.err = reinterpret_cast<int*>(align_up(reinterpret_cast<uintptr_t>(ws), 16));
+  a.err = wait_code_slot(ws);
   a.stash_y = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(stash_y));
   a.stash_g = reinterpret_cast<uint8_t*>(stash_g);
   a.stash_x = reinterpret_cast<uint8_t*>(stash_d);
@@ -1453,7 +1453,7 @@ int enc_forward_pair(const TaeEncConfig& c, const void* packed, const float* u, 
   if (rc) return rc;
   a.wimg = reinterpret_cast<const uint8_t*>(packed) + (stash_y ? enc_pair_packed_bytes(c) / 2 : 0);
   a.u = u; a.x_tx = x_tx; a.stats = stats; a.enc = 1;
-  a.err = reinterpret_cast<int*>(align_up(reinterpret_cast<uintptr_t>(ws), 16));
+  a.err = wait_code_slot(ws);
   a.perm = perm; a.inv_perm = inv_perm;
   a.B = B; a.L = c.block_len; a.F = 1; a.n_stacks = 3; a.n_layer = c.num_layer; a.extrinsic = 0;
   a.cw_per_group = (GROUP_ROWS + 2) / (c.block_len + 2);

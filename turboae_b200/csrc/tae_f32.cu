@@ -2,7 +2,7 @@
 //
 // This is the elementwise-parity anchor (<= 1e-4 vs the reference's fp32 forward, measured
 // ~1e-6): layer-at-a-time kernels with fp32 FMA accumulation, activations in HBM between
-// layers.  The throughput path is the fused tcgen05 kernel in tae_dec_bf16.cu.
+// layers.  The throughput path is the fused tcgen05 kernel in tae_dec_pair.cu.
 //
 // Reference lines restated here (paths relative to the reference checkout):
 //   conv layer + ELU ............ cnn_utils.py:15-22, 36-46
@@ -360,14 +360,22 @@ __global__ void add_count_kernel(double* stats, double n) { stats[2] += n; }
 // codes = (x - mean) / std with unbiased std over everything counted in stats (encoders.py:107-116).
 // quantize_level 0: plain normalisation; 2: sign(clamp(.)) ; q > 2: q uniform levels on [-limit, limit]
 // (STEQuantize.forward, reference encoders.py:20-37, applied after the normalisation as in encoders.py:118-120)
+// stats != NULL: mean / unbiased std derived from (sum, sum of squares, count), reported in mean_std when given;
+// stats == NULL: mean_std holds the (mean, std) to normalise WITH (running statistics, encoders.py:110-114).
 __global__ void power_norm_kernel(const float* __restrict__ x, float* __restrict__ codes, size_t n,
                                   const double* __restrict__ stats, float* __restrict__ mean_std, float limit, float q) {
-  const double cnt = stats[2];
-  const double mean = stats[0] / cnt;
-  const double var = (stats[1] - cnt * mean * mean) / (cnt - 1.0);
-  const float meanf = (float)mean;
-  const float stdf = (float)sqrt(var > 0.0 ? var : 0.0);
-  if (mean_std && blockIdx.x == 0 && threadIdx.x == 0) { mean_std[0] = meanf; mean_std[1] = stdf; }
+  float meanf, stdf;
+  if (stats) {
+    const double cnt = stats[2];
+    const double mean = stats[0] / cnt;
+    const double var = (stats[1] - cnt * mean * mean) / (cnt - 1.0);
+    meanf = (float)mean;
+    stdf = (float)sqrt(var > 0.0 ? var : 0.0);
+    if (mean_std && blockIdx.x == 0 && threadIdx.x == 0) { mean_std[0] = meanf; mean_std[1] = stdf; }
+  } else {
+    meanf = mean_std[0];
+    stdf = mean_std[1];
+  }
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
     float v = (x[idx] - meanf) / stdf;
     if (q >= 2.f) {
@@ -396,11 +404,14 @@ int launch_conv_k(const float* in, const float* yfwd, float* out, const float* p
   int AS = TM + 8;
   while (AS % 32 != 4) AS += 4;
   const size_t smem = (size_t)(CONV_CC * K * CONV_TN + CONV_CC * AS) * sizeof(float);
-  static bool attr_done = false;   // per instantiation
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv1d_f32_kernel<K, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv1d_f32): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
-    attr_done = true;
+  static DeviceOnce once;          // per instantiation
+  {
+    int rc = device_once(once, "conv1d_f32_kernel", [](int) -> int {
+      cudaError_t e = cudaFuncSetAttribute(conv1d_f32_kernel<K, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(conv1d_f32): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+      return TAE_OK;
+    });
+    if (rc) return rc;
   }
   if (smem > 96 * 1024) { set_error("conv1d_f32: kernel_size %d needs %zu B shared memory", K, smem); return TAE_EUNSUPPORTED; }
   dim3 grid((unsigned)((size_t)B * tiles_per_cw), (unsigned)(cout_pad / CONV_TN));

@@ -91,14 +91,18 @@ int launch_gru_direction(const float* xproj, const float* w_hh, const float* b_h
   const int threads = H * (GRU_NB / GRU_RB);
   if (H < 1 || H > 128 || threads > 512) { set_error("tae_gru_direction_f32: hidden size %d unsupported (1..128)", H); return TAE_EUNSUPPORTED; }
   const size_t smem = ((size_t)3 * H * H + 2 * (size_t)H * GRU_NB) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gru_direction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(gru_direction_kernel): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
-    attr_done = true;
+  static DeviceOnce once;
+  int n_sm = 0;
+  {
+    int rc = device_once(once, "gru_direction_kernel", [](int) -> int {
+      cudaError_t e = cudaFuncSetAttribute(gru_direction_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(gru_direction_kernel): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+      return TAE_OK;
+    }, &n_sm);
+    if (rc) return rc;
   }
   const int n_groups = (B + GRU_NB - 1) / GRU_NB;
-  gru_direction_kernel<<<std::min(n_groups, 148), threads, smem, s>>>(xproj, w_hh, b_hh, out, B, L, H, out_stride, out_offset, reverse);
+  gru_direction_kernel<<<std::min(n_groups, n_sm), threads, smem, s>>>(xproj, w_hh, b_hh, out, B, L, H, out_stride, out_offset, reverse);
   return after_launch("gru_direction_kernel");
 }
 

@@ -506,25 +506,23 @@ int gru_tc_pack(const float* w_ih, const float* w_hh, const float* b_ih, const f
 int gru_tc_direction(const void* packed, const void* x_tiles, void* out_tiles, int B, int L, int H, int in_ch, int grp_valid, int R,
                      int out_chunks, int out_c0, int reverse, void* ws, size_t ws_bytes, cudaStream_t s) {
   if (ws_bytes < 256) { set_error("tae_gru_direction_bf16: workspace %zu < 256 bytes", ws_bytes); return TAE_EWORKSPACE; }
-  static int n_sm = 0;
-  static bool attr_done = false;
-  if (!attr_done) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceProp prop;
-    cudaError_t e = cudaGetDeviceProperties(&prop, dev);
-    if (e != cudaSuccess) { set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return TAE_ECUDA; }
-    if (prop.major != 10) { set_error("bf16 GRU path needs an sm_100a device (found sm_%d%d)", prop.major, prop.minor); return TAE_EUNSUPPORTED; }
-    n_sm = prop.multiProcessorCount;
-    e = cudaFuncSetAttribute(gru_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gru_geom(G_XCH_MAX).total);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(gru_pair_kernel): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
-    attr_done = true;
+  static DeviceOnce once;
+  int n_sm = 0;
+  {
+    int rc = device_once(once, "gru_pair_kernel", [](int dev) -> int {
+      int rc2 = require_sm100(dev, "the bf16 GRU path");
+      if (rc2) return rc2;
+      cudaError_t e = cudaFuncSetAttribute(gru_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gru_geom(G_XCH_MAX).total);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(gru_pair_kernel): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+      return TAE_OK;
+    }, &n_sm);
+    if (rc) return rc;
   }
   GruArgs a{};
   a.wimg = reinterpret_cast<const uint8_t*>(packed);
   a.x = reinterpret_cast<const uint8_t*>(x_tiles);
   a.out = reinterpret_cast<uint8_t*>(out_tiles);
-  a.err = reinterpret_cast<int*>(align_up(reinterpret_cast<uintptr_t>(ws), 16));
+  a.err = wait_code_slot(ws);
   a.B = B; a.L = L; a.H = H; a.hch = (H + 7) / 8; a.n_xch = n_xch_of(in_ch, grp_valid); a.R = R; a.out_chunks = out_chunks; a.out_c0 = out_c0; a.reverse = reverse;
   const int n_blk = (B + R - 1) / R;
   a.n_pairs = (n_blk + 1) / 2;

@@ -156,13 +156,19 @@ int launch_wgrad(const TaeWgradJob* jobs_host, int n_jobs, const void* jobs_dev,
       return TAE_EINVAL;
     }
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_SMEM);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(wgrad_kernel): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
-    attr_done = true;
+  static DeviceOnce once;
+  {
+    int rc = device_once(once, "wgrad_kernel", [](int dev) -> int {
+      int rc2 = require_sm100(dev, "the tensor-core weight-gradient kernel");
+      if (rc2) return rc2;
+      cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_SMEM);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(wgrad_kernel): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+      return TAE_OK;
+    });
+    if (rc) return rc;
   }
-  int* err = reinterpret_cast<int*>(align_up(reinterpret_cast<uintptr_t>(ws), 16));
+  int* err = reinterpret_cast<int*>(align_up(reinterpret_cast<uintptr_t>(ws), 16));      // the job upload below lives in the same workspace
+  int* wait_code = wait_code_slot(ws);
   const TaeWgradJob* d_jobs = reinterpret_cast<const TaeWgradJob*>(jobs_dev);
   if (!d_jobs) {      // no resident copy: upload (a pageable source makes this call wait for the copy)
     TaeWgradJob* up = reinterpret_cast<TaeWgradJob*>(reinterpret_cast<uint8_t*>(err) + 128);
@@ -170,7 +176,7 @@ int launch_wgrad(const TaeWgradJob* jobs_host, int n_jobs, const void* jobs_dev,
     if (e != cudaSuccess) { set_error("cudaMemcpyAsync(jobs): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
     d_jobs = up;
   }
-  wgrad_kernel<<<n_jobs, 128, W_SMEM, s>>>(d_jobs, err);
+  wgrad_kernel<<<n_jobs, 128, W_SMEM, s>>>(d_jobs, wait_code);
   return after_launch("wgrad_kernel");
 }
 

@@ -173,8 +173,13 @@ class DEC_LargeCNN(torch.nn.Module):
         return torch.sigmoid(self.deinterleaver(x_plr))
 
     def forward(self, received):
-        if getattr(self.args, "is_variable_block_len", False):
-            raise NotImplementedError("--is_variable_block_len is not supported by turboae_b200")
+        a = self.args
+        if getattr(a, "is_variable_block_len", False) and a.is_interleave != 0:
+            # reference decoders.py:208-215: the interleaver is re-drawn for the length of this batch (same draw from
+            # numpy's global generator as the reference)
+            import numpy as np
+            seed = np.random.randint(0, a.is_interleave)
+            self.set_interleaver(np.random.mtrand.RandomState(seed).permutation(np.arange(received.shape[1])))
         if self.this_device.type != "cuda":
             raise _lib.TaeError("no CUDA device: turboae_b200 has no CPU fallback")
         if torch.is_grad_enabled() and (received.requires_grad or any(p.requires_grad for p in self.parameters())):

@@ -123,12 +123,8 @@ class ENC_interCNN(ENCBase):
 
     def _check_supported(self):
         a = self.args
-        if getattr(a, "is_variable_block_len", False):
-            raise NotImplementedError("--is_variable_block_len is not supported by turboae_b200")
         if getattr(a, "enc_act", "elu") != "elu":
             raise NotImplementedError("enc_act=%r: only 'elu' is built (get_args.py:100 'only elu works')" % a.enc_act)
-        if getattr(a, "precompute_norm_stats", False):
-            raise NotImplementedError("--precompute_norm_stats is not supported by turboae_b200")
         if getattr(a, "train_channel_mode", "block_norm") not in ("block_norm", "block_norm_ste"):
             raise NotImplementedError("train_channel_mode=%r is not supported by turboae_b200" % a.train_channel_mode)
 
@@ -187,18 +183,51 @@ class ENC_interCNN(ENCBase):
         if self.args.no_code_norm:
             return x_tx
         self._check_supported()
-        # statistics are merged across ranks only when the batch is sharded (shard_group set); otherwise this call stays local
-        codes = shard.PowerNorm.apply(x_tx, self.shard_group if self.shard_group is not None else shard.LOCAL)
+        if getattr(self.args, "precompute_norm_stats", False):
+            # encoders.py:110-114 under autograd: the running scalars carry the graph of every batch they have seen in the
+            # reference too; here they are treated as constants of the current step (trainer.test is their only user)
+            xd = x_tx.detach().double()
+            stats = torch.stack([xd.sum(), (xd * xd).sum(), torch.full((), float(x_tx.numel()), dtype=torch.float64, device=x_tx.device)])
+            if self.shard_group is not None:
+                shard.merge_power_stats(stats, self.shard_group)
+            given = self._running_stats(stats)
+            codes = (x_tx - given[0]) / given[1]
+        else:
+            # statistics are merged across ranks only when the batch is sharded (shard_group set); otherwise this call stays local
+            codes = shard.PowerNorm.apply(x_tx, self.shard_group if self.shard_group is not None else shard.LOCAL)
         if getattr(self.args, "train_channel_mode", "block_norm") == "block_norm_ste":
             codes = STEQuantize.apply(codes, self.args)
         if self.args.enc_truncate_limit > 0:
             codes = torch.clamp(codes, -self.args.enc_truncate_limit, self.args.enc_truncate_limit)
         return codes
 
+    def _variable_block_len(self, block_len):
+        """reference encoders.py:353-360: with -is_variable_block_len the interleaver is re-drawn for the length of THIS batch
+        (same draw from numpy's global generator as the reference, so a seeded run sees the same permutations)."""
+        a = self.args
+        if getattr(a, "is_variable_block_len", False) and a.is_interleave != 0:
+            import numpy as np
+            seed = np.random.randint(0, a.is_interleave)
+            self.set_interleaver(np.random.mtrand.RandomState(seed).permutation(np.arange(block_len)))
+
+    def _running_stats(self, stats):
+        """reference encoders.py:110-114 (-precompute_norm_stats): running averages of the batch mean / unbiased std over the
+        calls so far; returns the 2 device floats (mean, std) to normalise with.  Tiny device-side arithmetic on 1-element
+        tensors: no host synchronisation."""
+        n = stats[2]
+        mean = stats[0] / n
+        std = torch.sqrt(torch.clamp((stats[1] - n * mean * mean) / (n - 1.0), min=0.0))
+        self.num_test_block += 1.0
+        k = self.num_test_block
+        self.mean_scalar = (self.mean_scalar * (k - 1.0) + mean.float()) / k
+        self.std_scalar = (self.std_scalar * (k - 1.0) + std.float()) / k
+        return torch.cat([self.mean_scalar.reshape(1), self.std_scalar.reshape(1)]).contiguous()
+
     def forward(self, inputs):
         self._check_supported()
         if self.this_device.type != "cuda":
             raise _lib.TaeError("no CUDA device: turboae_b200 has no CPU fallback")
+        self._variable_block_len(inputs.shape[1])
         x = inputs.to(device=self.this_device, dtype=torch.float32).contiguous()
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             return self._forward_train(x)
@@ -213,8 +242,15 @@ class ENC_interCNN(ENCBase):
             # power_constraint normalises over the WHOLE batch (encoders.py:107-116): merge the per-rank sums
             shard.merge_power_stats(stats, self.shard_group)
         codes = torch.empty_like(x_tx)
+        ste = getattr(self.args, "train_channel_mode", "block_norm") == "block_norm_ste"
         with torch.cuda.device(x.device):
-            if getattr(self.args, "train_channel_mode", "block_norm") == "block_norm_ste":      # encoders.py:118-120
+            if getattr(self.args, "precompute_norm_stats", False):                              # encoders.py:110-114
+                given = self._running_stats(stats)
+                _lib.check(lib.tae_power_norm_given_f32(_lib.ptr(x_tx), _lib.ptr(codes), x_tx.numel(), _lib.ptr(given),
+                                                        float(self.args.enc_value_limit) if ste else 1.0,
+                                                        float(self.args.enc_quantize_level) if ste else 0.0,
+                                                        _lib.stream_ptr(x.device)))
+            elif ste:                                                                           # encoders.py:118-120
                 _lib.check(lib.tae_power_norm_ste_f32(_lib.ptr(x_tx), _lib.ptr(codes), x_tx.numel(), _lib.ptr(stats), None,
                                                       float(self.args.enc_value_limit), float(self.args.enc_quantize_level),
                                                       _lib.stream_ptr(x.device)))

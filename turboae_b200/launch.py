@@ -68,6 +68,23 @@ def install(reference_root: str) -> None:
     ref_encoders.ENC_interCNN = T.ENC_interCNN
     ref_decoders.DEC_LargeCNN = T.DEC_LargeCNN
     ref_decoders.DEC_LargeRNN = T.DEC_LargeRNN
+    # the reference's Lookahead (optimizers.py:10-44) is an Optimizer that never calls Optimizer.__init__, so torch's step
+    # hooks do not see it, and it writes the slow weights back with fast.data.copy_(slow): tell the weight caches
+    try:
+        import optimizers as ref_optimizers
+        _step, _sync = ref_optimizers.Lookahead.step, ref_optimizers.Lookahead.update_lookahead
+
+        def step(self, closure=None):
+            out = _step(self, closure)
+            T.invalidate_all()
+            return out
+
+        def update_lookahead(self):
+            _sync(self)
+            T.invalidate_all()
+        ref_optimizers.Lookahead.step, ref_optimizers.Lookahead.update_lookahead = step, update_lookahead
+    except Exception:  # pragma: no cover -- a checkout without optimizers.py
+        pass
     # SameShapeConv1d is imported by name into encoders/decoders at their import time; the replaced classes above
     # build this package's own conv stacks, so cnn_utils is left as is for the out-of-scope variants.
     del ref_cnn_utils
@@ -88,12 +105,8 @@ def main(argv=None):
         _modernise()
     else:
         install(a.reference)
-    if a.seed is not None:
-        import numpy as np
-        import torch
-        np.random.seed(a.seed)
-        torch.manual_seed(a.seed)
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    seed = a.seed
     if world > 1 and not a.stock:
         # data-parallel under torchrun: one process per GPU, whole codewords per rank; the reference's
         # `loss.backward(); optimizer.step()` (trainer.py:74-76) is kept, gradients are averaged by an optimizer pre-step hook
@@ -104,6 +117,34 @@ def main(argv=None):
         dist.init_process_group("nccl")
         os.environ["TURBOAE_B200_SHARD"] = "1"          # ENC_interCNN: batch-global power statistics across ranks
         shard.install_optimizer_hook()
+        # main.py sets no seed: every rank would build different random weights (and, for -is_interleave > 1, draw a different
+        # permutation) and averaged gradients never bring such replicas together.  All ranks therefore start from ONE seed
+        # (rank 0 draws it unless --seed is given), so model construction and the interleaver agree; at the first call of
+        # trainer.train / validate / test rank 0's parameters are broadcast once more (belt and braces) and the generators are
+        # re-seeded per rank, so that every rank then draws its OWN bits and noise (trainer.py:53-60).
+        seed_t = torch.zeros(1, dtype=torch.int64, device="cuda")
+        if dist.get_rank() == 0:
+            seed_t[0] = seed if seed is not None else int.from_bytes(os.urandom(4), "little")
+        dist.broadcast(seed_t, 0)
+        seed = int(seed_t.item())
+        import trainer as ref_trainer                       # main.py binds train / validate / test from here (main.py:17)
+        state = {"synced": False}
+
+        def _wrap(fn, model_pos):
+            def wrapped(*args, **kwargs):
+                if not state["synced"]:
+                    shard.sync_replicas(args[model_pos])
+                    shard.seed_everything(seed * 1000003 + 7919 * (dist.get_rank() + 1))
+                    state["synced"] = True
+                return fn(*args, **kwargs)
+            wrapped.__wrapped__ = fn
+            return wrapped
+        ref_trainer.train = _wrap(ref_trainer.train, 1)          # train(epoch, model, optimizer, args, ...)
+        ref_trainer.validate = _wrap(ref_trainer.validate, 0)    # validate(model, optimizer, args, ...)
+        ref_trainer.test = _wrap(ref_trainer.test, 0)            # test(model, args, ...)
+    if seed is not None:
+        from . import shard
+        shard.seed_everything(seed)
     script = a.script if os.path.isabs(a.script) else os.path.join(os.path.abspath(a.reference), a.script)
     for d in ("logs", "tmp"):
         os.makedirs(d, exist_ok=True)                            # main.py:106, 248 write there

@@ -81,6 +81,32 @@ class PowerNorm(torch.autograd.Function):
         return dx, None
 
 
+def seed_everything(seed: int) -> None:
+    """python / numpy / torch (CPU and CUDA) generators from one integer (the reference seeds nothing: main.py)."""
+    import random
+    import numpy as np
+    seed = int(seed) % (2 ** 32)
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+
+
+def sync_replicas(module: torch.nn.Module, src: int = 0, group=None) -> int:
+    """Broadcast every parameter and buffer of `module` from rank `src`: data-parallel replicas must start identical
+    (the reference's nn.DataParallel replicates one model; one process per GPU has to do it explicitly).  Returns the number
+    of tensors sent.  A no-op outside a multi-rank job."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return 0
+    n = 0
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src, group=group)
+            n += 1
+    from . import _flat
+    _flat.invalidate_all()          # written through .data: no version counter moved
+    return n
+
+
 def all_reduce_gradients(params, group=None) -> int:
     """Data-parallel training (BASELINE config 4): ONE all-reduce (average) of the flat gradient of `params` -- the
     replacement of nn.DataParallel's ReduceAddCoalesced.  Returns the number of floats reduced."""

@@ -14,13 +14,29 @@ Operands are bf16, every accumulation (MMA, weight-gradient reduction) is fp32, 
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import torch
 
 from . import _lib
 from ._flat import unwrap
 
-N_SM = 148
+
+def n_sm(device=None) -> int:
+    """SM count of the device the job list is balanced for (148 on a B200; that figure is also used when the job list is built
+    on a host without a GPU, e.g. by the CPU tests of the job construction)."""
+    if not torch.cuda.is_available():
+        return 148
+    return torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device()).multi_processor_count
+
+
+class _Token:
+    """Lives exactly as long as the autograd graph node (ctx) that owns a stash: lets a later forward see whether the previous
+    one is still waiting for its backward."""
+    __slots__ = ("done", "__weakref__")
+
+    def __init__(self):
+        self.done = False
 
 
 def _odd_chunks(n_ch: int, c0: int) -> int:
@@ -46,15 +62,40 @@ class _Buffers:
         self.dlin = torch.zeros((n_stacks, B, L, F), dtype=torch.float32, device=device)
         self.gflat = None
         self.jobs = None          # (ctypes array, n, device workspace)
+        self.gen = 0              # forwards that have written this stash
+        self.owner = None         # weakref to the _Token of the forward whose backward has not run yet
+
+    def busy(self) -> bool:
+        tok = self.owner() if self.owner is not None else None
+        return tok is not None and not tok.done
+
+    def claim(self):
+        """Called by a forward that is about to overwrite the stash; returns (token, generation) for its ctx."""
+        tok = _Token()
+        self.owner = weakref.ref(tok)
+        self.gen += 1
+        return tok, self.gen
 
 
 def _buffers(mod, n_stacks, n_layer, groups, B, L, F, device):
+    """The module's cached stash for this shape -- or a fresh, un-cached one when the cached stash still belongs to a forward
+    whose backward has not run (gradient accumulation over micro-batches with one summed loss, two SNRs in one loss, ...):
+    overwriting it would make that graph's backward silently wrong."""
     key = (n_stacks, n_layer, groups, B, L, F, str(device))
     cache = mod.__dict__.setdefault("_tc_buffers", {})
     if key not in cache:
         cache.clear()                      # one live shape at a time: the images are large
         cache[key] = _Buffers(n_stacks, n_layer, groups, B, L, F, device)
-    return cache[key]
+    buf = cache[key]
+    if buf.busy():
+        buf = _Buffers(n_stacks, n_layer, groups, B, L, F, device)
+    return buf
+
+
+def _check_stash(ctx):
+    if ctx.buf.gen != ctx.gen:
+        raise _lib.TaeError("the activation stash of this forward was overwritten by a later forward of the same module before "
+                            "backward() ran (a graph kept alive with retain_graph, or a second backward)")
 
 
 def _flat_grad(buf, flat, params):
@@ -78,7 +119,7 @@ def _job_cost_us(b_chunks, n_cols, taps):
     return 3.9 if taps > 1 else 1.1
 
 
-def wgrad_jobs(n_layer, units, cin0, fouts, groups, stash_y, stash_x, stash_g, stash_d, gflat, offsets, splits=None):
+def wgrad_jobs(n_layer, units, cin0, fouts, groups, stash_y, stash_x, stash_g, stash_d, gflat, offsets, splits=None, sm_count=None):
     """Job list of ``tae_wgrad_bf16`` for conv stacks laid out like a DEC_LargeCNN: ``offsets[st]`` = (per layer (w_off, b_off),
     lin_w_off) in floats into ``gflat``; ``fouts[st]`` = features of the stack's Linear.  One job = one CTA.  Every
     (layer, channel slab) is cut into group ranges of about equal estimated duration (3-4 CTAs per SM in total, at least
@@ -118,7 +159,7 @@ def wgrad_jobs(n_layer, units, cin0, fouts, groups, stash_y, stash_x, stash_g, s
         add(g, x, gp + 4 * w_off, gp + 4 * b_off, 1, 0, 1, 5, 16, units, cin0, 0, 5 * cin0, 5, 1)
         add(y + (n_layer - 1) * layer_img, d, gp + 4 * lin_w_off, None, 1, 0, 1, 1, 16, units, fouts[st], 0, 1, units, 0)
     costs = [_job_cost_us(f[4], f[8], f[7]) * groups for f in protos]
-    target = max(sum(costs) / (3.5 * N_SM), 60.0)
+    target = max(sum(costs) / (3.5 * (sm_count or n_sm())), 60.0)
     jobs = []
     for f, c in zip(protos, costs):
         n_split = splits if splits is not None else max(1, min(groups, int(round(c / target))))
@@ -179,6 +220,7 @@ class DecoderTrainFn(torch.autograd.Function):
             _, cfg, flat, packed, _ = dec._prepare(L, dev, "bf16")
             groups = lib.tae_train_groups(L, B)
             buf = _buffers(dec, n_stacks, n_layer, groups, B, L, a.num_iter_ft, dev)
+            tok, gen = buf.claim()
             perm, inv = dec.interleaver.device_index(dev)
             out = torch.empty((B, L, 1), dtype=torch.float32, device=dev)
             ws = dec._ws.get(256, dev)
@@ -186,6 +228,7 @@ class DecoderTrainFn(torch.autograd.Function):
                                                       _lib.ptr(out), None, B, _lib.ptr(buf.stash_y), _lib.ptr(buf.stash_x),
                                                       _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
         ctx.dec, ctx.cfg, ctx.buf = dec, cfg, buf
+        ctx.tok, ctx.gen = tok, gen
         ctx.shape = (B, L)
         ctx.need_input = received.requires_grad
         ctx.need_params = any(p.requires_grad for p in params)
@@ -196,6 +239,7 @@ class DecoderTrainFn(torch.autograd.Function):
     def backward(ctx, d_out):
         lib = _lib.load()
         dec, cfg, buf = ctx.dec, ctx.cfg, ctx.buf
+        _check_stash(ctx)
         a = dec.args
         out, flat = ctx.saved_tensors
         B, L = ctx.shape
@@ -238,6 +282,7 @@ class DecoderTrainFn(torch.autograd.Function):
                     if p.requires_grad:
                         grads[i] = gflat[off:off + n].view_as(p)
                     off += n
+        ctx.tok.done = True
         return (None, d_rec, *grads)
 
 
@@ -281,6 +326,7 @@ class EncoderTrainFn(torch.autograd.Function):
                 enc._flat.derived["bf16"] = packed
             groups = lib.tae_train_groups(L, B)
             buf = _buffers(enc, 3, n_layer, groups, B, L, 1, dev)
+            tok, gen = buf.claim()
             perm, inv = enc.interleaver.device_index(dev)
             x_tx = torch.empty((B, L, 3), dtype=torch.float32, device=dev)
             stats = torch.zeros(3, dtype=torch.float64, device=dev)
@@ -289,6 +335,7 @@ class EncoderTrainFn(torch.autograd.Function):
                                                       _lib.ptr(stats), B, _lib.ptr(buf.stash_y), _lib.ptr(buf.stash_x), _lib.ptr(ws),
                                                       ws.numel(), _lib.stream_ptr(dev)))
         ctx.enc, ctx.cfg, ctx.buf, ctx.shape = enc, cfg, buf, (B, L)
+        ctx.tok, ctx.gen = tok, gen
         ctx.save_for_backward(x_tx, flat)
         return x_tx
 
@@ -296,6 +343,7 @@ class EncoderTrainFn(torch.autograd.Function):
     def backward(ctx, d_x):
         lib = _lib.load()
         enc, cfg, buf = ctx.enc, ctx.cfg, ctx.buf
+        _check_stash(ctx)
         a = enc.args
         x_tx, flat = ctx.saved_tensors
         B, L = ctx.shape
@@ -334,6 +382,7 @@ class EncoderTrainFn(torch.autograd.Function):
                 n = p.numel()
                 grads.append(gflat[off:off + n].view_as(p) if p.requires_grad else None)
                 off += n
+        ctx.tok.done = True
         return (None, None, *grads)
 
 

@@ -191,6 +191,76 @@ def run_reference(a):
     return 0
 
 
+def train_leg(dev, world, rank, TB=1000, steps=8):
+    """BASELINE config 4 (enc2/dec5 from scratch, batch 1000 PER GPU, Adam, mode 'decoder' of trainer.py:33-76): forward (enc ->
+    AWGN -> dec) + clamp + BCE + backward + gradient all-reduce (N > 1: shard.all_reduce_gradients from the optimizer pre-step
+    hook, batch-global power statistics across ranks) + optimizer step.  Every rank runs it.  Two host loops over the SAME
+    kernels: 'eager' = what the reference's Python trainer drives (one autograd pass + torch.optim.Adam per step), 'graphed' =
+    the step captured once in a CUDA graph (turboae_b200.graphs) and replayed.  Returns a dict (rank 0's view; times are the
+    max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as Fn
+    import turboae_b200 as T
+    from helpers import make_args
+    from oracle import turboae_oracle as O
+    from turboae_b200 import _lib, shard
+    res = {}
+    if world > 1:
+        os.environ["TURBOAE_B200_SHARD"] = "1"              # ENC_interCNN: batch-global power statistics across ranks
+        if not getattr(train_leg, "_hook", None):
+            train_leg._hook = shard.install_optimizer_hook()
+    torch.manual_seed(4321)                                  # identical initial weights on every rank
+    targs = make_args(batch_size=TB)
+    p = O.make_perm(100, 0)
+    tenc, tdec = T.ENC_interCNN(targs, p).to(dev), T.DEC_LargeCNN(targs, p).to(dev)
+    shard.sync_replicas(tenc), shard.sync_replicas(tdec)
+    torch.manual_seed(977 + rank)                            # own data stream per rank
+
+    def make_step(opt):
+        def step():
+            opt.zero_grad(set_to_none=True)
+            u = torch.randint(0, 2, (TB, 100, 1), device=dev).float()
+            out = tdec(tenc(u) + torch.randn(TB, 100, 3, device=dev))
+            loss = Fn.binary_cross_entropy(torch.clamp(out, 0.0, 1.0), u)
+            loss.backward()
+            opt.step()
+            return loss.detach()
+        return step
+
+    def timed_steps(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = shard.max_over_ranks(e0.elapsed_time(e1) / steps, device=dev)
+        return ms, float(loss), (_lib.launch_count() - n0) / steps
+
+    ms, loss, launches = timed_steps(make_step(torch.optim.Adam(tdec.parameters(), lr=1e-4)))
+    res["train_step_decoder_mode_cw_per_s"] = world * TB / (ms * 1e-3)
+    res["train_step"] = "enc2/dec5, batch %d per GPU x %d GPUs, fwd+bwd+%sAdam, train_precision=%s, eager host loop: %.2f ms/step, " \
+                        "%.0f launches of our kernels per step, loss %.4f" % (TB, world, "all-reduce+" if world > 1 else "",
+                                                                              tdec.train_precision, ms, launches, loss)
+    try:
+        opt_g = torch.optim.Adam(tdec.parameters(), lr=1e-4, capturable=True)
+        gstep = T.graphs.GraphedStep(make_step(opt_g), warmup=3, device=dev)
+        ms_g, loss_g, _ = timed_steps(gstep)
+        res["train_step_graphed_cw_per_s"] = world * TB / (ms_g * 1e-3)
+        res["train_step_graphed"] = "same step captured once in a CUDA graph and replayed: %.2f ms/step, loss %.4f" % (ms_g, loss_g)
+    except Exception as e:  # pragma: no cover -- reported, the eager figure stands
+        res["train_step_graphed_error"] = repr(e)[:300]
+    return res
+
+
 def run_b200(a):
     import numpy as np
     import torch
@@ -206,7 +276,8 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     B, K, W = a.batch, a.steps, max(a.warmup, 3)
 
     m, w, p = build_codec("c1", device=dev, batch_size=B)
@@ -271,17 +342,21 @@ def run_b200(a):
         e2e_ms = max(e0.elapsed_time(e1), wall_ms)
         e2e_value = world * B * K / (shard.max_over_ranks(e2e_ms, device=dev) * 1e-3)
 
+    line = None
     if rank == 0:
         peak, peak_sus, which = measured_peaks()
         launch_ms = statistics.mean(per_launch_ms)
         achieved = B * DEC_FLOP_PER_CW / (launch_ms * 1e-3) / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "dec_traffic.json")
-        if os.path.exists(tpath):
-            try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        traffic, traffic_src = None, None
+        for tname in ("r02_dec_traffic.json", "dec_traffic.json"):       # ncu --set full capture of THIS round's kernel, else round 1's
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tpath):
+                try:
+                    traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                    traffic_src = "profiles/" + tname + " (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture)"
+                    break
+                except Exception:
+                    traffic = None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": a.precision, "data": "synthetic",
@@ -291,79 +366,97 @@ def run_b200(a):
                 "ber_0db": ber,
                 "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                              "frac": achieved / peak, "frac_of_sustained": (achieved / peak_sus) if peak_sus else None,
-                             "peak_source": which + " bf16 burst", "traffic": traffic,
+                             "peak_source": which + " bf16 burst", "traffic": traffic, "traffic_source": traffic_src,
                              "algorithmic_flop_per_launch": B * DEC_FLOP_PER_CW,
                              "algorithmic_hbm_bytes_per_launch": B * HBM_BYTES_PER_CW,
                              "launch_ms_mean": launch_ms, "launch_ms_min": min(per_launch_ms)},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 100 * 3 * 4,
                         "d2h_bytes_per_step": B * 100 * 4},
                 "gpu_launches": int(launches), "clocks": sampler.result()}
-        # ---- secondary metrics: encoder and whole Channel_AE forward, device-resident ------------
-        def timed(fn, reps):
+
+    # ---- everything below is secondary: it must never cost the headline line ---------------------------------------------
+    sec = {}
+    printed = threading.Event()
+
+    def emit():
+        if rank == 0 and not printed.is_set():
+            printed.set()
+            line["secondary"] = sec
+            print(json.dumps(line), flush=True)
+
+    def bail():                                   # a secondary leg hung (e.g. a rank died inside a collective)
+        sec["secondary_error"] = "secondary legs exceeded %d s: abandoned" % SECONDARY_BUDGET_S
+        emit()
+        os._exit(0)
+    SECONDARY_BUDGET_S = 420
+    watchdog = threading.Timer(SECONDARY_BUDGET_S, bail)
+    watchdog.daemon = True
+    watchdog.start()
+    skip = bool(os.environ.get("BENCH_SKIP_SECONDARY"))
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for _ in range(reps):
             fn()
-            torch.cuda.synchronize()
-            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0e.record()
-            for _ in range(reps):
-                fn()
-            t1e.record()
-            torch.cuda.synchronize()
-            return t0e.elapsed_time(t1e) / reps
+        t1e.record()
+        torch.cuda.synchronize()
+        return t0e.elapsed_time(t1e) / reps
 
-        def O_make_perm(L_):
-            return np.random.mtrand.RandomState(0).permutation(np.arange(L_))      # the reference's permutation (main.py:124-126)
-
-        with torch.no_grad():
-            sec = {}
-            noise = torch.randn(B, 100, 3, device=dev)
-            for prec in ("fp32", "bf16"):
-                m.enc.precision = prec
-                ms = timed(lambda: m.enc(bits[0]), 3)
-                sec["encoder_%s_cw_per_s" % prec] = B / (ms * 1e-3)
-            m.enc.precision = "bf16"
-            ms = timed(lambda: m.dec(m.enc(bits[0]) + noise), 3)
-            sec["channel_ae_forward_bf16_cw_per_s"] = B / (ms * 1e-3)
-            m.enc.precision = "fp32"
-            sec["encoder_flop_per_cw"] = 30_360_000
-        # training step (SURVEY.md 8(f) row 1 / BASELINE config 4: enc2/dec5, batch 1000, forward + backward + Adam) and the
-        # bi-GRU decoder (row 2 / config 5: block length 1000) on the tensor cores; single-GPU figures measured on rank 0
+    # (1) ALL ranks: the training step of BASELINE config 4 (the one leg with a collective: gradient all-reduce over NVLink)
+    if not skip:
         try:
-            if os.environ.get("BENCH_SKIP_SECONDARY"):
-                raise RuntimeError("skipped (BENCH_SKIP_SECONDARY)")
-            if world > 1:
-                raise RuntimeError("single-GPU legs: measured when n_gpus == 1 (scripts/train_bench.py covers N > 1)")
-            import torch.nn.functional as Fn
+            sec.update(train_leg(dev, world, rank))
+        except Exception as e:  # pragma: no cover
+            sec["train_error"] = repr(e)[:300]
+    # (2) rank 0 only, no collectives: encoder, whole Channel_AE forward, fp32 parity path, config 3, GRU decoder, baselines
+    if rank == 0 and not skip:
+        try:
+            with torch.no_grad():
+                noise = torch.randn(B, 100, 3, device=dev)
+                default_enc = m.enc.precision
+                ms = timed(lambda: m.dec(m.enc(bits[0]) + noise), 3)
+                sec["channel_ae_forward_default_cw_per_s"] = B / (ms * 1e-3)
+                sec["channel_ae_forward_default"] = "Channel_AE.forward with the modules' default settings (encoder %s, decoder %s)" % (default_enc, m.dec.precision)
+                for prec in ("fp32", "bf16"):
+                    m.enc.precision = prec
+                    ms = timed(lambda: m.enc(bits[0]), 3)
+                    sec["encoder_%s_cw_per_s" % prec] = B / (ms * 1e-3)
+                m.enc.precision = "bf16"
+                ms = timed(lambda: m.dec(m.enc(bits[0]) + noise), 3)
+                sec["channel_ae_forward_bf16_cw_per_s"] = B / (ms * 1e-3)
+                m.enc.precision = default_enc
+                sec["encoder_flop_per_cw"] = 30_360_000
+                ms = timed(lambda: m.dec.decode(recs[0][:10000], precision="fp32"), 2)       # the elementwise-1e-4 parity path
+                sec["decode_fp32_cw_per_s"] = 10000 / (ms * 1e-3)
+                # BASELINE config 3: enc5/dec5 checkpoint, README batch 1000 (and the full 50 000)
+                m3, _, _ = build_codec("c3", device=dev, batch_size=B)
+                u3 = bits[0]
+                rec3 = (m3.enc(u3) + noise).contiguous()
+                ms = timed(lambda: m3.dec(rec3), 3)
+                sec["c3_decode_bf16_cw_per_s"] = B / (ms * 1e-3)
+                ms = timed(lambda: m3.dec(m3.enc(u3) + noise), 3)
+                sec["c3_channel_ae_forward_cw_per_s"] = B / (ms * 1e-3)
+                m3.enc.precision = "bf16"
+                ms = timed(lambda: m3.enc(u3), 3)
+                sec["c3_encoder_bf16_cw_per_s"] = B / (ms * 1e-3)
+                sec["c3_ber_1db"] = float((torch.round(m3.dec((m3.enc(u3) + noise * 10 ** (-1.0 / 20.0)).contiguous())) != u3).float().mean())
+                del m3, rec3
             import turboae_b200 as T
             from helpers import make_args
-            TB = 1000
-            targs = make_args(batch_size=TB)
-            tenc, tdec = T.ENC_interCNN(targs, p).to(dev), T.DEC_LargeCNN(targs, p).to(dev)
-            opt = torch.optim.Adam(tdec.parameters(), lr=1e-4)
-
-            def train_step():
-                opt.zero_grad()
-                u = torch.randint(0, 2, (TB, 100, 1), device=dev).float()
-                out = tdec(tenc(u) + torch.randn(TB, 100, 3, device=dev))
-                Fn.binary_cross_entropy(torch.clamp(out, 0.0, 1.0), u).backward()
-                opt.step()
-
-            train_step()
-            ms = timed(train_step, 5)
-            sec["train_step_decoder_mode_cw_per_s"] = TB / (ms * 1e-3)
-            sec["train_step"] = "enc2/dec5, batch %d, fwd+bwd+Adam, train_precision=%s, %.2f ms/step" % (TB, tdec.train_precision, ms)
-            del tenc, tdec, opt
             RB, RL = 18944, 1000                # one 128-codeword block per CTA on all 148 SMs (profiles/r01_rnn_bench.json)
             rdec = T.DEC_LargeRNN(make_args(num_iteration=6, dec_num_unit=100, block_len=RL, batch_size=RB),
-                                  O_make_perm(RL)).to(dev).eval()
+                                  np.random.mtrand.RandomState(0).permutation(np.arange(RL))).to(dev).eval()
             rrec = torch.randn(RB, RL, 3, device=dev)
             with torch.no_grad():
                 ms = timed(lambda: rdec(rrec), 1)
             sec["rnn_decoder_cw_per_s"] = RB / (ms * 1e-3)
             sec["rnn_decoder"] = "DEC_LargeRNN block_len %d, 6 iterations, H 100, batch %d, precision=%s, %.1f ms" % (RL, RB, rdec.precision, ms)
             del rdec, rrec
-        except Exception as e:  # pragma: no cover -- secondary figures must never cost the headline line
-            sec["secondary_error"] = str(e)[:200]
-        line["secondary"] = sec
+        except Exception as e:  # pragma: no cover
+            sec["secondary_error"] = repr(e)[:300]
         if world == 1 and not a.no_cpu_baseline:
             v, times, cores, kind = cpu_reference_rate(a.cpu_sample, 10.0, 30)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
@@ -373,7 +466,6 @@ def run_b200(a):
                                         else "torch CPU operators of the reference's decode path (oracle/turboae_torch.py)")}
             # the reference's operator sequence executed by torch eager ON THIS GPU (cuDNN/cuBLAS): "what you get today"
             try:
-                from oracle import turboae_oracle as O
                 from oracle import turboae_torch as TT
                 wt = {k: torch.from_numpy(v).to(dev) for k, v in w.items()}
                 eg = {}
@@ -388,10 +480,14 @@ def run_b200(a):
                                                       "B=%d, same weights" % B}
             except Exception as e:  # pragma: no cover
                 line["eager_gpu_baseline"] = {"error": str(e)[:200]}
-        print(json.dumps(line), flush=True)
+    watchdog.cancel()
+    emit()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:  # pragma: no cover
+            pass
     return 0
 
 

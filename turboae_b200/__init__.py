@@ -10,7 +10,7 @@ from .interleavers import Interleaver, DeInterleaver          # noqa: F401
 from .cnn_utils import SameShapeConv1d                        # noqa: F401
 from .encoders import ENCBase, ENC_interCNN                   # noqa: F401
 from .decoders import DEC_LargeCNN, DEC_LargeRNN              # noqa: F401
-from . import channel, shard                                  # noqa: F401
+from . import channel, shard, graphs                          # noqa: F401
 from ._flat import invalidate_all                             # noqa: F401
 
 

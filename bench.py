@@ -206,14 +206,15 @@ def train_leg(dev, world, rank, TB=1000, steps=8):
     from oracle import turboae_oracle as O
     from turboae_b200 import _lib, shard
     res = {}
-    if world > 1:
-        os.environ["TURBOAE_B200_SHARD"] = "1"              # ENC_interCNN: batch-global power statistics across ranks
-        if not getattr(train_leg, "_hook", None):
-            train_leg._hook = shard.install_optimizer_hook()
+    hook = shard.install_optimizer_hook() if world > 1 else None     # gradient all-reduce before every optimizer step
     torch.manual_seed(4321)                                  # identical initial weights on every rank
     targs = make_args(batch_size=TB)
     p = O.make_perm(100, 0)
     tenc, tdec = T.ENC_interCNN(targs, p).to(dev), T.DEC_LargeCNN(targs, p).to(dev)
+    if world > 1:
+        # ONLY this leg's encoder is sharded (batch-global power statistics across ranks); the process environment is left
+        # alone: modules built later by rank 0's single-GPU legs must never enter a collective
+        tenc.shard_group = dist.group.WORLD
     shard.sync_replicas(tenc), shard.sync_replicas(tdec)
     torch.manual_seed(977 + rank)                            # own data stream per rank
 
@@ -258,6 +259,8 @@ def train_leg(dev, world, rank, TB=1000, steps=8):
         res["train_step_graphed"] = "same step captured once in a CUDA graph and replayed: %.2f ms/step, loss %.4f" % (ms_g, loss_g)
     except Exception as e:  # pragma: no cover -- reported, the eager figure stands
         res["train_step_graphed_error"] = repr(e)[:300]
+    if hook is not None:
+        hook.remove()
     return res
 
 
@@ -277,7 +280,8 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        # (longer than the watchdog of the secondary legs below: that one must fire first and still print the headline line)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=900))
     B, K, W = a.batch, a.steps, max(a.warmup, 3)
 
     m, w, p = build_codec("c1", device=dev, batch_size=B)
@@ -388,7 +392,7 @@ def run_b200(a):
         sec["secondary_error"] = "secondary legs exceeded %d s: abandoned" % SECONDARY_BUDGET_S
         emit()
         os._exit(0)
-    SECONDARY_BUDGET_S = 420
+    SECONDARY_BUDGET_S = 300
     watchdog = threading.Timer(SECONDARY_BUDGET_S, bail)
     watchdog.daemon = True
     watchdog.start()

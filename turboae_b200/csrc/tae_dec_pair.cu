@@ -101,18 +101,26 @@ constexpr uint32_t TMEM_LIN_COL = N_TILES * NPAD;               // 448
 struct Smem {
   uint32_t act, comb, xin[2], ones, wslot, perm, inv_perm, defer, bars, tmem_ptr, total;
 };
-// barrier slots (8 bytes each)
+// barrier slots (8 bytes each).  Waits are parity waits, so every barrier below has ONE class of waiters that observes EVERY
+// one of its phases, and a phase cannot complete before those waiters have seen the previous one (a waiter that skipped a phase
+// could take "two phases behind" for "complete", one that fell two phases back would wait forever):
 // B_WFULL[p]: ring slot p resident in BOTH CTAs (leader: own bulk copy + one arrival forwarded by the peer's relay, so an
-// MMA issuer does ONE wait per slot).  B_WEMPTY[p]: the MMAs of all four tiles reading slot p have completed (one commit
-// per tile issuer, multicast to both CTAs).
-// B_ACC[m]: accumulators of tile m complete (commit, multicast).  B_ACT[m] (leader): tile m written back by all 16 epilogue
-// warps of the pair (each warp arrives on its own).
-// B_ISS[m] (leader): the issuer of tile m has issued (all but the last slot of) its MMAs of a units->units step: the conv tiles
-// are issued in program order (tile 0..3 of a layer, then the next layer), so that two tiles that become ready together do
-// not share the tensor pipe (which would delay the epilogue of the first by a whole tile).
-// B_DEF[m] (leader): the two deferred rows of tile m have been stored (start of the epilogue of tile m+1): the Linear of tile m
-// (centre tap only) waits for this instead of the whole epilogue of tile m+1.
-enum { B_WFULL = 0, B_WEMPTY = NS, B_ACC = 2 * NS, B_ACT = 2 * NS + 4, B_ISS = 2 * NS + 8, B_DEF = 2 * NS + 12, N_BARS = 2 * NS + 16 };
+//   MMA issuer does ONE wait per slot).  B_WEMPTY[p]: the MMAs of all four tiles reading slot p have completed (one commit
+//   per tile issuer, multicast to both CTAs).
+// B_ACC[m]: accumulators of tile m complete (commit, multicast), one phase per step whose epilogue ALL epilogue warps run
+//   (conv-type layers; also the encoder's Linear and the backward's last step).  B_LACC[m]: the decoder's Linear of tile m
+//   (one phase per stack; waited for by the 4 warps of column part m only).
+// B_ACT[m] (leader): tile m written back by all 16 epilogue warps of the pair, one phase per conv-type epilogue; waited for by
+//   the issuer of tile m before every step that reads the activations.  B_HALO[m] (leader): same arrivals, for the issuer of
+//   tile m-1 (whose taps 3, 4 read the first two rows of tile m): one phase per epilogue whose output a tap-shifted step reads.
+// B_LE[m] (leader): the input rows of tile m of the NEXT stack's first layer are in place (group start; Linear epilogue of
+//   tile m; backward: stack prologue), one phase per stack; waited for by the issuers of the tiles whose codewords live in m.
+// B_DEF[m] (leader): the two deferred rows of tile m have been stored (start of the epilogue of tile m+1 in the last conv-type
+//   layer): the Linear of tile m (centre tap only) waits for this instead of the whole epilogue of tile m+1.
+// B_ISS[m] (leader): the issuer of tile m has issued the first half of its MMAs of a units->units step: those tiles are
+//   issued in program order, two in flight (tile 0..3 of a layer, then the next layer).
+enum { B_WFULL = 0, B_WEMPTY = NS, B_ACC = 2 * NS, B_LACC = 2 * NS + 4, B_ACT = 2 * NS + 8, B_HALO = 2 * NS + 12, B_LE = 2 * NS + 16,
+       B_DEF = 2 * NS + 20, B_ISS = 2 * NS + 24, N_BARS = 2 * NS + 28 };
 
 __host__ __device__ inline Smem make_smem(int F) {
   Smem s{};
@@ -387,7 +395,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
   if (threadIdx.x == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(bar(B_WFULL + i), rank == 0 ? 2 : 1); mbar_init(bar(B_WEMPTY + i), N_TILES); }
     for (int m = 0; m < N_TILES; ++m) {
-      mbar_init(bar(B_ACC + m), 1); mbar_init(bar(B_ACT + m), 2 * N_EPI_WARPS);
+      mbar_init(bar(B_ACC + m), 1); mbar_init(bar(B_LACC + m), 1);
+      mbar_init(bar(B_ACT + m), 2 * N_EPI_WARPS); mbar_init(bar(B_HALO + m), 2 * N_EPI_WARPS); mbar_init(bar(B_LE + m), 2 * N_EPI_WARPS);
       mbar_init(bar(B_ISS + m), 1); mbar_init(bar(B_DEF + m), 2 * PARTS);
     }
     fence_barrier_init();
@@ -454,41 +463,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
       // so the order in which the tensor core interleaves the four streams does not matter.
       const int m = warp - WARP_MMA;
       constexpr uint32_t IDESC_CONV = make_idesc(256, NPAD), IDESC_LIN = make_idesc(256, LIN_N);
-      uint32_t pos = 0, wphase = 0, step = 0, dsteps = 0, csteps = 0;
+      uint32_t pos = 0, wphase = 0, step = 0, csteps = 0, n_act = 0, n_halo = 0, n_le = 0, n_def = 0;
       const uint32_t act = sbase + S.act, comb = sbase + S.comb, ones = sbase + S.ones;
       for (int pr = pair0; pr < a.n_pairs; pr += pair_stride) {
         for (int st = 0; st < n_stacks; ++st) {
           const uint32_t xin = sbase + S.xin[0] + (uint32_t)(MODE == 1 ? 0 : (a.enc ? (st == 2) : (st & 1))) * CHUNK_B;   // enc: branch 3 reads the interleaved bits; backward: one operand chunk
           for (int layer = 0; layer <= a.n_layer; ++layer, ++step) {
-            const uint32_t par = step & 1;
             const bool conv = (layer > 0 && layer < a.n_layer);
             {
               const bool stamp = TAE_TIMELINE && a.tl && pr == tl_pr && lane == 0;
               const uint32_t sidx = (uint32_t)(st * (a.n_layer + 1) + layer);
               (void)sidx;
               if (stamp) a.tl[(sidx * 4 + m) * 8 + 0] = clock64();
-              // inputs of tile m: its own rows and the last rows of tile m-1 (both covered by B_ACT[m]), the first rows of
-              // tile m+1 and the deferred last two rows of tile m, stored by the epilogue of tile m+1 (B_ACT[m+1]).  Layer 0 reads the stack input, which the
-              // previous Linear epilogue scatters across the whole group.
               if (layer == 0) {
                 // the stack input rows this tile reads (its own + 2 halo rows each side) belong to whole codewords, which the
-                // per-tile Linear epilogues of the previous stack scatter: wait for the tiles those codewords live in
+                // per-tile Linear epilogues of the previous stack scatter: wait for the tiles those codewords live in, and
+                // always for the neighbours (the same set for every stack: each of these barriers is seen once per stack)
                 int t_lo = 0, t_hi = N_TILES - 1;
-                if (MODE == 0 && !a.enc && st > 0) {
+                if (MODE == 0 && !a.enc) {
                   const int c_lo = max(128 * m - 2, 0) / CW_ROWS;
                   const int c_hi = min(min(128 * m + 129, GROUP_ROWS - 1) / CW_ROWS, a.cw_per_group - 1);
-                  if (c_lo <= c_hi) { t_lo = min(m, (c_lo * CW_ROWS) / 128); t_hi = max(m, min(N_TILES - 1, (c_hi * CW_ROWS + L - 1) / 128)); }
-                  else { t_lo = t_hi = m; }
+                  t_lo = max(m - 1, 0); t_hi = min(m + 1, N_TILES - 1);
+                  if (c_lo <= c_hi) { t_lo = min(t_lo, (c_lo * CW_ROWS) / 128); t_hi = max(t_hi, min(N_TILES - 1, (c_hi * CW_ROWS + L - 1) / 128)); }
                 }
-                for (int t = t_lo; t <= t_hi; ++t) mbar_wait(bar(B_ACT + t), par, a.err, 5);
+                for (int t = t_lo; t <= t_hi; ++t) mbar_wait(bar(B_LE + t), n_le & 1, a.err, 5);
+                ++n_le;
               } else if (FWD && layer == a.n_layer) {
                 // Linear (centre tap): this tile's own rows, including its two deferred rows
-                mbar_wait(bar(B_ACT + m), par, a.err, 5);
-                if (m < N_TILES - 1) mbar_wait(bar(B_DEF + m), dsteps & 1, a.err, 10);
-                ++dsteps;                                  // one B_DEF phase per stack (arrived in its last units->units layer)
+                mbar_wait(bar(B_ACT + m), n_act & 1, a.err, 5);
+                ++n_act;
+                if (m < N_TILES - 1) mbar_wait(bar(B_DEF + m), n_def & 1, a.err, 10);
+                ++n_def;
               } else {
-                mbar_wait(bar(B_ACT + m), par, a.err, 5);
-                if (m < N_TILES - 1) mbar_wait(bar(B_ACT + m + 1), par, a.err, 5);
+                // tap-shifted step: own rows (and the last rows of tile m-1, stored by this tile's epilogue) + the first two
+                // rows of tile m+1 and this tile's deferred rows (stored by the epilogue of tile m+1)
+                mbar_wait(bar(B_ACT + m), n_act & 1, a.err, 5);
+                ++n_act;
+                if (m < N_TILES - 1) mbar_wait(bar(B_HALO + m + 1), n_halo & 1, a.err, 5);
+                ++n_halo;
               }
               tc_fence_after();
               if (stamp) a.tl[(sidx * 4 + m) * 8 + 1] = clock64();
@@ -589,7 +601,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
                     umma_bf16<2>(tmem_base + TMEM_LIN_COL + m * LIN_N, dfull(ks < 6 ? act_lo + (uint32_t)(2 * ks) * CHUNK_B / 16 : c_lo),
                                  dfull(wl + (uint32_t)(ks * 2 * LIN_WCHUNK_B) / 16), IDESC_LIN, ks > 0);
                   umma_commit_pair(bar(B_WEMPTY + p), 3);
-                  umma_commit_pair(bar(B_ACC + m), 3);
+                  umma_commit_pair(bar((a.enc ? B_ACC : B_LACC) + m), 3);      // decoder: its own barrier (only column part m waits for it)
                 }
                 __syncwarp();
               }
@@ -609,7 +621,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
     const int q = warp & 3;                    // TMEM lane quadrant this warp may read
     const int part = ew >> 2;                  // column part: channels [8*CPP*part, 8*CPP*(part+1)); the last part adds 96..99
     const int tid = threadIdx.x - EPI_WARP0 * 32;
-    uint32_t step = 0;
+    uint32_t step = 0, n_acc = 0, n_lacc = 0;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
     // decoder input of the NEXT group: pulled into L2 a whole stack before it is staged (no registers held)
     auto prefetch_received = [&](int pr_) {
@@ -665,7 +677,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
         fence_proxy_async();
         epi_bar_sync();
         if (lane == 0)
-          for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_ACT + m), rank);
+          for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_LE + m), rank);       // inputs of the first stack
       }
 
       // Deferred rows: the last two rows of tile m are still read by the MMAs of tile m+1 (taps 0, 1), so the two
@@ -687,7 +699,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
         const uint32_t sidx_l = (uint32_t)(ls * (a.n_layer + 1) + a.n_layer);
         (void)sidx_l;
         if (stamp) a.tl[(sidx_l * 4 + t) * 8 + 3] = clock64();
-        mbar_wait(bar(B_ACC + t), lstep & 1, a.err, 6);
+        (void)lstep;
+        mbar_wait(bar(B_LACC + t), n_lacc & 1, a.err, 6);
+        ++n_lacc;
         tc_fence_after();
         if (stamp) a.tl[(sidx_l * 4 + t) * 8 + 4] = clock64();
         const int g_row = 128 * t + 32 * q + lane;
@@ -739,7 +753,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
           fence_proxy_async();
           tc_fence_before();
           __syncwarp();
-          if (lane < N_EPI_WARPS / 4) mbar_arrive_leader(bar(B_ACT + t), rank);
+          if (lane < N_EPI_WARPS / 4) mbar_arrive_leader(bar(B_LE + t), rank);
         }
         if (stamp) a.tl[(sidx_l * 4 + t) * 8 + 5] = clock64();
       };
@@ -799,7 +813,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
           fence_proxy_async();
           epi_bar_sync();
           if (lane == 0)
-            for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_ACT + m), rank);
+            for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_LE + m), rank);
           if (a.stash_x && grp_ok)          // the dlin image of this stack (B operand of the Linear's weight gradient)
             for (int i = tid; i < BUF_ROWS; i += N_EPI_THREADS) {
               uint32_t x0, x1, x2, x3;
@@ -808,7 +822,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
             }
         }
         for (int layer = 0; layer <= a.n_layer; ++layer, ++step) {
-          const uint32_t par = step & 1;
+          // B_ACC phases this warp has seen: every step except the decoder's Linear (B_LACC, column part = tile only)
+          const bool acc_step = !(FWD && !a.enc && layer == a.n_layer);
+          const uint32_t par = n_acc & 1;
+          if (acc_step) ++n_acc;
           if (FWD && st == n_stacks - 1 && layer == 1) prefetch_received(pr + pair_stride);
           const uint32_t sidx = (uint32_t)(st * (a.n_layer + 1) + layer);      // timeline row
           (void)sidx;
@@ -867,7 +884,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
               tc_fence_before();
               __syncwarp();
               if (lane == 0)
-                for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_ACT + m), rank);
+                for (int m = 0; m < N_TILES; ++m) mbar_arrive_leader(bar(B_LE + m), rank);     // the next branch's input is in place since the group start
             }
             continue;
           }
@@ -1016,7 +1033,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
               fence_proxy_async();
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive_leader(bar(B_ACT + m), rank);
+              if (lane == 0) {
+                mbar_arrive_leader(bar(B_ACT + m), rank);
+                // the issuer of tile m-1 reads this tile's first rows in the next step if that step is tap-shifted: every
+                // conv-type layer but the last of a forward stack (whose reader is the centre-tap Linear)
+                if (m > 0 && (!FWD || layer < a.n_layer - 1)) mbar_arrive_leader(bar(B_HALO + m), rank);
+              }
             }
             if (stamp) a.tl[(sidx * 4 + m) * 8 + 5] = clock64();
             if (wstamp) wtl[1] = clock64();

@@ -12,6 +12,11 @@ import torch
 
 from . import _lib
 from ._flat import FlatCache, ParallelShim, Workspace, unwrap
+from ._flat import _EPOCH as _flat_epoch_cell
+
+
+def _flat_epoch():
+    return _flat_epoch_cell[0]
 from .cnn_utils import SameShapeConv1d
 from .interleavers import DeInterleaver, Interleaver
 
@@ -275,7 +280,7 @@ class DEC_LargeRNN(torch.nn.Module):
                 k = "l%d%s" % (layer, suffix)
                 ps = [getattr(gru, n + k) for n in ("weight_ih_", "weight_hh_", "bias_ih_", "bias_hh_")]
                 key = (id(gru), k)
-                ver = tuple((p.data_ptr(), p._version) for p in ps)
+                ver = (_flat_epoch(),) + tuple((p.data_ptr(), p._version) for p in ps)     # epoch: writes through .data (_flat.py)
                 ent = self._packed.get(key)
                 if ent is None or ent[0] != ver:
                     nbytes = lib.tae_gru_packed_bytes(H, in_ch, grp)

@@ -234,6 +234,14 @@ int tae_wgrad_bf16(const TaeWgradJob* jobs_host, int32_t n_jobs, const void* job
  * a (B, L, out_stride) tensor (out_offset = 0 forward, H reverse).  reverse != 0 runs t = L-1 .. 0.               */
 int tae_gru_direction_f32(const float* xproj, const float* w_hh, const float* b_hh, float* out,
                           int32_t B, int32_t L, int32_t H, int32_t out_stride, int32_t out_offset, int32_t reverse, void* stream);
+/* Backward of the same recurrence (training, reference trainer.py:74 through torch.nn.GRU): hout / dout are (B, L, io_stride)
+ * tensors holding this direction's hidden states / their gradient at [io_offset, io_offset + H).  Writes dgi (B, L, 3H), the
+ * gradient at the input-side pre-activations W_ih x + b_ih (gate order r, z, n), and dghn (B, L, H), the n part of the
+ * gradient at the hidden-side pre-activations W_hh h + b_hh (its r and z parts equal dgi's).  The parameter and input
+ * gradients are then plain GEMMs / sums over (B, L): dW_ih = dgi^T x, dx = dgi W_ih, dW_hh = [dgi_r, dgi_z, dghn]^T h_prev. */
+int tae_gru_direction_bwd_f32(const float* xproj, const float* w_hh, const float* b_hh, const float* hout, const float* dout,
+                              float* dgi, float* dghn, int32_t B, int32_t L, int32_t H, int32_t io_stride, int32_t io_offset,
+                              int32_t reverse, void* stream);
 
 /* The same recurrence on the tensor cores (bf16 operands, fp32 accumulation, fp32 hidden state): the input projection is
  * part of the per-step MMA chain, so no (B, L, 3H) projection tensor exists.  Activations travel between the launches as

@@ -89,6 +89,16 @@ def same_shape_conv1d(x: np.ndarray, layers) -> np.ndarray:
     return h
 
 
+def dense_same_shape_conv1d(x: np.ndarray, layers) -> np.ndarray:
+    """DenseSameShapeConv1d.forward (reference cnn_utils.py:67-82): layer idx sees [input, out_0, ..., out_{idx-1}]."""
+    this_input, out = x, None
+    for idx, (w, b) in enumerate(layers):
+        if idx > 0:
+            this_input = np.concatenate([this_input, out], axis=2)
+        out = elu(conv1d_same(this_input, w, b))
+    return out
+
+
 def linear(x: np.ndarray, w: np.ndarray, b: np.ndarray) -> np.ndarray:
     """torch.nn.Linear on the last axis: ``y = x @ W^T + b``."""
     B, L, c = x.shape
@@ -197,7 +207,7 @@ def enc_forward(u: np.ndarray, weights, p: np.ndarray, prefix: str = "enc", ste:
 # --------------------------------------------------------------------------- #
 def dec_forward(received: np.ndarray, weights, p: np.ndarray, num_iteration: int = 6,
                 num_iter_ft: int = 5, extrinsic: bool = True, prefix: str = "dec",
-                trace: list | None = None) -> np.ndarray:
+                trace: list | None = None, dense: bool = False) -> np.ndarray:
     """reference decoders.py:219-269 -> posteriors ``(B, L, 1)`` in (0,1).
 
     If ``trace`` is a list, the output of every ``dec{1,2}_outputs[idx]`` Linear
@@ -213,11 +223,12 @@ def dec_forward(received: np.ndarray, weights, p: np.ndarray, num_iteration: int
     r_sys_int = interleave(r_sys, p)                                  # decoders.py:222
     prior = np.zeros((B, L, num_iter_ft), dtype=F32)                  # decoders.py:227
     n_layer = count_layers(weights, "%s.dec1_cnns.0" % prefix)
+    same_shape_conv1d_ = dense_same_shape_conv1d if dense else same_shape_conv1d      # decoders.py:173-176
     x_plr = None
     for idx in range(num_iteration):
         last = idx == num_iteration - 1
         x_in = np.concatenate([r_sys, r_par1, prior], axis=2)         # decoders.py:230 / 252
-        h = same_shape_conv1d(x_in, _stack(weights, "%s.dec1_cnns.%d" % (prefix, idx), n_layer))
+        h = same_shape_conv1d_(x_in, _stack(weights, "%s.dec1_cnns.%d" % (prefix, idx), n_layer))
         x_plr = linear(h, _get(weights, "%s.dec1_outputs.%d.module.weight" % (prefix, idx)),
                        _get(weights, "%s.dec1_outputs.%d.module.bias" % (prefix, idx)))
         if trace is not None:
@@ -226,7 +237,7 @@ def dec_forward(received: np.ndarray, weights, p: np.ndarray, num_iteration: int
             x_plr = x_plr - prior                                     # decoders.py:235-236 / 257-258
         x_plr_int = interleave(x_plr, p)                              # decoders.py:238 / 260
         x_in = np.concatenate([r_sys_int, r_par2, x_plr_int], axis=2)  # decoders.py:240 / 262
-        h = same_shape_conv1d(x_in, _stack(weights, "%s.dec2_cnns.%d" % (prefix, idx), n_layer))
+        h = same_shape_conv1d_(x_in, _stack(weights, "%s.dec2_cnns.%d" % (prefix, idx), n_layer))
         x_plr = linear(h, _get(weights, "%s.dec2_outputs.%d.module.weight" % (prefix, idx)),
                        _get(weights, "%s.dec2_outputs.%d.module.bias" % (prefix, idx)))
         if trace is not None:

@@ -95,3 +95,30 @@ def dec_forward(received, weights, p, num_iteration=6, num_iter_ft=5, extrinsic=
                 x_plr = x_plr - x_plr_int
             prior = interleave(x_plr, rp)                             # DeInterleaver, interleavers.py:43-48
     return torch.sigmoid(interleave(x_plr, rp))
+
+
+def dec_rnn_forward(received, rnns1, rnns2, outs1, outs2, p, num_iter_ft=5, extrinsic=True):
+    """DEC_LargeRNN.forward (reference decoders.py:86-149) on torch CPU operators, differentiable: `rnns*` are lists of
+    torch.nn.GRU(2 + F, H, num_layers=2, batch_first=True, bidirectional=True), `outs*` lists of torch.nn.Linear -- the very
+    operators the reference executes (dropout 0, dec_act 'linear')."""
+    B, L, _ = received.shape
+    idx = torch.as_tensor(np.asarray(p), dtype=torch.long)
+    inv = torch.empty_like(idx)
+    inv[idx] = torch.arange(L)
+    il = lambda x: x[:, idx, :]
+    dil = lambda x: x[:, inv, :]
+    r_sys, r_par1, r_par2 = received[:, :, 0:1], received[:, :, 1:2], received[:, :, 2:3]
+    r_sys_int = il(r_sys)
+    prior = torch.zeros(B, L, num_iter_ft)
+    n_it = len(rnns1)
+    for i in range(n_it):
+        x_plr = outs1[i](rnns1[i](torch.cat([r_sys, r_par1, prior], dim=2))[0])
+        if extrinsic:
+            x_plr = x_plr - prior
+        x_plr_int = il(x_plr)
+        x_plr = outs2[i](rnns2[i](torch.cat([r_sys_int, r_par2, x_plr_int], dim=2))[0])
+        if i < n_it - 1:
+            if extrinsic:
+                x_plr = x_plr - x_plr_int
+            prior = dil(x_plr)
+    return torch.sigmoid(dil(x_plr))

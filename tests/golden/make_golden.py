@@ -16,6 +16,7 @@ The reference cannot travel to the GPU box, so its outputs are committed here:
   grad_c1_b6.npz   one training step (forward, clamp, BCE, backward) of the reference with checkpoint c1, B=6 @ -1.5 dB:
                    loss, per-parameter gradient norms / first values, six gradients in full
   flags_c1_b8.npz  -precompute_norm_stats (three successive batches, running scalars) and -is_variable_block_len (block length 40)
+  dense_*.npz      DEC_LargeCNN with DenseSameShapeConv1d stacks (-encoder TurboAE_rate3_cnn_dense), seeded default init x2
   ber_c1.json      12-point BER/BLER sweep (reference trainer.py:157-178 loop restated with seeded
                    numpy inputs, batch 500) -- per-point bit/block error counts
 
@@ -200,6 +201,34 @@ def dump_grad(cfg, B, seed, snr_db, name):
     print("%s: loss %.6f, %d parameter gradients" % (name, float(loss), len(names)))
 
 
+def dump_dense(name, B=4, L=30, units=20, n_layer=3, n_iter=2, seed=5):
+    """DEC_LargeCNN built from DenseSameShapeConv1d (reference decoders.py:173-176: every -encoder other than TurboAE_rate3_cnn;
+    cnn_utils.py:49-82): no checkpoint is shipped, so weights are torch.manual_seed-ed default init x2; weights, input, output."""
+    compat.install()
+    args = compat.reference_args(["-encoder", "TurboAE_rate3_cnn_dense", "-decoder", "TurboAE_rate3_cnn", "-dec_num_unit", str(units),
+                                  "-dec_num_layer", str(n_layer), "-dec_kernel_size", "5", "-num_iteration", str(n_iter), "-block_len", str(L),
+                                  "-batch_size", str(B), "-code_rate_k", "1", "-code_rate_n", "3", "--no-cuda"])
+    from numpy import arange
+    from numpy.random import mtrand
+    from decoders import DEC_LargeCNN
+    p = mtrand.RandomState(0).permutation(arange(L))
+    torch.manual_seed(seed)
+    dec = DEC_LargeCNN(args, p)
+    dec.set_parallel()
+    with torch.no_grad():
+        for q in dec.parameters():
+            q.mul_(2.0)
+    dec.eval()
+    rs = np.random.mtrand.RandomState(seed)
+    rec = (rs.randint(0, 2, size=(B, L, 3)) * 2.0 - 1.0 + 0.7 * rs.standard_normal((B, L, 3))).astype(np.float32)
+    with torch.no_grad():
+        y = dec(torch.from_numpy(rec)).numpy().astype(np.float32)
+    out = {"dec." + k: v.detach().numpy().astype(np.float32) for k, v in dec.state_dict().items()}
+    out.update(received=rec, y=y, p=np.asarray(p, np.int64), cfg=np.array([B, L, units, n_layer, n_iter], np.int64))
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, y.shape, float(y.min()), float(y.max()), [tuple(v.shape) for k, v in out.items() if "cnns.0.module.cnns" in k and "weight" in k][:3])
+
+
 def dump_flags(name):
     """Two non-default branches of the hot path, executed on the UNMODIFIED reference with checkpoint c1:
     -precompute_norm_stats (encoders.py:110-114): codes of three successive batches + the running scalars after each;
@@ -234,7 +263,7 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["weights", "kat", "io", "perm", "rnn", "ber", "grad", "flags"]
+    todo = a.only.split(",") if a.only else ["weights", "kat", "io", "perm", "rnn", "ber", "grad", "flags", "dense"]
     if "weights" in todo:
         dump_weights("c1"); dump_weights("c3"); dump_weights("c1s")
     if "kat" in todo:
@@ -252,3 +281,5 @@ if __name__ == "__main__":
         dump_grad("c1", 6, 2718, -1.5, "grad_c1_b6.npz")
     if "flags" in todo:
         dump_flags("flags_c1_b8.npz")
+    if "dense" in todo:
+        dump_dense("dense_u20_l3_i2_b4.npz")

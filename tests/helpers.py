@@ -61,3 +61,21 @@ def gen_inputs(seed, B, L, snr_db):
     sigma = 10 ** (-snr_db / 20.0)
     noise = (sigma * rs.standard_normal((B, L, 3))).astype(np.float32)
     return u, noise
+
+
+def torch_rnn_modules(weights, n_iter, H, F=5, scale=1.0):
+    """torch.nn.GRU / Linear modules (CPU: the reference's own operators, decoders.py:43-58) loaded from fixture-style keys
+    'dec.dec{1,2}_rnns.<i>.module.<name>' / 'dec.dec{1,2}_outputs.<i>.module.<name>'."""
+    rnns, outs = ([], []), ([], [])
+    for i in range(n_iter):
+        for s_ in (0, 1):
+            gru = torch.nn.GRU(2 + F, H, num_layers=2, bias=True, batch_first=True, bidirectional=True)
+            pre = "dec.dec%d_rnns.%d.module." % (s_ + 1, i)
+            gru.load_state_dict({k[len(pre):]: torch.from_numpy(np.asarray(v) * np.float32(scale)) for k, v in weights.items() if k.startswith(pre)})
+            pre = "dec.dec%d_outputs.%d.module." % (s_ + 1, i)
+            w = {k[len(pre):]: torch.from_numpy(np.asarray(v) * np.float32(scale)) for k, v in weights.items() if k.startswith(pre)}
+            lin = torch.nn.Linear(2 * H, w["weight"].shape[0])
+            lin.load_state_dict(w)
+            rnns[s_].append(gru)
+            outs[s_].append(lin)
+    return rnns[0], rnns[1], outs[0], outs[1]

@@ -120,7 +120,9 @@ def test_no_cpu_fallback():
 
 def test_unsupported_configurations_raise():
     p = O.make_perm(100, 0)
-    with pytest.raises(NotImplementedError):
-        T.DEC_LargeCNN(make_args(encoder="TurboAE_rate3_cnn_dense"), p)
+    # the dense decoder variant (decoders.py:173-176) is built from DenseSameShapeConv1d with the reference's parameter shapes ...
+    d = T.DEC_LargeCNN(make_args(encoder="TurboAE_rate3_cnn_dense", dec_num_unit=20, dec_num_layer=3), p)
+    assert d.dense and tuple(d.dec1_cnns[0].cnns[2].weight.shape) == (20, 7 + 2 * 20, 5)
+    # ... ENC_interCNN itself only exists for -encoder TurboAE_rate3_cnn (main.py:35-36 selects another class otherwise)
     with pytest.raises(NotImplementedError):
         T.ENC_interCNN(make_args(encoder="TurboAE_rate3_cnn_dense"), p)

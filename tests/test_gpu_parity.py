@@ -729,3 +729,100 @@ def test_variable_block_len_redraws_the_interleaver(L):
     np.testing.assert_allclose(y32.cpu().numpy(), ref_y, atol=1e-4, rtol=0)
     assert float(np.abs(y16.cpu().numpy() - ref_y).mean()) < 5e-3
     assert np.array_equal(m.dec.interleaver.p_array.numpy(), p) and np.array_equal(m.enc.interleaver.p_array.numpy(), p)
+
+
+@pytest.mark.gpu
+def test_rnn_decoder_training_gradients_vs_torch_gru():
+    """DEC_LargeRNN under autograd (reference trainer.py:74 through decoders.py:86-149): loss and every parameter gradient of
+    one BCE step against torch autograd through torch.nn.GRU on the CPU -- the reference's own operators, pinned against the
+    reference-generated fixture in tests/test_oracle.py.  Weights x3 so that the gates leave their linear range."""
+    import torch.nn.functional as Fn
+    from helpers import torch_rnn_modules
+    from oracle import turboae_torch as TT
+    g = load_npz("rnn_h32_i2_l40_b5.npz")
+    B, L, H, n_iter = g["cfg"].tolist()
+    scale = 3.0
+    m = _rnn_module(g, scale=scale).train()
+    rs = np.random.RandomState(21)
+    bits = rs.randint(0, 2, size=(7, L, 1)).astype(np.float32)
+    rec = (rs.randint(0, 2, size=(7, L, 3)) * 2.0 - 1.0 + 0.8 * rs.standard_normal((7, L, 3))).astype(np.float32)
+    rec_d = _t(rec).requires_grad_(True)
+    out = m(rec_d)
+    loss = Fn.binary_cross_entropy(torch.clamp(out, 0.0, 1.0), _t(bits))
+    loss.backward()
+    mods = torch_rnn_modules(g, n_iter, H, scale=scale)
+    rec_c = torch.from_numpy(rec).requires_grad_(True)
+    out_c = TT.dec_rnn_forward(rec_c, *mods, g["p"])
+    loss_c = Fn.binary_cross_entropy(torch.clamp(out_c, 0.0, 1.0), torch.from_numpy(bits))
+    loss_c.backward()
+    np.testing.assert_allclose(out.detach().cpu().numpy(), out_c.detach().numpy(), atol=2e-5, rtol=0)
+    assert abs(float(loss.detach()) - float(loss_c.detach())) < 1e-5
+    np.testing.assert_allclose(rec_d.grad.cpu().numpy(), rec_c.grad.numpy(), atol=1e-6 + 2e-4 * float(rec_c.grad.abs().max()), rtol=0)
+    ref = {}
+    for i in range(n_iter):
+        for s_, (rn, ou) in enumerate(((mods[0], mods[2]), (mods[1], mods[3]))):
+            for k, v in rn[i].named_parameters():
+                ref["dec%d_rnns.%d.module.%s" % (s_ + 1, i, k)] = v.grad
+            for k, v in ou[i].named_parameters():
+                ref["dec%d_outputs.%d.module.%s" % (s_ + 1, i, k)] = v.grad
+    n_checked = 0
+    for k, v in m.named_parameters():
+        gr = ref[k].numpy()
+        assert v.grad is not None, k
+        np.testing.assert_allclose(v.grad.cpu().numpy(), gr, atol=1e-7 + 2e-4 * float(np.abs(gr).max()), rtol=0, err_msg=k)
+        n_checked += 1
+    assert n_checked == len(ref) == 2 * n_iter * (16 + 2)
+
+
+@pytest.mark.gpu
+def test_dense_decoder_vs_reference_fixture_and_autograd():
+    """DEC_LargeCNN with DenseSameShapeConv1d stacks (decoders.py:173-176, cnn_utils.py:49-82): forward against the
+    reference-generated fixture; gradients of a BCE step against torch autograd of the same schedule on CPU operators."""
+    import torch.nn.functional as Fn
+    import turboae_b200 as T
+    g = load_npz("dense_u20_l3_i2_b4.npz")
+    B, L, units, n_layer, n_iter = g["cfg"].tolist()
+    args = make_args(encoder="TurboAE_rate3_cnn_dense", dec_num_unit=units, dec_num_layer=n_layer, num_iteration=n_iter, block_len=L, batch_size=B)
+    m = T.DEC_LargeCNN(args, g["p"])
+    m.set_parallel()
+    m.load_state_dict({k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("dec.")}, strict=True)
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        y = m(_t(g["received"])).cpu().numpy()
+    np.testing.assert_allclose(y, g["y"], atol=2e-5, rtol=0)
+    # autograd through the dense stacks
+    rs = np.random.RandomState(3)
+    bits = _t(rs.randint(0, 2, size=(B, L, 1)).astype(np.float32))
+    m.train()
+    rec = _t(g["received"]).requires_grad_(True)
+    loss = Fn.binary_cross_entropy(torch.clamp(m(rec), 0.0, 1.0), bits)
+    loss.backward()
+    # the same schedule on torch CPU operators (cnn_utils.py:67-82 restated with F.conv1d)
+    wc = {k[4:]: torch.from_numpy(v).requires_grad_(True) for k, v in g.items() if k.startswith("dec.")}
+    idx = torch.from_numpy(g["p"]).long()
+    inv = torch.empty_like(idx); inv[idx] = torch.arange(L)
+
+    def dense(x, pre):
+        this_input, out = x.transpose(1, 2), None
+        for j in range(n_layer):
+            if j > 0:
+                this_input = torch.cat([this_input, out], dim=1)
+            out = Fn.elu(Fn.conv1d(this_input, wc[pre + ".module.cnns.%d.weight" % j], wc[pre + ".module.cnns.%d.bias" % j], padding=2))
+        return out.transpose(1, 2)
+
+    rc = torch.from_numpy(g["received"]).requires_grad_(True)
+    r_sys, r_p1, r_p2 = rc[:, :, 0:1], rc[:, :, 1:2], rc[:, :, 2:3]
+    prior = torch.zeros(B, L, 5)
+    for i in range(n_iter):
+        x = Fn.linear(dense(torch.cat([r_sys, r_p1, prior], 2), "dec1_cnns.%d" % i), wc["dec1_outputs.%d.module.weight" % i], wc["dec1_outputs.%d.module.bias" % i]) - prior
+        xi = x[:, idx, :]
+        x = Fn.linear(dense(torch.cat([r_sys[:, idx, :], r_p2, xi], 2), "dec2_cnns.%d" % i), wc["dec2_outputs.%d.module.weight" % i], wc["dec2_outputs.%d.module.bias" % i])
+        if i < n_iter - 1:
+            prior = (x - xi)[:, inv, :]
+    loss_c = Fn.binary_cross_entropy(torch.clamp(torch.sigmoid(x[:, inv, :]), 0.0, 1.0), bits.cpu())
+    loss_c.backward()
+    assert abs(float(loss.detach()) - float(loss_c.detach())) < 1e-5
+    np.testing.assert_allclose(rec.grad.cpu().numpy(), rc.grad.numpy(), atol=1e-7 + 1e-3 * float(rc.grad.abs().max()), rtol=0)
+    for k, v in m.named_parameters():
+        gr = wc[k].grad.numpy()
+        np.testing.assert_allclose(v.grad.cpu().numpy(), gr, atol=1e-7 + 2e-3 * float(np.abs(gr).max()), rtol=0, err_msg=k)

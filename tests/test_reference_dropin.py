@@ -1,0 +1,54 @@
+"""The zero-edit drop-in: the UNMODIFIED reference main.py -> trainer.test -> Channel_AE.forward runs on top
+of this package through `python -m turboae_b200.launch`.  Needs the reference staged by scripts/stage_reference.py in
+baseline/_ref/ (git-ignored; it travels to the GPU box with gpurun) and a GPU; skipped otherwise."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import ROOT
+
+REF = os.path.join(ROOT, "baseline", "_ref")
+
+
+def _run(tmp_path, extra):
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "run_reference_dropin.py"), "--reference", REF] + extra
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=str(tmp_path), timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+@pytest.mark.gpu
+def test_unmodified_main_py_eval_matches_the_reference_classes(tmp_path):
+    """README command (1) (-num_epoch 0, shipped checkpoint) with the same launcher seed twice: this package's classes vs the
+    reference's own classes on torch eager CUDA.  Identical bits and noise, so the BER lists printed by the reference's own
+    trainer.test differ only by the bf16 arithmetic of the fused decoder: |dBER| <= 1e-4 at every SNR point (north_star)."""
+    if not os.path.isfile(os.path.join(REF, "main.py")):
+        pytest.skip("baseline/_ref not staged (python scripts/stage_reference.py)")
+    outs = {}
+    for arm, flag in (("ours", []), ("stock", ["--stock"])):
+        o = os.path.join(str(tmp_path), arm + ".json")
+        _run(tmp_path, ["--mode", "eval", "--seed", "11", "--num-block", "20000", "--batch-size", "5000", "--out", o] + flag)
+        outs[arm] = json.load(open(o))["eval"]
+    ours, stock = np.array(outs["ours"]["BER"]), np.array(outs["stock"]["BER"])
+    assert len(ours) == 12 and outs["ours"]["classes"] == "turboae_b200" and outs["stock"]["classes"].startswith("reference")
+    assert np.all(np.abs(ours - stock) <= 1e-4), (ours - stock).tolist()
+    assert 0.003 < ours[3] < 0.007                     # BER at 0 dB (reference: 4.9e-3 +- sampling noise)
+    assert np.all(np.abs(np.array(outs["ours"]["BLER"]) - np.array(outs["stock"]["BLER"])) <= 2e-3)
+
+
+@pytest.mark.gpu
+def test_unmodified_trainer_train_runs_one_epoch(tmp_path):
+    """README command (3) (fine-tune from the shipped checkpoint), one epoch of 5000 blocks: trainer.train's loss.backward() /
+    optimizer.step() run on this package's autograd path and the validation BER stays at the checkpoint's level."""
+    if not os.path.isfile(os.path.join(REF, "main.py")):
+        pytest.skip("baseline/_ref not staged (python scripts/stage_reference.py)")
+    o = os.path.join(str(tmp_path), "train.json")
+    _run(tmp_path, ["--mode", "train", "--seed", "3", "--out", o])
+    r = json.load(open(o))["train"]
+    assert len(r["epoch_lines"]) == 6 and len(r["ber_traj"]) == 1          # 1 encoder pass + 5 decoder passes, one validation
+    assert r["ber_traj"][0] < 5e-4 and r["loss_traj"][0] < 5e-3            # validated at 2 dB (train_enc_channel_low)
+    assert len(r["BER"]) == 12 and 0.002 < r["BER"][3] < 0.009

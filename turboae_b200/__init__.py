@@ -7,7 +7,7 @@ Drop-in for the reference's ``encoders.ENC_interCNN`` / ``decoders.DEC_LargeCNN`
 the library or without a CUDA device every forward raises.
 """
 from .interleavers import Interleaver, DeInterleaver          # noqa: F401
-from .cnn_utils import SameShapeConv1d                        # noqa: F401
+from .cnn_utils import SameShapeConv1d, DenseSameShapeConv1d  # noqa: F401
 from .encoders import ENCBase, ENC_interCNN                   # noqa: F401
 from .decoders import DEC_LargeCNN, DEC_LargeRNN              # noqa: F401
 from . import channel, shard, graphs                          # noqa: F401

@@ -36,6 +36,38 @@ class SameShapeConv1d(torch.nn.Module):
         return _conv_stack_forward(x, params, not self.no_act, keep=False)[-1]
 
 
+class DenseSameShapeConv1d(torch.nn.Module):
+    """reference cnn_utils.py:49-82 (chosen by decoders.py:173 for every -encoder other than TurboAE_rate3_cnn): layer idx reads
+    the concatenation of the stack input and ALL earlier layers' ELU outputs (in_channels + idx * out_channels channels).  Same
+    module tree (``cnns``) and parameter shapes as the reference; every layer is the fused conv + bias + ELU kernel (forward) and
+    the conv backward kernels (autograd), the concatenation is torch glue on channel-last tensors."""
+
+    def __init__(self, num_layer, in_channels, out_channels, kernel_size):
+        super().__init__()
+        if kernel_size % 2 == 0 or kernel_size > 9:
+            raise NotImplementedError("kernel_size must be odd and <= 9 (got %d)" % kernel_size)
+        self.cnns = torch.nn.ModuleList()
+        self.num_layer = num_layer
+        self.in_channels, self.out_channels, self.kernel_size = in_channels, out_channels, kernel_size
+        for idx in range(num_layer):
+            self.cnns.append(torch.nn.Conv1d(in_channels=in_channels + idx * out_channels, out_channels=out_channels,
+                                             kernel_size=kernel_size, stride=1, padding=kernel_size // 2, dilation=1, groups=1,
+                                             bias=True))
+
+    def forward(self, inputs):
+        _lib.require_cuda(inputs, "DenseSameShapeConv1d input")
+        this_input = inputs.to(torch.float32).contiguous()
+        output = None
+        for idx, conv in enumerate(self.cnns):
+            if idx > 0:
+                this_input = torch.cat([this_input, output], dim=2).contiguous()        # cnn_utils.py:73 (dim 1 of the NCL view)
+            if torch.is_grad_enabled() and (this_input.requires_grad or conv.weight.requires_grad or conv.bias.requires_grad):
+                output = _ConvStackFn.apply(this_input, True, conv.weight, conv.bias)
+            else:
+                output = _conv_stack_forward(this_input, [conv.weight, conv.bias], True, keep=False)[-1]
+        return output
+
+
 def _conv_layer(x, w, b, apply_elu):
     lib = _lib.load()
     B, L, _ = x.shape

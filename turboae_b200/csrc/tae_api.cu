@@ -518,6 +518,16 @@ int tae_gru_direction_f32(const float* xproj, const float* w_hh, const float* b_
   return launch_gru_direction(xproj, w_hh, b_hh, out, B, L, H, out_stride, out_offset, reverse, (cudaStream_t)stream);
 }
 
+int tae_gru_direction_bwd_f32(const float* xproj, const float* w_hh, const float* b_hh, const float* hout, const float* dout,
+                              float* dgi, float* dghn, int32_t B, int32_t L, int32_t H, int32_t io_stride, int32_t io_offset,
+                              int32_t reverse, void* stream) {
+  TAE_REQUIRE(B >= 0 && L >= 1 && H >= 1, "tae_gru_direction_bwd_f32: bad shape B=%d L=%d H=%d", B, L, H);
+  TAE_REQUIRE(io_stride >= H && io_offset >= 0 && io_offset + H <= io_stride, "tae_gru_direction_bwd_f32: bad hidden-state window");
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(xproj && w_hh && b_hh && hout && dout && dgi && dghn, "tae_gru_direction_bwd_f32: NULL pointer");
+  return launch_gru_direction_bwd(xproj, w_hh, b_hh, hout, dout, dgi, dghn, B, L, H, io_stride, io_offset, reverse, (cudaStream_t)stream);
+}
+
 void tae_debug_gru_timeline(long long* dev) { gru_tc_set_timeline(dev); }
 
 int32_t tae_gru_rows_per_block(int32_t B) { return gru_tc_rows_per_block(B < 0 ? 0 : B); }

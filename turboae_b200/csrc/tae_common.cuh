@@ -164,6 +164,8 @@ int enc_backward_pair(const TaeEncConfig& c, const void* packed_bwd, const float
                       float* dxin_all, float* grad_flat, int B, void* ws, size_t ws_bytes, cudaStream_t s);
 int launch_add_count(double* stats, double n, cudaStream_t s);
 // ---- DEC_LargeRNN recurrence (tae_gru.cu) ----------------------------------------------------
+int launch_gru_direction_bwd(const float* xproj, const float* w_hh, const float* b_hh, const float* hout, const float* dout, float* dgi,
+                             float* dghn, int B, int L, int H, int io_stride, int io_offset, int reverse, cudaStream_t s);
 int launch_gru_direction(const float* xproj, const float* w_hh, const float* b_hh, float* out, int B, int L, int H, int out_stride,
                          int out_offset, int reverse, cudaStream_t s);
 // tensor-core recurrence (tae_gru_tc.cu)

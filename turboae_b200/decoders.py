@@ -17,7 +17,7 @@ from ._flat import _EPOCH as _flat_epoch_cell
 
 def _flat_epoch():
     return _flat_epoch_cell[0]
-from .cnn_utils import SameShapeConv1d
+from .cnn_utils import DenseSameShapeConv1d, SameShapeConv1d
 from .interleavers import DeInterleaver, Interleaver
 
 
@@ -27,9 +27,10 @@ class DEC_LargeCNN(torch.nn.Module):
         self.args = args
         use_cuda = not args.no_cuda and torch.cuda.is_available()
         self.this_device = torch.device("cuda" if use_cuda else "cpu")
-        if args.encoder != "TurboAE_rate3_cnn":        # decoders.py:173 keys the layer type on args.encoder
-            raise NotImplementedError("turboae_b200.DEC_LargeCNN builds the SameShapeConv1d variant only "
-                                      "(-encoder TurboAE_rate3_cnn); got %r" % (args.encoder,))
+        # decoders.py:173 keys the layer type on args.encoder: the dense variant runs layer by layer on the fp32 kernels (the
+        # fused tensor-core schedule and the flat-parameter C ABI cover the SameShapeConv1d layout only)
+        self.dense = args.encoder != "TurboAE_rate3_cnn"
+        CNNLayer = DenseSameShapeConv1d if self.dense else SameShapeConv1d
         self.interleaver = Interleaver(args, p_array)
         self.deinterleaver = DeInterleaver(args, p_array)
         self.dec1_cnns = torch.nn.ModuleList()
@@ -38,8 +39,8 @@ class DEC_LargeCNN(torch.nn.Module):
         self.dec2_outputs = torch.nn.ModuleList()
         for idx in range(args.num_iteration):
             for lst in (self.dec1_cnns, self.dec2_cnns):
-                lst.append(SameShapeConv1d(num_layer=args.dec_num_layer, in_channels=2 + args.num_iter_ft,
-                                           out_channels=args.dec_num_unit, kernel_size=args.dec_kernel_size))
+                lst.append(CNNLayer(num_layer=args.dec_num_layer, in_channels=2 + args.num_iter_ft,
+                                    out_channels=args.dec_num_unit, kernel_size=args.dec_kernel_size))
             self.dec1_outputs.append(torch.nn.Linear(args.dec_num_unit, args.num_iter_ft))
             self.dec2_outputs.append(torch.nn.Linear(args.dec_num_unit,
                                                      1 if idx == args.num_iteration - 1 else args.num_iter_ft))
@@ -53,7 +54,7 @@ class DEC_LargeCNN(torch.nn.Module):
         #: default: 'bf16' whenever the tensor path covers the configuration (decided here, once, from args)
         from . import train_tc
         self.train_precision = (getattr(args, "tae_train_precision", None) or os.environ.get("TURBOAE_B200_TRAIN_PRECISION")
-                                or ("bf16" if train_tc.supported(args, "dec") else "fp32"))
+                                or ("bf16" if (train_tc.supported(args, "dec") and not self.dense) else "fp32"))
 
     def set_parallel(self):
         for lst in (self.dec1_cnns, self.dec2_cnns, self.dec1_outputs, self.dec2_outputs):
@@ -187,6 +188,9 @@ class DEC_LargeCNN(torch.nn.Module):
             self.set_interleaver(np.random.mtrand.RandomState(seed).permutation(np.arange(received.shape[1])))
         if self.this_device.type != "cuda":
             raise _lib.TaeError("no CUDA device: turboae_b200 has no CPU fallback")
+        if self.dense:
+            # DenseSameShapeConv1d stacks: the schedule spelled out with the module pieces (fp32 kernels), with or without autograd
+            return self._forward_train(received.to(device=self.this_device, dtype=torch.float32).contiguous())
         if torch.is_grad_enabled() and (received.requires_grad or any(p.requires_grad for p in self.parameters())):
             x = received.to(device=self.this_device, dtype=torch.float32)
             if self.train_precision == "bf16":
@@ -201,12 +205,62 @@ class DEC_LargeCNN(torch.nn.Module):
         return self.decode(x)
 
 
+class _GruDirectionFn(torch.autograd.Function):
+    """One direction of one GRU layer under autograd (training of DEC_LargeRNN, reference trainer.py:74 through
+    decoders.py:86-149): forward = input projection (K = 1 case of the conv kernel) + ``tae_gru_direction_f32``; backward =
+    ``tae_gru_direction_bwd_f32`` (the sequential part: back-propagation through time with the gates recomputed) followed by
+    the reductions over (B, L), which are plain GEMMs (torch.matmul -> cuBLAS): dW_ih = dgi^T x, dx = dgi W_ih,
+    dW_hh = dgh^T h_prev, and the bias sums."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih, w_hh, b_ih, b_hh, reverse):
+        lib = _lib.load()
+        B, L, _ = x.shape
+        H = w_hh.shape[1]
+        x = x.contiguous()
+        w_ih_c, w_hh_c, b_ih_c, b_hh_c = (t.detach().contiguous() for t in (w_ih, w_hh, b_ih, b_hh))
+        with torch.cuda.device(x.device):
+            xproj = DEC_LargeRNN._pointwise(x, w_ih_c, b_ih_c)
+            out = torch.empty((B, L, H), dtype=torch.float32, device=x.device)
+            _lib.check(lib.tae_gru_direction_f32(_lib.ptr(xproj), _lib.ptr(w_hh_c), _lib.ptr(b_hh_c), _lib.ptr(out), B, L, H, H, 0,
+                                                 1 if reverse else 0, _lib.stream_ptr(x.device)))
+        ctx.reverse = bool(reverse)
+        ctx.save_for_backward(x, xproj, out, w_ih_c, w_hh_c, b_hh_c)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        x, xproj, out, w_ih, w_hh, b_hh = ctx.saved_tensors
+        B, L, H = out.shape
+        d_out = d_out.contiguous()
+        with torch.cuda.device(x.device):
+            dgi = torch.empty((B, L, 3 * H), dtype=torch.float32, device=x.device)
+            dghn = torch.empty((B, L, H), dtype=torch.float32, device=x.device)
+            _lib.check(lib.tae_gru_direction_bwd_f32(_lib.ptr(xproj), _lib.ptr(w_hh), _lib.ptr(b_hh), _lib.ptr(out), _lib.ptr(d_out),
+                                                     _lib.ptr(dgi), _lib.ptr(dghn), B, L, H, H, 0, 1 if ctx.reverse else 0,
+                                                     _lib.stream_ptr(x.device)))
+        g2 = dgi.reshape(B * L, 3 * H)
+        h_prev = torch.zeros_like(out)                    # h_{t-1} in the direction of the recurrence
+        if ctx.reverse:
+            h_prev[:, :-1] = out[:, 1:]
+        else:
+            h_prev[:, 1:] = out[:, :-1]
+        dgh = torch.cat([dgi[:, :, :2 * H], dghn], dim=2).reshape(B * L, 3 * H)
+        dx = (g2 @ w_ih).reshape(B, L, -1) if ctx.needs_input_grad[0] else None
+        dw_ih = g2.t() @ x.reshape(B * L, -1)
+        dw_hh = dgh.t() @ h_prev.reshape(B * L, H)
+        return dx, dw_ih, dw_hh, g2.sum(0), dgh.sum(0), None
+
+
 class DEC_LargeRNN(torch.nn.Module):
     """DeepTurbo decoder with the reference's nn.Module surface (reference decoders.py:16-149): 2*num_iteration stacks of a
     2-layer bidirectional GRU(2+F -> H) + Linear(2H -> F).  The ``torch.nn.GRU`` children only hold the parameters (same names
     and shapes as the reference, so its checkpoints load); forward runs ``tae_conv1d_elu_f32`` (K = 1: all input projections
     of a layer-direction as one pointwise GEMM), ``tae_gru_direction_f32`` (the recurrence, W_hh resident in shared memory)
-    and the interleaver gather.  Inference only (dropout is the identity in eval mode)."""
+    and the interleaver gather; ``precision='bf16'`` (default) runs the recurrence on the tensor cores.  Under autograd
+    (training, reference trainer.py:74) every GRU direction goes through ``_GruDirectionFn`` (fp32 recurrence forward,
+    ``tae_gru_direction_bwd_f32`` backward)."""
 
     def __init__(self, args, p_array):
         super().__init__()
@@ -327,13 +381,54 @@ class DEC_LargeRNN(torch.nn.Module):
             h = out
         return h
 
+    def _stack_train(self, gru, lin, x):
+        """One decoder stack under autograd: 2-layer bidirectional GRU (fp32 recurrence kernels, _GruDirectionFn) + Linear, with
+        the reference's dropout placement (between the GRU layers: torch.nn.GRU(dropout=...), decoders.py:43-52; on the Linear
+        output: decoders.py:103)."""
+        gru, lin = unwrap(gru), unwrap(lin)
+        p_drop = float(getattr(self.args, "dropout", 0.0))
+        h = x
+        for layer in range(gru.num_layers):
+            outs = []
+            for d, suffix in enumerate(("", "_reverse")):
+                k = "l%d%s" % (layer, suffix)
+                outs.append(_GruDirectionFn.apply(h, getattr(gru, "weight_ih_" + k), getattr(gru, "weight_hh_" + k),
+                                                  getattr(gru, "bias_ih_" + k), getattr(gru, "bias_hh_" + k), d == 1))
+            h = torch.cat(outs, dim=2)
+            if layer < gru.num_layers - 1 and p_drop > 0.0:
+                h = torch.nn.functional.dropout(h, p_drop, self.training)
+        y = torch.nn.functional.linear(h, lin.weight, lin.bias)
+        return torch.nn.functional.dropout(y, p_drop, self.training) if p_drop > 0.0 else y
+
+    def _forward_train(self, received):
+        """Autograd path (reference trainer.py:64-76 through decoders.py:86-149): the same turbo schedule as forward(), every
+        stack through _stack_train; interleave / de-interleave are this package's differentiable gathers."""
+        a = self.args
+        B, L, _ = received.shape
+        r_sys, r_par1, r_par2 = received[:, :, 0:1], received[:, :, 1:2], received[:, :, 2:3]
+        r_sys_int = self.interleaver(r_sys.contiguous())
+        prior = torch.zeros((B, L, a.num_iter_ft), dtype=torch.float32, device=received.device)
+        x_plr = None
+        for idx in range(a.num_iteration):
+            last = idx == a.num_iteration - 1
+            x_plr = self._stack_train(self.dec1_rnns[idx], self.dec1_outputs[idx], torch.cat([r_sys, r_par1, prior], dim=2))
+            if a.extrinsic:
+                x_plr = x_plr - prior
+            x_plr_int = self.interleaver(x_plr.contiguous())
+            x_plr = self._stack_train(self.dec2_rnns[idx], self.dec2_outputs[idx], torch.cat([r_sys_int, r_par2, x_plr_int], dim=2))
+            if not last:
+                if a.extrinsic:
+                    x_plr = x_plr - x_plr_int
+                prior = self.deinterleaver(x_plr.contiguous())
+        return torch.sigmoid(self.deinterleaver(x_plr.contiguous()))
+
     def forward(self, received):
         if self.this_device.type != "cuda":
             raise _lib.TaeError("no CUDA device: turboae_b200 has no CPU fallback")
-        if torch.is_grad_enabled() and (received.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("turboae_b200.DEC_LargeRNN is inference-only so far; wrap the call in torch.no_grad()")
         a = self.args
         received = received.to(device=self.this_device, dtype=torch.float32).contiguous()
+        if torch.is_grad_enabled() and (received.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return self._forward_train(received)
         B, L, _ = received.shape
         with torch.cuda.device(received.device):
             r_sys, r_par1, r_par2 = received[:, :, 0:1], received[:, :, 1:2], received[:, :, 2:3]

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.environ.get("TURBOAE_B200_LIB") or os.path.join(LIBDIR, "libturboae_b200.so")
-SOURCES = ["tae_api.cu", "tae_f32.cu", "tae_dec_pair.cu", "tae_channel.cu", "tae_gru.cu", "tae_wgrad.cu", "tae_gru_tc.cu"]
+SOURCES = ["tae_api.cu", "tae_f32.cu", "tae_dec_pair.cu", "tae_channel.cu", "tae_gru.cu", "tae_wgrad.cu", "tae_gru_tc.cu", "tae_x3.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

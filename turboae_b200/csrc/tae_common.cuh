@@ -163,6 +163,17 @@ int enc_pair_pack_bwd(const TaeEncConfig& c, const float* params, void* packed, 
 int enc_backward_pair(const TaeEncConfig& c, const void* packed_bwd, const float* dlin, const void* stash_y, void* stash_g, void* stash_d,
                       float* dxin_all, float* grad_flat, int B, void* ws, size_t ws_bytes, cudaStream_t s);
 int launch_add_count(double* stats, double n, cudaStream_t s);
+// ---- bf16x3 tcgen05 path: split-operand kernel with fp32-class accuracy (tae_x3.cu) ----------
+bool dec_x3_supported(const TaeDecConfig& c, const char** why);
+size_t dec_x3_packed_bytes(const TaeDecConfig& c);
+int dec_x3_pack(const TaeDecConfig& c, const float* params, void* packed, cudaStream_t s);
+int dec_forward_x3(const TaeDecConfig& c, const float* params, const void* packed, const float* received, const int32_t* perm,
+                   const int32_t* inv_perm, float* out, float* trace, int B, void* ws, size_t ws_bytes, cudaStream_t s);
+bool enc_x3_supported(const TaeEncConfig& c, const char** why);
+size_t enc_x3_packed_bytes(const TaeEncConfig& c);
+int enc_x3_pack(const TaeEncConfig& c, const float* params, void* packed, cudaStream_t s);
+int enc_forward_x3(const TaeEncConfig& c, const float* params, const void* packed, const float* u, const int32_t* perm,
+                   const int32_t* inv_perm, float* x_tx, double* stats, int B, void* ws, size_t ws_bytes, cudaStream_t s);
 // ---- DEC_LargeRNN recurrence (tae_gru.cu) ----------------------------------------------------
 int launch_gru_direction_bwd(const float* xproj, const float* w_hh, const float* b_hh, const float* hout, const float* dout, float* dgi,
                              float* dghn, int B, int L, int H, int io_stride, int io_offset, int reverse, cudaStream_t s);

@@ -1,0 +1,592 @@
+// ENC_interCNN.forward and DEC_LargeCNN.forward on the 5th-gen tensor cores with fp32-class accuracy (TAE_PRECISION_BF16X3),
+// sm_100a only.
+//
+// Reference arithmetic restated (paths relative to the reference checkout):
+//   encoders.py:362-373 (three branches, Linear + ELU), decoders.py:219-269 (turbo schedule),
+//   cnn_utils.py:36-46 (conv + ELU stack), interleavers.py:15-21, 43-48 (row permutations).
+//
+// Why: the plain bf16 tensor path rounds activations and weights to 8 mantissa bits (codes off by up to 5e-3, posteriors by
+// 1.6e-2 on the reference fixtures): it meets the BER gate, not north_star's elementwise 1e-4.  Here every operand of a conv
+// layer is split into two bf16 terms, x = x_hi + x_lo and W = W_hi + W_lo (16 mantissa bits together), and the layer is the
+// three tcgen05.mma chains  x_hi W_hi + x_lo W_hi + x_hi W_lo  accumulated in fp32 TMEM (the x_lo W_lo term is below 2^-16).
+// Bias, ELU, the Linear projections, the extrinsic subtraction and the priors stay in fp32 on the CUDA cores.  Measured on the
+// reference fixtures: codes within 1e-5, posteriors within 3e-5 (tests/test_gpu_x3.py), at ~13x the rate of the fp32
+// CUDA-core path.
+//
+// Execution model (deliberately simpler than tae_dec_pair.cu: one CTA per SM, no cluster):
+//   * a CTA owns one "group" = a 256-row activation buffer holding floor(258/(L+2)) codewords, each followed by 2 all-zero
+//     separator rows (the zero padding of cnn_utils.py:16); 2 MMA tiles of 128 rows, M = 128, N = 112, cta_group::1.
+//   * activations live in shared memory twice (hi and lo images), bf16, canonical no-swizzle K-major layout
+//     [13 chunks of 8 channels][264 rows][8]: tap t of the convolution is the same buffer addressed 16*t bytes later.
+//     K of a units->units layer = 33 k-steps of 16: 5 taps x 6 pairs of chunks (LBO = one chunk) + chunk 12 with two taps per
+//     k-step (LBO = 16 bytes: taps (0,1), (2,3), (4,-)).  The first layer ((2+F) or 1 -> units) is 3 k-steps of its one chunk.
+//   * weights stream from L2 through a bulk-copy ring: per layer 11 slots of W_hi (each used by the x_hi and the x_lo chain of
+//     both tiles) then 11 slots of W_lo (x_hi chain).
+//   * a layer = [MMA warp: 198 MMAs, one commit] -> [8 epilogue warps, one row per thread: tcgen05.ld, + bias, ELU, split into
+//     hi / lo, st.shared in place] -> next layer.  The last layer of a stack keeps its output in registers and applies the
+//     Linear there (fp32), so no activation is rounded between the last conv layer and the stack output.
+//   * decoder: the stack inputs (received values and priors) are kept as an fp32 master copy [row][8] next to their hi / lo
+//     operand chunks; the extrinsic subtraction uses the fp32 prior, and (de)interleave is the row index of the store.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdio>
+
+#include "tae_common.cuh"
+#include "tae_umma.cuh"
+
+namespace tae {
+
+namespace {
+namespace x3 {
+
+constexpr int GROUP_ROWS = 256;
+constexpr int N_TILES = 2;
+constexpr int HALO_LO = 2, HALO_HI = 6;                 // rows in front / behind (the two-taps-per-k-step scheme reads "tap 5")
+constexpr int BUF_ROWS = GROUP_ROWS + HALO_LO + HALO_HI;   // 264
+constexpr uint32_t ROW_B = 16;
+constexpr uint32_t CHUNK_B = BUF_ROWS * ROW_B;          // 4224
+constexpr int NPAD = 112;                               // UMMA N
+constexpr int N_CHUNKS = 13;                            // 104 channels
+constexpr int UNITS_MAX = 104;
+constexpr int TAPS = 5;
+constexpr int KS_CONV = 33, KS_L0 = 3, KS_PER_SLOT = 3;
+constexpr int SLOTS_PASS = KS_CONV / KS_PER_SLOT;       // 11 slots of W_hi, 11 of W_lo per units->units layer
+constexpr uint32_t WCHUNK_B = NPAD * ROW_B;             // 1792: 8 K elements of 112 columns
+constexpr uint32_t KSTEP_B = 2 * WCHUNK_B;              // 3584
+constexpr uint32_t SLOT_B = KS_PER_SLOT * KSTEP_B;      // 10752
+constexpr int NS = 6;                                   // ring slots
+constexpr int MAX_LAYER = 8, MAX_F = 5;
+constexpr int TAB_BIAS = 0, TAB_V = MAX_LAYER * NPAD, TAB_C = TAB_V + MAX_F * NPAD, TAB_FLOATS = TAB_C + 8;
+constexpr int N_EPI_WARPS = 8, N_EPI_THREADS = 256;     // warp w: tile w >> 2, TMEM lane quadrant w & 3
+constexpr int WARP_MMA = 8, WARP_PRODUCER = 9;
+constexpr int N_THREADS = 320;
+constexpr uint32_t TMEM_COLS = 256;
+
+struct Smem {
+  uint32_t act_hi, act_lo, xin_hi[2], xin_lo[2], master[2], wslot, tab, perm, inv_perm, bars, tmem_ptr, total;
+};
+enum { B_WFULL = 0, B_WEMPTY = NS, B_ACC = 2 * NS, B_ACT = 2 * NS + 1, N_BARS = 2 * NS + 2 };
+
+__host__ __device__ inline Smem make_smem() {
+  Smem s{};
+  uint32_t o = 0;
+  s.act_hi = o; o += N_CHUNKS * CHUNK_B;
+  s.act_lo = o; o += N_CHUNKS * CHUNK_B;
+  s.xin_hi[0] = o; o += CHUNK_B;
+  s.xin_hi[1] = o; o += CHUNK_B;
+  s.xin_lo[0] = o; o += CHUNK_B;
+  s.xin_lo[1] = o; o += CHUNK_B;
+  s.master[0] = o; o += BUF_ROWS * 32;
+  s.master[1] = o; o += BUF_ROWS * 32;
+  s.wslot = o; o += NS * SLOT_B;
+  s.tab = o; o += TAB_FLOATS * 4;
+  s.perm = o; o += 512;
+  s.inv_perm = o; o += 512;
+  s.bars = o; o += N_BARS * 8;
+  s.tmem_ptr = o; o += 16;
+  s.total = o;
+  return s;
+}
+
+// flat-parameter layout of a sequence of conv stacks + Linear (same arithmetic as dec_layout / enc_layout of tae_common.cuh)
+struct Layout {
+  int n_stacks, n_layer, units, cin0, f_regular, f_last;
+  __host__ __device__ size_t l0() const { return (size_t)units * cin0 * TAPS + units; }
+  __host__ __device__ size_t lj() const { return (size_t)units * units * TAPS + units; }
+  __host__ __device__ size_t base(int st) const { return (size_t)st * (l0() + (size_t)(n_layer - 1) * lj() + (size_t)f_regular * units + f_regular); }
+  __host__ __device__ int fout(int st) const { return st == n_stacks - 1 ? f_last : f_regular; }
+  __host__ __device__ size_t conv_w(int st, int j) const { return base(st) + (j == 0 ? 0 : l0() + (size_t)(j - 1) * lj()); }
+  __host__ __device__ size_t conv_b(int st, int j) const { return conv_w(st, j) + (size_t)units * (j == 0 ? cin0 : units) * TAPS; }
+  __host__ __device__ size_t lin_w(int st) const { return base(st) + l0() + (size_t)(n_layer - 1) * lj(); }
+  __host__ __device__ size_t lin_b(int st) const { return lin_w(st) + (size_t)fout(st) * units; }
+};
+
+struct Args {
+  const uint8_t* wimg;
+  const float* params;
+  const float* received;       // dec: (B, L, 3)
+  float* out;                  // dec: (B, L, 1)
+  float* trace;                // dec: NULL or (n_stacks, B, L, F)
+  const float* u;              // enc: bits (B, L, 1)
+  float* x_tx;                 // enc: un-normalised codes (B, L, 3)
+  double* stats;               // enc: running (sum, sum of squares)
+  int* err;
+  const int32_t* perm;
+  const int32_t* inv_perm;
+  int B, L, F, n_stacks, n_layer, extrinsic, n_groups, cw_per_group, enc;
+  uint32_t stack_bytes;
+  Layout lay;
+};
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// K element e (0..15) of k-step ks of a units->units layer -> weight W[o, c, t] (0 for padding)
+__device__ __forceinline__ float conv_w_elem(const float* __restrict__ w, int units, int o, int ks, int e) {
+  if (o >= units) return 0.f;
+  int c, t;
+  if (ks < 30) { t = ks / 6; c = 16 * (ks % 6) + e; }
+  else { t = 2 * (ks - 30) + (e >> 3); c = 96 + (e & 7); }
+  if (t >= TAPS || c >= units) return 0.f;
+  return w[((size_t)o * units + c) * TAPS + t];
+}
+__device__ __forceinline__ float l0_w_elem(const float* __restrict__ w, int units, int cin, int o, int ks, int e) {
+  if (o >= units) return 0.f;
+  const int t = 2 * ks + (e >> 3), c = e & 7;
+  if (t >= TAPS || c >= cin) return 0.f;
+  return w[((size_t)o * cin + c) * TAPS + t];
+}
+
+// weight image (bf16), per stack: [L0 hi slot][L0 lo slot][(n_layer-1) x (11 hi slots, 11 lo slots)]; one slot = 3 k-steps,
+// one k-step = 2 chunks [112 columns][8 K elements]
+__global__ void pack_x3_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ img, const Layout lay, uint32_t stack_elems) {
+  const size_t total = (size_t)lay.n_stacks * stack_elems;
+  constexpr uint32_t slot_elems = SLOT_B / 2;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int st = (int)(idx / stack_elems);
+    uint32_t r = (uint32_t)(idx % stack_elems);
+    const int sl = (int)(r / slot_elems);
+    r %= slot_elems;
+    const int k3 = (int)(r / (KSTEP_B / 2)), h = (int)(r / (NPAD * 8)) & 1, n = (int)(r / 8) % NPAD, e = h * 8 + (int)(r % 8);
+    float v;
+    int part;
+    if (sl < 2) {
+      part = sl;
+      v = l0_w_elem(params + lay.conv_w(st, 0), lay.units, lay.cin0, n, k3, e);
+    } else {
+      const int q = sl - 2, j = 1 + q / (2 * SLOTS_PASS), within = q % (2 * SLOTS_PASS);
+      part = within / SLOTS_PASS;
+      v = conv_w_elem(params + lay.conv_w(st, j), lay.units, n, (within % SLOTS_PASS) * KS_PER_SLOT + k3, e);
+    }
+    const float hi = bf16_round(v);
+    img[idx] = __float2bfloat16_rn(part == 0 ? hi : v - hi);
+  }
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N_EPI_THREADS) : "memory"); }
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// ELU (alpha 1, cnn_utils.py:24-25): ex2.approx is accurate to ~2^-22 of its result, so e^v - 1 carries an absolute error of
+// ~2.4e-7, far inside the 1e-4 gate
+__device__ __forceinline__ float elu_x3(float v) { return v > 0.f ? v : fast_exp2(v * 1.4426950408889634f) - 1.0f; }
+// v -> (bf16 hi, bf16 lo) with hi + lo = v to 16 mantissa bits; returned as the two 16-bit patterns
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const Smem S = make_smem();
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = a.L, F = a.F, CW_ROWS = a.L + 2;
+  const int n_stacks = a.n_stacks, n_layer = a.n_layer;
+  const int slots_per_stack = 2 + 2 * SLOTS_PASS * (n_layer - 1);
+  auto bar = [&](int i) { return sbase + S.bars + 8u * (uint32_t)i; };
+
+  // ---- one-time setup ----------------------------------------------------------------------
+  for (uint32_t i = threadIdx.x * 16; i < S.bars; i += N_THREADS * 16) st_shared_v4(sbase + i, 0u, 0u, 0u, 0u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
+    mbar_init(bar(B_ACC), 1);
+    mbar_init(bar(B_ACT), N_EPI_WARPS);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < L; i += N_THREADS) {
+    st_shared_u16(sbase + S.perm + 2 * i, (uint16_t)a.perm[i]);
+    st_shared_u16(sbase + S.inv_perm + 2 * i, (uint16_t)a.inv_perm[i]);
+  }
+  if (warp == WARP_MMA) tmem_alloc<1>(sbase + S.tmem_ptr, TMEM_COLS);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sbase + S.tmem_ptr) : "memory");
+
+  if (warp == WARP_PRODUCER) {
+    // ================= weight producer ==================================================================
+    if (lane == 0) {
+      uint32_t pos = 0, phase = 0;
+      for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x)
+        for (int st = 0; st < n_stacks; ++st) {
+          const uint8_t* src = a.wimg + (size_t)st * a.stack_bytes;
+          for (int i = 0; i < slots_per_stack; ++i) {
+            mbar_wait(bar(B_WEMPTY + pos), phase ^ 1, a.err, 21);
+            mbar_arrive_expect_tx(bar(B_WFULL + pos), SLOT_B);
+            bulk_g2s(sbase + S.wslot + pos * SLOT_B, src, SLOT_B, bar(B_WFULL + pos));
+            src += SLOT_B;
+            if (++pos == NS) { pos = 0; phase ^= 1; }
+          }
+        }
+    }
+  } else if (warp == WARP_MMA) {
+    // ================= MMA issuer: the warp runs converged, one elected lane issues =====================
+    constexpr uint32_t IDESC = make_idesc(128, NPAD);
+    uint32_t pos = 0, wphase = 0, n_act = 0;
+    const uint32_t act_hi = sbase + S.act_hi, act_lo = sbase + S.act_lo;
+    for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x)
+      for (int st = 0; st < n_stacks; ++st) {
+        const uint32_t xsel = (uint32_t)(a.enc ? (st == 2) : (st & 1));     // enc: branch 3 reads the interleaved bits
+        const uint32_t xin_hi = sbase + S.xin_hi[0] + xsel * CHUNK_B, xin_lo = sbase + S.xin_lo[0] + xsel * CHUNK_B;
+        for (int layer = 0; layer < n_layer; ++layer) {
+          mbar_wait(bar(B_ACT), n_act & 1, a.err, 22);       // this layer's input is in place (and the accumulators are drained)
+          ++n_act;
+          tc_fence_after();
+          if (layer == 0) {
+            // slots: W0_hi (x_hi and x_lo chains), W0_lo (x_hi chain)
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+              mbar_wait(bar(B_WFULL + pos), wphase, a.err, 23);
+              tc_fence_after();
+              const uint32_t wlo = dlo(sbase + S.wslot + pos * SLOT_B, WCHUNK_B);
+              if (elect_one()) {
+#pragma unroll
+                for (int m = 0; m < N_TILES; ++m) {
+                  const uint32_t d_tmem = tmem_base + (uint32_t)(m * NPAD);
+#pragma unroll
+                  for (int ks = 0; ks < KS_L0; ++ks) {
+                    const uint32_t off = (uint32_t)(128 * m + 2 * ks) * ROW_B;
+                    umma_bf16<1>(d_tmem, dfull(dlo(xin_hi + off, ROW_B)), dfull(wlo + (uint32_t)(ks * KSTEP_B) / 16), IDESC, (part | ks) != 0);
+                    if (part == 0)
+                      umma_bf16<1>(d_tmem, dfull(dlo(xin_lo + off, ROW_B)), dfull(wlo + (uint32_t)(ks * KSTEP_B) / 16), IDESC, 1);
+                  }
+                }
+                umma_commit_1(bar(B_WEMPTY + pos));
+                if (part == 1) umma_commit_1(bar(B_ACC));
+              }
+              __syncwarp();
+              if (++pos == NS) { pos = 0; wphase ^= 1; }
+            }
+          } else {
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+#pragma unroll
+              for (int s = 0; s < SLOTS_PASS; ++s) {
+                mbar_wait(bar(B_WFULL + pos), wphase, a.err, 23);
+                tc_fence_after();
+                const uint32_t wlo = dlo(sbase + S.wslot + pos * SLOT_B, WCHUNK_B);
+                if (elect_one()) {
+#pragma unroll
+                  for (int m = 0; m < N_TILES; ++m) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(m * NPAD);
+#pragma unroll
+                    for (int k3 = 0; k3 < KS_PER_SLOT; ++k3) {
+                      const int ks = s * KS_PER_SLOT + k3;
+                      // A operand: (chunk pair, tap) for ks < 30, else chunk 12 with two taps in one k-step
+                      const uint32_t off = ks < 30 ? (uint32_t)(2 * (ks % 6)) * CHUNK_B + (uint32_t)(128 * m + ks / 6) * ROW_B
+                                                   : (uint32_t)12 * CHUNK_B + (uint32_t)(128 * m + 2 * (ks - 30)) * ROW_B;
+                      const uint32_t lbo = ks < 30 ? CHUNK_B : ROW_B;
+                      const uint64_t bdesc = dfull(wlo + (uint32_t)(k3 * KSTEP_B) / 16);
+                      umma_bf16<1>(d_tmem, dfull(dlo(act_hi + off, lbo)), bdesc, IDESC, (part | s | k3) != 0);
+                      if (part == 0) umma_bf16<1>(d_tmem, dfull(dlo(act_lo + off, lbo)), bdesc, IDESC, 1);
+                    }
+                  }
+                  umma_commit_1(bar(B_WEMPTY + pos));
+                  if (part == 1 && s == SLOTS_PASS - 1) umma_commit_1(bar(B_ACC));
+                }
+                __syncwarp();
+                if (++pos == NS) { pos = 0; wphase ^= 1; }
+              }
+            }
+          }
+        }
+      }
+  } else {
+    // ================= epilogue warps: one activation row per thread =====================================
+    const int tile = warp >> 2, q = warp & 3;
+    const int tid = threadIdx.x;                      // 0..255
+    const int g_row = 128 * tile + 32 * q + lane;     // row of the group this thread owns in every epilogue
+    const uint32_t brow = (uint32_t)(g_row + HALO_LO);
+    const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(tile * NPAD);
+    const uint32_t tab = sbase + S.tab;
+    uint32_t n_acc = 0;
+    for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
+      const int cw0 = g * a.cw_per_group;
+      const int n_cw = max(0, min(a.cw_per_group, a.B - cw0));
+      const int g_cw = g_row / CW_ROWS, g_l = g_row - g_cw * CW_ROWS;
+      const bool valid = (g_l < L) && (g_cw < n_cw);
+      const uint32_t keep = valid ? 0xFFFFFFFFu : 0u;
+
+      // ---- group start: stack inputs (prior channels = 0, decoders.py:227) ------------------------------
+      epi_bar_sync();                                 // (every thread is done with the previous group's buffers)
+#pragma unroll 1
+      for (uint32_t i = tid * 16; i < S.wslot - S.xin_hi[0]; i += N_EPI_THREADS * 16) st_shared_v4(sbase + S.xin_hi[0] + i, 0u, 0u, 0u, 0u);
+      epi_bar_sync();
+      {
+        const int sc = tid / L, sl = tid - sc * L;
+        if (tid < n_cw * L) {
+          const uint32_t row = (uint32_t)(sc * CW_ROWS + sl + HALO_LO);
+          const uint32_t row_i = (uint32_t)(sc * CW_ROWS + ld_shared_u16(sbase + S.inv_perm + 2 * sl) + HALO_LO);
+          if (a.enc) {
+            const uint16_t x = bf16_bits(2.0f * a.u[(size_t)cw0 * L + tid] - 1.0f);              // encoders.py:362 (+-1: exact in bf16)
+            st_shared_u16(sbase + S.xin_hi[0] + row * ROW_B, x);          // branches 1, 2
+            st_shared_u16(sbase + S.xin_hi[1] + row_i * ROW_B, x);        // branch 3: x_int[i] = x[p[i]]   (encoders.py:369)
+          } else {
+            const float* rsrc = a.received + ((size_t)cw0 * L + tid) * 3;
+            const float r0 = __ldg(rsrc), r1 = __ldg(rsrc + 1), r2 = __ldg(rsrc + 2);
+            uint32_t h01, l01, h2, l2;
+            split2(r0, r1, h01, l01);
+            split2(r2, 0.f, h2, l2);
+            // stack "dec1" input: [r_sys, r_par1, prior...]  (decoders.py:221, 223, 230)
+            st_shared_f32(sbase + S.master[0] + row * 32, r0);
+            st_shared_f32(sbase + S.master[0] + row * 32 + 4, r1);
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + S.xin_hi[0] + row * ROW_B), "r"(h01) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + S.xin_lo[0] + row * ROW_B), "r"(l01) : "memory");
+            // stack "dec2" input: [r_sys_int, r_par2, x_plr_int...], r_sys_int[i] = r_sys[p[i]]   (decoders.py:222, 224, 240)
+            st_shared_f32(sbase + S.master[1] + row_i * 32, r0);
+            st_shared_f32(sbase + S.master[1] + row * 32 + 4, r2);
+            st_shared_u16(sbase + S.xin_hi[1] + row_i * ROW_B, (uint16_t)(h01 & 0xFFFFu));
+            st_shared_u16(sbase + S.xin_lo[1] + row_i * ROW_B, (uint16_t)(l01 & 0xFFFFu));
+            st_shared_u16(sbase + S.xin_hi[1] + row * ROW_B + 2, (uint16_t)(h2 & 0xFFFFu));
+            st_shared_u16(sbase + S.xin_lo[1] + row * ROW_B + 2, (uint16_t)(l2 & 0xFFFFu));
+          }
+        }
+      }
+      bool first_arrive = true;       // the group start and the first stack's tables are published by ONE arrival
+
+      for (int st = 0; st < n_stacks; ++st) {
+        const int fout = a.lay.fout(st);
+        const bool last_stack = (st == n_stacks - 1);
+        // ---- this stack's fp32 tables: conv biases, Linear weights and bias ----------------------------
+        if (st > 0) epi_bar_sync();                    // every warp is done with the previous stack's tables
+        for (int i = tid; i < n_layer * NPAD; i += N_EPI_THREADS) {
+          const int j = i / NPAD, c = i - j * NPAD;
+          st_shared_f32(tab + 4u * (uint32_t)(TAB_BIAS + i), c < a.lay.units ? __ldg(a.params + a.lay.conv_b(st, j) + c) : 0.f);
+        }
+        for (int i = tid; i < MAX_F * NPAD; i += N_EPI_THREADS) {
+          const int f = i / NPAD, c = i - f * NPAD;
+          st_shared_f32(tab + 4u * (uint32_t)(TAB_V + i), (f < fout && c < a.lay.units) ? __ldg(a.params + a.lay.lin_w(st) + (size_t)f * a.lay.units + c) : 0.f);
+        }
+        if (tid < 8) st_shared_f32(tab + 4u * (uint32_t)(TAB_C + tid), tid < fout ? __ldg(a.params + a.lay.lin_b(st) + tid) : 0.f);
+        if (first_arrive) {
+          fence_proxy_async();                         // the stack inputs were written with generic stores
+          epi_bar_sync();
+          if (lane == 0) mbar_arrive_local(bar(B_ACT));
+          first_arrive = false;
+        } else {
+          epi_bar_sync();
+        }
+
+        for (int layer = 0; layer < n_layer; ++layer) {
+          const bool lin_layer = (layer == n_layer - 1);
+          mbar_wait(bar(B_ACC), n_acc & 1, a.err, 24);
+          ++n_acc;
+          tc_fence_after();
+          const uint32_t btab = tab + 4u * (uint32_t)(TAB_BIAS + layer * NPAD);
+          float lin[MAX_F] = {0.f, 0.f, 0.f, 0.f, 0.f};
+          uint32_t ra[16], rb[16];
+          tmem_ld16(taddr, ra);
+#pragma unroll
+          for (int cb = 0; cb < 7; ++cb) {
+            tmem_ld_wait();
+            uint32_t* cur = (cb & 1) ? rb : ra;
+            if (cb < 6) tmem_ld16(taddr + 16 * (cb + 1), (cb & 1) ? ra : rb);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int c = 2 * cb + half;
+              if (c >= N_CHUNKS) break;
+              const float4 b0 = ld_shared_f4(btab + (uint32_t)(c * 32)), b1 = ld_shared_f4(btab + (uint32_t)(c * 32 + 16));
+              float v[8];
+              v[0] = elu_x3(__uint_as_float(cur[8 * half + 0]) + b0.x);
+              v[1] = elu_x3(__uint_as_float(cur[8 * half + 1]) + b0.y);
+              v[2] = elu_x3(__uint_as_float(cur[8 * half + 2]) + b0.z);
+              v[3] = elu_x3(__uint_as_float(cur[8 * half + 3]) + b0.w);
+              v[4] = elu_x3(__uint_as_float(cur[8 * half + 4]) + b1.x);
+              v[5] = elu_x3(__uint_as_float(cur[8 * half + 5]) + b1.y);
+              v[6] = elu_x3(__uint_as_float(cur[8 * half + 6]) + b1.z);
+              v[7] = elu_x3(__uint_as_float(cur[8 * half + 7]) + b1.w);
+              if (!lin_layer) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) split2(v[2 * j], v[2 * j + 1], h[j], l[j]);
+                st_shared_v4(sbase + S.act_hi + (uint32_t)c * CHUNK_B + brow * ROW_B, h[0] & keep, h[1] & keep, h[2] & keep, h[3] & keep);
+                st_shared_v4(sbase + S.act_lo + (uint32_t)c * CHUNK_B + brow * ROW_B, l[0] & keep, l[1] & keep, l[2] & keep, l[3] & keep);
+              } else {
+                // Linear of the stack output, in fp32 straight from the accumulators (decoders.py:232, 243; encoders.py:364)
+#pragma unroll
+                for (int f = 0; f < MAX_F; ++f) {
+                  if (f >= fout) break;
+                  const float4 w0 = ld_shared_f4(tab + 4u * (uint32_t)(TAB_V + f * NPAD + c * 8)), w1 = ld_shared_f4(tab + 4u * (uint32_t)(TAB_V + f * NPAD + c * 8 + 4));
+                  float s = lin[f];
+                  s = fmaf(w0.x, v[0], s); s = fmaf(w0.y, v[1], s); s = fmaf(w0.z, v[2], s); s = fmaf(w0.w, v[3], s);
+                  s = fmaf(w1.x, v[4], s); s = fmaf(w1.y, v[5], s); s = fmaf(w1.z, v[6], s); s = fmaf(w1.w, v[7], s);
+                  lin[f] = s;
+                }
+              }
+            }
+          }
+          if (lin_layer) {
+            const float4 c0 = ld_shared_f4(tab + 4u * (uint32_t)TAB_C);
+            const float c4 = ld_shared_f32(tab + 4u * (uint32_t)(TAB_C + 4));
+            lin[0] += c0.x; lin[1] += c0.y; lin[2] += c0.z; lin[3] += c0.w; lin[4] += c4;
+            if (a.enc) {
+              // x_tx[:, :, branch] = ELU(Linear(h)) (encoders.py:364, 367, 371) + the power sums
+              double s1 = 0.0, s2 = 0.0;
+              if (valid) {
+                const float z = lin[0];
+                const float v = z > 0.f ? z : expm1f(z);
+                a.x_tx[((size_t)(cw0 + g_cw) * L + g_l) * 3 + st] = v;
+                s1 = (double)v;
+                s2 = (double)v * (double)v;
+              }
+#pragma unroll
+              for (int d = 16; d > 0; d >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+              }
+              if (lane == 0 && (s1 != 0.0 || s2 != 0.0)) { atomicAdd(a.stats + 0, s1); atomicAdd(a.stats + 1, s2); }
+            } else if (valid) {
+              const int cw = cw0 + g_cw;
+              if (a.trace) {
+                float* tr = a.trace + (((size_t)st * a.B + cw) * L + g_l) * F;
+                const int nf = last_stack ? 1 : F;
+#pragma unroll
+                for (int f = 0; f < MAX_F; ++f)
+                  if (f < nf) tr[f] = lin[f];
+              }
+              // where position l lands: interleave after dec1 (x_int[i] = x[p[i]]: l -> rp[l]), de-interleave after dec2 (l -> p[l])
+              const uint32_t dl = ld_shared_u16(sbase + ((st & 1) ? S.perm : S.inv_perm) + 2 * g_l);
+              if (last_stack) {
+                a.out[(size_t)cw * L + dl] = 1.f / (1.f + __expf(-lin[0]));                     // decoders.py:267
+              } else {
+                const uint32_t cur_m = sbase + S.master[st & 1] + brow * 32, nxt = (uint32_t)((st & 1) ^ 1);
+                const uint32_t drow = (uint32_t)(g_cw * CW_ROWS) + dl + HALO_LO;
+                float e[6];
+#pragma unroll
+                for (int f = 0; f < 5; ++f) {
+                  const float prior = a.extrinsic ? ld_shared_f32(cur_m + 8 + 4 * f) : 0.f;     // decoders.py:235-236, 246-247
+                  e[f] = f < F ? lin[f] - prior : 0.f;
+                  st_shared_f32(sbase + S.master[nxt] + drow * 32 + 8 + 4 * f, e[f]);
+                }
+                e[5] = 0.f;
+                uint32_t h0, l0, h1, l1, h2, l2;
+                split2(e[0], e[1], h0, l0);
+                split2(e[2], e[3], h1, l1);
+                split2(e[4], e[5], h2, l2);
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + S.xin_hi[nxt] + drow * ROW_B + 4), "r"(h0) : "memory");
+                st_shared_v2(sbase + S.xin_hi[nxt] + drow * ROW_B + 8, h1, h2);
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + S.xin_lo[nxt] + drow * ROW_B + 4), "r"(l0) : "memory");
+                st_shared_v2(sbase + S.xin_lo[nxt] + drow * ROW_B + 8, l1, l2);
+              }
+            }
+          }
+          // the next layer's (or stack's) MMAs may start: every warp reports on its own; the group's very last epilogue
+          // is followed by the next group's start, which reports instead
+          if (!(last_stack && lin_layer)) {
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_local(bar(B_ACT));
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, TMEM_COLS);
+  }
+}
+
+uint32_t stack_bytes(int n_layer) { return (uint32_t)(2 + 2 * SLOTS_PASS * (n_layer - 1)) * SLOT_B; }
+
+bool supported(int L, int n_layer, int units, int k, int F, const char** why) {
+  static thread_local char msg[160];
+  *why = msg;
+  if (k != TAPS) { snprintf(msg, sizeof msg, "kernel_size %d (only 5 is built for the tensor paths)", k); return false; }
+  if (units < 1 || units > UNITS_MAX) { snprintf(msg, sizeof msg, "num_unit %d > %d", units, UNITS_MAX); return false; }
+  if (F < 1 || F > MAX_F) { snprintf(msg, sizeof msg, "num_iter_ft %d > %d", F, MAX_F); return false; }
+  if (n_layer < 1 || n_layer > MAX_LAYER) { snprintf(msg, sizeof msg, "num_layer %d outside 1..%d", n_layer, MAX_LAYER); return false; }
+  if (L < 1 || L > GROUP_ROWS) { snprintf(msg, sizeof msg, "block_len %d > %d (one codeword must fit a 256-row group)", L, GROUP_ROWS); return false; }
+  *why = nullptr;
+  return true;
+}
+
+int launch_setup(int* n_sm_out) {
+  static DeviceOnce once;
+  return device_once(once, "x3_kernel", [](int dev) -> int {
+    int rc = require_sm100(dev, "the bf16x3 tensor path");
+    if (rc) return rc;
+    cudaError_t e = cudaFuncSetAttribute(x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)make_smem().total);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(x3_kernel): %s", cudaGetErrorString(e)); return TAE_ECUDA; }
+    return TAE_OK;
+  }, n_sm_out);
+}
+
+int pack(const Layout& lay, const float* params, void* packed, cudaStream_t s) {
+  const uint32_t stack_elems = stack_bytes(lay.n_layer) / 2;
+  const size_t total = (size_t)lay.n_stacks * stack_elems;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+  pack_x3_kernel<<<blocks, 256, 0, s>>>(params, reinterpret_cast<__nv_bfloat16*>(packed), lay, stack_elems);
+  return after_launch("pack_x3_kernel");
+}
+
+int launch(Args& a, void* ws, size_t ws_bytes, cudaStream_t s, const char* who) {
+  if (ws_bytes < 256) { set_error("%s: workspace %zu < 256 bytes", who, ws_bytes); return TAE_EWORKSPACE; }
+  int n_sm = 0;
+  int rc = launch_setup(&n_sm);
+  if (rc) return rc;
+  a.err = wait_code_slot(ws);
+  a.cw_per_group = (GROUP_ROWS + 2) / (a.L + 2);
+  a.n_groups = (a.B + a.cw_per_group - 1) / a.cw_per_group;
+  a.stack_bytes = stack_bytes(a.n_layer);
+  const int grid = std::min(a.n_groups, n_sm);
+  x3_kernel<<<grid, N_THREADS, make_smem().total, s>>>(a);
+  return after_launch(who);
+}
+
+}  // namespace x3
+}  // namespace
+
+bool dec_x3_supported(const TaeDecConfig& c, const char** why) {
+  return x3::supported(c.block_len, c.num_layer, c.num_unit, c.kernel_size, c.num_iter_ft, why);
+}
+size_t dec_x3_packed_bytes(const TaeDecConfig& c) { return (size_t)2 * c.num_iteration * x3::stack_bytes(c.num_layer); }
+int dec_x3_pack(const TaeDecConfig& c, const float* params, void* packed, cudaStream_t s) {
+  const x3::Layout lay{2 * c.num_iteration, c.num_layer, c.num_unit, 2 + c.num_iter_ft, c.num_iter_ft, 1};
+  return x3::pack(lay, params, packed, s);
+}
+int dec_forward_x3(const TaeDecConfig& c, const float* params, const void* packed, const float* received, const int32_t* perm,
+                   const int32_t* inv_perm, float* out, float* trace, int B, void* ws, size_t ws_bytes, cudaStream_t s) {
+  x3::Args a{};
+  a.wimg = reinterpret_cast<const uint8_t*>(packed);
+  a.params = params; a.received = received; a.out = out; a.trace = trace; a.perm = perm; a.inv_perm = inv_perm;
+  a.B = B; a.L = c.block_len; a.F = c.num_iter_ft; a.n_stacks = 2 * c.num_iteration; a.n_layer = c.num_layer;
+  a.extrinsic = c.extrinsic; a.enc = 0;
+  a.lay = x3::Layout{a.n_stacks, c.num_layer, c.num_unit, 2 + c.num_iter_ft, c.num_iter_ft, 1};
+  return x3::launch(a, ws, ws_bytes, s, "x3_kernel(dec)");
+}
+
+bool enc_x3_supported(const TaeEncConfig& c, const char** why) {
+  return x3::supported(c.block_len, c.num_layer, c.num_unit, c.kernel_size, 1, why);
+}
+size_t enc_x3_packed_bytes(const TaeEncConfig& c) { return (size_t)3 * x3::stack_bytes(c.num_layer); }
+int enc_x3_pack(const TaeEncConfig& c, const float* params, void* packed, cudaStream_t s) {
+  const x3::Layout lay{3, c.num_layer, c.num_unit, 1, 1, 1};
+  return x3::pack(lay, params, packed, s);
+}
+int enc_forward_x3(const TaeEncConfig& c, const float* params, const void* packed, const float* u, const int32_t* perm,
+                   const int32_t* inv_perm, float* x_tx, double* stats, int B, void* ws, size_t ws_bytes, cudaStream_t s) {
+  x3::Args a{};
+  a.wimg = reinterpret_cast<const uint8_t*>(packed);
+  a.params = params; a.u = u; a.x_tx = x_tx; a.stats = stats; a.perm = perm; a.inv_perm = inv_perm;
+  a.B = B; a.L = c.block_len; a.F = 1; a.n_stacks = 3; a.n_layer = c.num_layer; a.extrinsic = 0; a.enc = 1;
+  a.lay = x3::Layout{3, c.num_layer, c.num_unit, 1, 1, 1};
+  return x3::launch(a, ws, ws_bytes, s, "x3_kernel(enc)");
+}
+
+}  // namespace tae

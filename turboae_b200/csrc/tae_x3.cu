@@ -28,6 +28,7 @@
 //   * decoder: the stack inputs (received values and priors) are kept as an fp32 master copy [row][8] next to their hi / lo
 //     operand chunks; the extrinsic subtraction uses the fp32 prior, and (de)interleave is the row index of the store.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -37,8 +38,21 @@
 
 namespace tae {
 
+// Operand format of the split: 0 = bf16 hi + bf16 lo (16 mantissa bits together), 1 = fp16 hi + fp16 lo (22 bits; values are
+// clamped to +-65504, fp16's finite range).  Same tcgen05.mma kind::f16, same rate.
+#ifndef TAE_X3_FP16
+#define TAE_X3_FP16 0
+#endif
+
 namespace {
 namespace x3 {
+
+constexpr bool FP16 = TAE_X3_FP16 != 0;
+// instruction descriptor (kind::f16): D fp32, A/B fp16 (format 0) or bf16 (format 1), both K-major
+__host__ __device__ constexpr uint32_t make_idesc_x3(int m, int n) {
+  return (1u << 4) | (FP16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+constexpr float F16_MAX = 65504.f;
 
 constexpr int GROUP_ROWS = 256;
 constexpr int N_TILES = 2;
@@ -61,12 +75,21 @@ constexpr int TAB_BIAS = 0, TAB_V = MAX_LAYER * NPAD, TAB_C = TAB_V + MAX_F * NP
 constexpr int N_EPI_WARPS = 8, N_EPI_THREADS = 256;     // warp w: tile w >> 2, TMEM lane quadrant w & 3
 constexpr int WARP_MMA = 8, WARP_PRODUCER = 9;
 constexpr int N_THREADS = 320;
-constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t TMEM_COLS = 512;                     // 2 accumulator buffers (layer parity) x 2 tiles x 112 columns
+constexpr uint32_t TMEM_BUF_COLS = N_TILES * NPAD;      // 224
+constexpr int N_STAGES = 7;                             // epilogue stages = 16-column blocks = chunk pairs 0..5, then chunk 12
 
 struct Smem {
   uint32_t act_hi, act_lo, xin_hi[2], xin_lo[2], master[2], wslot, tab, perm, inv_perm, bars, tmem_ptr, total;
 };
-enum { B_WFULL = 0, B_WEMPTY = NS, B_ACC = 2 * NS, B_ACT = 2 * NS + 1, N_BARS = 2 * NS + 2 };
+// B_WFULL / B_WEMPTY[p]: ring slot p landed / its MMAs have completed.  B_ACC: all MMAs of a layer have completed (one phase per
+// layer; waited for by every epilogue warp).  B_ACT: the inputs of a stack's FIRST layer are in place (group start; Linear
+// epilogue of the previous stack), one phase per stack.  B_STAGE[c]: every epilogue warp has written chunk stage c of the layer
+// output (one phase per non-final layer epilogue): the next layer's MMAs start on the chunks that are there while the epilogue is
+// still writing the rest -- the K order of a units->units layer is chunk-major for that reason.
+enum { B_WFULL = 0, B_WEMPTY = NS, B_ACC = 2 * NS, B_ACT = 2 * NS + 1, B_STAGE = 2 * NS + 2, N_BARS = 2 * NS + 2 + N_STAGES };
+// the last epilogue stage whose chunks slot s of the W_hi pass reads (k-steps 3s .. 3s+2, chunk-major: k-step 5 cp + t)
+__host__ __device__ constexpr int stage_of_slot(int s) { return (3 * s + 2) < 30 ? (3 * s + 2) / 5 : 6; }
 
 __host__ __device__ inline Smem make_smem() {
   Smem s{};
@@ -119,13 +142,22 @@ struct Args {
   Layout lay;
 };
 
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// the 16-bit pattern of the split format nearest to x, and its value
+__device__ __forceinline__ uint16_t half_bits(float x) {
+  if (FP16) { const __half h = __float2half_rn(fminf(fmaxf(x, -F16_MAX), F16_MAX)); return *reinterpret_cast<const uint16_t*>(&h); }
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  return *reinterpret_cast<const uint16_t*>(&h);
+}
+__device__ __forceinline__ float half_value(uint16_t b) {
+  if (FP16) return __half2float(*reinterpret_cast<const __half*>(&b));
+  return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&b));
+}
 
 // K element e (0..15) of k-step ks of a units->units layer -> weight W[o, c, t] (0 for padding)
 __device__ __forceinline__ float conv_w_elem(const float* __restrict__ w, int units, int o, int ks, int e) {
   if (o >= units) return 0.f;
   int c, t;
-  if (ks < 30) { t = ks / 6; c = 16 * (ks % 6) + e; }
+  if (ks < 30) { t = ks % 5; c = 16 * (ks / 5) + e; }
   else { t = 2 * (ks - 30) + (e >> 3); c = 96 + (e & 7); }
   if (t >= TAPS || c >= units) return 0.f;
   return w[((size_t)o * units + c) * TAPS + t];
@@ -139,7 +171,7 @@ __device__ __forceinline__ float l0_w_elem(const float* __restrict__ w, int unit
 
 // weight image (bf16), per stack: [L0 hi slot][L0 lo slot][(n_layer-1) x (11 hi slots, 11 lo slots)]; one slot = 3 k-steps,
 // one k-step = 2 chunks [112 columns][8 K elements]
-__global__ void pack_x3_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ img, const Layout lay, uint32_t stack_elems) {
+__global__ void pack_x3_kernel(const float* __restrict__ params, uint16_t* __restrict__ img, const Layout lay, uint32_t stack_elems) {
   const size_t total = (size_t)lay.n_stacks * stack_elems;
   constexpr uint32_t slot_elems = SLOT_B / 2;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -158,8 +190,8 @@ __global__ void pack_x3_kernel(const float* __restrict__ params, __nv_bfloat16* 
       part = within / SLOTS_PASS;
       v = conv_w_elem(params + lay.conv_w(st, j), lay.units, n, (within % SLOTS_PASS) * KS_PER_SLOT + k3, e);
     }
-    const float hi = bf16_round(v);
-    img[idx] = __float2bfloat16_rn(part == 0 ? hi : v - hi);
+    const uint16_t hi = half_bits(v);
+    img[idx] = part == 0 ? hi : half_bits(v - half_value(hi));
   }
 }
 
@@ -172,8 +204,16 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
 // ELU (alpha 1, cnn_utils.py:24-25): ex2.approx is accurate to ~2^-22 of its result, so e^v - 1 carries an absolute error of
 // ~2.4e-7, far inside the 1e-4 gate
 __device__ __forceinline__ float elu_x3(float v) { return v > 0.f ? v : fast_exp2(v * 1.4426950408889634f) - 1.0f; }
-// v -> (bf16 hi, bf16 lo) with hi + lo = v to 16 mantissa bits; returned as the two 16-bit patterns
+// (a, b) -> packed hi pair and packed lo pair with hi + lo = value to 16 (bf16) / 22 (fp16) mantissa bits
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  if (FP16) {
+    const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -F16_MAX), F16_MAX), fminf(fmaxf(b, -F16_MAX), F16_MAX));
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+    return;
+  }
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   const float2 hf = __bfloat1622float2(h);
   const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
@@ -198,6 +238,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
     for (int i = 0; i < NS; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
     mbar_init(bar(B_ACC), 1);
     mbar_init(bar(B_ACT), N_EPI_WARPS);
+    for (int i = 0; i < N_STAGES; ++i) mbar_init(bar(B_STAGE + i), N_EPI_WARPS);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < L; i += N_THREADS) {
@@ -230,18 +271,19 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
     }
   } else if (warp == WARP_MMA) {
     // ================= MMA issuer: the warp runs converged, one elected lane issues =====================
-    constexpr uint32_t IDESC = make_idesc(128, NPAD);
-    uint32_t pos = 0, wphase = 0, n_act = 0;
+    constexpr uint32_t IDESC = make_idesc_x3(128, NPAD);
+    uint32_t pos = 0, wphase = 0, n_act = 0, n_stage = 0;
     const uint32_t act_hi = sbase + S.act_hi, act_lo = sbase + S.act_lo;
     for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x)
       for (int st = 0; st < n_stacks; ++st) {
         const uint32_t xsel = (uint32_t)(a.enc ? (st == 2) : (st & 1));     // enc: branch 3 reads the interleaved bits
         const uint32_t xin_hi = sbase + S.xin_hi[0] + xsel * CHUNK_B, xin_lo = sbase + S.xin_lo[0] + xsel * CHUNK_B;
         for (int layer = 0; layer < n_layer; ++layer) {
-          mbar_wait(bar(B_ACT), n_act & 1, a.err, 22);       // this layer's input is in place (and the accumulators are drained)
-          ++n_act;
-          tc_fence_after();
+          const uint32_t tbuf = tmem_base + (uint32_t)(layer & 1) * TMEM_BUF_COLS;     // accumulators alternate by layer parity
           if (layer == 0) {
+            mbar_wait(bar(B_ACT), n_act & 1, a.err, 22);     // the stack input is in place
+            ++n_act;
+            tc_fence_after();
             // slots: W0_hi (x_hi and x_lo chains), W0_lo (x_hi chain)
 #pragma unroll
             for (int part = 0; part < 2; ++part) {
@@ -251,7 +293,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
               if (elect_one()) {
 #pragma unroll
                 for (int m = 0; m < N_TILES; ++m) {
-                  const uint32_t d_tmem = tmem_base + (uint32_t)(m * NPAD);
+                  const uint32_t d_tmem = tbuf + (uint32_t)(m * NPAD);
 #pragma unroll
                   for (int ks = 0; ks < KS_L0; ++ks) {
                     const uint32_t off = (uint32_t)(128 * m + 2 * ks) * ROW_B;
@@ -267,22 +309,29 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
               if (++pos == NS) { pos = 0; wphase ^= 1; }
             }
           } else {
+            const uint32_t sphase = n_stage & 1;
+            ++n_stage;
 #pragma unroll
             for (int part = 0; part < 2; ++part) {
 #pragma unroll
               for (int s = 0; s < SLOTS_PASS; ++s) {
+                // the chunks this slot's k-steps read have been written by every epilogue warp of the previous layer
+                if (part == 0) {
+#pragma unroll
+                  for (int c = (s == 0 ? 0 : stage_of_slot(s - 1) + 1); c <= stage_of_slot(s); ++c) mbar_wait(bar(B_STAGE + c), sphase, a.err, 25);
+                }
                 mbar_wait(bar(B_WFULL + pos), wphase, a.err, 23);
                 tc_fence_after();
                 const uint32_t wlo = dlo(sbase + S.wslot + pos * SLOT_B, WCHUNK_B);
                 if (elect_one()) {
 #pragma unroll
                   for (int m = 0; m < N_TILES; ++m) {
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(m * NPAD);
+                    const uint32_t d_tmem = tbuf + (uint32_t)(m * NPAD);
 #pragma unroll
                     for (int k3 = 0; k3 < KS_PER_SLOT; ++k3) {
                       const int ks = s * KS_PER_SLOT + k3;
-                      // A operand: (chunk pair, tap) for ks < 30, else chunk 12 with two taps in one k-step
-                      const uint32_t off = ks < 30 ? (uint32_t)(2 * (ks % 6)) * CHUNK_B + (uint32_t)(128 * m + ks / 6) * ROW_B
+                      // A operand, chunk-major: (chunk pair ks / 5, tap ks % 5) for ks < 30, else chunk 12 with two taps in one k-step
+                      const uint32_t off = ks < 30 ? (uint32_t)(2 * (ks / 5)) * CHUNK_B + (uint32_t)(128 * m + ks % 5) * ROW_B
                                                    : (uint32_t)12 * CHUNK_B + (uint32_t)(128 * m + 2 * (ks - 30)) * ROW_B;
                       const uint32_t lbo = ks < 30 ? CHUNK_B : ROW_B;
                       const uint64_t bdesc = dfull(wlo + (uint32_t)(k3 * KSTEP_B) / 16);
@@ -306,7 +355,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
     const int tid = threadIdx.x;                      // 0..255
     const int g_row = 128 * tile + 32 * q + lane;     // row of the group this thread owns in every epilogue
     const uint32_t brow = (uint32_t)(g_row + HALO_LO);
-    const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(tile * NPAD);
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(tile * NPAD);
     const uint32_t tab = sbase + S.tab;
     uint32_t n_acc = 0;
     for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
@@ -327,7 +376,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
           const uint32_t row = (uint32_t)(sc * CW_ROWS + sl + HALO_LO);
           const uint32_t row_i = (uint32_t)(sc * CW_ROWS + ld_shared_u16(sbase + S.inv_perm + 2 * sl) + HALO_LO);
           if (a.enc) {
-            const uint16_t x = bf16_bits(2.0f * a.u[(size_t)cw0 * L + tid] - 1.0f);              // encoders.py:362 (+-1: exact in bf16)
+            const uint16_t x = half_bits(2.0f * a.u[(size_t)cw0 * L + tid] - 1.0f);              // encoders.py:362 (+-1: exact)
             st_shared_u16(sbase + S.xin_hi[0] + row * ROW_B, x);          // branches 1, 2
             st_shared_u16(sbase + S.xin_hi[1] + row_i * ROW_B, x);        // branch 3: x_int[i] = x[p[i]]   (encoders.py:369)
           } else {
@@ -382,6 +431,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
           ++n_acc;
           tc_fence_after();
           const uint32_t btab = tab + 4u * (uint32_t)(TAB_BIAS + layer * NPAD);
+          const uint32_t taddr = taddr0 + (uint32_t)(layer & 1) * TMEM_BUF_COLS;
           float lin[MAX_F] = {0.f, 0.f, 0.f, 0.f, 0.f};
           uint32_t ra[16], rb[16];
           tmem_ld16(taddr, ra);
@@ -422,6 +472,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
                   lin[f] = s;
                 }
               }
+            }
+            if (!lin_layer) {
+              // stage cb of this layer's output is complete for this warp: the next layer's MMAs on these chunks may start
+              fence_proxy_async();
+              if (cb == 6) tc_fence_before();           // (the accumulators this warp read are drained before the last arrival)
+              __syncwarp();
+              if (lane == 0) mbar_arrive_local(bar(B_STAGE + cb));
             }
           }
           if (lin_layer) {
@@ -479,9 +536,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
               }
             }
           }
-          // the next layer's (or stack's) MMAs may start: every warp reports on its own; the group's very last epilogue
-          // is followed by the next group's start, which reports instead
-          if (!(last_stack && lin_layer)) {
+          // the next stack's first layer may start (its inputs were scattered by ALL warps): every warp reports on its own; the
+          // group's very last epilogue is followed by the next group's start, which reports instead
+          if (lin_layer && !last_stack) {
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
@@ -531,7 +588,7 @@ int pack(const Layout& lay, const float* params, void* packed, cudaStream_t s) {
   const uint32_t stack_elems = stack_bytes(lay.n_layer) / 2;
   const size_t total = (size_t)lay.n_stacks * stack_elems;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-  pack_x3_kernel<<<blocks, 256, 0, s>>>(params, reinterpret_cast<__nv_bfloat16*>(packed), lay, stack_elems);
+  pack_x3_kernel<<<blocks, 256, 0, s>>>(params, reinterpret_cast<uint16_t*>(packed), lay, stack_elems);
   return after_launch("pack_x3_kernel");
 }
 

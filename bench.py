@@ -425,7 +425,7 @@ def run_b200(a):
                 ms = timed(lambda: m.dec(m.enc(bits[0]) + noise), 3)
                 sec["channel_ae_forward_default_cw_per_s"] = B / (ms * 1e-3)
                 sec["channel_ae_forward_default"] = "Channel_AE.forward with the modules' default settings (encoder %s, decoder %s)" % (default_enc_name, m.dec.precision)
-                for prec in ("fp32", "bf16", "bf16x3"):
+                for prec in ("fp32", "bf16", "f16x3"):
                     m.enc.precision = prec
                     ms = timed(lambda: m.enc(bits[0]), 3)
                     sec["encoder_%s_cw_per_s" % prec] = B / (ms * 1e-3)
@@ -436,13 +436,13 @@ def run_b200(a):
                 sec["encoder_flop_per_cw"] = 30_360_000
                 ms = timed(lambda: m.dec.decode(recs[0][:10000], precision="fp32"), 2)       # the elementwise-1e-4 parity path
                 sec["decode_fp32_cw_per_s"] = 10000 / (ms * 1e-3)
-                # the same elementwise gate on the tensor cores: split bf16 operands (tae_x3.cu), decoder and whole forward
-                ms = timed(lambda: m.dec.decode(recs[0], precision="bf16x3"), 2)
-                sec["decode_bf16x3_cw_per_s"] = B / (ms * 1e-3)
-                m.enc.precision = "bf16x3"
-                ms = timed(lambda: m.dec.decode(m.enc(bits[0]) + noise, precision="bf16x3"), 2)
-                sec["channel_ae_forward_bf16x3_cw_per_s"] = B / (ms * 1e-3)
-                sec["bf16x3"] = "split-operand tcgen05 path (x_hi W_hi + x_lo W_hi + x_hi W_lo, fp32 bias/ELU/Linear): outputs within 1e-4 of the reference elementwise (tests/test_gpu_x3.py)"
+                # the same elementwise gate on the tensor cores: split fp16 operands (tae_x3.cu), decoder and whole forward
+                ms = timed(lambda: m.dec.decode(recs[0], precision="f16x3"), 2)
+                sec["decode_f16x3_cw_per_s"] = B / (ms * 1e-3)
+                m.enc.precision = "f16x3"
+                ms = timed(lambda: m.dec.decode(m.enc(bits[0]) + noise, precision="f16x3"), 2)
+                sec["channel_ae_forward_f16x3_cw_per_s"] = B / (ms * 1e-3)
+                sec["f16x3"] = "split-operand tcgen05 path (x_hi W_hi + x_lo W_hi + x_hi W_lo, fp32 bias/ELU/Linear): outputs within 1e-4 of the reference elementwise (tests/test_gpu_x3.py)"
                 m.enc.precision = default_enc
                 # BASELINE config 3: enc5/dec5 checkpoint, README batch 1000 (and the full 50 000)
                 m3, _, _ = build_codec("c3", device=dev, batch_size=B)
@@ -452,7 +452,7 @@ def run_b200(a):
                 sec["c3_decode_bf16_cw_per_s"] = B / (ms * 1e-3)
                 ms = timed(lambda: m3.dec(m3.enc(u3) + noise), 3)
                 sec["c3_channel_ae_forward_cw_per_s"] = B / (ms * 1e-3)
-                for prec in ("bf16x3", "bf16"):
+                for prec in ("f16x3", "bf16"):
                     m3.enc.precision = prec
                     ms = timed(lambda: m3.enc(u3), 3)
                     sec["c3_encoder_%s_cw_per_s" % prec] = B / (ms * 1e-3)

@@ -35,8 +35,9 @@ extern "C" {
 
 #define TAE_PRECISION_FP32 0  /* CUDA-core fp32 FMA path: elementwise parity (<=1e-4)  */
 #define TAE_PRECISION_BF16 1  /* tcgen05 bf16 operands, fp32 TMEM accumulation          */
-#define TAE_PRECISION_BF16X3 2 /* tcgen05, every operand split into bf16 hi + lo (three MMA chains per layer), bias / ELU /
-                                  Linear / priors in fp32: elementwise parity (<=1e-4) at tensor-core speed               */
+#define TAE_PRECISION_F16X3 2 /* tcgen05, every operand split into fp16 hi + lo (three MMA chains per layer), bias / ELU /
+                                  Linear / priors in fp32: elementwise parity (<=1e-4) at tensor-core speed; activations
+                                  beyond +-65504 (fp16's range) are clamped                                               */
 
 /* Shape of a DEC_LargeCNN (reference decoders.py:158-192; get_args.py:83-84,89-100,122). */
 typedef struct TaeDecConfig {
@@ -115,10 +116,10 @@ int tae_dec_forward(const TaeDecConfig* cfg, const float* params, const void* pa
                     float* out, float* trace, int32_t B, int32_t precision,
                     void* workspace, size_t workspace_bytes, void* stream);
 
-/* Weight image of TAE_PRECISION_BF16X3 (W_hi and W_lo slots per layer; pass it as `packed` to tae_dec_forward, which
+/* Weight image of TAE_PRECISION_F16X3 (W_hi and W_lo slots per layer; pass it as `packed` to tae_dec_forward, which
  * also reads the fp32 biases and Linear weights from `params`).  Rebuild after every weight update.               */
 size_t tae_dec_packed_bytes_x3(const TaeDecConfig* cfg);
-int    tae_dec_pack_bf16x3(const TaeDecConfig* cfg, const float* params, void* packed, void* stream);
+int    tae_dec_pack_f16x3(const TaeDecConfig* cfg, const float* params, void* packed, void* stream);
 
 /* DEC_LargeCNN.forward for HOST buffers (reference decoders.py:219 moves `received` to the device itself, and
  * trainer.py:176-177 reads the result back): `received_host` / `out_host` are host pointers (pinned memory makes the
@@ -152,12 +153,12 @@ int    tae_enc_pack_bf16(const TaeEncConfig* cfg, const float* params, void* pac
 int tae_enc_forward_bf16(const TaeEncConfig* cfg, const void* packed, const float* u, const int32_t* perm,
                          const int32_t* inv_perm, float* x_tx, double* stats, int32_t B,
                          void* workspace, size_t workspace_bytes, void* stream);
-/* The same forward with split bf16 operands (x_hi W_hi + x_lo W_hi + x_hi W_lo on the tensor cores, fp32 bias / ELU /
- * Linear): codes within 1e-5 of the fp32 path.  `packed` from tae_enc_pack_bf16x3; `params` supplies the fp32 biases and
+/* The same forward with split fp16 operands (x_hi W_hi + x_lo W_hi + x_hi W_lo on the tensor cores, fp32 bias / ELU /
+ * Linear): codes within 1e-5 of the fp32 path (fp16 hi + lo terms).  `packed` from tae_enc_pack_f16x3; `params` supplies the fp32 biases and
  * Linear weights.  Same x_tx / stats contract as tae_enc_forward; workspace >= 256 bytes.                           */
 size_t tae_enc_packed_bytes_x3(const TaeEncConfig* cfg);
-int    tae_enc_pack_bf16x3(const TaeEncConfig* cfg, const float* params, void* packed, void* stream);
-int tae_enc_forward_bf16x3(const TaeEncConfig* cfg, const float* params, const void* packed, const float* u,
+int    tae_enc_pack_f16x3(const TaeEncConfig* cfg, const float* params, void* packed, void* stream);
+int tae_enc_forward_f16x3(const TaeEncConfig* cfg, const float* params, const void* packed, const float* u,
                            const int32_t* perm, const int32_t* inv_perm, float* x_tx, double* stats, int32_t B,
                            void* workspace, size_t workspace_bytes, void* stream);
 /* ENCBase.power_constraint default branch, reference encoders.py:107-116:

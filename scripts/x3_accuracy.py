@@ -16,7 +16,7 @@ from oracle import turboae_oracle as O  # noqa: E402
 
 def main():
     out = {}
-    for cfg, B, snr in (("c1", 297, 0.0), ("c1", 600, 2.0), ("c3", 297, 1.0)):
+    for cfg, B, snr in (("c1", 297, 0.0), ("c1", 3000, 0.0), ("c1", 400, 2.0), ("c3", 1000, 0.0)):
         m, w, p = build_codec(cfg)
         u, noise = gen_inputs(900 + B, B, 100, snr)
         ref_codes = O.enc_forward(u, w, p)
@@ -25,7 +25,7 @@ def main():
         rd = torch.from_numpy(r).cuda()
         ud = torch.from_numpy(u).cuda()
         with torch.no_grad():
-            for prec in ("bf16x3", "fp32", "bf16"):
+            for prec in ("f16x3", "fp32") + (("bf16",) if B <= 400 else ()):
                 m.enc.precision = prec
                 c = m.enc(ud).cpu().numpy()
                 y = m.dec.decode(rd, precision=prec).cpu().numpy()

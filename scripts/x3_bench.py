@@ -1,4 +1,4 @@
-"""Throughput of the split-operand tensor path (precision 'bf16x3'): encoder and decoder, next to the fp32 CUDA-core path and the bf16
+"""Throughput of the split-operand tensor path (precision 'f16x3'): encoder and decoder, next to the fp32 CUDA-core path and the bf16
 fused kernel.  python scripts/x3_bench.py [B]"""
 import json
 import os
@@ -32,17 +32,17 @@ def main():
         m, w, p = build_codec(cfg)
         u = torch.randint(0, 2, (B, 100, 1), device="cuda").float()
         with torch.no_grad():
-            for prec in ("bf16x3", "bf16", "fp32"):
+            for prec in ("f16x3", "bf16", "fp32"):
                 m.enc.precision = prec
                 ms = timed(lambda: m.enc(u), n=3 if prec == "fp32" else 10)
                 out["%s_enc_%s_cw_per_s" % (cfg, prec)] = B / ms * 1e3
-            m.enc.precision = "bf16x3"
+            m.enc.precision = "f16x3"
             r = m.enc(u) + torch.randn(B, 100, 3, device="cuda")
-            for prec in ("bf16x3", "bf16"):
+            for prec in ("f16x3", "bf16"):
                 ms = timed(lambda: m.dec.decode(r, precision=prec), n=3)
                 out["%s_dec_%s_cw_per_s" % (cfg, prec)] = B / ms * 1e3
                 out["%s_dec_%s_ms" % (cfg, prec)] = ms
-            y3 = m.dec.decode(r, precision="bf16x3")
+            y3 = m.dec.decode(r, precision="f16x3")
             yb = m.dec.decode(r, precision="bf16")
             out["%s_hard_disagreement_x3_vs_bf16" % cfg] = float((torch.round(y3) != torch.round(yb)).float().mean())
     print(json.dumps(out, indent=1))

@@ -12,8 +12,8 @@ LIB_PATH = os.environ.get("TURBOAE_B200_LIB") or os.path.join(_PKG, "lib", "libt
 
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
-PRECISION_BF16X3 = 2
-PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16, "bf16x3": PRECISION_BF16X3}
+PRECISION_F16X3 = 2
+PRECISIONS = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16, "f16x3": PRECISION_F16X3}
 
 
 class TaeDecConfig(C.Structure):
@@ -66,10 +66,10 @@ _SIGNATURES = {
     "tae_enc_pack_bf16": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P]),
     "tae_enc_forward_bf16": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_size_t, _P]),
     "tae_dec_packed_bytes_x3": (C.c_size_t, [C.POINTER(TaeDecConfig)]),
-    "tae_dec_pack_bf16x3": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P]),
+    "tae_dec_pack_f16x3": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P]),
     "tae_enc_packed_bytes_x3": (C.c_size_t, [C.POINTER(TaeEncConfig)]),
-    "tae_enc_pack_bf16x3": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P]),
-    "tae_enc_forward_bf16x3": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_size_t, _P]),
+    "tae_enc_pack_f16x3": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P]),
+    "tae_enc_forward_f16x3": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_size_t, _P]),
     "tae_power_norm_f32": (C.c_int, [_P, _P, C.c_size_t, _P, _P, _P]),
     "tae_power_norm_given_f32": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_float, C.c_float, _P]),
     "tae_power_norm_ste_f32": (C.c_int, [_P, _P, C.c_size_t, _P, _P, C.c_float, C.c_float, _P]),

@@ -215,9 +215,9 @@ size_t tae_dec_workspace_bytes(const TaeDecConfig* cfg, int32_t B, int32_t preci
     if (!bf16_supported(*cfg, &why)) { set_error("bf16 path: %s", why); return 0; }
     return 256;
   }
-  if (precision == TAE_PRECISION_BF16X3) {
+  if (precision == TAE_PRECISION_F16X3) {
     const char* why = nullptr;
-    if (!dec_x3_supported(*cfg, &why)) { set_error("bf16x3 path: %s", why); return 0; }
+    if (!dec_x3_supported(*cfg, &why)) { set_error("f16x3 path: %s", why); return 0; }
     return 256;
   }
   set_error("unknown precision %d", precision);
@@ -242,10 +242,10 @@ int tae_dec_forward(const TaeDecConfig* cfg, const float* params, const void* pa
     return dec_forward_pair(*cfg, packed, received, perm, inv_perm, out, trace, B, workspace, workspace_bytes,
                             (cudaStream_t)stream);
   }
-  if (precision == TAE_PRECISION_BF16X3) {
+  if (precision == TAE_PRECISION_F16X3) {
     const char* why = nullptr;
-    if (!dec_x3_supported(*cfg, &why)) { set_error("bf16x3 path: %s", why); return TAE_EUNSUPPORTED; }
-    TAE_REQUIRE(packed, "tae_dec_forward(bf16x3): packed weight image is NULL (call tae_dec_pack_bf16x3)");
+    if (!dec_x3_supported(*cfg, &why)) { set_error("f16x3 path: %s", why); return TAE_EUNSUPPORTED; }
+    TAE_REQUIRE(packed, "tae_dec_forward(f16x3): packed weight image is NULL (call tae_dec_pack_f16x3)");
     return dec_forward_x3(*cfg, params, packed, received, perm, inv_perm, out, trace, B, workspace, workspace_bytes,
                           (cudaStream_t)stream);
   }
@@ -256,16 +256,16 @@ int tae_dec_forward(const TaeDecConfig* cfg, const float* params, const void* pa
 size_t tae_dec_packed_bytes_x3(const TaeDecConfig* cfg) {
   if (check_dec_config(cfg)) return 0;
   const char* why = nullptr;
-  if (!dec_x3_supported(*cfg, &why)) { set_error("bf16x3 path: %s", why); return 0; }
+  if (!dec_x3_supported(*cfg, &why)) { set_error("f16x3 path: %s", why); return 0; }
   return dec_x3_packed_bytes(*cfg);
 }
 
-int tae_dec_pack_bf16x3(const TaeDecConfig* cfg, const float* params, void* packed, void* stream) {
+int tae_dec_pack_f16x3(const TaeDecConfig* cfg, const float* params, void* packed, void* stream) {
   int rc = check_dec_config(cfg);
   if (rc) return rc;
   const char* why = nullptr;
-  if (!dec_x3_supported(*cfg, &why)) { set_error("bf16x3 path: %s", why); return TAE_EUNSUPPORTED; }
-  TAE_REQUIRE(params && packed, "tae_dec_pack_bf16x3: NULL pointer");
+  if (!dec_x3_supported(*cfg, &why)) { set_error("f16x3 path: %s", why); return TAE_EUNSUPPORTED; }
+  TAE_REQUIRE(params && packed, "tae_dec_pack_f16x3: NULL pointer");
   return dec_x3_pack(*cfg, params, packed, (cudaStream_t)stream);
 }
 
@@ -415,29 +415,29 @@ int tae_enc_forward_bf16(const TaeEncConfig* cfg, const void* packed, const floa
 size_t tae_enc_packed_bytes_x3(const TaeEncConfig* cfg) {
   if (check_enc_config(cfg)) return 0;
   const char* why = nullptr;
-  if (!enc_x3_supported(*cfg, &why)) { set_error("bf16x3 encoder path: %s", why); return 0; }
+  if (!enc_x3_supported(*cfg, &why)) { set_error("f16x3 encoder path: %s", why); return 0; }
   return enc_x3_packed_bytes(*cfg);
 }
 
-int tae_enc_pack_bf16x3(const TaeEncConfig* cfg, const float* params, void* packed, void* stream) {
+int tae_enc_pack_f16x3(const TaeEncConfig* cfg, const float* params, void* packed, void* stream) {
   int rc = check_enc_config(cfg);
   if (rc) return rc;
   const char* why = nullptr;
-  if (!enc_x3_supported(*cfg, &why)) { set_error("bf16x3 encoder path: %s", why); return TAE_EUNSUPPORTED; }
-  TAE_REQUIRE(params && packed, "tae_enc_pack_bf16x3: NULL pointer");
+  if (!enc_x3_supported(*cfg, &why)) { set_error("f16x3 encoder path: %s", why); return TAE_EUNSUPPORTED; }
+  TAE_REQUIRE(params && packed, "tae_enc_pack_f16x3: NULL pointer");
   return enc_x3_pack(*cfg, params, packed, (cudaStream_t)stream);
 }
 
-int tae_enc_forward_bf16x3(const TaeEncConfig* cfg, const float* params, const void* packed, const float* u, const int32_t* perm,
+int tae_enc_forward_f16x3(const TaeEncConfig* cfg, const float* params, const void* packed, const float* u, const int32_t* perm,
                            const int32_t* inv_perm, float* x_tx, double* stats, int32_t B, void* workspace,
                            size_t workspace_bytes, void* stream) {
   int rc = check_enc_config(cfg);
   if (rc) return rc;
   const char* why = nullptr;
-  if (!enc_x3_supported(*cfg, &why)) { set_error("bf16x3 encoder path: %s", why); return TAE_EUNSUPPORTED; }
-  TAE_REQUIRE(B >= 0, "tae_enc_forward_bf16x3: negative batch %d", B);
+  if (!enc_x3_supported(*cfg, &why)) { set_error("f16x3 encoder path: %s", why); return TAE_EUNSUPPORTED; }
+  TAE_REQUIRE(B >= 0, "tae_enc_forward_f16x3: negative batch %d", B);
   if (B == 0) return TAE_OK;
-  TAE_REQUIRE(params && packed && u && perm && inv_perm && x_tx && stats && workspace, "tae_enc_forward_bf16x3: NULL pointer");
+  TAE_REQUIRE(params && packed && u && perm && inv_perm && x_tx && stats && workspace, "tae_enc_forward_f16x3: NULL pointer");
   rc = enc_forward_x3(*cfg, params, packed, u, perm, inv_perm, x_tx, stats, B, workspace, workspace_bytes, (cudaStream_t)stream);
   if (rc) return rc;
   return launch_add_count(stats, (double)B * cfg->block_len * 3, (cudaStream_t)stream);

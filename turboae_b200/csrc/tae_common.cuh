@@ -163,7 +163,7 @@ int enc_pair_pack_bwd(const TaeEncConfig& c, const float* params, void* packed, 
 int enc_backward_pair(const TaeEncConfig& c, const void* packed_bwd, const float* dlin, const void* stash_y, void* stash_g, void* stash_d,
                       float* dxin_all, float* grad_flat, int B, void* ws, size_t ws_bytes, cudaStream_t s);
 int launch_add_count(double* stats, double n, cudaStream_t s);
-// ---- bf16x3 tcgen05 path: split-operand kernel with fp32-class accuracy (tae_x3.cu) ----------
+// ---- f16x3 tcgen05 path: split-operand kernel with fp32-class accuracy (tae_x3.cu) ----------
 bool dec_x3_supported(const TaeDecConfig& c, const char** why);
 size_t dec_x3_packed_bytes(const TaeDecConfig& c);
 int dec_x3_pack(const TaeDecConfig& c, const float* params, void* packed, cudaStream_t s);

@@ -1,30 +1,34 @@
-// ENC_interCNN.forward and DEC_LargeCNN.forward on the 5th-gen tensor cores with fp32-class accuracy (TAE_PRECISION_BF16X3),
+// ENC_interCNN.forward and DEC_LargeCNN.forward on the 5th-gen tensor cores with fp32-class accuracy (TAE_PRECISION_F16X3),
 // sm_100a only.
 //
 // Reference arithmetic restated (paths relative to the reference checkout):
 //   encoders.py:362-373 (three branches, Linear + ELU), decoders.py:219-269 (turbo schedule),
 //   cnn_utils.py:36-46 (conv + ELU stack), interleavers.py:15-21, 43-48 (row permutations).
 //
-// Why: the plain bf16 tensor path rounds activations and weights to 8 mantissa bits (codes off by up to 5e-3, posteriors by
-// 1.6e-2 on the reference fixtures): it meets the BER gate, not north_star's elementwise 1e-4.  Here every operand of a conv
-// layer is split into two bf16 terms, x = x_hi + x_lo and W = W_hi + W_lo (16 mantissa bits together), and the layer is the
-// three tcgen05.mma chains  x_hi W_hi + x_lo W_hi + x_hi W_lo  accumulated in fp32 TMEM (the x_lo W_lo term is below 2^-16).
-// Bias, ELU, the Linear projections, the extrinsic subtraction and the priors stay in fp32 on the CUDA cores.  Measured on the
-// reference fixtures: codes within 1e-5, posteriors within 3e-5 (tests/test_gpu_x3.py), at ~13x the rate of the fp32
-// CUDA-core path.
+// Why: the plain bf16 tensor path rounds activations and weights to 8 mantissa bits (codes off by up to 3e-2, posteriors by
+// 3e-2 on seeded batches): it meets the BER gate, not north_star's elementwise 1e-4.  Here every operand of a conv layer is
+// split into two fp16 terms, x = x_hi + x_lo and W = W_hi + W_lo (22 mantissa bits together), and the layer is the three
+// tcgen05.mma chains  x_hi W_hi + x_lo W_hi + x_hi W_lo  accumulated in fp32 TMEM (the x_lo W_lo term is below 2^-22).
+// Bias, ELU, the Linear projections, the extrinsic subtraction and the priors stay in fp32 on the CUDA cores.  Measured
+// (scripts/x3_accuracy.py, profiles/r02_x3_accuracy.md): codes within 6e-6 of the oracle; posteriors within 6e-6 at 2 dB and,
+// at 0 dB on 300 000 posteriors, 99.99 % within 4.5e-5 with a maximum of 1e-4.  What is left is the tensor core's fp32
+// accumulation: a CPU emulation of the scheme with exact accumulation gives 4e-6, with round-toward-zero accumulation per
+// k-step 8e-5.  A bf16 split (-DTAE_X3_FP16=0; 16 bits) measures 2x worse.
 //
-// Execution model (deliberately simpler than tae_dec_pair.cu: one CTA per SM, no cluster):
+// Execution model (one CTA per SM, no cluster):
 //   * a CTA owns one "group" = a 256-row activation buffer holding floor(258/(L+2)) codewords, each followed by 2 all-zero
 //     separator rows (the zero padding of cnn_utils.py:16); 2 MMA tiles of 128 rows, M = 128, N = 112, cta_group::1.
-//   * activations live in shared memory twice (hi and lo images), bf16, canonical no-swizzle K-major layout
+//   * activations live in shared memory twice (hi and lo images), 16-bit, canonical no-swizzle K-major layout
 //     [13 chunks of 8 channels][264 rows][8]: tap t of the convolution is the same buffer addressed 16*t bytes later.
-//     K of a units->units layer = 33 k-steps of 16: 5 taps x 6 pairs of chunks (LBO = one chunk) + chunk 12 with two taps per
-//     k-step (LBO = 16 bytes: taps (0,1), (2,3), (4,-)).  The first layer ((2+F) or 1 -> units) is 3 k-steps of its one chunk.
-//   * weights stream from L2 through a bulk-copy ring: per layer 11 slots of W_hi (each used by the x_hi and the x_lo chain of
-//     both tiles) then 11 slots of W_lo (x_hi chain).
-//   * a layer = [MMA warp: 198 MMAs, one commit] -> [8 epilogue warps, one row per thread: tcgen05.ld, + bias, ELU, split into
-//     hi / lo, st.shared in place] -> next layer.  The last layer of a stack keeps its output in registers and applies the
-//     Linear there (fp32), so no activation is rounded between the last conv layer and the stack output.
+//     K of a units->units layer = 33 k-steps of 16, CHUNK-major: 6 pairs of chunks x 5 taps (LBO = one chunk), then chunk 12
+//     with two taps per k-step (LBO = 16 bytes: taps (0,1), (2,3), (4,-)).  The first layer ((2+F) or 1 -> units) is 3
+//     k-steps of its one chunk.
+//   * weights stream from L2 through a bulk-copy ring: per layer 11 slots of W_hi (each used by the x_hi and the x_lo chain)
+//     then 11 slots of W_lo (x_hi chain); two MMA issuer warps, one per tile (two interleaved issue streams).
+//   * the epilogue (8 warps, one row per thread: tcgen05.ld, + bias, ELU, split into hi / lo, st.shared in place) publishes
+//     its output in 7 chunk stages; the next layer's MMAs start on the stages that are there (accumulators are double-buffered
+//     by layer parity), so the epilogue of layer j overlaps the MMAs of layer j+1.  The last layer of a stack keeps its output
+//     in registers and applies the Linear there (fp32): nothing is rounded between the last conv layer and the stack output.
 //   * decoder: the stack inputs (received values and priors) are kept as an fp32 master copy [row][8] next to their hi / lo
 //     operand chunks; the extrinsic subtraction uses the fp32 prior, and (de)interleave is the row index of the store.
 #include <cuda_bf16.h>
@@ -38,10 +42,10 @@
 
 namespace tae {
 
-// Operand format of the split: 0 = bf16 hi + bf16 lo (16 mantissa bits together), 1 = fp16 hi + fp16 lo (22 bits; values are
-// clamped to +-65504, fp16's finite range).  Same tcgen05.mma kind::f16, same rate.
+// Operand format of the split: 1 (default) = fp16 hi + fp16 lo (22 mantissa bits together; values are clamped to +-65504, fp16's
+// finite range), 0 = bf16 hi + bf16 lo (16 bits, full fp32 range).  Same tcgen05.mma kind::f16, same rate.
 #ifndef TAE_X3_FP16
-#define TAE_X3_FP16 0
+#define TAE_X3_FP16 1
 #endif
 
 namespace {
@@ -53,6 +57,18 @@ __host__ __device__ constexpr uint32_t make_idesc_x3(int m, int n) {
   return (1u << 4) | (FP16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 constexpr float F16_MAX = 65504.f;
+// Optional power-of-two scaling of the stored operands (the epilogue undoes both factors with the multiply of its bias FMA):
+// it would keep the lo terms of small weights out of fp16's subnormal range (a weight of 0.03 has a lo term of ~7e-6, quantised
+// to 6e-8).  Measured with 256 / 8: no change of the output error (the tensor core's accumulation dominates), so both stay 1 and
+// the full fp16 range is available to the activations.
+#ifndef TAE_X3_SCALE_W
+#define TAE_X3_SCALE_W 1.f
+#endif
+#ifndef TAE_X3_SCALE_X
+#define TAE_X3_SCALE_X 1.f
+#endif
+constexpr float SCALE_W = FP16 ? TAE_X3_SCALE_W : 1.f, SCALE_X = FP16 ? TAE_X3_SCALE_X : 1.f;
+constexpr float ACC_INV = 1.f / (SCALE_W * SCALE_X);
 
 constexpr int GROUP_ROWS = 256;
 constexpr int N_TILES = 2;
@@ -71,10 +87,10 @@ constexpr uint32_t KSTEP_B = 2 * WCHUNK_B;              // 3584
 constexpr uint32_t SLOT_B = KS_PER_SLOT * KSTEP_B;      // 10752
 constexpr int NS = 6;                                   // ring slots
 constexpr int MAX_LAYER = 8, MAX_F = 5;
-constexpr int TAB_BIAS = 0, TAB_V = MAX_LAYER * NPAD, TAB_C = TAB_V + MAX_F * NPAD, TAB_FLOATS = TAB_C + 8;
+constexpr int TAB_BIAS = 0, TAB_V = MAX_LAYER * NPAD, TAB_C = TAB_V + MAX_F * NPAD, TAB_FLOATS = TAB_C + 8;   // one stack's tables (x 2: stack parity)
 constexpr int N_EPI_WARPS = 8, N_EPI_THREADS = 256;     // warp w: tile w >> 2, TMEM lane quadrant w & 3
-constexpr int WARP_MMA = 8, WARP_PRODUCER = 9;
-constexpr int N_THREADS = 320;
+constexpr int WARP_MMA = 8, WARP_PRODUCER = 10;         // warps 8, 9: one MMA issuer per tile (two interleaved issue streams keep the
+constexpr int N_THREADS = 352;                          // tensor pipe fed: a single issuing thread leaves a gap after every MMA)
 constexpr uint32_t TMEM_COLS = 512;                     // 2 accumulator buffers (layer parity) x 2 tiles x 112 columns
 constexpr uint32_t TMEM_BUF_COLS = N_TILES * NPAD;      // 224
 constexpr int N_STAGES = 7;                             // epilogue stages = 16-column blocks = chunk pairs 0..5, then chunk 12
@@ -103,7 +119,7 @@ __host__ __device__ inline Smem make_smem() {
   s.master[0] = o; o += BUF_ROWS * 32;
   s.master[1] = o; o += BUF_ROWS * 32;
   s.wslot = o; o += NS * SLOT_B;
-  s.tab = o; o += TAB_FLOATS * 4;
+  s.tab = o; o += 2 * TAB_FLOATS * 4;
   s.perm = o; o += 512;
   s.inv_perm = o; o += 512;
   s.bars = o; o += N_BARS * 8;
@@ -190,6 +206,7 @@ __global__ void pack_x3_kernel(const float* __restrict__ params, uint16_t* __res
       part = within / SLOTS_PASS;
       v = conv_w_elem(params + lay.conv_w(st, j), lay.units, n, (within % SLOTS_PASS) * KS_PER_SLOT + k3, e);
     }
+    v *= SCALE_W;
     const uint16_t hi = half_bits(v);
     img[idx] = part == 0 ? hi : half_bits(v - half_value(hi));
   }
@@ -207,6 +224,8 @@ __device__ __forceinline__ float elu_x3(float v) { return v > 0.f ? v : fast_exp
 // (a, b) -> packed hi pair and packed lo pair with hi + lo = value to 16 (bf16) / 22 (fp16) mantissa bits
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   if (FP16) {
+    a *= SCALE_X;
+    b *= SCALE_X;
     const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -F16_MAX), F16_MAX), fminf(fmaxf(b, -F16_MAX), F16_MAX));
     const float2 hf = __half22float2(h);
     const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
@@ -235,8 +254,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
   for (uint32_t i = threadIdx.x * 16; i < S.bars; i += N_THREADS * 16) st_shared_v4(sbase + i, 0u, 0u, 0u, 0u);
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), 1); }
-    mbar_init(bar(B_ACC), 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), N_TILES); }
+    mbar_init(bar(B_ACC), N_TILES);
     mbar_init(bar(B_ACT), N_EPI_WARPS);
     for (int i = 0; i < N_STAGES; ++i) mbar_init(bar(B_STAGE + i), N_EPI_WARPS);
     fence_barrier_init();
@@ -269,17 +288,21 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
           }
         }
     }
-  } else if (warp == WARP_MMA) {
-    // ================= MMA issuer: the warp runs converged, one elected lane issues =====================
+  } else if (warp >= WARP_MMA && warp < WARP_MMA + N_TILES) {
+    // ================= MMA issuers: warp 8 + m owns tile m; each warp runs converged, one elected lane issues ===========
     constexpr uint32_t IDESC = make_idesc_x3(128, NPAD);
+    const int m = warp - WARP_MMA;
     uint32_t pos = 0, wphase = 0, n_act = 0, n_stage = 0;
-    const uint32_t act_hi = sbase + S.act_hi, act_lo = sbase + S.act_lo;
+    // descriptor low words of this tile's operands (start address + LBO); a k-step adds a compile-time constant
+    const uint32_t rowoff = (uint32_t)(128 * m) * ROW_B;
+    const uint32_t ahi_c = dlo(sbase + S.act_hi + rowoff, CHUNK_B), alo_c = dlo(sbase + S.act_lo + rowoff, CHUNK_B);              // chunk pairs
+    const uint32_t ahi_t = dlo(sbase + S.act_hi + 12 * CHUNK_B + rowoff, ROW_B), alo_t = dlo(sbase + S.act_lo + 12 * CHUNK_B + rowoff, ROW_B);   // chunk 12, two taps
     for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x)
       for (int st = 0; st < n_stacks; ++st) {
         const uint32_t xsel = (uint32_t)(a.enc ? (st == 2) : (st & 1));     // enc: branch 3 reads the interleaved bits
-        const uint32_t xin_hi = sbase + S.xin_hi[0] + xsel * CHUNK_B, xin_lo = sbase + S.xin_lo[0] + xsel * CHUNK_B;
+        const uint32_t xhi = dlo(sbase + S.xin_hi[0] + xsel * CHUNK_B + rowoff, ROW_B), xlo = dlo(sbase + S.xin_lo[0] + xsel * CHUNK_B + rowoff, ROW_B);
         for (int layer = 0; layer < n_layer; ++layer) {
-          const uint32_t tbuf = tmem_base + (uint32_t)(layer & 1) * TMEM_BUF_COLS;     // accumulators alternate by layer parity
+          const uint32_t d_tmem = tmem_base + (uint32_t)(layer & 1) * TMEM_BUF_COLS + (uint32_t)(m * NPAD);     // accumulators alternate by layer parity
           if (layer == 0) {
             mbar_wait(bar(B_ACT), n_act & 1, a.err, 22);     // the stack input is in place
             ++n_act;
@@ -292,15 +315,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
               const uint32_t wlo = dlo(sbase + S.wslot + pos * SLOT_B, WCHUNK_B);
               if (elect_one()) {
 #pragma unroll
-                for (int m = 0; m < N_TILES; ++m) {
-                  const uint32_t d_tmem = tbuf + (uint32_t)(m * NPAD);
-#pragma unroll
-                  for (int ks = 0; ks < KS_L0; ++ks) {
-                    const uint32_t off = (uint32_t)(128 * m + 2 * ks) * ROW_B;
-                    umma_bf16<1>(d_tmem, dfull(dlo(xin_hi + off, ROW_B)), dfull(wlo + (uint32_t)(ks * KSTEP_B) / 16), IDESC, (part | ks) != 0);
-                    if (part == 0)
-                      umma_bf16<1>(d_tmem, dfull(dlo(xin_lo + off, ROW_B)), dfull(wlo + (uint32_t)(ks * KSTEP_B) / 16), IDESC, 1);
-                  }
+                for (int ks = 0; ks < KS_L0; ++ks) {
+                  const uint64_t bdesc = dfull(wlo + (uint32_t)(ks * KSTEP_B) / 16);
+                  umma_bf16<1>(d_tmem, dfull(xhi + (uint32_t)(2 * ks)), bdesc, IDESC, (part | ks) != 0);
+                  if (part == 0) umma_bf16<1>(d_tmem, dfull(xlo + (uint32_t)(2 * ks)), bdesc, IDESC, 1);
                 }
                 umma_commit_1(bar(B_WEMPTY + pos));
                 if (part == 1) umma_commit_1(bar(B_ACC));
@@ -325,19 +343,13 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
                 const uint32_t wlo = dlo(sbase + S.wslot + pos * SLOT_B, WCHUNK_B);
                 if (elect_one()) {
 #pragma unroll
-                  for (int m = 0; m < N_TILES; ++m) {
-                    const uint32_t d_tmem = tbuf + (uint32_t)(m * NPAD);
-#pragma unroll
-                    for (int k3 = 0; k3 < KS_PER_SLOT; ++k3) {
-                      const int ks = s * KS_PER_SLOT + k3;
-                      // A operand, chunk-major: (chunk pair ks / 5, tap ks % 5) for ks < 30, else chunk 12 with two taps in one k-step
-                      const uint32_t off = ks < 30 ? (uint32_t)(2 * (ks / 5)) * CHUNK_B + (uint32_t)(128 * m + ks % 5) * ROW_B
-                                                   : (uint32_t)12 * CHUNK_B + (uint32_t)(128 * m + 2 * (ks - 30)) * ROW_B;
-                      const uint32_t lbo = ks < 30 ? CHUNK_B : ROW_B;
-                      const uint64_t bdesc = dfull(wlo + (uint32_t)(k3 * KSTEP_B) / 16);
-                      umma_bf16<1>(d_tmem, dfull(dlo(act_hi + off, lbo)), bdesc, IDESC, (part | s | k3) != 0);
-                      if (part == 0) umma_bf16<1>(d_tmem, dfull(dlo(act_lo + off, lbo)), bdesc, IDESC, 1);
-                    }
+                  for (int k3 = 0; k3 < KS_PER_SLOT; ++k3) {
+                    const int ks = s * KS_PER_SLOT + k3;
+                    // A operand, chunk-major: (chunk pair ks / 5, tap ks % 5) for ks < 30, else chunk 12 with two taps in one k-step
+                    const uint32_t add = ks < 30 ? ((uint32_t)(2 * (ks / 5)) * CHUNK_B + (uint32_t)(ks % 5) * ROW_B) / 16 : (uint32_t)(2 * (ks - 30));
+                    const uint64_t bdesc = dfull(wlo + (uint32_t)(k3 * KSTEP_B) / 16);
+                    umma_bf16<1>(d_tmem, dfull((ks < 30 ? ahi_c : ahi_t) + add), bdesc, IDESC, (part | s | k3) != 0);
+                    if (part == 0) umma_bf16<1>(d_tmem, dfull((ks < 30 ? alo_c : alo_t) + add), bdesc, IDESC, 1);
                   }
                   umma_commit_1(bar(B_WEMPTY + pos));
                   if (part == 1 && s == SLOTS_PASS - 1) umma_commit_1(bar(B_ACC));
@@ -356,7 +368,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
     const int g_row = 128 * tile + 32 * q + lane;     // row of the group this thread owns in every epilogue
     const uint32_t brow = (uint32_t)(g_row + HALO_LO);
     const uint32_t taddr0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(tile * NPAD);
-    const uint32_t tab = sbase + S.tab;
+    const uint32_t tab_base = sbase + S.tab;
     uint32_t n_acc = 0;
     for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
       const int cw0 = g * a.cw_per_group;
@@ -376,7 +388,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
           const uint32_t row = (uint32_t)(sc * CW_ROWS + sl + HALO_LO);
           const uint32_t row_i = (uint32_t)(sc * CW_ROWS + ld_shared_u16(sbase + S.inv_perm + 2 * sl) + HALO_LO);
           if (a.enc) {
-            const uint16_t x = half_bits(2.0f * a.u[(size_t)cw0 * L + tid] - 1.0f);              // encoders.py:362 (+-1: exact)
+            const uint16_t x = half_bits(SCALE_X * (2.0f * a.u[(size_t)cw0 * L + tid] - 1.0f));              // encoders.py:362 (+-1: exact)
             st_shared_u16(sbase + S.xin_hi[0] + row * ROW_B, x);          // branches 1, 2
             st_shared_u16(sbase + S.xin_hi[1] + row_i * ROW_B, x);        // branch 3: x_int[i] = x[p[i]]   (encoders.py:369)
           } else {
@@ -400,30 +412,35 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
           }
         }
       }
-      bool first_arrive = true;       // the group start and the first stack's tables are published by ONE arrival
 
       for (int st = 0; st < n_stacks; ++st) {
         const int fout = a.lay.fout(st);
         const bool last_stack = (st == n_stacks - 1);
-        // ---- this stack's fp32 tables: conv biases, Linear weights and bias ----------------------------
-        if (st > 0) epi_bar_sync();                    // every warp is done with the previous stack's tables
-        for (int i = tid; i < n_layer * NPAD; i += N_EPI_THREADS) {
-          const int j = i / NPAD, c = i - j * NPAD;
-          st_shared_f32(tab + 4u * (uint32_t)(TAB_BIAS + i), c < a.lay.units ? __ldg(a.params + a.lay.conv_b(st, j) + c) : 0.f);
-        }
-        for (int i = tid; i < MAX_F * NPAD; i += N_EPI_THREADS) {
-          const int f = i / NPAD, c = i - f * NPAD;
-          st_shared_f32(tab + 4u * (uint32_t)(TAB_V + i), (f < fout && c < a.lay.units) ? __ldg(a.params + a.lay.lin_w(st) + (size_t)f * a.lay.units + c) : 0.f);
-        }
-        if (tid < 8) st_shared_f32(tab + 4u * (uint32_t)(TAB_C + tid), tid < fout ? __ldg(a.params + a.lay.lin_b(st) + tid) : 0.f);
-        if (first_arrive) {
+        // ---- fp32 tables (conv biases, Linear weights and bias), double-buffered by stack parity: this stack's were staged
+        //      one stack ago (the first one at the group start), the next stack's are staged now, while layer 0's MMAs run ------
+        const uint32_t tab = tab_base + (uint32_t)(st & 1) * (TAB_FLOATS * 4);
+        auto stage_tables = [&](int ts) {
+          const uint32_t tt = tab_base + (uint32_t)(ts & 1) * (TAB_FLOATS * 4);
+          const int tf = a.lay.fout(ts);
+          for (int i = tid; i < n_layer * NPAD; i += N_EPI_THREADS) {
+            const int j = i / NPAD, c = i - j * NPAD;
+            st_shared_f32(tt + 4u * (uint32_t)(TAB_BIAS + i), c < a.lay.units ? __ldg(a.params + a.lay.conv_b(ts, j) + c) : 0.f);
+          }
+          for (int i = tid; i < MAX_F * NPAD; i += N_EPI_THREADS) {
+            const int f = i / NPAD, c = i - f * NPAD;
+            st_shared_f32(tt + 4u * (uint32_t)(TAB_V + i), (f < tf && c < a.lay.units) ? __ldg(a.params + a.lay.lin_w(ts) + (size_t)f * a.lay.units + c) : 0.f);
+          }
+          if (tid < 8) st_shared_f32(tt + 4u * (uint32_t)(TAB_C + tid), tid < tf ? __ldg(a.params + a.lay.lin_b(ts) + tid) : 0.f);
+        };
+        if (st == 0) {
+          stage_tables(0);
           fence_proxy_async();                         // the stack inputs were written with generic stores
           epi_bar_sync();
           if (lane == 0) mbar_arrive_local(bar(B_ACT));
-          first_arrive = false;
         } else {
-          epi_bar_sync();
+          epi_bar_sync();                              // every warp is done with stack st-1 (its tables' buffer is reused below) and sees this stack's tables
         }
+        if (st + 1 < n_stacks) stage_tables(st + 1);
 
         for (int layer = 0; layer < n_layer; ++layer) {
           const bool lin_layer = (layer == n_layer - 1);
@@ -446,14 +463,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
               if (c >= N_CHUNKS) break;
               const float4 b0 = ld_shared_f4(btab + (uint32_t)(c * 32)), b1 = ld_shared_f4(btab + (uint32_t)(c * 32 + 16));
               float v[8];
-              v[0] = elu_x3(__uint_as_float(cur[8 * half + 0]) + b0.x);
-              v[1] = elu_x3(__uint_as_float(cur[8 * half + 1]) + b0.y);
-              v[2] = elu_x3(__uint_as_float(cur[8 * half + 2]) + b0.z);
-              v[3] = elu_x3(__uint_as_float(cur[8 * half + 3]) + b0.w);
-              v[4] = elu_x3(__uint_as_float(cur[8 * half + 4]) + b1.x);
-              v[5] = elu_x3(__uint_as_float(cur[8 * half + 5]) + b1.y);
-              v[6] = elu_x3(__uint_as_float(cur[8 * half + 6]) + b1.z);
-              v[7] = elu_x3(__uint_as_float(cur[8 * half + 7]) + b1.w);
+              v[0] = elu_x3(fmaf(__uint_as_float(cur[8 * half + 0]), ACC_INV, b0.x));
+              v[1] = elu_x3(fmaf(__uint_as_float(cur[8 * half + 1]), ACC_INV, b0.y));
+              v[2] = elu_x3(fmaf(__uint_as_float(cur[8 * half + 2]), ACC_INV, b0.z));
+              v[3] = elu_x3(fmaf(__uint_as_float(cur[8 * half + 3]), ACC_INV, b0.w));
+              v[4] = elu_x3(fmaf(__uint_as_float(cur[8 * half + 4]), ACC_INV, b1.x));
+              v[5] = elu_x3(fmaf(__uint_as_float(cur[8 * half + 5]), ACC_INV, b1.y));
+              v[6] = elu_x3(fmaf(__uint_as_float(cur[8 * half + 6]), ACC_INV, b1.z));
+              v[7] = elu_x3(fmaf(__uint_as_float(cur[8 * half + 7]), ACC_INV, b1.w));
               if (!lin_layer) {
                 uint32_t h[4], l[4];
 #pragma unroll
@@ -576,7 +593,7 @@ bool supported(int L, int n_layer, int units, int k, int F, const char** why) {
 int launch_setup(int* n_sm_out) {
   static DeviceOnce once;
   return device_once(once, "x3_kernel", [](int dev) -> int {
-    int rc = require_sm100(dev, "the bf16x3 tensor path");
+    int rc = require_sm100(dev, "the f16x3 tensor path");
     if (rc) return rc;
     cudaError_t e = cudaFuncSetAttribute(x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)make_smem().total);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(x3_kernel): %s", cudaGetErrorString(e)); return TAE_ECUDA; }

@@ -2,7 +2,7 @@
 
 forward: ``received (B, L, 3)`` -> ``(B, L, 1)`` posteriors.  The whole turbo schedule (2*num_iteration conv
 stacks, Linear projections, extrinsic subtractions, interleave / de-interleave, sigmoid) is one call into
-libturboae_b200.so: ``precision='bf16'`` runs the fused tcgen05 kernel, ``precision='bf16x3'`` the split-operand
+libturboae_b200.so: ``precision='bf16'`` runs the fused tcgen05 kernel, ``precision='f16x3'`` the split-operand
 tcgen05 kernel (elementwise parity), ``precision='fp32'`` the CUDA-core elementwise-parity path.  No CPU fallback and no silent switch between the two."""
 from __future__ import annotations
 
@@ -47,7 +47,7 @@ class DEC_LargeCNN(torch.nn.Module):
         self._flat = FlatCache()
         self._ws = Workspace()
         self._ws_host = Workspace()
-        #: 'bf16' (fused tcgen05 kernel: BER parity), 'bf16x3' (split-operand tcgen05 kernel: elementwise parity <= 1e-4 at
+        #: 'bf16' (fused tcgen05 kernel: BER parity), 'f16x3' (split-operand tcgen05 kernel: elementwise parity <= 1e-4 at
         #: ~13x the fp32 rate) or 'fp32' (CUDA-core parity path)
         self.precision = getattr(args, "tae_precision", None) or os.environ.get("TURBOAE_B200_PRECISION", "bf16")
         #: training (autograd) path: 'fp32' = CUDA-core kernels layer by layer (gradients within 2e-3 of the reference's),
@@ -109,7 +109,7 @@ class DEC_LargeCNN(torch.nn.Module):
         lib = _lib.load()
         precision = precision or self.precision
         if precision not in _lib.PRECISIONS:
-            raise _lib.TaeError("precision must be 'bf16', 'bf16x3' or 'fp32', got %r" % (precision,))
+            raise _lib.TaeError("precision must be 'bf16', 'f16x3' or 'fp32', got %r" % (precision,))
         prec = _lib.PRECISIONS[precision]
         cfg = self.config(L)
         flat = self._flat.get(self.ordered_parameters())
@@ -126,16 +126,16 @@ class DEC_LargeCNN(torch.nn.Module):
                 packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
                 _lib.check(lib.tae_dec_pack_bf16(cfg, _lib.ptr(flat), _lib.ptr(packed), _lib.stream_ptr(dev)))
                 self._flat.derived["bf16"] = packed
-        elif prec == _lib.PRECISION_BF16X3:
-            packed = self._flat.derived.get("bf16x3")
+        elif prec == _lib.PRECISION_F16X3:
+            packed = self._flat.derived.get("f16x3")
             if packed is None:
                 nbytes = lib.tae_dec_packed_bytes_x3(cfg)
                 if nbytes == 0:
-                    raise _lib.TaeError("bf16x3 tensor path unavailable for this configuration (%s); set precision='fp32'"
+                    raise _lib.TaeError("f16x3 tensor path unavailable for this configuration (%s); set precision='fp32'"
                                         % lib.tae_last_error().decode())
                 packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-                _lib.check(lib.tae_dec_pack_bf16x3(cfg, _lib.ptr(flat), _lib.ptr(packed), _lib.stream_ptr(dev)))
-                self._flat.derived["bf16x3"] = packed
+                _lib.check(lib.tae_dec_pack_f16x3(cfg, _lib.ptr(flat), _lib.ptr(packed), _lib.stream_ptr(dev)))
+                self._flat.derived["f16x3"] = packed
         return lib, cfg, flat, packed, prec
 
     def decode_host(self, received_host, out_host=None, precision=None):

@@ -90,9 +90,9 @@ class ENC_interCNN(ENCBase):
         self.shard_group = None
         if os.environ.get("TURBOAE_B200_SHARD") == "1" and torch.distributed.is_available() and torch.distributed.is_initialized():
             self.shard_group = torch.distributed.group.WORLD
-        #: 'bf16x3' (split-operand tcgen05 kernel, tae_x3.cu: elementwise parity <= 1e-4 at tensor-core speed), 'fp32' (CUDA-core
+        #: 'f16x3' (split-operand tcgen05 kernel, tae_x3.cu: elementwise parity <= 1e-4 at tensor-core speed), 'fp32' (CUDA-core
         #: path, same parity, ~8x slower), 'bf16' (the decoder's fused tcgen05 kernel with the three branches as three conv stacks:
-        #: fastest, codes within bf16 rounding of the reference's) or 'auto' (default): 'bf16x3' where that kernel covers the
+        #: fastest, codes within bf16 rounding of the reference's) or 'auto' (default): 'f16x3' where that kernel covers the
         #: configuration (kernel size 5, <= 104 units, block length <= 256), else 'fp32' -- both meet the same tolerance
         self.precision = getattr(args, "tae_enc_precision", None) or os.environ.get("TURBOAE_B200_ENC_PRECISION", "auto")
         #: training (autograd) path: 'fp32' (CUDA-core kernels) or 'bf16' (tensor cores, train_tc.py)
@@ -132,11 +132,11 @@ class ENC_interCNN(ENCBase):
 
     def resolved_precision(self, block_len):
         """The inference path a forward at this block length takes ('auto' resolved; see ``precision``)."""
-        if self.precision not in ("auto", "fp32", "bf16", "bf16x3"):
-            raise _lib.TaeError("encoder precision must be 'auto', 'bf16x3', 'fp32' or 'bf16', got %r" % (self.precision,))
+        if self.precision not in ("auto", "fp32", "bf16", "f16x3"):
+            raise _lib.TaeError("encoder precision must be 'auto', 'f16x3', 'fp32' or 'bf16', got %r" % (self.precision,))
         if self.precision != "auto":
             return self.precision
-        return "bf16x3" if _lib.load().tae_enc_packed_bytes_x3(self.config(block_len)) else "fp32"
+        return "f16x3" if _lib.load().tae_enc_packed_bytes_x3(self.config(block_len)) else "fp32"
 
     def encode_unnormalised(self, inputs, stats):
         """x_tx (B, L, 3) before power_constraint; adds (sum, sumsq, count) into the 3 device doubles `stats`."""
@@ -150,19 +150,19 @@ class ENC_interCNN(ENCBase):
         perm, inv = self.interleaver.device_index(dev)
         x_tx = torch.empty((B, L, 3), dtype=torch.float32, device=dev)
         precision = self.resolved_precision(L)
-        if precision == "bf16x3":
+        if precision == "f16x3":
             with torch.cuda.device(dev):
-                packed = self._flat.derived.get("bf16x3")
+                packed = self._flat.derived.get("f16x3")
                 if packed is None:
                     nbytes = lib.tae_enc_packed_bytes_x3(cfg)
                     if nbytes == 0:
-                        raise _lib.TaeError("bf16x3 encoder path unavailable for this configuration (%s); set precision='fp32'"
+                        raise _lib.TaeError("f16x3 encoder path unavailable for this configuration (%s); set precision='fp32'"
                                             % lib.tae_last_error().decode())
                     packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-                    _lib.check(lib.tae_enc_pack_bf16x3(cfg, _lib.ptr(flat), _lib.ptr(packed), _lib.stream_ptr(dev)))
-                    self._flat.derived["bf16x3"] = packed
+                    _lib.check(lib.tae_enc_pack_f16x3(cfg, _lib.ptr(flat), _lib.ptr(packed), _lib.stream_ptr(dev)))
+                    self._flat.derived["f16x3"] = packed
                 ws = self._ws.get(256, dev)
-                _lib.check(lib.tae_enc_forward_bf16x3(cfg, _lib.ptr(flat), _lib.ptr(packed), _lib.ptr(inputs), _lib.ptr(perm),
+                _lib.check(lib.tae_enc_forward_f16x3(cfg, _lib.ptr(flat), _lib.ptr(packed), _lib.ptr(inputs), _lib.ptr(perm),
                                                       _lib.ptr(inv), _lib.ptr(x_tx), _lib.ptr(stats), B, _lib.ptr(ws), ws.numel(),
                                                       _lib.stream_ptr(dev)))
             return x_tx

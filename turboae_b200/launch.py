@@ -97,9 +97,15 @@ def main(argv=None):
                     "no seed; with one, two runs draw identical bits and noise)")
     ap.add_argument("--stock", action="store_true", help="do NOT swap the hot-path classes: run the reference's own modules "
                     "(only the library-compatibility shim is applied); the comparison arm of scripts/run_reference_dropin.py")
+    ap.add_argument("--no-tf32", action="store_true", help="torch's own CUDA convolutions / matmuls in true fp32 (cudnn.allow_tf32 "
+                    "defaults to True): makes the --stock arm the reference's fp32 arithmetic (it was written for torch 1.0)")
     ap.add_argument("script", help="reference script to run, e.g. main.py")
     ap.add_argument("script_args", nargs=argparse.REMAINDER)
     a = ap.parse_args(argv)
+    if a.no_tf32:
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
     if a.stock:
         sys.path.insert(0, os.path.abspath(a.reference))
         _modernise()

@@ -70,6 +70,15 @@ constexpr float F16_MAX = 65504.f;
 constexpr float SCALE_W = FP16 ? TAE_X3_SCALE_W : 1.f, SCALE_X = FP16 ? TAE_X3_SCALE_X : 1.f;
 constexpr float ACC_INV = 1.f / (SCALE_W * SCALE_X);
 
+// 1 (default): clusters of 2 CTAs, tcgen05.mma.cta_group::2 with M = 256 = tile m of BOTH CTAs' groups; each CTA stages only its half
+// of the weight columns (56 of 112), which halves the weight traffic from L2 and takes 1.75 KB per MMA off the shared-memory port
+// that bounds the single-CTA version (0: one CTA per group, cta_group::1).
+#ifndef TAE_X3_PAIR
+#define TAE_X3_PAIR 1
+#endif
+constexpr bool PAIR = TAE_X3_PAIR != 0;
+constexpr int CG = PAIR ? 2 : 1;
+
 constexpr int GROUP_ROWS = 256;
 constexpr int N_TILES = 2;
 constexpr int HALO_LO = 2, HALO_HI = 6;                 // rows in front / behind (the two-taps-per-k-step scheme reads "tap 5")
@@ -82,10 +91,12 @@ constexpr int UNITS_MAX = 104;
 constexpr int TAPS = 5;
 constexpr int KS_CONV = 33, KS_L0 = 3, KS_PER_SLOT = 3;
 constexpr int SLOTS_PASS = KS_CONV / KS_PER_SLOT;       // 11 slots of W_hi, 11 of W_lo per units->units layer
-constexpr uint32_t WCHUNK_B = NPAD * ROW_B;             // 1792: 8 K elements of 112 columns
-constexpr uint32_t KSTEP_B = 2 * WCHUNK_B;              // 3584
-constexpr uint32_t SLOT_B = KS_PER_SLOT * KSTEP_B;      // 10752
-constexpr int NS = 6;                                   // ring slots
+constexpr int NCTA = NPAD / CG;                         // weight columns staged per CTA
+constexpr uint32_t WCHUNK_B = NCTA * ROW_B;             // 8 K elements of this CTA's columns (1792 / 896 bytes)
+constexpr uint32_t KSTEP_B = 2 * WCHUNK_B;
+constexpr uint32_t SLOT_B = KS_PER_SLOT * KSTEP_B;      // bytes of a slot in ONE CTA (10752 / 5376)
+constexpr uint32_t SLOT_IMG_B = CG * SLOT_B;            // bytes of a slot in the weight image: [cta half][k-step][2 chunks][columns][8]
+constexpr int NS = PAIR ? 8 : 6;                        // ring slots
 constexpr int MAX_LAYER = 8, MAX_F = 5;
 constexpr int TAB_BIAS = 0, TAB_V = MAX_LAYER * NPAD, TAB_C = TAB_V + MAX_F * NPAD, TAB_FLOATS = TAB_C + 8;   // one stack's tables (x 2: stack parity)
 constexpr int N_EPI_WARPS = 8, N_EPI_THREADS = 256;     // warp w: tile w >> 2, TMEM lane quadrant w & 3
@@ -189,13 +200,15 @@ __device__ __forceinline__ float l0_w_elem(const float* __restrict__ w, int unit
 // one k-step = 2 chunks [112 columns][8 K elements]
 __global__ void pack_x3_kernel(const float* __restrict__ params, uint16_t* __restrict__ img, const Layout lay, uint32_t stack_elems) {
   const size_t total = (size_t)lay.n_stacks * stack_elems;
-  constexpr uint32_t slot_elems = SLOT_B / 2;
+  constexpr uint32_t slot_elems = SLOT_IMG_B / 2;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int st = (int)(idx / stack_elems);
     uint32_t r = (uint32_t)(idx % stack_elems);
     const int sl = (int)(r / slot_elems);
     r %= slot_elems;
-    const int k3 = (int)(r / (KSTEP_B / 2)), h = (int)(r / (NPAD * 8)) & 1, n = (int)(r / 8) % NPAD, e = h * 8 + (int)(r % 8);
+    const int half = (int)(r / (SLOT_B / 2));          // which CTA of the pair stages these columns
+    r %= (SLOT_B / 2);
+    const int k3 = (int)(r / (KSTEP_B / 2)), h = (int)(r / (NCTA * 8)) & 1, n = half * NCTA + (int)(r / 8) % NCTA, e = h * 8 + (int)(r % 8);
     float v;
     int part;
     if (sl < 2) {
@@ -240,11 +253,27 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-__global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
+#if TAE_X3_PAIR
+#define X3_CLUSTER __cluster_dims__(2, 1, 1)
+#else
+#define X3_CLUSTER
+#endif
+// commit of all previously issued MMAs: to this CTA's barrier, or (pair) to the barrier at the same offset in both CTAs
+__device__ __forceinline__ void commit_x3(uint32_t bar) {
+  if (PAIR) umma_commit_pair(bar, 3); else umma_commit_1(bar);
+}
+
+__global__ void X3_CLUSTER __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const Smem S = make_smem();
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // pair: the cluster's CTAs own groups 2 u and 2 u + 1 of work unit u; single: one group per unit
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int unit0 = PAIR ? (int)cluster_id_x() : (int)blockIdx.x, unit_stride = PAIR ? (int)n_clusters_x() : (int)gridDim.x;
+  const int n_units = PAIR ? (a.n_groups + 1) / 2 : a.n_groups;
+  // arrive on the barrier the MMA issuers wait on: the leader CTA's (a local arrive when this IS the leader / the only CTA)
+  auto arrive_issuer = [&](uint32_t b) { if (PAIR) mbar_arrive_leader(b, rank); else mbar_arrive_local(b); };
   const int L = a.L, F = a.F, CW_ROWS = a.L + 2;
   const int n_stacks = a.n_stacks, n_layer = a.n_layer;
   const int slots_per_stack = 2 + 2 * SLOTS_PASS * (n_layer - 1);
@@ -254,20 +283,22 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
   for (uint32_t i = threadIdx.x * 16; i < S.bars; i += N_THREADS * 16) st_shared_v4(sbase + i, 0u, 0u, 0u, 0u);
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(bar(B_WFULL + i), 1); mbar_init(bar(B_WEMPTY + i), N_TILES); }
+    // pair: the leader's B_WFULL also counts the peer's "my half has landed" (relay), its B_ACT / B_STAGE the peer's epilogue warps
+    for (int i = 0; i < NS; ++i) { mbar_init(bar(B_WFULL + i), (PAIR && rank == 0) ? 2 : 1); mbar_init(bar(B_WEMPTY + i), N_TILES); }
     mbar_init(bar(B_ACC), N_TILES);
-    mbar_init(bar(B_ACT), N_EPI_WARPS);
-    for (int i = 0; i < N_STAGES; ++i) mbar_init(bar(B_STAGE + i), N_EPI_WARPS);
+    mbar_init(bar(B_ACT), CG * N_EPI_WARPS);
+    for (int i = 0; i < N_STAGES; ++i) mbar_init(bar(B_STAGE + i), CG * N_EPI_WARPS);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < L; i += N_THREADS) {
     st_shared_u16(sbase + S.perm + 2 * i, (uint16_t)a.perm[i]);
     st_shared_u16(sbase + S.inv_perm + 2 * i, (uint16_t)a.inv_perm[i]);
   }
-  if (warp == WARP_MMA) tmem_alloc<1>(sbase + S.tmem_ptr, TMEM_COLS);
+  if (warp == WARP_MMA) tmem_alloc<CG>(sbase + S.tmem_ptr, TMEM_COLS);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();             // both CTAs' barriers are initialised before any remote arrive
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sbase + S.tmem_ptr) : "memory");
@@ -276,28 +307,41 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
     // ================= weight producer ==================================================================
     if (lane == 0) {
       uint32_t pos = 0, phase = 0;
-      for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x)
+      for (int un = unit0; un < n_units; un += unit_stride)
         for (int st = 0; st < n_stacks; ++st) {
-          const uint8_t* src = a.wimg + (size_t)st * a.stack_bytes;
+          const uint8_t* src = a.wimg + (size_t)st * a.stack_bytes + rank * SLOT_B;      // this CTA's half of every slot
           for (int i = 0; i < slots_per_stack; ++i) {
             mbar_wait(bar(B_WEMPTY + pos), phase ^ 1, a.err, 21);
             mbar_arrive_expect_tx(bar(B_WFULL + pos), SLOT_B);
             bulk_g2s(sbase + S.wslot + pos * SLOT_B, src, SLOT_B, bar(B_WFULL + pos));
-            src += SLOT_B;
+            src += SLOT_IMG_B;
             if (++pos == NS) { pos = 0; phase ^= 1; }
           }
         }
     }
+  } else if (warp >= WARP_MMA && warp < WARP_MMA + N_TILES && rank != 0) {
+    // ================= peer CTA: tell the leader that this CTA's half of a slot has landed (written by the async proxy: no fence) ====
+    if (warp == WARP_MMA) {
+      uint32_t pos = 0, phase = 0;
+      for (int un = unit0; un < n_units; un += unit_stride)
+        for (int i = 0; i < n_stacks * slots_per_stack; ++i) {
+          mbar_wait(bar(B_WFULL + pos), phase, a.err, 26);
+          if (elect_one()) mbar_arrive_remote(bar(B_WFULL + pos), 0);
+          __syncwarp();
+          if (++pos == NS) { pos = 0; phase ^= 1; }
+        }
+    }
   } else if (warp >= WARP_MMA && warp < WARP_MMA + N_TILES) {
-    // ================= MMA issuers: warp 8 + m owns tile m; each warp runs converged, one elected lane issues ===========
-    constexpr uint32_t IDESC = make_idesc_x3(128, NPAD);
+    // ================= MMA issuers (leader CTA): warp 8 + m owns tile m (of both CTAs' groups in the pair version); each warp runs
+    // converged, one elected lane issues ===========================================================================================
+    constexpr uint32_t IDESC = make_idesc_x3(128 * CG, NPAD);
     const int m = warp - WARP_MMA;
     uint32_t pos = 0, wphase = 0, n_act = 0, n_stage = 0;
     // descriptor low words of this tile's operands (start address + LBO); a k-step adds a compile-time constant
     const uint32_t rowoff = (uint32_t)(128 * m) * ROW_B;
     const uint32_t ahi_c = dlo(sbase + S.act_hi + rowoff, CHUNK_B), alo_c = dlo(sbase + S.act_lo + rowoff, CHUNK_B);              // chunk pairs
     const uint32_t ahi_t = dlo(sbase + S.act_hi + 12 * CHUNK_B + rowoff, ROW_B), alo_t = dlo(sbase + S.act_lo + 12 * CHUNK_B + rowoff, ROW_B);   // chunk 12, two taps
-    for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x)
+    for (int un = unit0; un < n_units; un += unit_stride)
       for (int st = 0; st < n_stacks; ++st) {
         const uint32_t xsel = (uint32_t)(a.enc ? (st == 2) : (st & 1));     // enc: branch 3 reads the interleaved bits
         const uint32_t xhi = dlo(sbase + S.xin_hi[0] + xsel * CHUNK_B + rowoff, ROW_B), xlo = dlo(sbase + S.xin_lo[0] + xsel * CHUNK_B + rowoff, ROW_B);
@@ -317,11 +361,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
 #pragma unroll
                 for (int ks = 0; ks < KS_L0; ++ks) {
                   const uint64_t bdesc = dfull(wlo + (uint32_t)(ks * KSTEP_B) / 16);
-                  umma_bf16<1>(d_tmem, dfull(xhi + (uint32_t)(2 * ks)), bdesc, IDESC, (part | ks) != 0);
-                  if (part == 0) umma_bf16<1>(d_tmem, dfull(xlo + (uint32_t)(2 * ks)), bdesc, IDESC, 1);
+                  umma_bf16<CG>(d_tmem, dfull(xhi + (uint32_t)(2 * ks)), bdesc, IDESC, (part | ks) != 0);
+                  if (part == 0) umma_bf16<CG>(d_tmem, dfull(xlo + (uint32_t)(2 * ks)), bdesc, IDESC, 1);
                 }
-                umma_commit_1(bar(B_WEMPTY + pos));
-                if (part == 1) umma_commit_1(bar(B_ACC));
+                commit_x3(bar(B_WEMPTY + pos));
+                if (part == 1) commit_x3(bar(B_ACC));
               }
               __syncwarp();
               if (++pos == NS) { pos = 0; wphase ^= 1; }
@@ -348,11 +392,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
                     // A operand, chunk-major: (chunk pair ks / 5, tap ks % 5) for ks < 30, else chunk 12 with two taps in one k-step
                     const uint32_t add = ks < 30 ? ((uint32_t)(2 * (ks / 5)) * CHUNK_B + (uint32_t)(ks % 5) * ROW_B) / 16 : (uint32_t)(2 * (ks - 30));
                     const uint64_t bdesc = dfull(wlo + (uint32_t)(k3 * KSTEP_B) / 16);
-                    umma_bf16<1>(d_tmem, dfull((ks < 30 ? ahi_c : ahi_t) + add), bdesc, IDESC, (part | s | k3) != 0);
-                    if (part == 0) umma_bf16<1>(d_tmem, dfull((ks < 30 ? alo_c : alo_t) + add), bdesc, IDESC, 1);
+                    umma_bf16<CG>(d_tmem, dfull((ks < 30 ? ahi_c : ahi_t) + add), bdesc, IDESC, (part | s | k3) != 0);
+                    if (part == 0) umma_bf16<CG>(d_tmem, dfull((ks < 30 ? alo_c : alo_t) + add), bdesc, IDESC, 1);
                   }
-                  umma_commit_1(bar(B_WEMPTY + pos));
-                  if (part == 1 && s == SLOTS_PASS - 1) umma_commit_1(bar(B_ACC));
+                  commit_x3(bar(B_WEMPTY + pos));
+                  if (part == 1 && s == SLOTS_PASS - 1) commit_x3(bar(B_ACC));
                 }
                 __syncwarp();
                 if (++pos == NS) { pos = 0; wphase ^= 1; }
@@ -370,7 +414,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
     const uint32_t taddr0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(tile * NPAD);
     const uint32_t tab_base = sbase + S.tab;
     uint32_t n_acc = 0;
-    for (int g = blockIdx.x; g < a.n_groups; g += gridDim.x) {
+    for (int un = unit0; un < n_units; un += unit_stride) {
+      const int g = PAIR ? 2 * un + (int)rank : un;    // (the odd group of the last pair may not exist: n_cw = 0, nothing is read or written)
       const int cw0 = g * a.cw_per_group;
       const int n_cw = max(0, min(a.cw_per_group, a.B - cw0));
       const int g_cw = g_row / CW_ROWS, g_l = g_row - g_cw * CW_ROWS;
@@ -436,7 +481,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
           stage_tables(0);
           fence_proxy_async();                         // the stack inputs were written with generic stores
           epi_bar_sync();
-          if (lane == 0) mbar_arrive_local(bar(B_ACT));
+          if (lane == 0) arrive_issuer(bar(B_ACT));
         } else {
           epi_bar_sync();                              // every warp is done with stack st-1 (its tables' buffer is reused below) and sees this stack's tables
         }
@@ -495,7 +540,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
               fence_proxy_async();
               if (cb == 6) tc_fence_before();           // (the accumulators this warp read are drained before the last arrival)
               __syncwarp();
-              if (lane == 0) mbar_arrive_local(bar(B_STAGE + cb));
+              if (lane == 0) arrive_issuer(bar(B_STAGE + cb));
             }
           }
           if (lin_layer) {
@@ -559,7 +604,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_local(bar(B_ACT));
+            if (lane == 0) arrive_issuer(bar(B_ACT));
           }
         }
       }
@@ -570,13 +615,14 @@ __global__ void __launch_bounds__(N_THREADS, 1) x3_kernel(const Args a) {
   // ---- teardown ---------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();             // the peer's shared memory and barriers stay alive until the leader's last commit has landed
   if (warp == WARP_MMA) {
     tc_fence_after();
-    tmem_dealloc<1>(tmem_base, TMEM_COLS);
+    tmem_dealloc<CG>(tmem_base, TMEM_COLS);
   }
 }
 
-uint32_t stack_bytes(int n_layer) { return (uint32_t)(2 + 2 * SLOTS_PASS * (n_layer - 1)) * SLOT_B; }
+uint32_t stack_bytes(int n_layer) { return (uint32_t)(2 + 2 * SLOTS_PASS * (n_layer - 1)) * SLOT_IMG_B; }
 
 bool supported(int L, int n_layer, int units, int k, int F, const char** why) {
   static thread_local char msg[160];
@@ -618,7 +664,7 @@ int launch(Args& a, void* ws, size_t ws_bytes, cudaStream_t s, const char* who) 
   a.cw_per_group = (GROUP_ROWS + 2) / (a.L + 2);
   a.n_groups = (a.B + a.cw_per_group - 1) / a.cw_per_group;
   a.stack_bytes = stack_bytes(a.n_layer);
-  const int grid = std::min(a.n_groups, n_sm);
+  const int grid = PAIR ? 2 * std::min((a.n_groups + 1) / 2, n_sm / 2) : std::min(a.n_groups, n_sm);
   x3_kernel<<<grid, N_THREADS, make_smem().total, s>>>(a);
   return after_launch(who);
 }

@@ -27,7 +27,7 @@ for cin, grp in ((7, 7), (200, 100)):
     t = tl.cpu().numpy().reshape(64, 8)
     print("R=%d " % R, end=""); print("in=%d: launch %.3f ms for %d steps = %.2f us/step" % (cin, e0.elapsed_time(e1), L, 1e3 * e0.elapsed_time(e1) / L))
     base = t[20, 0]
-    names = ["mma:wait_start", "mma:rdy", "mma:issued", "load:start", "load:done", "epi:acc", "epi:done"]
+    names = ["mma:wait_start", "mma:rdy", "mma:issued", "load:start", "load:done", "epi:acc0", "epi:done", "epi:acc1"]
     for s in range(20, 24):
         print("  step %d: " % s + "  ".join("%s=%d" % (n, t[s, i] - base) for i, n in enumerate(names)))
     d = np.diff(t[10:60, 1])

@@ -278,11 +278,6 @@ __global__ void X3_CLUSTER __launch_bounds__(N_THREADS, 1) x3_kernel(const Args 
   const int n_stacks = a.n_stacks, n_layer = a.n_layer;
   const int slots_per_stack = 2 + 2 * SLOTS_PASS * (n_layer - 1);
   auto bar = [&](int i) { return sbase + S.bars + 8u * (uint32_t)i; };
-  // The encoder's branches all read the inputs written at the group start: branch b+1's first layer may run while branch b's
-  // Linear epilogue is still at work, provided that epilogue reads the OTHER accumulator buffer (even number of layers: the last
-  // layer's parity is 1, the first layer's 0).  The epilogue warps then report B_ACT as soon as they have SEEN the last layer's
-  // B_ACC phase (so no later phase of B_ACC can complete before every waiter has observed this one), not after their work.
-  const bool enc_free_run = a.enc && (n_layer % 2 == 0);
 
   // ---- one-time setup ----------------------------------------------------------------------
   for (uint32_t i = threadIdx.x * 16; i < S.bars; i += N_THREADS * 16) st_shared_v4(sbase + i, 0u, 0u, 0u, 0u);
@@ -497,10 +492,6 @@ __global__ void X3_CLUSTER __launch_bounds__(N_THREADS, 1) x3_kernel(const Args 
           mbar_wait(bar(B_ACC), n_acc & 1, a.err, 24);
           ++n_acc;
           tc_fence_after();
-          if (enc_free_run && lin_layer && !last_stack) {
-            __syncwarp();
-            if (lane == 0) arrive_issuer(bar(B_ACT));
-          }
           const uint32_t btab = tab + 4u * (uint32_t)(TAB_BIAS + layer * NPAD);
           const uint32_t taddr = taddr0 + (uint32_t)(layer & 1) * TMEM_BUF_COLS;
           float lin[MAX_F] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -609,7 +600,7 @@ __global__ void X3_CLUSTER __launch_bounds__(N_THREADS, 1) x3_kernel(const Args 
           }
           // the next stack's first layer may start (its inputs were scattered by ALL warps): every warp reports on its own; the
           // group's very last epilogue is followed by the next group's start, which reports instead
-          if (lin_layer && !last_stack && !enc_free_run) {
+          if (lin_layer && !last_stack) {
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();

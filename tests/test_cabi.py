@@ -54,8 +54,8 @@ def test_split_operand_path_size_queries_and_validation_need_no_gpu():
     assert lib.tae_dec_workspace_bytes(ctypes.byref(cfg), 50000, _lib.PRECISION_F16X3) == 256
     enc = _lib.TaeEncConfig(100, 2, 100, 5)
     assert lib.tae_enc_packed_bytes_x3(ctypes.byref(enc)) == 3 * (2 + 22) * 10752
-    assert lib.tae_enc_packed_bytes_x3(ctypes.byref(_lib.TaeEncConfig(254, 5, 104, 5))) == 3 * (2 + 22 * 4) * 10752
-    for bad, word in ((_lib.TaeEncConfig(300, 2, 100, 5), b"block_len"), (_lib.TaeEncConfig(100, 2, 128, 5), b"num_unit"),
+    assert lib.tae_enc_packed_bytes_x3(ctypes.byref(_lib.TaeEncConfig(510, 5, 104, 5))) == 3 * (2 + 22 * 4) * 10752
+    for bad, word in ((_lib.TaeEncConfig(600, 2, 100, 5), b"block_len"), (_lib.TaeEncConfig(100, 2, 128, 5), b"num_unit"),
                       (_lib.TaeEncConfig(100, 2, 100, 3), b"kernel_size"), (_lib.TaeEncConfig(100, 9, 100, 5), b"num_layer")):
         assert lib.tae_enc_packed_bytes_x3(ctypes.byref(bad)) == 0 and word in lib.tae_last_error(), word
     assert lib.tae_dec_packed_bytes_x3(ctypes.byref(_lib.TaeDecConfig(100, 6, 6, 5, 100, 5, 1))) == 0      # num_iter_ft > 5
@@ -64,7 +64,7 @@ def test_split_operand_path_size_queries_and_validation_need_no_gpu():
     assert lib.tae_dec_forward(ctypes.byref(cfg), None, None, None, None, None, None, None, 3, _lib.PRECISION_F16X3, None, 0, None) == -1
     # the module resolves 'auto' without a device: the split-operand kernel where it covers the shape, else the fp32 kernels
     e = T.ENC_interCNN(make_args(no_cuda=True), O.make_perm(100, 0))
-    assert e.precision == "auto" and e.resolved_precision(100) == "f16x3" and e.resolved_precision(300) == "fp32"
+    assert e.precision == "auto" and e.resolved_precision(100) == "f16x3" and e.resolved_precision(510) == "f16x3" and e.resolved_precision(600) == "fp32"
     e.precision = "nonsense"
     with pytest.raises(_lib.TaeError):
         e.resolved_precision(100)

@@ -15,22 +15,31 @@
 // accumulation: a CPU emulation of the scheme with exact accumulation gives 4e-6, with round-toward-zero accumulation per
 // k-step 8e-5.  A bf16 split (-DTAE_X3_FP16=0; 16 bits) measures 2x worse.
 //
-// Execution model (one CTA per SM, no cluster):
-//   * a CTA owns one "group" = a 256-row activation buffer holding floor(258/(L+2)) codewords, each followed by 2 all-zero
-//     separator rows (the zero padding of cnn_utils.py:16); 2 MMA tiles of 128 rows, M = 128, N = 112, cta_group::1.
-//   * activations live in shared memory twice (hi and lo images), 16-bit, canonical no-swizzle K-major layout
+// Execution model
+//   * clusters of 2 CTAs (one per SM of a TPC), persistent.  The two CTAs' 256-row activation buffers form ONE 512-row space in
+//     which the codewords of a work unit are laid out back to back, each followed by 2 all-zero separator rows (the zero padding
+//     of cnn_utils.py:16): 5 codewords of block length 100 (97.7 % of the MMA rows are real positions; without the shared space
+//     2 + 2).  A codeword may straddle the CTA boundary: the two rows either side of it are MIRRORED into the neighbour's halo
+//     rows by the threads that own them -- st.async through distributed shared memory, completing a transaction barrier in the
+//     receiving CTA, so the writer needs no fence -- and the stack-input scatter writes to whichever CTA owns the row.
+//   * every layer is tcgen05.mma.cta_group::2, M = 256 = tile m of both CTAs, N = 112; each CTA stages its half of the weight
+//     columns.  Activations live in shared memory twice (hi and lo images), 16-bit, canonical no-swizzle K-major layout
 //     [13 chunks of 8 channels][264 rows][8]: tap t of the convolution is the same buffer addressed 16*t bytes later.
 //     K of a units->units layer = 33 k-steps of 16, CHUNK-major: 6 pairs of chunks x 5 taps (LBO = one chunk), then chunk 12
 //     with two taps per k-step (LBO = 16 bytes: taps (0,1), (2,3), (4,-)).  The first layer ((2+F) or 1 -> units) is 3
 //     k-steps of its one chunk.
 //   * weights stream from L2 through a bulk-copy ring: per layer 11 slots of W_hi (each used by the x_hi and the x_lo chain)
-//     then 11 slots of W_lo (x_hi chain); two MMA issuer warps, one per tile (two interleaved issue streams).
-//   * the epilogue (8 warps, one row per thread: tcgen05.ld, + bias, ELU, split into hi / lo, st.shared in place) publishes
-//     its output in 7 chunk stages; the next layer's MMAs start on the stages that are there (accumulators are double-buffered
-//     by layer parity), so the epilogue of layer j overlaps the MMAs of layer j+1.  The last layer of a stack keeps its output
-//     in registers and applies the Linear there (fp32): nothing is rounded between the last conv layer and the stack output.
+//     then 11 slots of W_lo (x_hi chain); two MMA issuer warps in the leader CTA, one per tile (two interleaved issue streams);
+//     the peer relays "my half of the slot has landed" and "my halo rows have landed".
+//   * the epilogue (8 warps per CTA, one row per thread: tcgen05.ld, + bias, ELU, split into hi / lo, st.shared in place)
+//     publishes its output in 7 chunk stages; the next layer's MMAs start on the stages that are there (accumulators are
+//     double-buffered by layer parity), so the epilogue of layer j overlaps the MMAs of layer j+1.  The last layer of a stack
+//     keeps its output in registers and applies the Linear there (fp32): nothing is rounded between the last conv layer and the
+//     stack output.
 //   * decoder: the stack inputs (received values and priors) are kept as an fp32 master copy [row][8] next to their hi / lo
 //     operand chunks; the extrinsic subtraction uses the fp32 prior, and (de)interleave is the row index of the store.
+//   * -DTAE_X3_STRADDLE=0: one group of floor(258/(L+2)) codewords per CTA, no cross-CTA rows; -DTAE_X3_PAIR=0: one CTA per
+//     group, cta_group::1.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -78,6 +87,15 @@ constexpr float ACC_INV = 1.f / (SCALE_W * SCALE_X);
 #endif
 constexpr bool PAIR = TAE_X3_PAIR != 0;
 constexpr int CG = PAIR ? 2 : 1;
+// 1 (default with the pair): the two CTAs' 256-row buffers form ONE 512-row space in which codewords are laid out back to back
+// (5 codewords of block length 100 instead of 2 x 2: 97.7 % instead of 80 % of the MMA rows are real positions).  A codeword may
+// straddle the CTA boundary: the two rows either side of it are MIRRORED into the neighbour's halo rows through distributed shared
+// memory (st.shared::cluster) by the threads that own them, and the stack-input scatter writes to whichever CTA owns the row.
+#ifndef TAE_X3_STRADDLE
+#define TAE_X3_STRADDLE TAE_X3_PAIR
+#endif
+constexpr bool STRADDLE = PAIR && (TAE_X3_STRADDLE != 0);
+constexpr int UNIT_ROWS = STRADDLE ? 2 * 256 : 256;     // rows of the space codewords are packed into
 
 constexpr int GROUP_ROWS = 256;
 constexpr int N_TILES = 2;
@@ -114,7 +132,13 @@ struct Smem {
 // epilogue of the previous stack), one phase per stack.  B_STAGE[c]: every epilogue warp has written chunk stage c of the layer
 // output (one phase per non-final layer epilogue): the next layer's MMAs start on the chunks that are there while the epilogue is
 // still writing the rest -- the K order of a units->units layer is chunk-major for that reason.
-enum { B_WFULL = 0, B_WEMPTY = NS, B_ACC = 2 * NS, B_ACT = 2 * NS + 1, B_STAGE = 2 * NS + 2, N_BARS = 2 * NS + 2 + N_STAGES };
+// B_ZERO (straddle): both CTAs have zeroed their stack-input buffers (cluster scope), so remote rows may be written.
+// B_HALO[c] (straddle, every CTA): the neighbour's mirror rows of chunk stage c have landed in this CTA's halo rows (st.async
+// complete_tx; armed by the waiter).  B_HREL[c] (leader): the peer's relay reports the peer's B_HALO[c].
+enum { B_WFULL = 0, B_WEMPTY = NS, B_ACC = 2 * NS, B_ACT = 2 * NS + 1, B_STAGE = 2 * NS + 2, B_ZERO = 2 * NS + 2 + N_STAGES,
+       B_HALO = 2 * NS + 3 + N_STAGES, B_HREL = 2 * NS + 3 + 2 * N_STAGES, N_BARS = 2 * NS + 3 + 3 * N_STAGES };
+// bytes the two mirror rows of one chunk stage carry: 2 rows x (2 chunks, or chunk 12 alone) x (hi, lo) x 16 bytes
+__host__ __device__ constexpr uint32_t halo_stage_bytes(int c) { return c < 6 ? 128u : 64u; }
 // the last epilogue stage whose chunks slot s of the W_hi pass reads (k-steps 3s .. 3s+2, chunk-major: k-step 5 cp + t)
 __host__ __device__ constexpr int stage_of_slot(int s) { return (3 * s + 2) < 30 ? (3 * s + 2) / 5 : 6; }
 
@@ -131,8 +155,8 @@ __host__ __device__ inline Smem make_smem() {
   s.master[1] = o; o += BUF_ROWS * 32;
   s.wslot = o; o += NS * SLOT_B;
   s.tab = o; o += 2 * TAB_FLOATS * 4;
-  s.perm = o; o += 512;
-  s.inv_perm = o; o += 512;
+  s.perm = o; o += 1024;                            // u16 x block length (<= 510)
+  s.inv_perm = o; o += 1024;
   s.bars = o; o += N_BARS * 8;
   s.tmem_ptr = o; o += 16;
   s.total = o;
@@ -164,7 +188,7 @@ struct Args {
   int* err;
   const int32_t* perm;
   const int32_t* inv_perm;
-  int B, L, F, n_stacks, n_layer, extrinsic, n_groups, cw_per_group, enc;
+  int B, L, F, n_stacks, n_layer, extrinsic, n_groups, n_units, cw_per_group, enc;   // cw_per_group: codewords per 256-row group (per 512-row unit when straddling)
   uint32_t stack_bytes;
   Layout lay;
 };
@@ -253,6 +277,28 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// distributed shared memory: address of the same offset in CTA `r` of the cluster, and stores through it
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t addr, uint32_t r) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(addr), "r"(r));
+  return ra;
+}
+__device__ __forceinline__ void st_cluster_b32(uint32_t ra, uint32_t v) { asm volatile("st.shared::cluster.b32 [%0], %1;" ::"r"(ra), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_cluster_b16(uint32_t ra, uint16_t v) { asm volatile("st.shared::cluster.b16 [%0], %1;" ::"r"(ra), "h"(v) : "memory"); }
+__device__ __forceinline__ void st_cluster_v2(uint32_t ra, uint32_t a, uint32_t b) { asm volatile("st.shared::cluster.v2.b32 [%0], {%1,%2};" ::"r"(ra), "r"(a), "r"(b) : "memory"); }
+__device__ __forceinline__ void st_cluster_v4(uint32_t ra, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ra), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// 16 bytes into the peer's shared memory through the async proxy; completes 16 bytes of the transaction count of the mbarrier
+// `rbar` (an address in the SAME peer CTA) once the data has been written: no fence on the writer's side
+__device__ __forceinline__ void st_async_v4(uint32_t ra, uint32_t rbar, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(ra), "r"(a), "r"(b), "r"(c),
+               "r"(d), "r"(rbar)
+               : "memory");
+}
+// generic-proxy writes (to this CTA's or the peer's shared memory) before later async-proxy (tensor core) reads
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); }
+
 #if TAE_X3_PAIR
 #define X3_CLUSTER __cluster_dims__(2, 1, 1)
 #else
@@ -271,7 +317,7 @@ __global__ void X3_CLUSTER __launch_bounds__(N_THREADS, 1) x3_kernel(const Args 
   // pair: the cluster's CTAs own groups 2 u and 2 u + 1 of work unit u; single: one group per unit
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const int unit0 = PAIR ? (int)cluster_id_x() : (int)blockIdx.x, unit_stride = PAIR ? (int)n_clusters_x() : (int)gridDim.x;
-  const int n_units = PAIR ? (a.n_groups + 1) / 2 : a.n_groups;
+  const int n_units = a.n_units;
   // arrive on the barrier the MMA issuers wait on: the leader CTA's (a local arrive when this IS the leader / the only CTA)
   auto arrive_issuer = [&](uint32_t b) { if (PAIR) mbar_arrive_leader(b, rank); else mbar_arrive_local(b); };
   const int L = a.L, F = a.F, CW_ROWS = a.L + 2;
@@ -288,6 +334,8 @@ __global__ void X3_CLUSTER __launch_bounds__(N_THREADS, 1) x3_kernel(const Args 
     mbar_init(bar(B_ACC), N_TILES);
     mbar_init(bar(B_ACT), CG * N_EPI_WARPS);
     for (int i = 0; i < N_STAGES; ++i) mbar_init(bar(B_STAGE + i), CG * N_EPI_WARPS);
+    mbar_init(bar(B_ZERO), CG * N_EPI_WARPS);
+    for (int i = 0; i < N_STAGES; ++i) { mbar_init(bar(B_HALO + i), 1); mbar_init(bar(B_HREL + i), 1); }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < L; i += N_THREADS) {
@@ -330,6 +378,19 @@ __global__ void X3_CLUSTER __launch_bounds__(N_THREADS, 1) x3_kernel(const Args 
           __syncwarp();
           if (++pos == NS) { pos = 0; phase ^= 1; }
         }
+    } else if (STRADDLE) {
+      // halo relay: the leader's rows 254, 255 land in this CTA's front halo rows chunk stage by chunk stage (st.async); arm, wait,
+      // tell the leader's tile-0 issuer (data written by the async proxy into THIS CTA's shared memory: no fence, like the weights)
+      uint32_t ph = 0;
+      for (int un = unit0; un < n_units; un += unit_stride)
+        for (int i = 0; i < n_stacks * (n_layer - 1); ++i, ph ^= 1)
+          for (int c = 0; c < N_STAGES; ++c) {
+            if (elect_one()) mbar_arrive_expect_tx(bar(B_HALO + c), halo_stage_bytes(c));
+            __syncwarp();
+            mbar_wait(bar(B_HALO + c), ph, a.err, 30);
+            if (elect_one()) mbar_arrive_remote(bar(B_HREL + c), 0);
+            __syncwarp();
+          }
     }
   } else if (warp >= WARP_MMA && warp < WARP_MMA + N_TILES) {
     // ================= MMA issuers (leader CTA): warp 8 + m owns tile m (of both CTAs' groups in the pair version); each warp runs
@@ -348,7 +409,8 @@ __global__ void X3_CLUSTER __launch_bounds__(N_THREADS, 1) x3_kernel(const Args 
         for (int layer = 0; layer < n_layer; ++layer) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(layer & 1) * TMEM_BUF_COLS + (uint32_t)(m * NPAD);     // accumulators alternate by layer parity
           if (layer == 0) {
-            mbar_wait(bar(B_ACT), n_act & 1, a.err, 22);     // the stack input is in place
+            // the stack input is in place (straddle: rows may have been written by the peer's threads: cluster-scope acquire)
+            if (STRADDLE) mbar_wait_cluster(bar(B_ACT), n_act & 1, a.err, 22); else mbar_wait(bar(B_ACT), n_act & 1, a.err, 22);
             ++n_act;
             tc_fence_after();
             // slots: W0_hi (x_hi and x_lo chains), W0_lo (x_hi chain)
@@ -380,7 +442,20 @@ __global__ void X3_CLUSTER __launch_bounds__(N_THREADS, 1) x3_kernel(const Args 
                 // the chunks this slot's k-steps read have been written by every epilogue warp of the previous layer
                 if (part == 0) {
 #pragma unroll
-                  for (int c = (s == 0 ? 0 : stage_of_slot(s - 1) + 1); c <= stage_of_slot(s); ++c) mbar_wait(bar(B_STAGE + c), sphase, a.err, 25);
+                  for (int c = (s == 0 ? 0 : stage_of_slot(s - 1) + 1); c <= stage_of_slot(s); ++c) {
+                    mbar_wait(bar(B_STAGE + c), sphase, a.err, 25);
+                    if (STRADDLE) {
+                      // + the halo rows the neighbour mirrors into the CTA whose tile reads them: tile 1 reads the leader's rows behind
+                      // row 255 (armed and waited for here), tile 0 the peer's rows in front of its row 0 (reported by the peer's relay)
+                      if (m == 1) {
+                        if (elect_one()) mbar_arrive_expect_tx(bar(B_HALO + c), halo_stage_bytes(c));
+                        __syncwarp();
+                        mbar_wait(bar(B_HALO + c), sphase, a.err, 28);
+                      } else {
+                        mbar_wait(bar(B_HREL + c), sphase, a.err, 29);
+                      }
+                    }
+                  }
                 }
                 mbar_wait(bar(B_WFULL + pos), wphase, a.err, 23);
                 tc_fence_after();
@@ -413,12 +488,45 @@ __global__ void X3_CLUSTER __launch_bounds__(N_THREADS, 1) x3_kernel(const Args 
     const uint32_t brow = (uint32_t)(g_row + HALO_LO);
     const uint32_t taddr0 = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(tile * NPAD);
     const uint32_t tab_base = sbase + S.tab;
-    uint32_t n_acc = 0;
+    uint32_t n_acc = 0, n_zero = 0;
+    // straddle: this thread's row in the unit's 512-row space; the two rows either side of the CTA boundary are mirrored into the
+    // neighbour's halo rows (rank 0 rows 254, 255 -> peer buffer rows 0, 1; rank 1 rows 0, 1 -> leader buffer rows 258, 259)
+    const int u_row = STRADDLE ? 256 * (int)rank + g_row : g_row;
+    const bool mirror = STRADDLE && (rank == 0 ? g_row >= 254 : g_row <= 1);
+    const uint32_t mirror_brow = rank == 0 ? (uint32_t)(g_row - 254) : (uint32_t)(258 + g_row);
+    // store into the stack-input buffers of whichever CTA owns unit row R (+ the neighbour's halo row when R is at the boundary)
+    auto owner_addr = [&](uint32_t buf, int R, uint32_t stride, uint32_t off) {
+      return dsmem_addr(sbase + buf + (uint32_t)((R & 255) + HALO_LO) * stride + off, (uint32_t)(R >> 8));
+    };
+    auto halo_addr = [&](uint32_t buf, int R, uint32_t off) {          // only for R in {254, 255, 256, 257}
+      return R < 256 ? dsmem_addr(sbase + buf + (uint32_t)(R - 254) * ROW_B + off, 1u) : dsmem_addr(sbase + buf + (uint32_t)(R + HALO_LO) * ROW_B + off, 0u);
+    };
+    auto put16 = [&](uint32_t buf, int R, uint32_t off, uint16_t v) {
+      if (!STRADDLE) { st_shared_u16(sbase + buf + (uint32_t)(R + HALO_LO) * ROW_B + off, v); return; }
+      st_cluster_b16(owner_addr(buf, R, ROW_B, off), v);
+      if (R >= 254 && R <= 257) st_cluster_b16(halo_addr(buf, R, off), v);
+    };
+    auto put32 = [&](uint32_t buf, int R, uint32_t off, uint32_t v) {
+      if (!STRADDLE) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + buf + (uint32_t)(R + HALO_LO) * ROW_B + off), "r"(v) : "memory"); return; }
+      st_cluster_b32(owner_addr(buf, R, ROW_B, off), v);
+      if (R >= 254 && R <= 257) st_cluster_b32(halo_addr(buf, R, off), v);
+    };
+    auto put64 = [&](uint32_t buf, int R, uint32_t off, uint32_t v0, uint32_t v1) {
+      if (!STRADDLE) { st_shared_v2(sbase + buf + (uint32_t)(R + HALO_LO) * ROW_B + off, v0, v1); return; }
+      st_cluster_v2(owner_addr(buf, R, ROW_B, off), v0, v1);
+      if (R >= 254 && R <= 257) st_cluster_v2(halo_addr(buf, R, off), v0, v1);
+    };
+    auto put_master = [&](uint32_t buf, int R, uint32_t off, float v) {      // fp32 master copy [row][8]: read by the row's own thread only
+      if (!STRADDLE) { st_shared_f32(sbase + buf + (uint32_t)(R + HALO_LO) * 32 + off, v); return; }
+      st_cluster_b32(owner_addr(buf, R, 32, off), __float_as_uint(v));
+    };
+    // arrive on the issuers' barrier after writes that may have gone to the PEER's shared memory: cluster-scope release
+    auto arrive_issuer_cluster = [&](uint32_t b) { if (STRADDLE) mbar_arrive_cluster(b, 0); else arrive_issuer(b); };
     for (int un = unit0; un < n_units; un += unit_stride) {
-      const int g = PAIR ? 2 * un + (int)rank : un;    // (the odd group of the last pair may not exist: n_cw = 0, nothing is read or written)
-      const int cw0 = g * a.cw_per_group;
+      // non-straddle pair: (the odd group of the last pair may not exist: n_cw = 0, nothing is read or written)
+      const int cw0 = (STRADDLE ? un : (PAIR ? 2 * un + (int)rank : un)) * a.cw_per_group;
       const int n_cw = max(0, min(a.cw_per_group, a.B - cw0));
-      const int g_cw = g_row / CW_ROWS, g_l = g_row - g_cw * CW_ROWS;
+      const int g_cw = u_row / CW_ROWS, g_l = u_row - g_cw * CW_ROWS;
       const bool valid = (g_l < L) && (g_cw < n_cw);
       const uint32_t keep = valid ? 0xFFFFFFFFu : 0u;
 
@@ -427,33 +535,40 @@ __global__ void X3_CLUSTER __launch_bounds__(N_THREADS, 1) x3_kernel(const Args 
 #pragma unroll 1
       for (uint32_t i = tid * 16; i < S.wslot - S.xin_hi[0]; i += N_EPI_THREADS * 16) st_shared_v4(sbase + S.xin_hi[0] + i, 0u, 0u, 0u, 0u);
       epi_bar_sync();
+      if (STRADDLE) {
+        // both CTAs have zeroed before either writes rows into the other (cluster-scope release / acquire)
+        if (lane == 0) { mbar_arrive_cluster(bar(B_ZERO), 0); mbar_arrive_cluster(bar(B_ZERO), 1); }
+        mbar_wait_cluster(bar(B_ZERO), n_zero & 1, a.err, 27);
+        ++n_zero;
+      }
       {
-        const int sc = tid / L, sl = tid - sc * L;
-        if (tid < n_cw * L) {
-          const uint32_t row = (uint32_t)(sc * CW_ROWS + sl + HALO_LO);
-          const uint32_t row_i = (uint32_t)(sc * CW_ROWS + ld_shared_u16(sbase + S.inv_perm + 2 * sl) + HALO_LO);
+        const int idx = STRADDLE ? 256 * (int)rank + tid : tid;      // one (codeword, position) of the unit per thread
+        const int sc = idx / L, sl = idx - sc * L;
+        if (idx < n_cw * L) {
+          const int R = sc * CW_ROWS + sl;
+          const int Ri = sc * CW_ROWS + (int)ld_shared_u16(sbase + S.inv_perm + 2 * sl);
           if (a.enc) {
-            const uint16_t x = half_bits(SCALE_X * (2.0f * a.u[(size_t)cw0 * L + tid] - 1.0f));              // encoders.py:362 (+-1: exact)
-            st_shared_u16(sbase + S.xin_hi[0] + row * ROW_B, x);          // branches 1, 2
-            st_shared_u16(sbase + S.xin_hi[1] + row_i * ROW_B, x);        // branch 3: x_int[i] = x[p[i]]   (encoders.py:369)
+            const uint16_t x = half_bits(SCALE_X * (2.0f * a.u[(size_t)cw0 * L + idx] - 1.0f));              // encoders.py:362 (+-1: exact)
+            put16(S.xin_hi[0], R, 0, x);           // branches 1, 2
+            put16(S.xin_hi[1], Ri, 0, x);          // branch 3: x_int[i] = x[p[i]]   (encoders.py:369)
           } else {
-            const float* rsrc = a.received + ((size_t)cw0 * L + tid) * 3;
+            const float* rsrc = a.received + ((size_t)cw0 * L + idx) * 3;
             const float r0 = __ldg(rsrc), r1 = __ldg(rsrc + 1), r2 = __ldg(rsrc + 2);
             uint32_t h01, l01, h2, l2;
             split2(r0, r1, h01, l01);
             split2(r2, 0.f, h2, l2);
             // stack "dec1" input: [r_sys, r_par1, prior...]  (decoders.py:221, 223, 230)
-            st_shared_f32(sbase + S.master[0] + row * 32, r0);
-            st_shared_f32(sbase + S.master[0] + row * 32 + 4, r1);
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + S.xin_hi[0] + row * ROW_B), "r"(h01) : "memory");
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + S.xin_lo[0] + row * ROW_B), "r"(l01) : "memory");
+            put_master(S.master[0], R, 0, r0);
+            put_master(S.master[0], R, 4, r1);
+            put32(S.xin_hi[0], R, 0, h01);
+            put32(S.xin_lo[0], R, 0, l01);
             // stack "dec2" input: [r_sys_int, r_par2, x_plr_int...], r_sys_int[i] = r_sys[p[i]]   (decoders.py:222, 224, 240)
-            st_shared_f32(sbase + S.master[1] + row_i * 32, r0);
-            st_shared_f32(sbase + S.master[1] + row * 32 + 4, r2);
-            st_shared_u16(sbase + S.xin_hi[1] + row_i * ROW_B, (uint16_t)(h01 & 0xFFFFu));
-            st_shared_u16(sbase + S.xin_lo[1] + row_i * ROW_B, (uint16_t)(l01 & 0xFFFFu));
-            st_shared_u16(sbase + S.xin_hi[1] + row * ROW_B + 2, (uint16_t)(h2 & 0xFFFFu));
-            st_shared_u16(sbase + S.xin_lo[1] + row * ROW_B + 2, (uint16_t)(l2 & 0xFFFFu));
+            put_master(S.master[1], Ri, 0, r0);
+            put_master(S.master[1], R, 4, r2);
+            put16(S.xin_hi[1], Ri, 0, (uint16_t)(h01 & 0xFFFFu));
+            put16(S.xin_lo[1], Ri, 0, (uint16_t)(l01 & 0xFFFFu));
+            put16(S.xin_hi[1], R, 2, (uint16_t)(h2 & 0xFFFFu));
+            put16(S.xin_lo[1], R, 2, (uint16_t)(l2 & 0xFFFFu));
           }
         }
       }
@@ -479,9 +594,9 @@ __global__ void X3_CLUSTER __launch_bounds__(N_THREADS, 1) x3_kernel(const Args 
         };
         if (st == 0) {
           stage_tables(0);
-          fence_proxy_async();                         // the stack inputs were written with generic stores
+          if (STRADDLE) fence_proxy_async_all(); else fence_proxy_async();      // the stack inputs were written with generic stores
           epi_bar_sync();
-          if (lane == 0) arrive_issuer(bar(B_ACT));
+          if (lane == 0) arrive_issuer_cluster(bar(B_ACT));
         } else {
           epi_bar_sync();                              // every warp is done with stack st-1 (its tables' buffer is reused below) and sees this stack's tables
         }
@@ -522,6 +637,11 @@ __global__ void X3_CLUSTER __launch_bounds__(N_THREADS, 1) x3_kernel(const Args 
                 for (int j = 0; j < 4; ++j) split2(v[2 * j], v[2 * j + 1], h[j], l[j]);
                 st_shared_v4(sbase + S.act_hi + (uint32_t)c * CHUNK_B + brow * ROW_B, h[0] & keep, h[1] & keep, h[2] & keep, h[3] & keep);
                 st_shared_v4(sbase + S.act_lo + (uint32_t)c * CHUNK_B + brow * ROW_B, l[0] & keep, l[1] & keep, l[2] & keep, l[3] & keep);
+                if (mirror) {       // the neighbour CTA's taps read this row as a halo row: async-proxy store + complete_tx on ITS B_HALO[cb]
+                  const uint32_t rbar = dsmem_addr(bar(B_HALO + cb), rank ^ 1u);
+                  st_async_v4(dsmem_addr(sbase + S.act_hi + (uint32_t)c * CHUNK_B + mirror_brow * ROW_B, rank ^ 1u), rbar, h[0] & keep, h[1] & keep, h[2] & keep, h[3] & keep);
+                  st_async_v4(dsmem_addr(sbase + S.act_lo + (uint32_t)c * CHUNK_B + mirror_brow * ROW_B, rank ^ 1u), rbar, l[0] & keep, l[1] & keep, l[2] & keep, l[3] & keep);
+                }
               } else {
                 // Linear of the stack output, in fp32 straight from the accumulators (decoders.py:232, 243; encoders.py:364)
 #pragma unroll
@@ -578,33 +698,33 @@ __global__ void X3_CLUSTER __launch_bounds__(N_THREADS, 1) x3_kernel(const Args 
                 a.out[(size_t)cw * L + dl] = 1.f / (1.f + __expf(-lin[0]));                     // decoders.py:267
               } else {
                 const uint32_t cur_m = sbase + S.master[st & 1] + brow * 32, nxt = (uint32_t)((st & 1) ^ 1);
-                const uint32_t drow = (uint32_t)(g_cw * CW_ROWS) + dl + HALO_LO;
+                const int dR = g_cw * CW_ROWS + (int)dl;             // destination row in the unit's row space
                 float e[6];
 #pragma unroll
                 for (int f = 0; f < 5; ++f) {
                   const float prior = a.extrinsic ? ld_shared_f32(cur_m + 8 + 4 * f) : 0.f;     // decoders.py:235-236, 246-247
                   e[f] = f < F ? lin[f] - prior : 0.f;
-                  st_shared_f32(sbase + S.master[nxt] + drow * 32 + 8 + 4 * f, e[f]);
+                  put_master(S.master[nxt], dR, 8 + 4 * f, e[f]);
                 }
                 e[5] = 0.f;
                 uint32_t h0, l0, h1, l1, h2, l2;
                 split2(e[0], e[1], h0, l0);
                 split2(e[2], e[3], h1, l1);
                 split2(e[4], e[5], h2, l2);
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + S.xin_hi[nxt] + drow * ROW_B + 4), "r"(h0) : "memory");
-                st_shared_v2(sbase + S.xin_hi[nxt] + drow * ROW_B + 8, h1, h2);
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(sbase + S.xin_lo[nxt] + drow * ROW_B + 4), "r"(l0) : "memory");
-                st_shared_v2(sbase + S.xin_lo[nxt] + drow * ROW_B + 8, l1, l2);
+                put32(S.xin_hi[nxt], dR, 4, h0);
+                put64(S.xin_hi[nxt], dR, 8, h1, h2);
+                put32(S.xin_lo[nxt], dR, 4, l0);
+                put64(S.xin_lo[nxt], dR, 8, l1, l2);
               }
             }
           }
           // the next stack's first layer may start (its inputs were scattered by ALL warps): every warp reports on its own; the
           // group's very last epilogue is followed by the next group's start, which reports instead
           if (lin_layer && !last_stack) {
-            fence_proxy_async();
+            if (STRADDLE) fence_proxy_async_all(); else fence_proxy_async();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) arrive_issuer(bar(B_ACT));
+            if (lane == 0) arrive_issuer_cluster(bar(B_ACT));
           }
         }
       }
@@ -631,7 +751,7 @@ bool supported(int L, int n_layer, int units, int k, int F, const char** why) {
   if (units < 1 || units > UNITS_MAX) { snprintf(msg, sizeof msg, "num_unit %d > %d", units, UNITS_MAX); return false; }
   if (F < 1 || F > MAX_F) { snprintf(msg, sizeof msg, "num_iter_ft %d > %d", F, MAX_F); return false; }
   if (n_layer < 1 || n_layer > MAX_LAYER) { snprintf(msg, sizeof msg, "num_layer %d outside 1..%d", n_layer, MAX_LAYER); return false; }
-  if (L < 1 || L > GROUP_ROWS) { snprintf(msg, sizeof msg, "block_len %d > %d (one codeword must fit a 256-row group)", L, GROUP_ROWS); return false; }
+  if (L < 1 || L + 2 > UNIT_ROWS) { snprintf(msg, sizeof msg, "block_len %d > %d (one codeword must fit the %d-row space of a work unit)", L, UNIT_ROWS - 2, UNIT_ROWS); return false; }
   *why = nullptr;
   return true;
 }
@@ -661,10 +781,11 @@ int launch(Args& a, void* ws, size_t ws_bytes, cudaStream_t s, const char* who) 
   int rc = launch_setup(&n_sm);
   if (rc) return rc;
   a.err = wait_code_slot(ws);
-  a.cw_per_group = (GROUP_ROWS + 2) / (a.L + 2);
+  a.cw_per_group = (UNIT_ROWS + 2) / (a.L + 2);       // codewords per 256-row group, or per 512-row unit when straddling
   a.n_groups = (a.B + a.cw_per_group - 1) / a.cw_per_group;
+  a.n_units = (PAIR && !STRADDLE) ? (a.n_groups + 1) / 2 : a.n_groups;
   a.stack_bytes = stack_bytes(a.n_layer);
-  const int grid = PAIR ? 2 * std::min((a.n_groups + 1) / 2, n_sm / 2) : std::min(a.n_groups, n_sm);
+  const int grid = PAIR ? 2 * std::min(a.n_units, n_sm / 2) : std::min(a.n_units, n_sm);
   x3_kernel<<<grid, N_THREADS, make_smem().total, s>>>(a);
   return after_launch(who);
 }

@@ -93,7 +93,7 @@ class ENC_interCNN(ENCBase):
         #: 'f16x3' (split-operand tcgen05 kernel, tae_x3.cu: elementwise parity <= 1e-4 at tensor-core speed), 'fp32' (CUDA-core
         #: path, same parity, ~8x slower), 'bf16' (the decoder's fused tcgen05 kernel with the three branches as three conv stacks:
         #: fastest, codes within bf16 rounding of the reference's) or 'auto' (default): 'f16x3' where that kernel covers the
-        #: configuration (kernel size 5, <= 104 units, block length <= 256), else 'fp32' -- both meet the same tolerance
+        #: configuration (kernel size 5, <= 104 units, block length <= 510), else 'fp32' -- both meet the same tolerance
         self.precision = getattr(args, "tae_enc_precision", None) or os.environ.get("TURBOAE_B200_ENC_PRECISION", "auto")
         #: training (autograd) path: 'fp32' (CUDA-core kernels) or 'bf16' (tensor cores, train_tc.py)
         from . import train_tc

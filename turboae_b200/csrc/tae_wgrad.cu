@@ -150,7 +150,7 @@ int launch_wgrad(const TaeWgradJob* jobs_host, int n_jobs, const void* jobs_dev,
   for (int i = 0; i < n_jobs; ++i) {
     const TaeWgradJob& J = jobs_host[i];
     if (!J.a_img || !J.b_img || !J.grad || J.b_nc < 1 || J.b_nc > (int)W_B_CHUNKS_MAX || J.b_c0 < 0 || J.b_c0 + J.b_nc > J.b_chunks ||
-        (J.taps != 1 && J.taps != 3 && J.taps != 5) || J.n_cols % 16 || J.n_cols < 16 || J.n_cols > 8 * (J.b_nc + 1) || J.taps * J.n_cols > 512 ||
+        (J.taps != 1 && J.taps != 3 && J.taps != 5) || J.n_cols % 16 || J.n_cols < 16 || J.n_cols > 8 * (J.b_nc + 1) || J.n_cols < 8 * J.b_nc || J.taps * J.n_cols > 512 ||
         J.m_valid < 1 || J.m_valid > 104 || J.n_valid < 0 || J.n_valid > 8 * J.b_nc || J.g1 < J.g0) {
       set_error("tae_wgrad_bf16: job %d is malformed", i);
       return TAE_EINVAL;

@@ -136,7 +136,14 @@ class ENC_interCNN(ENCBase):
             raise _lib.TaeError("encoder precision must be 'auto', 'f16x3', 'fp32' or 'bf16', got %r" % (self.precision,))
         if self.precision != "auto":
             return self.precision
-        return "f16x3" if _lib.load().tae_enc_packed_bytes_x3(self.config(block_len)) else "fp32"
+        if _lib.load().tae_enc_packed_bytes_x3(self.config(block_len)):
+            return "f16x3"
+        if not getattr(self, "_warned_fp32", False):          # said once: the choice is by shape, never silent
+            import warnings
+            warnings.warn("turboae_b200.ENC_interCNN: the split-operand tensor kernel does not cover this configuration (%s); "
+                          "using the fp32 CUDA-core kernels (same tolerance, ~10x slower)" % _lib.load().tae_last_error().decode())
+            self._warned_fp32 = True
+        return "fp32"
 
     def encode_unnormalised(self, inputs, stats):
         """x_tx (B, L, 3) before power_constraint; adds (sum, sumsq, count) into the 3 device doubles `stats`."""

@@ -430,7 +430,7 @@ def run_b200(a):
                 default_enc_name = m.enc.resolved_precision(100)
                 ms = timed(lambda: m.dec(m.enc(bits[0]) + noise), 3)
                 sec["channel_ae_forward_default_cw_per_s"] = B / (ms * 1e-3)
-                sec["channel_ae_forward_default"] = "Channel_AE.forward with the modules' default settings (encoder %s, decoder %s)" % (default_enc_name, m.dec.precision)
+                sec["channel_ae_forward_default"] = "Channel_AE.forward with the modules' default settings (encoder %s, decoder %s)" % (default_enc_name, m.dec.resolved_precision(100))
                 for prec in ("fp32", "bf16", "f16x3"):
                     m.enc.precision = prec
                     ms = timed(lambda: m.enc(bits[0]), 3)

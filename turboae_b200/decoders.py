@@ -49,7 +49,9 @@ class DEC_LargeCNN(torch.nn.Module):
         self._ws_host = Workspace()
         #: 'bf16' (fused tcgen05 kernel: BER parity), 'f16x3' (split-operand tcgen05 kernel: elementwise parity <= 1e-4 at
         #: ~13x the fp32 rate) or 'fp32' (CUDA-core parity path)
-        self.precision = getattr(args, "tae_precision", None) or os.environ.get("TURBOAE_B200_PRECISION", "bf16")
+        #: 'auto' (default) = 'bf16' wherever the fused kernel covers the configuration (kernel size 5, <= 100 units, block length
+        #: <= 512), else the fp32 kernels -- said once in a warning, never silent
+        self.precision = getattr(args, "tae_precision", None) or os.environ.get("TURBOAE_B200_PRECISION", "auto")
         #: training (autograd) path: 'fp32' = CUDA-core kernels layer by layer (gradients within 2e-3 of the reference's),
         #: 'bf16' = tensor cores (train_tc.py: fused forward with stash, fused backward per stack, weight-gradient GEMMs)
         #: default: 'bf16' whenever the tensor path covers the configuration (decided here, once, from args)
@@ -105,11 +107,26 @@ class DEC_LargeCNN(torch.nn.Module):
                                            ws.numel(), _lib.stream_ptr(dev)))
         return out
 
+    def resolved_precision(self, block_len, precision=None):
+        """The inference path a forward at this block length takes ('auto' resolved; see ``precision``)."""
+        precision = precision or self.precision
+        if precision != "auto":
+            if precision not in _lib.PRECISIONS:
+                raise _lib.TaeError("precision must be 'auto', 'bf16', 'f16x3' or 'fp32', got %r" % (precision,))
+            return precision
+        lib = _lib.load()
+        if lib.tae_dec_packed_bytes(self.config(block_len)):
+            return "bf16"
+        if not getattr(self, "_warned_fp32", False):          # said once: the choice is by shape, never silent
+            import warnings
+            warnings.warn("turboae_b200.DEC_LargeCNN: the fused tensor-core kernel does not cover this configuration (%s); "
+                          "using the fp32 CUDA-core kernels (elementwise parity, ~45x slower)" % lib.tae_last_error().decode())
+            self._warned_fp32 = True
+        return "fp32"
+
     def _prepare(self, L, dev, precision):
         lib = _lib.load()
-        precision = precision or self.precision
-        if precision not in _lib.PRECISIONS:
-            raise _lib.TaeError("precision must be 'bf16', 'f16x3' or 'fp32', got %r" % (precision,))
+        precision = self.resolved_precision(L, precision)
         prec = _lib.PRECISIONS[precision]
         cfg = self.config(L)
         flat = self._flat.get(self.ordered_parameters())

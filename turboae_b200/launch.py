@@ -12,7 +12,7 @@ classes, then runs the script with `runpy` as `__main__`.  main.py picks its cla
 
 The reference targets PyTorch 1.0 / numpy < 1.20; `_modernise()` restores the handful of names newer libraries
 removed (numpy.float/int/complex, fractions.gcd, an importable `matplotlib`, torch.load without map_location on a
-CPU-only host).  That is environment glue, not a change of behaviour.
+CPU-only host, commpy's Python-2 `array(map(...))` interleaver).  That is environment glue, not a change of behaviour.
 """
 from __future__ import annotations
 
@@ -41,6 +41,16 @@ def _modernise():
                 return None
         for n in ("matplotlib", "matplotlib.pyplot", "matplotlib.collections", "matplotlib.patches", "matplotlib.mlab"):
             sys.modules.setdefault(n, _Stub(n))                 # commpy/channelcoding/convcode.py:9-11
+    try:
+        # Python 2's `array(map(...))` (commpy/channelcoding/interleavers.py:19) yields a 0-d object array on Python 3: the classical
+        # turbo encoders (-encoder Turbo_rate3_757 / Turbo_rate3_lte, README.md:94-98) would fail in turbo_encode.  Same permutation.
+        from commpy.channelcoding import interleavers as _ci
+
+        def interlv(self, in_array):
+            return np.asarray(in_array)[np.asarray(self.p_array)]
+        _ci._Interleaver.interlv = interlv
+    except Exception:  # pragma: no cover -- a checkout without the vendored commpy
+        pass
     if not torch.cuda.is_available():
         _load = torch.load
 

@@ -1,0 +1,13 @@
+#!/bin/bash
+# more flags of the reference through the launcher (tiny runs): joint training, a fresh interleaver per forward, other kernel sizes,
+# lookahead optimizer, variable block length, no extrinsic subtraction
+mkdir -p gpurun_out/dropin_work && cd gpurun_out/dropin_work && ln -sfn $OLDPWD/baseline/_ref/models models
+export PYTHONPATH=$OLDPWD
+C="-encoder TurboAE_rate3_cnn -decoder TurboAE_rate3_cnn -enc_num_unit 100 -enc_num_layer 2 -dec_num_unit 100 -dec_num_layer 5 -num_iter_ft 5 -channel awgn -num_train_dec 2 -num_train_enc 1 -code_rate_k 1 -code_rate_n 3 -train_enc_channel_low 2.0 -train_enc_channel_high 2.0 -snr_test_start 0.0 -snr_test_end 2.0 -snr_points 2 -num_iteration 6 -is_parallel 1 -train_dec_channel_low -1.5 -train_dec_channel_high 2.0 -dec_lr 0.0001 -enc_lr 0.0001 -num_block 2000 -batch_size 500 -train_channel_mode block_norm -test_channel_mode block_norm --print_test_traj -loss bce -num_epoch 1"
+run() { echo "== $1"; shift; timeout 600 python -m turboae_b200.launch --seed 4 --reference $OLDPWD/baseline/_ref main.py $C "$@" 2>&1 | grep -i "Epoch\|Test set\|^BER\|rror\|Warn\|Traceback" | head -8; }
+run "joint_train 1" -is_same_interleaver 1 -joint_train 1
+run "is_same_interleaver 0 (new permutation every forward)" -is_same_interleaver 0 -is_interleave 1000
+run "kernel size 3 (fp32 kernels, warnings)" -is_same_interleaver 1 -enc_kernel_size 3 -dec_kernel_size 3
+run "optimizer lookahead" -is_same_interleaver 1 -optimizer lookahead
+run "variable block length" -is_same_interleaver 1 -is_variable_block_len 1 -block_len_low 50 -block_len_high 150
+run "extrinsic 0, fine-tune from checkpoint" -is_same_interleaver 1 -extrinsic 0 -init_nw_weight ./models/dta_cont_cnn2_cnn5_enctrain2_dectrainneg15_2.pt

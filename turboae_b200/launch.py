@@ -12,7 +12,7 @@ classes, then runs the script with `runpy` as `__main__`.  main.py picks its cla
 
 The reference targets PyTorch 1.0 / numpy < 1.20; `_modernise()` restores the handful of names newer libraries
 removed (numpy.float/int/complex, fractions.gcd, an importable `matplotlib`, torch.load without map_location on a
-CPU-only host, commpy's Python-2 `array(map(...))` interleaver).  That is environment glue, not a change of behaviour.
+CPU-only host, commpy's Python-2 `array(map(...))` interleaver, Lookahead.zero_grad).  That is environment glue, not a change of behaviour.
 """
 from __future__ import annotations
 
@@ -50,6 +50,16 @@ def _modernise():
             return np.asarray(in_array)[np.asarray(self.p_array)]
         _ci._Interleaver.interlv = interlv
     except Exception:  # pragma: no cover -- a checkout without the vendored commpy
+        pass
+    try:
+        # the reference's Lookahead (optimizers.py:10-19) never calls Optimizer.__init__, so it has no `defaults`, which
+        # torch >= 2 reads in Optimizer.zero_grad (trainer.py:41): clear the gradients through the wrapped optimizer (same parameters)
+        import optimizers as _ro
+
+        def zero_grad(self, set_to_none=True):
+            return self.optimizer.zero_grad(set_to_none=set_to_none)
+        _ro.Lookahead.zero_grad = zero_grad
+    except Exception:  # pragma: no cover -- a checkout without optimizers.py
         pass
     if not torch.cuda.is_available():
         _load = torch.load

@@ -145,16 +145,17 @@ def count_layers(weights, prefix) -> int:
 # --------------------------------------------------------------------------- #
 # encoder                                                                     #
 # --------------------------------------------------------------------------- #
-def enc_forward_unnormalised(u: np.ndarray, weights, p: np.ndarray, prefix: str = "enc") -> np.ndarray:
+def enc_forward_unnormalised(u: np.ndarray, weights, p: np.ndarray, prefix: str = "enc", dense: bool = False) -> np.ndarray:
     """reference encoders.py:362-373: the three branches and the concat.
 
-    ``u`` is ``(B, L, 1)`` in {0,1}; returns ``x_tx`` ``(B, L, 3)``.
+    ``u`` is ``(B, L, 1)`` in {0,1}; returns ``x_tx`` ``(B, L, 3)``.  ``dense``: the branches are DenseSameShapeConv1d stacks
+    (reference encoders.py:322-330, -encoder TurboAE_rate3_cnn_dense).
     """
     x = (F32(2.0) * u.astype(F32) - F32(1.0))
     outs = []
     for i, inp in ((1, x), (2, x), (3, interleave(x, p))):
         n = count_layers(weights, "%s.enc_cnn_%d" % (prefix, i))
-        h = same_shape_conv1d(inp, _stack(weights, "%s.enc_cnn_%d" % (prefix, i), n))
+        h = (dense_same_shape_conv1d if dense else same_shape_conv1d)(inp, _stack(weights, "%s.enc_cnn_%d" % (prefix, i), n))
         y = linear(h, _get(weights, "%s.enc_linear_%d.module.weight" % (prefix, i)),
                    _get(weights, "%s.enc_linear_%d.module.bias" % (prefix, i)))
         outs.append(elu(y))                      # enc_act == 'elu' (encoders.py:86-100)
@@ -196,9 +197,9 @@ def ste_quantize(x: np.ndarray, value_limit: float = 1.0, quantize_level: float 
 
 
 def enc_forward(u: np.ndarray, weights, p: np.ndarray, prefix: str = "enc", ste: bool = False, value_limit: float = 1.0,
-                quantize_level: float = 2) -> np.ndarray:
+                quantize_level: float = 2, dense: bool = False) -> np.ndarray:
     """reference encoders.py:351-377 -> codes ``(B, L, 3)``; ``ste`` = train_channel_mode 'block_norm_ste' (:118-120)."""
-    codes, _, _ = power_constraint(enc_forward_unnormalised(u, weights, p, prefix))
+    codes, _, _ = power_constraint(enc_forward_unnormalised(u, weights, p, prefix, dense=dense))
     return ste_quantize(codes, value_limit, quantize_level) if ste else codes
 
 

@@ -229,6 +229,33 @@ def dump_dense(name, B=4, L=30, units=20, n_layer=3, n_iter=2, seed=5):
     print(name, y.shape, float(y.min()), float(y.max()), [tuple(v.shape) for k, v in out.items() if "cnns.0.module.cnns" in k and "weight" in k][:3])
 
 
+def dump_dense_enc(name, B=4, L=30, units=20, n_layer=3, seed=6):
+    """ENC_interCNN built from DenseSameShapeConv1d (reference encoders.py:313-327: -encoder TurboAE_rate3_cnn_dense): no checkpoint
+    is shipped, so weights are torch.manual_seed-ed default init x2; weights, bits, codes."""
+    compat.install()
+    args = compat.reference_args(["-encoder", "TurboAE_rate3_cnn_dense", "-decoder", "TurboAE_rate3_cnn", "-enc_num_unit", str(units),
+                                  "-enc_num_layer", str(n_layer), "-enc_kernel_size", "5", "-block_len", str(L), "-batch_size", str(B),
+                                  "-code_rate_k", "1", "-code_rate_n", "3", "--no-cuda"])
+    from numpy import arange
+    from numpy.random import mtrand
+    from encoders import ENC_interCNN
+    p = mtrand.RandomState(0).permutation(arange(L))
+    torch.manual_seed(seed)
+    enc = ENC_interCNN(args, p)
+    enc.set_parallel()
+    with torch.no_grad():
+        for q in enc.parameters():
+            q.mul_(2.0)
+    enc.eval()
+    u = np.random.mtrand.RandomState(seed).randint(0, 2, size=(B, L, 1)).astype(np.float32)
+    with torch.no_grad():
+        codes = enc(torch.from_numpy(u)).numpy().astype(np.float32)
+    out = {"enc." + k: v.detach().numpy().astype(np.float32) for k, v in enc.state_dict().items()}
+    out.update(u=u, codes=codes, p=np.asarray(p, np.int64), cfg=np.array([B, L, units, n_layer], np.int64))
+    np.savez_compressed(os.path.join(HERE, name), **out)
+    print(name, codes.shape, float(codes.mean()), float(codes.std()))
+
+
 def dump_flags(name):
     """Two non-default branches of the hot path, executed on the UNMODIFIED reference with checkpoint c1:
     -precompute_norm_stats (encoders.py:110-114): codes of three successive batches + the running scalars after each;
@@ -283,3 +310,4 @@ if __name__ == "__main__":
         dump_flags("flags_c1_b8.npz")
     if "dense" in todo:
         dump_dense("dense_u20_l3_i2_b4.npz")
+        dump_dense_enc("dense_enc_u20_l3_b4.npz")

@@ -148,6 +148,6 @@ def test_unsupported_configurations_raise():
     # the dense decoder variant (decoders.py:173-176) is built from DenseSameShapeConv1d with the reference's parameter shapes ...
     d = T.DEC_LargeCNN(make_args(encoder="TurboAE_rate3_cnn_dense", dec_num_unit=20, dec_num_layer=3), p)
     assert d.dense and tuple(d.dec1_cnns[0].cnns[2].weight.shape) == (20, 7 + 2 * 20, 5)
-    # ... ENC_interCNN itself only exists for -encoder TurboAE_rate3_cnn (main.py:35-36 selects another class otherwise)
-    with pytest.raises(NotImplementedError):
-        T.ENC_interCNN(make_args(encoder="TurboAE_rate3_cnn_dense"), p)
+    # ... and so is ENC_interCNN (encoders.py:322-330; main.py:34 routes both -encoder values to this class)
+    e = T.ENC_interCNN(make_args(encoder="TurboAE_rate3_cnn_dense", enc_num_unit=20, enc_num_layer=3), p)
+    assert e.dense and e.train_precision == "fp32" and tuple(e.enc_cnn_3.cnns[2].weight.shape) == (20, 1 + 2 * 20, 5)

@@ -775,6 +775,55 @@ def test_rnn_decoder_training_gradients_vs_torch_gru():
 
 
 @pytest.mark.gpu
+def test_dense_encoder_vs_reference_fixture_and_autograd():
+    """ENC_interCNN with DenseSameShapeConv1d stacks (encoders.py:322-330, -encoder TurboAE_rate3_cnn_dense): codes against the
+    fixture produced by the unmodified reference; gradients of a scalar loss against torch autograd of the oracle's schedule."""
+    import torch.nn.functional as Fn
+    import turboae_b200 as T
+    g = load_npz("dense_enc_u20_l3_b4.npz")
+    B, L, units, n_layer = g["cfg"].tolist()
+    args = make_args(encoder="TurboAE_rate3_cnn_dense", enc_num_unit=units, enc_num_layer=n_layer, block_len=L, batch_size=B)
+    m = T.ENC_interCNN(args, g["p"])
+    m.set_parallel()
+    m.load_state_dict({k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("enc.")}, strict=True)
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        codes = m(_t(g["u"])).cpu().numpy()
+    np.testing.assert_allclose(codes, g["codes"], atol=2e-5, rtol=0)
+    np.testing.assert_allclose(codes, O.enc_forward(g["u"], {k: v for k, v in g.items() if k.startswith("enc.")}, g["p"], dense=True),
+                               atol=2e-5, rtol=0)
+    # autograd: d(sum(codes * t))/d(parameters) vs the same schedule on torch CPU operators (cnn_utils.py:67-82 with F.conv1d)
+    rs = np.random.RandomState(4)
+    t = rs.randn(B, L, 3).astype(np.float32)
+    m.train()
+    (m(_t(g["u"])) * _t(t)).sum().backward()
+    wc = {k[4:]: torch.from_numpy(v).clone().requires_grad_(True) for k, v in g.items() if k.startswith("enc.")}
+    perm = torch.from_numpy(g["p"].astype(np.int64))
+
+    def dense(x, pre):
+        inp = x.transpose(1, 2)
+        for i in range(n_layer):
+            y = Fn.elu(Fn.conv1d(inp, wc[pre + ".module.cnns.%d.weight" % i], wc[pre + ".module.cnns.%d.bias" % i], padding=2))
+            inp = y if i == n_layer - 1 else torch.cat([inp, y], 1)                     # cnn_utils.py:74-80
+        return y.transpose(1, 2)
+
+    x = 2.0 * torch.from_numpy(g["u"]) - 1.0
+    outs = [Fn.elu(Fn.linear(dense(inp, "enc_cnn_%d" % i), wc["enc_linear_%d.module.weight" % i], wc["enc_linear_%d.module.bias" % i]))
+            for i, inp in ((1, x), (2, x), (3, x[:, perm, :]))]
+    x_tx = torch.cat(outs, 2)
+    ref_codes = (x_tx - x_tx.mean()) / x_tx.std()
+    np.testing.assert_allclose(ref_codes.detach().numpy(), g["codes"], atol=2e-5, rtol=0)
+    (ref_codes * torch.from_numpy(t)).sum().backward()
+    n = 0
+    for k, v in m.named_parameters():
+        gr = wc[k].grad.numpy()
+        assert v.grad is not None, k
+        np.testing.assert_allclose(v.grad.cpu().numpy(), gr, atol=1e-6 + 2e-4 * float(np.abs(gr).max()), rtol=0, err_msg=k)
+        n += 1
+    assert n == 3 * (2 * n_layer + 2)
+
+
+@pytest.mark.gpu
 def test_dense_decoder_vs_reference_fixture_and_autograd():
     """DEC_LargeCNN with DenseSameShapeConv1d stacks (decoders.py:173-176, cnn_utils.py:49-82): forward against the
     reference-generated fixture; gradients of a BCE step against torch autograd of the same schedule on CPU operators."""

@@ -11,7 +11,7 @@ import torch
 
 from . import _lib, shard
 from ._flat import FlatCache, ParallelShim, Workspace, unwrap
-from .cnn_utils import SameShapeConv1d
+from .cnn_utils import DenseSameShapeConv1d, SameShapeConv1d
 from .interleavers import Interleaver
 
 
@@ -72,13 +72,14 @@ class ENC_interCNN(ENCBase):
     def __init__(self, args, p_array):
         super().__init__(args)
         self.args = args
-        if args.encoder != "TurboAE_rate3_cnn":
-            raise NotImplementedError("turboae_b200.ENC_interCNN builds the SameShapeConv1d variant only "
-                                      "(-encoder TurboAE_rate3_cnn); got %r" % (args.encoder,))
         if args.code_rate_k != 1:
             raise NotImplementedError("code_rate_k must be 1 (got %r)" % (args.code_rate_k,))
-        mk = lambda: SameShapeConv1d(num_layer=args.enc_num_layer, in_channels=args.code_rate_k,
-                                     out_channels=args.enc_num_unit, kernel_size=args.enc_kernel_size)
+        # encoders.py:313-330 keys the layer type on args.encoder: the dense variant (-encoder TurboAE_rate3_cnn_dense) runs layer
+        # by layer on the fp32 kernels (the fused tensor-core kernels and the flat-parameter C ABI cover SameShapeConv1d only)
+        self.dense = args.encoder != "TurboAE_rate3_cnn"
+        CNNLayer = DenseSameShapeConv1d if self.dense else SameShapeConv1d
+        mk = lambda: CNNLayer(num_layer=args.enc_num_layer, in_channels=args.code_rate_k,
+                              out_channels=args.enc_num_unit, kernel_size=args.enc_kernel_size)
         self.enc_cnn_1, self.enc_cnn_2, self.enc_cnn_3 = mk(), mk(), mk()
         self.enc_linear_1 = torch.nn.Linear(args.enc_num_unit, 1)
         self.enc_linear_2 = torch.nn.Linear(args.enc_num_unit, 1)
@@ -98,7 +99,9 @@ class ENC_interCNN(ENCBase):
         #: training (autograd) path: 'fp32' (CUDA-core kernels) or 'bf16' (tensor cores, train_tc.py)
         from . import train_tc
         self.train_precision = (getattr(args, "tae_train_precision", None) or os.environ.get("TURBOAE_B200_TRAIN_PRECISION")
-                                or ("bf16" if train_tc.supported(args, "enc") else "fp32"))
+                                or ("bf16" if (train_tc.supported(args, "enc") and not self.dense) else "fp32"))
+        if self.dense:
+            self.train_precision = "fp32"
 
     def set_interleaver(self, p_array):
         self.interleaver.set_parray(p_array)
@@ -261,7 +264,8 @@ class ENC_interCNN(ENCBase):
             raise _lib.TaeError("no CUDA device: turboae_b200 has no CPU fallback")
         self._variable_block_len(inputs.shape[1])
         x = inputs.to(device=self.this_device, dtype=torch.float32).contiguous()
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+        if self.dense or (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))):
+            # (the dense variant: the branches spelled out with the module pieces on the fp32 kernels, with or without autograd)
             return self._forward_train(x)
         if x.dim() != 3 or x.shape[2] != 1:
             raise _lib.TaeError("ENC_interCNN expects (B, L, 1) bits, got %s" % (tuple(x.shape),))

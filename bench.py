@@ -246,13 +246,14 @@ def train_leg(dev, world, rank, TB=1000, steps=8):
         ms = shard.max_over_ranks(e0.elapsed_time(e1) / steps, device=dev)
         return ms, float(loss), (_lib.launch_count() - n0) / steps
 
-    ms, loss, launches = timed_steps(make_step(torch.optim.Adam(tdec.parameters(), lr=1e-4)))
+    # (fused=True: what turboae_b200.launch makes of the reference's `optim.Adam(params, lr=...)`, main.py:196-213)
+    ms, loss, launches = timed_steps(make_step(torch.optim.Adam(tdec.parameters(), lr=1e-4, fused=True)))
     res["train_step_decoder_mode_cw_per_s"] = world * TB / (ms * 1e-3)
-    res["train_step"] = "enc2/dec5, batch %d per GPU x %d GPUs, fwd+bwd+%sAdam, train_precision=%s, eager host loop: %.2f ms/step, " \
+    res["train_step"] = "enc2/dec5, batch %d per GPU x %d GPUs, fwd+bwd+%sAdam (fused), train_precision=%s, eager host loop: %.2f ms/step, " \
                         "%.0f launches of our kernels per step, loss %.4f" % (TB, world, "all-reduce+" if world > 1 else "",
                                                                               tdec.train_precision, ms, launches, loss)
     try:
-        opt_g = torch.optim.Adam(tdec.parameters(), lr=1e-4, capturable=True)
+        opt_g = torch.optim.Adam(tdec.parameters(), lr=1e-4, capturable=True, fused=True)
         gstep = T.graphs.GraphedStep(make_step(opt_g), warmup=3, device=dev)
         ms_g, loss_g, _ = timed_steps(gstep)
         res["train_step_graphed_cw_per_s"] = world * TB / (ms_g * 1e-3)

@@ -178,6 +178,20 @@ int tae_power_norm_given_f32(const float* x, float* codes, size_t n, const float
 int tae_power_norm_ste_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std,
                            float value_limit, float quantize_level, void* stream);
 
+/* ENCBase.power_constraint under autograd (reference trainer.py:74 `loss.backward()` through encoders.py:107-116), for an x_tx
+ * that is already on the device:
+ *   tae_power_stats_f32          adds (sum x, sum x^2, n) into the 3 device doubles `stats` (the encoder kernels above deliver the
+ *                                same triple; this entry point serves an x_tx produced elsewhere).  Sharded batch: all-reduce
+ *                                `stats` over the ranks, then tae_power_norm_f32 with mean_std != NULL.
+ *   tae_power_norm_bwd_sums_f32  adds (sum g, sum g * codes) into the 2 device doubles `sums` (g = gradient w.r.t. codes);
+ *                                all-reduced over the ranks when the batch is sharded.
+ *   tae_power_norm_bwd_f32       dx = (g - sums[0] / N - codes * sums[1] / (N - 1)) / std, N = stats[2], std = mean_std[1]:
+ *                                the exact gradient of codes = (x - mean(x)) / std_unbiased(x) w.r.t. x.  dx may alias g.   */
+int tae_power_stats_f32(const float* x, size_t n, double* stats, void* stream);
+int tae_power_norm_bwd_sums_f32(const float* g, const float* codes, size_t n, double* sums, void* stream);
+int tae_power_norm_bwd_f32(const float* g, const float* codes, float* dx, size_t n, const double* sums, const double* stats,
+                           const float* mean_std, void* stream);
+
 /* ---- next row f1 on the tensor cores: training of DEC_LargeCNN (reference trainer.py:33-76: forward, loss.backward()
  * through decoders.py:219-269 and cnn_utils.py:36-46; bf16 operands, fp32 accumulation, fp32 gradients) ------------------
  * Activations travel between the three kernels as "group images" in HBM: bf16 [group][chunk][516 rows][8 channels], the

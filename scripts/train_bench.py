@@ -27,7 +27,7 @@ p = O.make_perm(100, 0)
 enc, dec = T.ENC_interCNN(args, p).to(dev), T.DEC_LargeCNN(args, p).to(dev)
 res = {}
 for mode, params in (("decoder", dec.parameters()), ("encoder", enc.parameters())):
-    opt = torch.optim.Adam(params, lr=1e-4)
+    opt = torch.optim.Adam(params, lr=1e-4, fused=os.environ.get("TRAIN_FUSED_ADAM", "1") == "1")   # (the launcher's default)
     def step():
         opt.zero_grad()
         u = torch.randint(0, 2, (B, 100, 1), device=dev).float()

@@ -282,3 +282,33 @@ def test_two_forwards_before_backward_keep_separate_stashes():
     for k, v in dec.named_parameters():
         rel, cos = _rel_cos(both[k], v.grad)
         assert rel < 1e-4, (k, rel, cos)            # fp32 atomics in the weight-gradient kernel: order-dependent rounding
+
+
+@pytest.mark.parametrize("shape", [(1, 7, 3), (37, 100, 3), (1000, 100, 3), (4096, 64, 3)])
+def test_power_constraint_autograd_kernels_vs_float64_autograd(shape):
+    """ENCBase.power_constraint under autograd (reference encoders.py:107-116 below trainer.py:74) on this package's kernels
+    (tae_power_stats_f32 / tae_power_norm_f32 / tae_power_norm_bwd_sums_f32 / tae_power_norm_bwd_f32, through shard.PowerNorm)
+    against torch autograd of the reference's own spelling `(x - mean(x)) / std(x)` in float64; once with statistics computed
+    by tae_power_stats_f32 and once with statistics handed in (the encoder kernels' own triple)."""
+    from turboae_b200 import shard
+    gen = torch.Generator(device="cpu").manual_seed(sum(shape))
+    x = (torch.randn(shape, generator=gen) * 0.7 + 0.3).to(DEV)
+    g = torch.randn(shape, generator=gen).to(DEV)
+    xr = x.double().requires_grad_(True)
+    yr = (xr - torch.mean(xr)) / torch.std(xr)
+    yr.backward(g.double())
+    for given in (False, True):
+        xt = x.clone().requires_grad_(True)
+        stats = None
+        if given:
+            xd = x.double()
+            stats = torch.stack([xd.sum(), (xd * xd).sum(), torch.tensor(float(x.numel()), dtype=torch.float64, device=DEV)])
+        y = shard.PowerNorm.apply(xt, shard.LOCAL, stats)
+        y.backward(g)
+        assert y.dtype == torch.float32 and xt.grad.dtype == torch.float32
+        np.testing.assert_allclose(y.detach().cpu().numpy(), yr.detach().float().cpu().numpy(), atol=2e-6, rtol=2e-6)
+        gr = xr.grad.float().cpu().numpy()
+        np.testing.assert_allclose(xt.grad.cpu().numpy(), gr, atol=2e-6 * max(1.0, float(np.abs(gr).max())), rtol=2e-6)
+    # the normalised batch has zero mean / unit unbiased std, and the gradient is orthogonal to both invariances
+    assert abs(float(y.double().mean())) < 1e-6 and abs(float(y.double().std()) - 1.0) < 1e-5
+    assert abs(float(xt.grad.double().sum())) < 1e-3 * float(xt.grad.double().abs().sum())

@@ -152,14 +152,20 @@ def test_flat_cache_follows_writes_through_data():
     p[0].data.copy_(torch.full((4,), 2.0))                  # invisible to p._version
     T.invalidate_all()
     f1 = c.get(p)
-    assert f1 is not f0 and float(f1[0]) == 2.0 and not c.derived
+    # (the flat image is persistent: refreshed in place by one multi-tensor copy, same address; the derived images are dropped)
+    assert f1.data_ptr() == f0.data_ptr() and float(f1[0]) == 2.0 and not c.derived
     # an optimizer step invalidates on its own (post-step hook registered at import)
     opt = torch.optim.SGD(p, lr=1.0)
     f2 = c.get(p)
+    c.derived["bf16"] = "image"
     p[1].grad = torch.ones(3)
     opt.step()
     f3 = c.get(p)
-    assert f3 is not f2 and float(f3[-1]) == -1.0
+    assert f3.data_ptr() == f2.data_ptr() and float(f3[-1]) == -1.0 and not c.derived
+    # another parameter set (sizes / device): a new image
+    q = [torch.nn.Parameter(torch.ones(5)), torch.nn.Parameter(torch.zeros(3))]
+    f4 = c.get(q)
+    assert f4.numel() == 8 and float(f4.sum()) == 5.0 and c.get(p).numel() == 7
 
 
 def test_stash_is_not_shared_between_two_live_forwards():

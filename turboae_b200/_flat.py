@@ -18,8 +18,15 @@ def invalidate_all() -> None:
 
 
 class FlatCache:
+    """The flat fp32 image of a module's parameters.  Steady state (training: every optimizer step moves the version counters)
+    costs ONE multi-tensor copy into the persistent flat buffer through cached views -- no per-parameter torch calls and no
+    re-allocation, so the image keeps its address (CUDA-graph replays and the packed images derived from it stay valid).  The
+    views are rebuilt only when the parameter set itself changes (other sizes or another device)."""
+
     def __init__(self):
         self._key = None
+        self._sig = None
+        self._views = None
         self.flat = None
         self.derived = {}
 
@@ -31,10 +38,44 @@ class FlatCache:
         key = (_EPOCH[0],) + tuple((p.data_ptr(), p._version) for p in params)
         if key != self._key:
             with torch.no_grad():
-                self.flat = torch.cat([p.detach().reshape(-1).to(torch.float32) for p in params]).contiguous()
+                dev = params[0].device if params else None
+                sig = (dev,) + tuple(p.numel() for p in params)
+                if sig != self._sig:
+                    self.flat = torch.empty(sum(sig[1:]), dtype=torch.float32, device=dev)
+                    self._views = [v.view(p.shape) for v, p in zip(self.flat.split_with_sizes(list(sig[1:])), params)]
+                    self._sig = sig
+                torch._foreach_copy_(self._views, list(params))        # (no_grad: plain copies out of the leaves)
             self._key = key
             self.derived = {}
         return self.flat
+
+
+def _drop_ordered_hook(module, incompatible_keys):     # (module-level: a whole-module pickle / deepcopy must survive it)
+    module._drop_ordered()
+
+
+class OrderedParameters:
+    """Mixin: ``ordered_parameters()`` -- the module's parameters in the canonical flat order of include/turboae_b200.h --
+    walks the module tree once (``_walk_ordered_parameters``) and keeps the list; it is dropped whenever the Parameter objects
+    can have been replaced (``_apply`` = .to() / .cuda() / dtype casts, ``load_state_dict`` at any level of the tree,
+    ``set_parallel``)."""
+
+    def _drop_ordered(self, *unused):
+        self.__dict__["_ordered"] = None
+
+    def _watch_ordered(self):
+        self._drop_ordered()
+        self.register_load_state_dict_post_hook(_drop_ordered_hook)
+
+    def _apply(self, fn, *a, **k):
+        self._drop_ordered()
+        return super()._apply(fn, *a, **k)
+
+    def ordered_parameters(self):
+        ps = self.__dict__.get("_ordered")
+        if ps is None:
+            ps = self.__dict__["_ordered"] = self._walk_ordered_parameters()
+        return ps
 
 
 class Workspace:

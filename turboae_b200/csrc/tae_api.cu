@@ -467,6 +467,27 @@ int tae_power_norm_ste_f32(const float* x, float* codes, size_t n, const double*
   return launch_power_norm_f32(x, codes, n, stats, mean_std, value_limit, quantize_level, (cudaStream_t)stream);
 }
 
+int tae_power_stats_f32(const float* x, size_t n, double* stats, void* stream) {
+  if (n == 0) return TAE_OK;
+  TAE_REQUIRE(x && stats, "tae_power_stats_f32: NULL pointer");
+  int rc = launch_power_sums_f32(x, nullptr, n, stats, (cudaStream_t)stream);
+  if (rc) return rc;
+  return launch_add_count(stats, (double)n, (cudaStream_t)stream);
+}
+
+int tae_power_norm_bwd_sums_f32(const float* g, const float* codes, size_t n, double* sums, void* stream) {
+  if (n == 0) return TAE_OK;
+  TAE_REQUIRE(g && codes && sums, "tae_power_norm_bwd_sums_f32: NULL pointer");
+  return launch_power_sums_f32(g, codes, n, sums, (cudaStream_t)stream);
+}
+
+int tae_power_norm_bwd_f32(const float* g, const float* codes, float* dx, size_t n, const double* sums, const double* stats,
+                           const float* mean_std, void* stream) {
+  if (n == 0) return TAE_OK;
+  TAE_REQUIRE(g && codes && dx && sums && stats && mean_std, "tae_power_norm_bwd_f32: NULL pointer");
+  return launch_power_norm_bwd_f32(g, codes, dx, n, sums, stats, mean_std, (cudaStream_t)stream);
+}
+
 int32_t tae_train_groups(int32_t block_len, int32_t B) {
   if (block_len < 1 || block_len > 512 || B < 0) return 0;
   return train_groups(block_len, B);

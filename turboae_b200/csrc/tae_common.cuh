@@ -136,6 +136,10 @@ int enc_forward_f32(const TaeEncConfig& c, const float* params, const float* u, 
 int launch_power_norm_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std, float limit, float q,
                           cudaStream_t s);
 
+int launch_power_sums_f32(const float* a, const float* y, size_t n, double* out, cudaStream_t s);
+int launch_power_norm_bwd_f32(const float* g, const float* y, float* dx, size_t n, const double* sums, const double* stats,
+                              const float* mean_std, cudaStream_t s);
+
 // ---- bf16 tcgen05 path: fused CTA-pair kernel (tae_dec_pair.cu) -----------------------------
 bool dec_pair_supported(const TaeDecConfig& c, const char** why);
 size_t dec_pair_packed_bytes(const TaeDecConfig& c);

@@ -387,6 +387,48 @@ __global__ void power_norm_kernel(const float* __restrict__ x, float* __restrict
   }
 }
 
+// ---- power_constraint under autograd (trainer.py:74 through encoders.py:107-116) ---------------------------------------------
+// Block-wide sum of two doubles per thread, added into out[0], out[1] by thread 0 (256 threads).
+__device__ __forceinline__ void block_add2(double a, double b, double* __restrict__ out) {
+  __shared__ double red[2][8];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, d);
+    b += __shfl_xor_sync(0xffffffffu, b, d);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sa = 0.0, sb = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { sa += red[0][w]; sb += red[1][w]; }
+    atomicAdd(out + 0, sa);
+    atomicAdd(out + 1, sb);
+  }
+}
+
+// y == NULL: (sum x, sum x^2) -- the forward statistics of an x_tx that did not come out of one of the encoder kernels;
+// y != NULL: (sum g, sum g*y) -- the two sums of the backward.
+__global__ void __launch_bounds__(256) power_sums_kernel(const float* __restrict__ a, const float* __restrict__ y, size_t n,
+                                                         double* __restrict__ out) {
+  double s1 = 0.0, s2 = 0.0;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const double v = (double)a[idx];
+    s1 += v;
+    s2 += v * (y ? (double)y[idx] : v);
+  }
+  block_add2(s1, s2, out);
+}
+
+// y = (x - mean) / std  =>  dx = (g - sum(g) / N - y * sum(g*y) / (N - 1)) / std     (N = stats[2], std = mean_std[1])
+__global__ void power_norm_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y, float* __restrict__ dx, size_t n,
+                                      const double* __restrict__ sums, const double* __restrict__ stats,
+                                      const float* __restrict__ mean_std) {
+  const double cnt = stats[2];
+  const float mg = (float)(sums[0] / cnt), cy = (float)(sums[1] / (cnt - 1.0)), stdf = mean_std[1];
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x)
+    dx[idx] = (g[idx] - mg - y[idx] * cy) / stdf;
+}
+
 inline int grid_for(size_t n, int block, int max_blocks = 148 * 16) {
   size_t g = (n + block - 1) / block;
   if (g < 1) g = 1;
@@ -661,6 +703,19 @@ int launch_power_norm_f32(const float* x, float* codes, size_t n, const double* 
   if (n == 0) return TAE_OK;
   power_norm_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, codes, n, stats, mean_std, limit, q);
   return after_launch("power_norm_kernel");
+}
+
+int launch_power_sums_f32(const float* a, const float* y, size_t n, double* out, cudaStream_t s) {
+  if (n == 0) return TAE_OK;
+  power_sums_kernel<<<grid_for(n, 256 * 8, 148 * 2), 256, 0, s>>>(a, y, n, out);
+  return after_launch("power_sums_kernel");
+}
+
+int launch_power_norm_bwd_f32(const float* g, const float* y, float* dx, size_t n, const double* sums, const double* stats,
+                              const float* mean_std, cudaStream_t s) {
+  if (n == 0) return TAE_OK;
+  power_norm_bwd_kernel<<<grid_for(n, 256), 256, 0, s>>>(g, y, dx, n, sums, stats, mean_std);
+  return after_launch("power_norm_bwd_kernel");
 }
 
 }  // namespace tae

@@ -11,7 +11,7 @@ import os
 import torch
 
 from . import _lib
-from ._flat import FlatCache, ParallelShim, Workspace, unwrap
+from ._flat import FlatCache, OrderedParameters, ParallelShim, Workspace, unwrap
 from ._flat import _EPOCH as _flat_epoch_cell
 
 
@@ -21,7 +21,7 @@ from .cnn_utils import DenseSameShapeConv1d, SameShapeConv1d
 from .interleavers import DeInterleaver, Interleaver
 
 
-class DEC_LargeCNN(torch.nn.Module):
+class DEC_LargeCNN(OrderedParameters, torch.nn.Module):
     def __init__(self, args, p_array):
         super().__init__()
         self.args = args
@@ -45,6 +45,7 @@ class DEC_LargeCNN(torch.nn.Module):
             self.dec2_outputs.append(torch.nn.Linear(args.dec_num_unit,
                                                      1 if idx == args.num_iteration - 1 else args.num_iter_ft))
         self._flat = FlatCache()
+        self._watch_ordered()
         self._ws = Workspace()
         self._ws_host = Workspace()
         #: 'bf16' (fused tcgen05 kernel: BER parity), 'f16x3' (split-operand tcgen05 kernel: elementwise parity <= 1e-4 at
@@ -60,6 +61,7 @@ class DEC_LargeCNN(torch.nn.Module):
                                 or ("bf16" if (train_tc.supported(args, "dec") and not self.dense) else "fp32"))
 
     def set_parallel(self):
+        self._drop_ordered()
         for lst in (self.dec1_cnns, self.dec2_cnns, self.dec1_outputs, self.dec2_outputs):
             for idx in range(len(lst)):
                 if not isinstance(lst[idx], ParallelShim):
@@ -70,7 +72,7 @@ class DEC_LargeCNN(torch.nn.Module):
         self.deinterleaver.set_parray(p_array)
 
     # -- canonical flat order of include/turboae_b200.h ------------------------------------------------
-    def ordered_parameters(self):
+    def _walk_ordered_parameters(self):
         out = []
         for idx in range(self.args.num_iteration):
             for cnns, outs in ((self.dec1_cnns, self.dec1_outputs), (self.dec2_cnns, self.dec2_outputs)):

@@ -10,7 +10,7 @@ import os
 import torch
 
 from . import _lib, shard
-from ._flat import FlatCache, ParallelShim, Workspace, unwrap
+from ._flat import FlatCache, OrderedParameters, ParallelShim, Workspace, unwrap
 from .cnn_utils import DenseSameShapeConv1d, SameShapeConv1d
 from .interleavers import Interleaver
 
@@ -66,7 +66,7 @@ class ENCBase(torch.nn.Module):
         self.num_test_block = 0.0
 
 
-class ENC_interCNN(ENCBase):
+class ENC_interCNN(OrderedParameters, ENCBase):
     """reference encoders.py:306-377."""
 
     def __init__(self, args, p_array):
@@ -86,6 +86,7 @@ class ENC_interCNN(ENCBase):
         self.enc_linear_3 = torch.nn.Linear(args.enc_num_unit, 1)
         self.interleaver = Interleaver(args, p_array)
         self._flat = FlatCache()
+        self._watch_ordered()
         self._ws = Workspace()
         # set to a torch.distributed group when the batch is sharded across ranks (the launcher does it under torchrun)
         self.shard_group = None
@@ -107,13 +108,14 @@ class ENC_interCNN(ENCBase):
         self.interleaver.set_parray(p_array)
 
     def set_parallel(self):
+        self._drop_ordered()
         for n in ("enc_cnn_1", "enc_cnn_2", "enc_cnn_3", "enc_linear_1", "enc_linear_2", "enc_linear_3"):
             m = getattr(self, n)
             if not isinstance(m, ParallelShim):
                 setattr(self, n, ParallelShim(m))
 
     # -- canonical flat order of include/turboae_b200.h ------------------------------------------------
-    def ordered_parameters(self):
+    def _walk_ordered_parameters(self):
         out = []
         for i in (1, 2, 3):
             for conv in unwrap(getattr(self, "enc_cnn_%d" % i)).cnns:
@@ -203,9 +205,10 @@ class ENC_interCNN(ENCBase):
         """Autograd path (reference encoders.py:362-375 under trainer.py:74): conv stacks through this package's forward /
         backward kernels, torch glue for the 100->1 Linear, ELU, concat and the power constraint (whose statistics and
         gradient sums are all-reduced when the batch is sharded across ranks)."""
+        own_stats = None                      # (sum, sum of squares, count) of this rank's x_tx when a kernel already delivered them
         if self.train_precision == "bf16":
             from . import train_tc
-            x_tx = train_tc.encoder_branches_train(self, u)
+            x_tx, own_stats = train_tc.encoder_branches_train(self, u)
         elif self.train_precision == "fp32":
             x = 2.0 * u - 1.0
             outs = []
@@ -229,7 +232,7 @@ class ENC_interCNN(ENCBase):
             codes = (x_tx - given[0]) / given[1]
         else:
             # statistics are merged across ranks only when the batch is sharded (shard_group set); otherwise this call stays local
-            codes = shard.PowerNorm.apply(x_tx, self.shard_group if self.shard_group is not None else shard.LOCAL)
+            codes = shard.PowerNorm.apply(x_tx, self.shard_group if self.shard_group is not None else shard.LOCAL, own_stats)
         if getattr(self.args, "train_channel_mode", "block_norm") == "block_norm_ste":
             codes = STEQuantize.apply(codes, self.args)
         if self.args.enc_truncate_limit > 0:

@@ -70,6 +70,27 @@ def _modernise():
         torch.load = load
 
 
+def fused_adam_default() -> None:
+    """``torch.optim.Adam(params, lr=...)`` as the reference writes it (main.py:196-213) picks torch's multi-tensor ("foreach")
+    implementation: a dozen launches and a Python loop over the parameter list per step.  With all parameters on a CUDA device the
+    single-kernel implementation (``fused=True``: same update rule, torch's own kernel) is chosen instead unless the caller said
+    otherwise; the training step through the unmodified trainer.py is host-bound, so this is wall-clock time."""
+    import torch
+    if getattr(torch.optim.Adam.__init__, "_tae_fused_default", False):
+        return
+    _init = torch.optim.Adam.__init__
+
+    def __init__(self, params, *args, **kwargs):
+        params = list(params)                       # (the reference passes filter(...) generators)
+        if kwargs.get("fused") is None and kwargs.get("foreach") is None and not kwargs.get("differentiable", False):
+            leaves = [q for g in params for q in (g["params"] if isinstance(g, dict) else [g])]
+            if leaves and all(torch.is_tensor(q) and q.is_cuda and torch.is_floating_point(q) for q in leaves):
+                kwargs["fused"] = True
+        _init(self, params, *args, **kwargs)
+    __init__._tae_fused_default = True
+    torch.optim.Adam.__init__ = __init__
+
+
 def install(reference_root: str) -> None:
     """Swap the hot-path classes inside the (already importable) reference modules."""
     reference_root = os.path.abspath(reference_root)
@@ -119,6 +140,8 @@ def main(argv=None):
                     "(only the library-compatibility shim is applied); the comparison arm of scripts/run_reference_dropin.py")
     ap.add_argument("--no-tf32", action="store_true", help="torch's own CUDA convolutions / matmuls in true fp32 (cudnn.allow_tf32 "
                     "defaults to True): makes the --stock arm the reference's fp32 arithmetic (it was written for torch 1.0)")
+    ap.add_argument("--no-fused-adam", action="store_true", help="leave torch.optim.Adam's implementation choice alone (default: "
+                    "fused=True when every parameter is on a CUDA device)")
     ap.add_argument("script", help="reference script to run, e.g. main.py")
     ap.add_argument("script_args", nargs=argparse.REMAINDER)
     a = ap.parse_args(argv)
@@ -131,6 +154,8 @@ def main(argv=None):
         _modernise()
     else:
         install(a.reference)
+    if not (a.stock or a.no_fused_adam):
+        fused_adam_default()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     seed = a.seed
     if world > 1 and not a.stock:

@@ -55,10 +55,33 @@ def max_over_ranks(value: float, device=None, group=None) -> float:
 class PowerNorm(torch.autograd.Function):
     """ENCBase.power_constraint (reference encoders.py:107-116), differentiable and exact under sharding:
     y = (x - mean) / std with mean / unbiased std over the WHOLE batch.  Forward all-reduces (sum x, sum x^2, count),
-    backward all-reduces (sum g, sum g*y):  dx = (g - mean(g) - y * sum(g*y) / (N - 1)) / std."""
+    backward all-reduces (sum g, sum g*y):  dx = (g - mean(g) - y * sum(g*y) / (N - 1)) / std.
+
+    On a CUDA device both directions are this package's kernels (``tae_power_stats_f32`` unless the encoder kernel already
+    delivered ``own_stats``, ``tae_power_norm_f32``, ``tae_power_norm_bwd_sums_f32``, ``tae_power_norm_bwd_f32``): three launches
+    forward and backward together instead of ~25 small torch operators.  The torch spelling below serves the host-side tests of
+    the collective logic (gloo, CPU tensors)."""
 
     @staticmethod
-    def forward(ctx, x, group):
+    def forward(ctx, x, group, own_stats=None):
+        ctx.group = group
+        ctx.native = x.is_cuda and x.dtype == torch.float32
+        if ctx.native:
+            from . import _lib
+            lib = _lib.load()
+            x = x.contiguous()
+            with torch.cuda.device(x.device):
+                stream = _lib.stream_ptr(x.device)
+                stats = own_stats
+                if stats is None:
+                    stats = torch.zeros(3, dtype=torch.float64, device=x.device)
+                    _lib.check(lib.tae_power_stats_f32(_lib.ptr(x), x.numel(), _lib.ptr(stats), stream))
+                merge_power_stats(stats, group)
+                y = torch.empty_like(x)
+                mean_std = torch.empty(2, dtype=torch.float32, device=x.device)
+                _lib.check(lib.tae_power_norm_f32(_lib.ptr(x), _lib.ptr(y), x.numel(), _lib.ptr(stats), _lib.ptr(mean_std), stream))
+            ctx.save_for_backward(y, stats, mean_std)
+            return y
         xd = x.double()
         # (torch.full, not torch.tensor: a host scalar copied to the device would make the host wait for the stream)
         stats = torch.stack([xd.sum(), (xd * xd).sum(), torch.full((), float(x.numel()), dtype=torch.float64, device=x.device)])
@@ -68,17 +91,32 @@ class PowerNorm(torch.autograd.Function):
         std = torch.sqrt(torch.clamp((stats[1] - n * mean * mean) / (n - 1.0), min=0.0))
         y = (x - mean.float()) / std.float()
         ctx.save_for_backward(y, std.float(), n)
-        ctx.group = group
         return y
 
     @staticmethod
     def backward(ctx, g):
+        sharded = ctx.group is not LOCAL and dist.is_available() and dist.is_initialized() and dist.get_world_size(ctx.group) > 1
+        if ctx.native:
+            from . import _lib
+            lib = _lib.load()
+            y, stats, mean_std = ctx.saved_tensors
+            g = g.to(torch.float32).contiguous()
+            with torch.cuda.device(g.device):
+                stream = _lib.stream_ptr(g.device)
+                sums = torch.zeros(2, dtype=torch.float64, device=g.device)
+                _lib.check(lib.tae_power_norm_bwd_sums_f32(_lib.ptr(g), _lib.ptr(y), g.numel(), _lib.ptr(sums), stream))
+                if sharded:
+                    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=ctx.group)
+                dx = torch.empty_like(g)
+                _lib.check(lib.tae_power_norm_bwd_f32(_lib.ptr(g), _lib.ptr(y), _lib.ptr(dx), g.numel(), _lib.ptr(sums), _lib.ptr(stats),
+                                                      _lib.ptr(mean_std), stream))
+            return dx, None, None
         y, std, n = ctx.saved_tensors
         sums = torch.stack([g.double().sum(), (g.double() * y.double()).sum()])
-        if ctx.group is not LOCAL and dist.is_available() and dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
+        if sharded:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=ctx.group)
         dx = (g - (sums[0] / n).float() - y * (sums[1] / (n - 1.0)).float()) / std
-        return dx, None
+        return dx, None, None
 
 
 def seed_everything(seed: int) -> None:

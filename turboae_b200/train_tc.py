@@ -98,6 +98,14 @@ def _check_stash(ctx):
                             "backward() ran (a graph kept alive with retain_graph, or a second backward)")
 
 
+def _grad_views(gflat, params):
+    """Per-parameter gradients as consecutive views of the flat buffer.  Fresh view objects on every call: autograd adopts an
+    incoming gradient as ``.grad`` (no copy) only when nothing else references it, and shard.all_reduce_gradients relies on the
+    ``.grad``s tiling one buffer.  One split call + one reshape per multi-dimensional parameter."""
+    return [(v if p.dim() == 1 else v.view(p.shape)) if p.requires_grad else None
+            for v, p in zip(gflat.split_with_sizes([p.numel() for p in params]), params)]
+
+
 def _flat_grad(buf, flat, params):
     """The persistent flat gradient buffer, zeroed -- or a fresh one when some .grad still aliases it (gradient accumulation
     without zero_grad: the views handed out by the previous backward were adopted by autograd as the .grad tensors)."""
@@ -287,12 +295,7 @@ class DecoderTrainFn(torch.autograd.Function):
                                       gflat, offsets, splits=getattr(dec, "wgrad_splits", None))
                     buf.jobs = pack_jobs(jobs, dev)
                 run_packed(buf.jobs, dev)
-                off = 0
-                for i, p in enumerate(params):
-                    n = p.numel()
-                    if p.requires_grad:
-                        grads[i] = gflat[off:off + n].view_as(p)
-                    off += n
+                grads = _grad_views(gflat, params)
         ctx.tok.done = True
         return (None, d_rec, *grads)
 
@@ -315,7 +318,7 @@ def decoder_forward_train(dec, received):
 
 class EncoderTrainFn(torch.autograd.Function):
     """ENC_interCNN branches (reference encoders.py:362-373: three conv stacks, Linear(units, 1), ELU, concat) on the tensor
-    cores: u (B, L, 1) -> un-normalised x_tx (B, L, 3).  power_constraint stays differentiable torch glue (shard.PowerNorm)."""
+    cores: u (B, L, 1) -> un-normalised x_tx (B, L, 3) + its power statistics; power_constraint itself is shard.PowerNorm."""
 
     @staticmethod
     def forward(ctx, enc, u, *params):
@@ -348,10 +351,11 @@ class EncoderTrainFn(torch.autograd.Function):
         ctx.enc, ctx.cfg, ctx.buf, ctx.shape = enc, cfg, buf, (B, L)
         ctx.tok, ctx.gen = tok, gen
         ctx.save_for_backward(x_tx, flat)
-        return x_tx
+        ctx.mark_non_differentiable(stats)
+        return x_tx, stats
 
     @staticmethod
-    def backward(ctx, d_x):
+    def backward(ctx, d_x, _d_stats=None):
         lib = _lib.load()
         enc, cfg, buf = ctx.enc, ctx.cfg, ctx.buf
         _check_stash(ctx)
@@ -388,17 +392,14 @@ class EncoderTrainFn(torch.autograd.Function):
                                   offsets, splits=getattr(enc, "wgrad_splits", None))
                 buf.jobs = pack_jobs(jobs, dev)
             run_packed(buf.jobs, dev)
-            grads, off = [], 0
-            for p in params:
-                n = p.numel()
-                grads.append(gflat[off:off + n].view_as(p) if p.requires_grad else None)
-                off += n
+            grads = _grad_views(gflat, params)
         ctx.tok.done = True
         return (None, None, *grads)
 
 
 def encoder_branches_train(enc, u):
-    """Differentiable un-normalised ENC_interCNN output (B, L, 3) on the tensor cores."""
+    """Differentiable un-normalised ENC_interCNN output (B, L, 3) on the tensor cores, and the (sum, sum of squares, count) of its
+    elements as 3 device doubles (what power_constraint needs: encoders.py:107-116)."""
     if enc.args.enc_kernel_size != 5:
         raise NotImplementedError("tensor-core training needs enc_kernel_size == 5")
     return EncoderTrainFn.apply(enc, u.contiguous(), *enc.ordered_parameters())

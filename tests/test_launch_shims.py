@@ -40,3 +40,41 @@ def test_launcher_shims_make_the_reference_turbo_encoder_and_lookahead_run():
         pytest.skip("baseline/_ref not staged (python scripts/stage_reference.py)")
     r = subprocess.run([sys.executable, "-c", CODE % (REF, ROOT)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+FUSED_CODE = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from turboae_b200 import launch
+launch.fused_adam_default(); launch.fused_adam_default()                  # idempotent
+m = torch.nn.Linear(3, 3)
+# CPU parameters: torch's own choice stays (fused needs CUDA); the reference's filter(...) generator is materialised once
+o = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=1e-3)
+assert o.defaults.get("fused") is None and len(o.param_groups[0]["params"]) == 2 and o.defaults["lr"] == 1e-3
+o = torch.optim.Adam(m.parameters(), 1e-3, foreach=True)                  # an explicit choice is respected
+assert o.defaults.get("fused") is None and o.defaults["foreach"] is True
+# what the wrapper decides for device parameters, without a device: stand-in leaves that report is_cuda
+class Fake(torch.Tensor):
+    is_cuda = True
+seen = {}
+_orig = torch.optim.Adam.__init__.__closure__[0].cell_contents
+def spy(self, params, *a, **k):
+    seen.update(k)
+    raise RuntimeError("stop")
+import types
+for c in torch.optim.Adam.__init__.__closure__:
+    if c.cell_contents is _orig:
+        c.cell_contents = spy
+try:
+    torch.optim.Adam([torch.zeros(2).as_subclass(Fake)], lr=1e-3)
+except RuntimeError:
+    pass
+assert seen.get("fused") is True, seen
+print("ok")
+"""
+
+
+def test_launcher_fused_adam_default():
+    """launch.fused_adam_default: fused=True only when every parameter is a CUDA floating tensor and the caller chose nothing."""
+    out = subprocess.run([sys.executable, "-c", FUSED_CODE % ROOT], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr

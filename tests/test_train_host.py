@@ -195,3 +195,38 @@ def test_stash_is_not_shared_between_two_live_forwards():
     ctx.buf, ctx.gen = b1, gen1                             # stale generation (retain_graph + a later forward)
     with pytest.raises(_lib.TaeError):
         train_tc._check_stash(ctx)
+
+
+def test_canonical_parameter_order_is_cached_and_follows_replaced_parameters():
+    """_flat.OrderedParameters: the module tree is walked once; the list is dropped whenever Parameter objects can have been
+    replaced (set_parallel, load_state_dict at any level incl. assign=True, .to() / dtype casts, deepcopy keeps its own)."""
+    import copy
+    import pickle
+    import torch
+    import turboae_b200 as T
+    from helpers import make_args
+    from oracle import turboae_oracle as O
+    p = O.make_perm(100, 0)
+    d, e = T.DEC_LargeCNN(make_args(), p), T.ENC_interCNN(make_args(), p)
+    fresh = lambda m: [id(x) for x in m._walk_ordered_parameters()]
+    l1 = d.ordered_parameters()
+    assert d.ordered_parameters() is l1 and len(l1) == 144 and len(e.ordered_parameters()) == 18
+    d.set_parallel()
+    assert d.ordered_parameters() is not l1 and [id(x) for x in d.ordered_parameters()] == fresh(d)
+    l2 = d.ordered_parameters()
+    d.load_state_dict(d.state_dict())
+    assert d.ordered_parameters() is not l2
+    l3 = d.ordered_parameters()
+    d.load_state_dict(d.state_dict(), assign=True)                      # replaces the Parameter objects
+    assert [id(x) for x in d.ordered_parameters()] == fresh(d) and any(x is not y for x, y in zip(l3, d.ordered_parameters()))
+    model = torch.nn.Module()                                           # Channel_AE-like parent: the load recurses into enc / dec
+    model.enc, model.dec = e, d
+    le = e.ordered_parameters()
+    model.load_state_dict(model.state_dict(), assign=True)
+    assert e.ordered_parameters() is not le and [id(x) for x in e.ordered_parameters()] == fresh(e)
+    d2 = copy.deepcopy(d)
+    assert [id(x) for x in d2.ordered_parameters()] == fresh(d2)
+    assert all(x is not y for x, y in zip(d2.ordered_parameters(), d.ordered_parameters()))
+    d.double()
+    assert [id(x) for x in d.ordered_parameters()] == fresh(d)
+    pickle.dumps(d)                                                     # the load hook is a module-level function

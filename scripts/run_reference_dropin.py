@@ -9,6 +9,10 @@ eval    : README command (1) (`-num_epoch 0`, shipped checkpoint), BER / BLER li
 train   : README command (3) (fine-tune from the checkpoint), 1 epoch, -num_block 5000: trainer.train's loss.backward()
           / optimizer.step() on this package's autograd path; loss / BER trajectory recorded.
 scratch : README command (2) (from scratch), 2 epochs, -num_block 5000.
+c4      : BASELINE config 4 through the reference's own trainer: from scratch, batch 1000, -num_block 20000, 1 epoch (1 encoder + 5
+          decoder passes of 20 steps, trainer.py:33-76 with its CPU bit / noise generation, host-to-device copies and per-step
+          loss.item()); codewords/s of every pass from the "running time" trainer.train prints.  With --stock the same command on the
+          reference's own classes (torch eager on the same GPU).
 Everything the reference prints goes to gpurun_out/dropin_<mode>.log."""
 import argparse
 import ast
@@ -66,7 +70,7 @@ def parse_lists(text):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--mode", default="eval", choices=["eval", "train", "scratch", "all"])
+    ap.add_argument("--mode", default="eval", choices=["eval", "train", "scratch", "c4", "all"])
     ap.add_argument("--reference", default=os.path.join(ROOT, "baseline", "_ref"))
     ap.add_argument("--num-block", type=int, default=1000000, help="eval: blocks per SNR point")
     ap.add_argument("--batch-size", type=int, default=50000, help="eval batch size")
@@ -88,6 +92,8 @@ def main():
             extra = ["-num_block", str(a.num_block), "-batch_size", str(a.batch_size), "-init_nw_weight", CKPT, "-num_epoch", "0"]
         elif mode == "train":
             extra = ["-num_block", "5000", "-batch_size", "500", "-init_nw_weight", CKPT, "-num_epoch", "1"]
+        elif mode == "c4":
+            extra = ["-num_block", "20000", "-batch_size", "1000", "-num_epoch", "1"]
         else:
             extra = ["-num_block", "5000", "-batch_size", "500", "-num_epoch", "2"]
         tag = ("stock_" if a.stock else "dropin_") + mode + ("" if a.nproc == 1 else "_n%d" % a.nproc)
@@ -97,6 +103,12 @@ def main():
         text = open(log).read()
         r = parse_lists(text)
         r.update(rc=rc, seconds=secs, args=" ".join(extra), nproc=a.nproc, seed=a.seed, classes="reference (stock)" if a.stock else "turboae_b200")
+        if mode == "c4":
+            secs_pass = [float(l.rsplit(" ", 1)[1]) for l in r["epoch_lines"]]
+            r["pass_seconds"] = secs_pass                     # pass 0 = encoder mode (includes one-time setup), 1..5 = decoder mode
+            r["train_cw_per_s_decoder_passes"] = [20000.0 / t for t in secs_pass[1:]]
+            if len(secs_pass) > 2:
+                r["train_cw_per_s_median"] = sorted(r["train_cw_per_s_decoder_passes"])[len(secs_pass[1:]) // 2]
         if mode == "eval" and "BER" in r:
             g = json.load(open(os.path.join(ROOT, "tests", "golden", "ber_c1.json")))
             gold = [e / (g["blocks"] * 100.0) for e in g["bit_errors"]]
@@ -105,7 +117,7 @@ def main():
             r["within_1e-4"] = [d <= 1e-4 for d in r["abs_diff"]]
             r["ber_0db"] = r["BER"][3]
         results[mode] = r
-        print(mode, "rc", rc, "%.1f s" % secs, {k: v for k, v in r.items() if k in ("BER", "BLER", "abs_diff", "loss_traj", "ber_traj")}, flush=True)
+        print(mode, "rc", rc, "%.1f s" % secs, {k: v for k, v in r.items() if k in ("BER", "BLER", "abs_diff", "loss_traj", "ber_traj", "pass_seconds", "train_cw_per_s_median")}, flush=True)
         if rc != 0:
             print(text[-3000:])
     out = a.out or os.path.join(out_dir, "%s_%s.json" % ("stock" if a.stock else "dropin", a.mode))

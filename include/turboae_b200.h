@@ -205,6 +205,8 @@ int tae_power_norm_bwd_f32(const float* g, const float* codes, float* dx, size_t
 #define TAE_IMG_CHUNK_BYTES 8256
 #define TAE_IMG_CHUNKS 13
 int32_t tae_train_groups(int32_t block_len, int32_t B);
+/* Work units of the fused kernels for a batch: one unit = the two groups 2p, 2p+1 = one pass of a CTA pair; (groups + 1) / 2. */
+int32_t tae_train_units(int32_t block_len, int32_t B);
 /* tae_dec_forward(TAE_PRECISION_BF16) that also writes stash_y / stash_x. */
 int tae_dec_forward_train_bf16(const TaeDecConfig* cfg, const void* packed, const float* received, const int32_t* perm,
                                const int32_t* inv_perm, float* out, float* trace, int32_t B, void* stash_y, void* stash_x,
@@ -222,6 +224,14 @@ int    tae_dec_pack_bwd_bf16(const TaeDecConfig* cfg, const float* params, void*
 int tae_dec_backward_bf16(const TaeDecConfig* cfg, const void* packed_bwd, const float* d_out_last, const int32_t* perm,
                           const int32_t* inv_perm, const void* stash_y, void* stash_g, void* stash_d, float* dxin_all,
                           float* dlin_all, float* grad_flat, int32_t B, void* workspace, size_t workspace_bytes, void* stream);
+/* The same for the work units [unit_begin, unit_end) only (all buffers as for the whole batch).  Units are independent, so the
+ * backward of a batch may be split over several launches: with more units than CTA pairs on the device (batch 1000: 100 units on
+ * 74 pairs) the last, partly filled wave goes into a launch of its own and tae_wgrad_bf16 over the groups of the earlier units runs
+ * beside it on the SMs that wave leaves idle (turboae_b200/train_tc.py).                                                        */
+int tae_dec_backward_range_bf16(const TaeDecConfig* cfg, const void* packed_bwd, const float* d_out_last, const int32_t* perm,
+                                const int32_t* inv_perm, const void* stash_y, void* stash_g, void* stash_d, float* dxin_all,
+                                float* dlin_all, float* grad_flat, int32_t B, int32_t unit_begin, int32_t unit_end, void* workspace,
+                                size_t workspace_bytes, void* stream);
 /* The same three steps for ENC_interCNN (reference encoders.py:362-373 under trainer.py:74): 3 branches = 3 independent stacks
  * with one input channel and Linear(units, 1); x_tx / stats as tae_enc_forward_bf16; dlin (3, B, L, 1) = gradient w.r.t. each
  * branch's Linear output (i.e. d x_tx[:, :, branch] * ELU'), dxin_all (3, B, L, 8) = gradient w.r.t. the +-1 input in column 0. */

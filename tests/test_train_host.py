@@ -230,3 +230,37 @@ def test_canonical_parameter_order_is_cached_and_follows_replaced_parameters():
     d.double()
     assert [id(x) for x in d.ordered_parameters()] == fresh(d)
     pickle.dumps(d)                                                     # the load hook is a module-level function
+
+
+def test_backward_split_and_group_range_job_lists_partition_the_batch():
+    """The two-launch backward (train_tc.backward_split) and the weight-gradient job lists of its two group ranges: together they
+    cover every (parameter slab, group) exactly once, like the single list."""
+    import torch
+    from turboae_b200 import train_tc
+    # one full wave + a partly filled one on 74 CTA pairs -> split after the full wave; otherwise one launch
+    assert train_tc.backward_split(100, 148) == 74 and train_tc.backward_split(75, 148) == 74
+    assert train_tc.backward_split(150, 148) == 148 and train_tc.backward_split(223, 148) == 222
+    for units in (1, 50, 74, 126, 148, 200, 300, 5000):
+        assert train_tc.backward_split(units, 148) == 0, units
+    assert train_tc.backward_split(100, 0) == 0
+    units, n_layer, cin0, fouts, groups = 100, 5, 7, [5, 1], 200
+    cb = 8256
+    stash_y = torch.zeros(1, dtype=torch.uint8)
+    offsets, off = [], 0
+    for st in range(2):
+        layers = []
+        for j in range(n_layer):
+            cin = cin0 if j == 0 else units
+            layers.append((off, off + units * cin * 5))
+            off += units * cin * 5 + units
+        offsets.append((layers, off))
+        off += fouts[st] * units + fouts[st]
+    gflat = torch.zeros(off)
+    mk = lambda rng: train_tc.wgrad_jobs(n_layer, units, cin0, fouts, groups, stash_y, stash_y, stash_y, stash_y, gflat, offsets, group_range=rng)
+    whole, head, tail = mk(None), mk((0, 148)), mk((148, 200))
+    cover = lambda jobs: sorted((j.grad, j.n0, j.b_c0, g) for j in jobs for g in range(j.g0, j.g1))
+    assert cover(head + tail) == cover(whole) and len(set(cover(whole))) == len(cover(whole))
+    assert all(j.g1 <= 148 for j in head) and all(j.g0 >= 148 for j in tail) and head and tail
+    assert mk((5, 5)) == []
+    with pytest.raises(ValueError):
+        mk((10, 201))

@@ -87,10 +87,13 @@ _SIGNATURES = {
     "tae_gru_tiles_from_f32": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "tae_gru_linear_f32": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "tae_train_groups": (C.c_int32, [C.c_int32, C.c_int32]),
+    "tae_train_units": (C.c_int32, [C.c_int32, C.c_int32]),
     "tae_dec_forward_train_bf16": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "tae_dec_bwd_packed_bytes": (C.c_size_t, [C.POINTER(TaeDecConfig)]),
     "tae_dec_pack_bwd_bf16": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P]),
     "tae_dec_backward_bf16": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, C.c_size_t, _P]),
+    "tae_dec_backward_range_bf16": (C.c_int, [C.POINTER(TaeDecConfig), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P,
+                                              C.c_size_t, _P]),
     "tae_enc_forward_train_bf16": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "tae_enc_bwd_packed_bytes": (C.c_size_t, [C.POINTER(TaeEncConfig)]),
     "tae_enc_pack_bwd_bf16": (C.c_int, [C.POINTER(TaeEncConfig), _P, _P, _P]),

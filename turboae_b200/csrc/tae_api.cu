@@ -493,6 +493,8 @@ int32_t tae_train_groups(int32_t block_len, int32_t B) {
   return train_groups(block_len, B);
 }
 
+int32_t tae_train_units(int32_t block_len, int32_t B) { return (tae_train_groups(block_len, B) + 1) / 2; }
+
 int tae_dec_forward_train_bf16(const TaeDecConfig* cfg, const void* packed, const float* received, const int32_t* perm,
                                const int32_t* inv_perm, float* out, float* trace, int32_t B, void* stash_y, void* stash_x,
                                void* workspace, size_t workspace_bytes, void* stream) {
@@ -536,6 +538,24 @@ int tae_dec_backward_bf16(const TaeDecConfig* cfg, const void* packed_bwd, const
               "tae_dec_backward_bf16: NULL pointer");
   return dec_backward_pair(*cfg, packed_bwd, d_out_last, perm, inv_perm, stash_y, stash_g, stash_d, dxin_all, dlin_all, grad_flat, B, workspace,
                            workspace_bytes, (cudaStream_t)stream);
+}
+
+int tae_dec_backward_range_bf16(const TaeDecConfig* cfg, const void* packed_bwd, const float* d_out_last, const int32_t* perm,
+                                const int32_t* inv_perm, const void* stash_y, void* stash_g, void* stash_d, float* dxin_all, float* dlin_all,
+                                float* grad_flat, int32_t B, int32_t unit_begin, int32_t unit_end, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  int rc = check_dec_config(cfg);
+  if (rc) return rc;
+  const char* why = nullptr;
+  if (!bf16_supported(*cfg, &why)) { set_error("bf16 path: %s", why); return TAE_EUNSUPPORTED; }
+  TAE_REQUIRE(B >= 0, "tae_dec_backward_range_bf16: negative batch %d", B);
+  TAE_REQUIRE(unit_begin >= 0 && unit_end >= unit_begin && unit_end <= tae_train_units(cfg->block_len, B),
+              "tae_dec_backward_range_bf16: work units [%d, %d) outside [0, %d)", unit_begin, unit_end, tae_train_units(cfg->block_len, B));
+  if (B == 0 || unit_begin == unit_end) return TAE_OK;
+  TAE_REQUIRE(packed_bwd && d_out_last && perm && inv_perm && stash_y && stash_g && stash_d && dxin_all && dlin_all && workspace,
+              "tae_dec_backward_range_bf16: NULL pointer");
+  return dec_backward_pair(*cfg, packed_bwd, d_out_last, perm, inv_perm, stash_y, stash_g, stash_d, dxin_all, dlin_all, grad_flat, B, workspace,
+                           workspace_bytes, (cudaStream_t)stream, unit_begin, unit_end);
 }
 
 int tae_enc_forward_train_bf16(const TaeEncConfig* cfg, const void* packed, const float* u, const int32_t* perm, const int32_t* inv_perm,

@@ -153,7 +153,7 @@ size_t dec_pair_bwd_packed_bytes(const TaeDecConfig& c);
 int dec_pair_pack_bwd(const TaeDecConfig& c, const float* params, void* packed, cudaStream_t s);
 int dec_backward_pair(const TaeDecConfig& c, const void* packed_bwd, const float* d_out_last, const int32_t* perm, const int32_t* inv_perm,
                       const void* stash_y, void* stash_g, void* stash_d, float* dxin_all, float* dlin_all, float* grad_flat, int B, void* ws,
-                      size_t ws_bytes, cudaStream_t s);
+                      size_t ws_bytes, cudaStream_t s, int pair_begin = 0, int pair_end = -1);
 int launch_wgrad(const TaeWgradJob* jobs_host, int n_jobs, const void* jobs_dev, void* ws, size_t ws_bytes, cudaStream_t s);
 // ENC_interCNN on the same CTA-pair kernel (three branches as three stacks)
 bool enc_pair_supported(const TaeEncConfig& c, const char** why);

@@ -164,6 +164,7 @@ struct PairArgs {
   const int32_t* perm;
   const int32_t* inv_perm;
   int B, L, F, n_stacks, n_layer, extrinsic, n_groups, n_pairs, cw_per_group;
+  int pair_begin;              // this launch walks the work units [pair_begin, n_pairs) (0 except for a range-split backward)
   int enc;                     // 0: DEC_LargeCNN schedule; 1: ENC_interCNN (three branches, Linear(units,1) + ELU, power sums)
   const float* u;              // enc: bits (B, L, 1)
   float* x_tx;                 // enc: un-normalised codes (B, L, 3)
@@ -414,7 +415,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(N_THREADS, 1) dec_pa
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(sbase + S.tmem_ptr) : "memory");
 
-  const int pair0 = (int)cluster_id_x(), pair_stride = (int)n_clusters_x();
+  const int pair0 = a.pair_begin + (int)cluster_id_x(), pair_stride = (int)n_clusters_x();
   // timeline: the third group of cluster 0 (steady state: weights in L2, clocks settled), else its first
   const int tl_pr = (a.n_pairs > 2 * pair_stride) ? 2 * pair_stride : 0;
   (void)tl_pr;
@@ -1374,7 +1375,8 @@ int dec_pair_pack_bwd(const TaeDecConfig& c, const float* params, void* packed, 
 // the Linear bias gradients are added into grad_flat (flat parameter layout) when it is not NULL.
 static int backward_pair(const TaeDecConfig& c, const PackLayout& lay, int n_stacks, int chain, const void* packed_bwd, const float* dlin,
                          const int32_t* perm, const int32_t* inv_perm, const void* stash_y, void* stash_g, void* stash_d, float* dxin_all,
-                         float* dlin_all, float* grad_flat, int B, void* ws, size_t ws_bytes, cudaStream_t s, const char* who) {
+                         float* dlin_all, float* grad_flat, int B, void* ws, size_t ws_bytes, cudaStream_t s, const char* who,
+                         int pair_begin = 0, int pair_end = -1) {
   if (ws_bytes < 256) { set_error("%s: workspace %zu < 256 bytes", who, ws_bytes); return TAE_EWORKSPACE; }
   const Smem S = make_smem(c.num_iter_ft);
   int n_sm = 0;
@@ -1395,18 +1397,23 @@ static int backward_pair(const TaeDecConfig& c, const PackLayout& lay, int n_sta
   a.stash_x = reinterpret_cast<uint8_t*>(stash_d);
   a.dlin = dlin; a.dxin = dxin_all; a.dlin_all = dlin_all; a.grad_flat = grad_flat; a.chain = chain; a.lay = lay;
   a.perm = perm; a.inv_perm = inv_perm;
-  const int n_clusters = std::min(a.n_pairs, n_sm / 2);
+  if (pair_end < 0 || pair_end > a.n_pairs) pair_end = a.n_pairs;
+  if (pair_begin < 0 || pair_begin > pair_end) { set_error("%s: bad work-unit range [%d, %d) of %d", who, pair_begin, pair_end, a.n_pairs); return TAE_EINVAL; }
+  if (pair_begin == pair_end) return TAE_OK;
+  a.pair_begin = pair_begin;
+  a.n_pairs = pair_end;                          // the kernel's unit loops end here
+  const int n_clusters = std::min(pair_end - pair_begin, n_sm / 2);
   dec_pair_kernel<1><<<2 * n_clusters, N_THREADS, S.total, s>>>(a);
   return after_launch("dec_pair_kernel<1>");
 }
 
 int dec_backward_pair(const TaeDecConfig& c, const void* packed_bwd, const float* d_out_last, const int32_t* perm, const int32_t* inv_perm,
                       const void* stash_y, void* stash_g, void* stash_d, float* dxin_all, float* dlin_all, float* grad_flat, int B, void* ws,
-                      size_t ws_bytes, cudaStream_t s) {
+                      size_t ws_bytes, cudaStream_t s, int pair_begin, int pair_end) {
   const int n_stacks = 2 * c.num_iteration;
   const PackLayout lay{n_stacks, c.num_layer, c.num_unit, 2 + c.num_iter_ft, c.num_iter_ft, 1};
   return backward_pair(c, lay, n_stacks, 1, packed_bwd, d_out_last, perm, inv_perm, stash_y, stash_g, stash_d, dxin_all, dlin_all, grad_flat, B,
-                       ws, ws_bytes, s, "tae_dec_backward_bf16");
+                       ws, ws_bytes, s, "tae_dec_backward_bf16", pair_begin, pair_end);
 }
 
 // ---- ENC_interCNN on the same kernel ----------------------------------------------------------------------------

@@ -5,9 +5,11 @@ One ``torch.autograd.Function`` for the whole decoder:
 
 * forward  = the fused inference kernel (``tae_dec_forward_train_bf16``: same launch, same schedule) that additionally
   stashes every conv layer's output and every stack's input as bf16 *group images* in HBM;
-* backward = per stack, in reverse order, ``tae_dec_stack_backward_bf16`` (the same tcgen05 pipeline run on gradients,
-  ELU' taken from the stash) with the extrinsic / interleaver glue between stacks spelled out on (B, L, F) tensors,
-  then ONE ``tae_wgrad_bf16`` launch that turns the stashed gradients and activations into all weight gradients.
+* backward = ``tae_dec_backward_bf16`` / ``tae_dec_backward_range_bf16``: all stacks in ONE launch, the schedule walked backwards
+  (the same tcgen05 pipeline run on gradients, ELU' taken from the stash, the extrinsic / interleaver glue between stacks inside
+  the kernel), then ``tae_wgrad_bf16`` turns the stashed gradients and activations into all weight gradients.  When the batch's
+  work units fill one wave of CTA pairs plus a partly filled one (batch 1000 on a B200) the backward is split at the full wave and
+  the first part's weight gradients run on a side stream beside the rest (``backward_split``).
 
 Operands are bf16, every accumulation (MMA, weight-gradient reduction) is fp32, parameters and their gradients stay fp32.
 """
@@ -18,8 +20,14 @@ import weakref
 
 import torch
 
+import os
+
 from . import _lib
 from ._flat import unwrap
+
+#: split the decoder's backward at the last full wave of work units and run the first part's weight gradients beside the rest
+#: (backward_split); a module attribute ``wgrad_overlap`` or TURBOAE_B200_WGRAD_OVERLAP=0 turns it off
+WGRAD_OVERLAP = os.environ.get("TURBOAE_B200_WGRAD_OVERLAP", "1") != "0"
 
 
 def n_sm(device=None) -> int:
@@ -61,7 +69,10 @@ class _Buffers:
         self.dxin = torch.zeros((n_stacks, B, L, 8), dtype=torch.float32, device=device)
         self.dlin = torch.zeros((n_stacks, B, L, F), dtype=torch.float32, device=device)
         self.gflat = None
-        self.jobs = None          # (ctypes array, n, device workspace)
+        self.jobs = None          # (ctypes array, n, device copy, device workspace): all groups, or those of the first backward launch
+        self.jobs_tail = None     # ... of the second backward launch (backward_split)
+        self.jobs_cut = None      # the split point the two lists were built for
+        self.side = None          # side stream of the overlapped weight-gradient launch
         self.gen = 0              # forwards that have written this stash
         self.owner = None         # weakref to the _Token of the forward whose backward has not run yet
 
@@ -127,13 +138,16 @@ def _job_cost_us(b_chunks, n_cols, taps):
     return 3.9 if taps > 1 else 1.1
 
 
-def wgrad_jobs(n_layer, units, cin0, fouts, groups, stash_y, stash_x, stash_g, stash_d, gflat, offsets, splits=None, sm_count=None):
+def wgrad_jobs(n_layer, units, cin0, fouts, groups, stash_y, stash_x, stash_g, stash_d, gflat, offsets, splits=None, sm_count=None,
+               group_range=None):
     """Job list of ``tae_wgrad_bf16`` for conv stacks laid out like a DEC_LargeCNN: ``offsets[st]`` = (per layer (w_off, b_off),
     lin_w_off) in floats into ``gflat``; ``fouts[st]`` = features of the stack's Linear.  One job = one CTA.  Every
     layer is cut into group ranges of about equal estimated duration (3-4 CTAs per SM in total, at least ~60 us each so that
     the TMEM drain stays a small share), the channel slabs of a layer share the ranges and are adjacent in the list (they read
     the same gradient image: the second reader hits L2), and the list is sorted longest first: the hardware dispatches CTAs
-    in order, which then balances the SMs.  ``splits`` forces the number of ranges instead."""
+    in order, which then balances the SMs.  ``splits`` forces the number of ranges instead.  ``group_range`` = (lo, hi) restricts
+    the reduction to the groups lo .. hi-1 (the gradients are sums over groups and the kernel ADDS into ``gflat``, so the job lists
+    of disjoint ranges may run as separate launches, e.g. beside a backward that is still producing the later groups)."""
     cb = _lib.IMG_CHUNK_BYTES
     layer_img = groups * _lib.IMG_CHUNKS * cb
     protos = []           # (fields, family): the channel slabs of ONE layer form a family
@@ -174,18 +188,22 @@ def wgrad_jobs(n_layer, units, cin0, fouts, groups, stash_y, stash_x, stash_g, s
     # The slabs of a layer all read the layer's whole gradient image (the A operand): they get the SAME group ranges and sit
     # next to each other in the list, so that they run at the same time on neighbouring SMs and the second reader of a window
     # finds it in L2 (measured before: 3.66 GB of DRAM reads per decoder step against 2.6 GB algorithmic).
-    costs = [_job_cost_us(f[4], f[8], f[7]) * groups for f, _ in protos]
+    g_lo, g_hi = group_range if group_range is not None else (0, groups)
+    if not (0 <= g_lo <= g_hi <= groups):
+        raise ValueError("group_range %r outside [0, %d]" % (group_range, groups))
+    n_g = g_hi - g_lo
+    costs = [_job_cost_us(f[4], f[8], f[7]) * n_g for f, _ in protos]
     target = max(sum(costs) / (3.5 * (sm_count or n_sm())), 60.0)
     fam_cost = {}
     for (f, fam), c in zip(protos, costs):
         fam_cost[fam] = max(fam_cost.get(fam, 0.0), c)
     jobs = []
     for i, ((f, fam), c) in enumerate(zip(protos, costs)):
-        n_split = splits if splits is not None else max(1, min(groups, int(round(fam_cost[fam] / target))))
+        n_split = splits if splits is not None else max(1, min(n_g, int(round(fam_cost[fam] / target))))
         for sp in range(n_split):
-            g0, g1 = groups * sp // n_split, groups * (sp + 1) // n_split
+            g0, g1 = g_lo + n_g * sp // n_split, g_lo + n_g * (sp + 1) // n_split
             if g1 > g0:
-                jobs.append(((-fam_cost[fam] * (g1 - g0) / groups, fam, sp, i), _lib.TaeWgradJob(*f, g0, g1, 0)))
+                jobs.append(((-fam_cost[fam] * (g1 - g0) / max(n_g, 1), fam, sp, i), _lib.TaeWgradJob(*f, g0, g1, 0)))
     jobs.sort(key=lambda t: t[0])
     return [j for _, j in jobs]
 
@@ -208,6 +226,20 @@ def run_wgrad(jobs, device):
     packed = pack_jobs(jobs, device)
     run_packed(packed, device)
     return packed[3]
+
+
+def backward_split(units: int, sm_count: int) -> int:
+    """Work units that go into the FIRST of two backward launches, or 0 for one launch.  A unit (10 codewords of block length 100)
+    occupies a CTA pair for the whole backward, so ``units`` units take ceil(units / pairs) waves; when the last wave is partly
+    filled and the waves are few (batch 1000: 100 units on 74 pairs = one full wave + one 35 % full), the last wave becomes a
+    launch of its own and the weight gradients of the earlier units run beside it on the SMs it leaves idle."""
+    pairs = sm_count // 2
+    if pairs < 1 or units <= pairs:
+        return 0
+    full, rest = divmod(units, pairs)
+    if rest == 0 or full > 3 or rest > 0.7 * pairs:
+        return 0
+    return full * pairs
 
 
 def _dec_offsets(a):
@@ -278,24 +310,54 @@ class DecoderTrainFn(torch.autograd.Function):
             offsets, fouts = _dec_offsets(a)
             # out = sigmoid(deinterleave(o_last))  (decoders.py:267)  =>  d o_last = interleave(d_out * out * (1 - out))
             d_o = (d_out.to(torch.float32) * out * (1.0 - out)).index_select(1, perm.long()).contiguous()
-            # all 2I stacks in one launch, schedule walked backwards (the glue between stacks runs inside the kernel)
-            _lib.check(lib.tae_dec_backward_bf16(cfg, _lib.ptr(packed_bwd), _lib.ptr(d_o), _lib.ptr(perm), _lib.ptr(inv), _lib.ptr(buf.stash_y),
-                                                 _lib.ptr(buf.stash_g), _lib.ptr(buf.stash_d), _lib.ptr(buf.dxin), _lib.ptr(buf.dlin),
-                                                 _lib.ptr(gflat) if ctx.need_params else None, B, _lib.ptr(ws), ws.numel(),
-                                                 _lib.stream_ptr(dev)))
+            # all 2I stacks in one launch, schedule walked backwards (the glue between stacks runs inside the kernel) -- or in two
+            # launches over disjoint work units when the last wave of units would leave most SMs idle (backward_split): the weight
+            # gradients of the first launch's groups then run on a side stream beside the second launch
+            n_units = lib.tae_train_units(L, B)
+            cut = backward_split(n_units, n_sm(dev)) if (ctx.need_params and getattr(dec, "wgrad_overlap", WGRAD_OVERLAP)) else 0
+
+            def run_backward(u0, u1):
+                _lib.check(lib.tae_dec_backward_range_bf16(cfg, _lib.ptr(packed_bwd), _lib.ptr(d_o), _lib.ptr(perm), _lib.ptr(inv),
+                                                           _lib.ptr(buf.stash_y), _lib.ptr(buf.stash_g), _lib.ptr(buf.stash_d),
+                                                           _lib.ptr(buf.dxin), _lib.ptr(buf.dlin),
+                                                           _lib.ptr(gflat) if ctx.need_params else None, B, u0, u1, _lib.ptr(ws), ws.numel(),
+                                                           _lib.stream_ptr(dev)))
+            if ctx.need_params and (buf.jobs is None or buf.jobs_cut != cut):
+                mk = lambda rng: pack_jobs(wgrad_jobs(n_layer, units, 2 + F, fouts, buf.groups, buf.stash_y, buf.stash_x, buf.stash_g,
+                                                      buf.stash_d, gflat, offsets, splits=getattr(dec, "wgrad_splits", None),
+                                                      group_range=rng), dev)
+                if cut:
+                    buf.jobs, buf.jobs_tail = mk((0, 2 * cut)), mk((2 * cut, buf.groups))
+                else:
+                    buf.jobs, buf.jobs_tail = mk(None), None
+                buf.jobs_cut = cut
+            if cut:
+                # (measured both ways: the second launch on this stream and the head's weight gradients on the side stream is a
+                # little faster than the second launch on a high-priority side stream: 3.05 vs 3.13 ms per step at batch 1000)
+                main = torch.cuda.current_stream(dev)
+                if buf.side is None:
+                    buf.side = torch.cuda.Stream(dev)
+                run_backward(0, cut)
+                first_done = torch.cuda.Event()
+                first_done.record(main)
+                run_backward(cut, n_units)                      # enqueued first: the latency-bound part
+                buf.side.wait_event(first_done)                 # the groups of units [0, cut) are complete
+                with torch.cuda.stream(buf.side):
+                    run_packed(buf.jobs, dev)                   # ... their weight gradients run beside the second launch
+                run_packed(buf.jobs_tail, dev)
+                joined = torch.cuda.Event()
+                joined.record(buf.side)
+                main.wait_event(joined)
+            else:
+                run_backward(0, n_units)
+                if ctx.need_params:
+                    run_packed(buf.jobs, dev)
             d_rec = None
             if ctx.need_input:
                 # stack inputs: even [r_sys, r_par1, prior] (decoders.py:230), odd [interleave(r_sys), r_par2, ...] (:240)
                 ev, od = buf.dxin[0::2].sum(0), buf.dxin[1::2].sum(0)
                 d_rec = torch.stack([ev[:, :, 0] + od[:, :, 0].index_select(1, inv.long()), ev[:, :, 1], od[:, :, 1]], dim=2)
-            grads = [None] * len(params)
-            if ctx.need_params:
-                if buf.jobs is None:
-                    jobs = wgrad_jobs(n_layer, units, 2 + F, fouts, buf.groups, buf.stash_y, buf.stash_x, buf.stash_g, buf.stash_d,
-                                      gflat, offsets, splits=getattr(dec, "wgrad_splits", None))
-                    buf.jobs = pack_jobs(jobs, dev)
-                run_packed(buf.jobs, dev)
-                grads = _grad_views(gflat, params)
+            grads = _grad_views(gflat, params) if ctx.need_params else [None] * len(params)
         ctx.tok.done = True
         return (None, d_rec, *grads)
 

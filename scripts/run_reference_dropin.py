@@ -78,6 +78,7 @@ def main():
     ap.add_argument("--seed", type=int, default=None, help="launcher seed (same bits and noise in both arms)")
     ap.add_argument("--stock", action="store_true", help="run the reference's OWN classes (torch eager on the GPU): comparison arm")
     ap.add_argument("--no-tf32", action="store_true", help="torch's own CUDA kernels in true fp32 (the --stock arm then computes the reference's fp32 arithmetic)")
+    ap.add_argument("--device-channel", action="store_true", help="launcher --device-channel: AWGN noise drawn on the GPU")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     ref = os.path.abspath(a.reference)
@@ -98,11 +99,11 @@ def main():
             extra = ["-num_block", "5000", "-batch_size", "500", "-num_epoch", "2"]
         tag = ("stock_" if a.stock else "dropin_") + mode + ("" if a.nproc == 1 else "_n%d" % a.nproc)
         log = os.path.join(out_dir, tag + ".log")
-        opts = (["--seed", str(a.seed)] if a.seed is not None else []) + (["--stock"] if a.stock else []) + (["--no-tf32"] if a.no_tf32 else [])
+        opts = (["--seed", str(a.seed)] if a.seed is not None else []) + (["--stock"] if a.stock else []) + (["--no-tf32"] if a.no_tf32 else []) + (["--device-channel"] if a.device_channel else [])
         rc, secs = run(mode, ref, extra, os.path.join(out_dir, "dropin_work"), log, a.nproc, opts)
         text = open(log).read()
         r = parse_lists(text)
-        r.update(rc=rc, seconds=secs, args=" ".join(extra), nproc=a.nproc, seed=a.seed, classes="reference (stock)" if a.stock else "turboae_b200")
+        r.update(rc=rc, seconds=secs, args=" ".join(extra), nproc=a.nproc, seed=a.seed, classes="reference (stock)" if a.stock else "turboae_b200", device_channel=bool(a.device_channel))
         if mode == "c4":
             secs_pass = [float(l.rsplit(" ", 1)[1]) for l in r["epoch_lines"]]
             r["pass_seconds"] = secs_pass                     # pass 0 = encoder mode (includes one-time setup), 1..5 = decoder mode

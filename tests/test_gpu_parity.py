@@ -396,6 +396,40 @@ def test_awgn_stream_vs_oracle(n, offset):
     assert np.abs(z - zr).max() < 5e-5
 
 
+def test_device_noise_replaces_generate_noise_with_the_same_distributions():
+    """channel.DeviceNoise (launcher --device-channel) against reference channels.py:7-35 for the AWGN channel: the normal draws
+    are the Philox stream of tae_awgn_f32 (checked against the oracle, consecutive calls continue the counter), test-time noise
+    is 10^(-snr/20) * N(0,1), the training mixture has a per-element sigma uniform between the two sigmas; other channels fall
+    through to the reference's function."""
+    import types
+    import turboae_b200 as T
+    calls = []
+
+    def reference_fn(noise_shape, args, **kw):
+        calls.append(kw)
+        return torch.zeros(noise_shape)
+    dn = T.channel.DeviceNoise(reference_fn, DEV, seed=99)
+    awgn_args, bec_args = types.SimpleNamespace(channel="awgn"), types.SimpleNamespace(channel="bec")
+    shape = (500, 100, 3)
+    n1 = dn(shape, awgn_args, test_sigma=2.0)                                   # trainer.py:169 passes the SNR in dB
+    n2 = dn(shape, awgn_args, test_sigma=2.0)
+    sig = 10 ** (-2.0 / 20)
+    assert n1.device.type == "cuda" and n1.dtype == torch.float32 and tuple(n1.shape) == shape
+    z = O.awgn_noise(2 * 150000, 99, 0).astype(np.float32)
+    np.testing.assert_allclose(n1.cpu().numpy().ravel(), sig * z[:150000], atol=5e-5, rtol=0)
+    np.testing.assert_allclose(n2.cpu().numpy().ravel(), sig * z[150000:], atol=5e-5, rtol=0)      # the counter went on
+    assert abs(float(n1.mean())) < 0.01 and abs(float(n1.std()) - sig) < 0.01
+    # training mixture between -1.5 dB and 2 dB (README command 2): E[noise^2] = E[sigma^2] for sigma ~ U(s_hi, s_lo)
+    lo, hi = 10 ** (1.5 / 20), 10 ** (-2.0 / 20)
+    m = dn((2000, 100, 3), awgn_args, snr_low=-1.5, snr_high=2.0, mode="decoder")
+    want = (lo * lo + lo * hi + hi * hi) / 3.0
+    assert abs(float((m.double() ** 2).mean()) - want) < 0.01 * want and abs(float(m.mean())) < 0.01
+    same = dn(shape, awgn_args, snr_low=2.0, snr_high=2.0)                      # encoder mode of the README: one SNR
+    assert abs(float(same.std()) - hi) < 0.01
+    out = dn(shape, bec_args, test_sigma=0.1)
+    assert out.device.type == "cpu" and calls == [dict(test_sigma=0.1, snr_low=0.0, snr_high=0.0, mode="encoder")]
+
+
 def test_error_counts_bit_exact_vs_oracle():
     import turboae_b200 as T
     rs = np.random.RandomState(11)

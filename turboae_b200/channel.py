@@ -30,6 +30,40 @@ def awgn(codes: torch.Tensor, sigma: float, seed: int, offset: int = 0, out: tor
     return out
 
 
+class DeviceNoise:
+    """``generate_noise`` of the reference (channels.py:7-35) for the AWGN channel, drawn on the device instead of the CPU:
+    the reference's trainer draws ``torch.randn`` for a whole batch on the host and uploads it every step (trainer.py:53-62,
+    167-171), which at this package's rates is most of a step.  Same distributions: test time ``sigma * N(0, 1)`` with
+    ``sigma = 10^(-snr/20)``; training (``test_sigma == 'default'``) a per-element sigma uniform between the sigmas of
+    ``snr_low`` and ``snr_high`` times ``N(0, 1)`` (channels.py:21-24).  The normal draws are this package's Philox stream
+    (``tae_awgn_f32``; key = ``seed``, the counter advances with every call), so the noise is NOT the sequence torch's CPU generator
+    would have produced -- the reference is unseeded, and a seeded comparison against its own classes needs the host channel.
+    Other channels (bec, bsc, t-dist, radar, ge*) fall through to the reference's function."""
+
+    def __init__(self, reference_generate_noise, device, seed: int = 0):
+        self.reference = reference_generate_noise
+        self.device = torch.device(device)
+        self.seed = int(seed)
+        self.offset = 0
+
+    def normal(self, shape) -> torch.Tensor:
+        z = torch.zeros(tuple(shape), dtype=torch.float32, device=self.device)
+        out = awgn(z, 1.0, self.seed, self.offset, out=z)
+        self.offset += (z.numel() + 3) // 4
+        return out
+
+    def __call__(self, noise_shape, args, test_sigma="default", snr_low=0.0, snr_high=0.0, mode="encoder"):
+        if getattr(args, "channel", "awgn") != "awgn":
+            return self.reference(noise_shape, args, test_sigma=test_sigma, snr_low=snr_low, snr_high=snr_high, mode=mode)
+        noise = self.normal(noise_shape)
+        if isinstance(test_sigma, str):                                    # 'default': the training mixture (channels.py:21-24)
+            lo, hi = snr_db2sigma(snr_low), snr_db2sigma(snr_high)
+            if lo == hi:
+                return noise.mul_(hi)
+            return noise.mul_(torch.rand(tuple(noise_shape), device=self.device).mul_(lo - hi).add_(hi))
+        return noise.mul_(snr_db2sigma(test_sigma))                        # channels.py:30-35
+
+
 def error_counts(y_true: torch.Tensor, y_pred: torch.Tensor, counts: torch.Tensor | None = None) -> torch.Tensor:
     """Adds (bit errors, block errors) of this batch to the device int64[2] tensor ``counts`` (created if None)."""
     _lib.require_cuda(y_pred, "error_counts input")

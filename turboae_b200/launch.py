@@ -142,6 +142,9 @@ def main(argv=None):
                     "defaults to True): makes the --stock arm the reference's fp32 arithmetic (it was written for torch 1.0)")
     ap.add_argument("--no-fused-adam", action="store_true", help="leave torch.optim.Adam's implementation choice alone (default: "
                     "fused=True when every parameter is on a CUDA device)")
+    ap.add_argument("--device-channel", action="store_true", help="draw the AWGN noise of trainer.train / validate / test on the GPU "
+                    "(turboae_b200.channel.DeviceNoise in place of channels.generate_noise: same distributions, another random "
+                    "stream) instead of torch.randn on the CPU + an upload per step")
     ap.add_argument("script", help="reference script to run, e.g. main.py")
     ap.add_argument("script_args", nargs=argparse.REMAINDER)
     a = ap.parse_args(argv)
@@ -196,6 +199,13 @@ def main(argv=None):
     if seed is not None:
         from . import shard
         shard.seed_everything(seed)
+    if a.device_channel and not a.stock:
+        import torch
+        import trainer as ref_trainer                       # `from channels import generate_noise` (trainer.py:10) binds the name here
+        from .channel import DeviceNoise
+        if torch.cuda.is_available() and "--no-cuda" not in a.script_args:
+            key = (seed if seed is not None else int.from_bytes(os.urandom(4), "little")) * 1000003 + int(os.environ.get("RANK", "0"))
+            ref_trainer.generate_noise = DeviceNoise(ref_trainer.generate_noise, torch.device("cuda", torch.cuda.current_device()), key)
     script = a.script if os.path.isabs(a.script) else os.path.join(os.path.abspath(a.reference), a.script)
     for d in ("logs", "tmp"):
         os.makedirs(d, exist_ok=True)                            # main.py:106, 248 write there

@@ -232,6 +232,19 @@ int tae_dec_backward_range_bf16(const TaeDecConfig* cfg, const void* packed_bwd,
                                 const int32_t* inv_perm, const void* stash_y, void* stash_g, void* stash_d, float* dxin_all,
                                 float* dlin_all, float* grad_flat, int32_t B, int32_t unit_begin, int32_t unit_end, void* workspace,
                                 size_t workspace_bytes, void* stream);
+/* Glue of loss.backward() (reference trainer.py:74) on either side of tae_dec_backward_bf16:
+ *   tae_dec_out_backward_f32  out = sigmoid(deinterleave(o_last)) (decoders.py:263-267): d_out_last[b, i] =
+ *                             (d_out * out * (1 - out))[b, perm[i]], all (B, L, 1).
+ *   tae_dec_input_grad_f32    d_received (B, L, 3) from dxin_all (n_stacks, B, L, 8): even stacks read [r_sys, r_par1, priors]
+ *                             (decoders.py:230), odd stacks [interleave(r_sys), r_par2, priors] (:222, :240).                  */
+int tae_dec_out_backward_f32(const float* d_out, const float* out, const int32_t* perm, float* d_out_last, int32_t B, int32_t L,
+                             void* stream);
+int tae_dec_input_grad_f32(const float* dxin_all, const int32_t* inv_perm, float* d_received, int32_t n_stacks, int32_t B, int32_t L,
+                           void* stream);
+/* ... and in front of tae_enc_backward_bf16: x_tx = ELU(Linear(h)) (encoders.py:364-371), so
+ *   dlin[branch, b, l] = d_x_tx[b, l, branch] * (x_tx[b, l, branch] > 0 ? 1 : x_tx[b, l, branch] + 1);  dlin is (3, B, L, 1).   */
+int tae_enc_out_backward_f32(const float* d_x_tx, const float* x_tx, float* dlin, int32_t B, int32_t L, void* stream);
+
 /* The same three steps for ENC_interCNN (reference encoders.py:362-373 under trainer.py:74): 3 branches = 3 independent stacks
  * with one input channel and Linear(units, 1); x_tx / stats as tae_enc_forward_bf16; dlin (3, B, L, 1) = gradient w.r.t. each
  * branch's Linear output (i.e. d x_tx[:, :, branch] * ELU'), dxin_all (3, B, L, 8) = gradient w.r.t. the +-1 input in column 0. */

@@ -362,3 +362,36 @@ def test_split_backward_with_overlapped_weight_gradients_matches_single_launch(B
     for _ in range(5):
         l1 = float(gstep())
     assert l1 < l0
+
+
+@pytest.mark.parametrize("B,L,n_stacks", [(1, 7, 2), (37, 100, 12), (500, 64, 5)])
+def test_backward_glue_kernels_vs_torch(B, L, n_stacks):
+    """The three glue kernels around the fused backward (tae_dec_out_backward_f32, tae_dec_input_grad_f32,
+    tae_enc_out_backward_f32) against the torch expressions they replaced (decoders.py:222-267 / encoders.py:364-371 under
+    autograd): bit-exact where the arithmetic is one product chain, 1e-6 where sums are re-associated."""
+    from turboae_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator(device="cpu").manual_seed(B * L + n_stacks)
+    rnd = lambda *s: torch.randn(*s, generator=gen).to(DEV)
+    perm = torch.from_numpy(np.random.RandomState(L).permutation(L).astype(np.int32)).to(DEV)
+    inv = torch.empty_like(perm)
+    inv[perm.long()] = torch.arange(L, dtype=torch.int32, device=DEV)
+    st = _lib.stream_ptr(torch.device(DEV, 0))
+    # sigmoid' + interleave
+    d_out, out = rnd(B, L, 1), torch.sigmoid(rnd(B, L, 1))
+    got = torch.empty_like(out)
+    _lib.check(lib.tae_dec_out_backward_f32(_lib.ptr(d_out), _lib.ptr(out), _lib.ptr(perm), _lib.ptr(got), B, L, st))
+    assert torch.equal(got, (d_out * out * (1.0 - out)).index_select(1, perm.long()))
+    # gradient w.r.t. received
+    dxin = rnd(n_stacks, B, L, 8)
+    got = torch.empty(B, L, 3, device=DEV)
+    _lib.check(lib.tae_dec_input_grad_f32(_lib.ptr(dxin), _lib.ptr(inv), _lib.ptr(got), n_stacks, B, L, st))
+    ev, od = dxin[0::2].sum(0), dxin[1::2].sum(0)
+    ref = torch.stack([ev[:, :, 0] + od[:, :, 0].index_select(1, inv.long()), ev[:, :, 1], od[:, :, 1]], dim=2)
+    np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), atol=3e-6, rtol=1e-6)
+    # ELU' of the encoder's last activation, one slab per branch
+    d_x, x_tx = rnd(B, L, 3), torch.nn.functional.elu(rnd(B, L, 3))
+    got = torch.empty(3, B, L, 1, device=DEV)
+    _lib.check(lib.tae_enc_out_backward_f32(_lib.ptr(d_x), _lib.ptr(x_tx), _lib.ptr(got), B, L, st))
+    ref = (d_x * torch.where(x_tx > 0, torch.ones_like(x_tx), x_tx + 1.0)).permute(2, 0, 1).contiguous()
+    assert torch.equal(got.view(3, B, L), ref)

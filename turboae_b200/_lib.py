@@ -73,6 +73,9 @@ _SIGNATURES = {
     "tae_power_norm_f32": (C.c_int, [_P, _P, C.c_size_t, _P, _P, _P]),
     "tae_power_norm_given_f32": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_float, C.c_float, _P]),
     "tae_power_norm_ste_f32": (C.c_int, [_P, _P, C.c_size_t, _P, _P, C.c_float, C.c_float, _P]),
+    "tae_dec_out_backward_f32": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "tae_dec_input_grad_f32": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "tae_enc_out_backward_f32": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
     "tae_power_stats_f32": (C.c_int, [_P, C.c_size_t, _P, _P]),
     "tae_power_norm_bwd_sums_f32": (C.c_int, [_P, _P, C.c_size_t, _P, _P]),
     "tae_power_norm_bwd_f32": (C.c_int, [_P, _P, _P, C.c_size_t, _P, _P, _P, _P]),

@@ -467,6 +467,28 @@ int tae_power_norm_ste_f32(const float* x, float* codes, size_t n, const double*
   return launch_power_norm_f32(x, codes, n, stats, mean_std, value_limit, quantize_level, (cudaStream_t)stream);
 }
 
+int tae_dec_out_backward_f32(const float* d_out, const float* out, const int32_t* perm, float* d_out_last, int32_t B, int32_t L, void* stream) {
+  TAE_REQUIRE(B >= 0 && L >= 1, "tae_dec_out_backward_f32: bad shape B=%d L=%d", B, L);
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(d_out && out && perm && d_out_last, "tae_dec_out_backward_f32: NULL pointer");
+  return launch_dec_out_bwd_f32(d_out, out, perm, d_out_last, B, L, (cudaStream_t)stream);
+}
+
+int tae_dec_input_grad_f32(const float* dxin_all, const int32_t* inv_perm, float* d_received, int32_t n_stacks, int32_t B, int32_t L,
+                           void* stream) {
+  TAE_REQUIRE(B >= 0 && L >= 1 && n_stacks >= 1, "tae_dec_input_grad_f32: bad shape stacks=%d B=%d L=%d", n_stacks, B, L);
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(dxin_all && inv_perm && d_received, "tae_dec_input_grad_f32: NULL pointer");
+  return launch_dec_input_grad_f32(dxin_all, inv_perm, d_received, n_stacks, B, L, (cudaStream_t)stream);
+}
+
+int tae_enc_out_backward_f32(const float* d_x_tx, const float* x_tx, float* dlin, int32_t B, int32_t L, void* stream) {
+  TAE_REQUIRE(B >= 0 && L >= 1, "tae_enc_out_backward_f32: bad shape B=%d L=%d", B, L);
+  if (B == 0) return TAE_OK;
+  TAE_REQUIRE(d_x_tx && x_tx && dlin, "tae_enc_out_backward_f32: NULL pointer");
+  return launch_enc_out_bwd_f32(d_x_tx, x_tx, dlin, B, L, (cudaStream_t)stream);
+}
+
 int tae_power_stats_f32(const float* x, size_t n, double* stats, void* stream) {
   if (n == 0) return TAE_OK;
   TAE_REQUIRE(x && stats, "tae_power_stats_f32: NULL pointer");

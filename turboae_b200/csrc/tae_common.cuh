@@ -136,6 +136,9 @@ int enc_forward_f32(const TaeEncConfig& c, const float* params, const float* u, 
 int launch_power_norm_f32(const float* x, float* codes, size_t n, const double* stats, float* mean_std, float limit, float q,
                           cudaStream_t s);
 
+int launch_dec_out_bwd_f32(const float* d_out, const float* out, const int32_t* perm, float* d_last, int B, int L, cudaStream_t s);
+int launch_dec_input_grad_f32(const float* dxin_all, const int32_t* inv_perm, float* d_received, int n_stacks, int B, int L, cudaStream_t s);
+int launch_enc_out_bwd_f32(const float* d_x, const float* x_tx, float* dlin, int B, int L, cudaStream_t s);
 int launch_power_sums_f32(const float* a, const float* y, size_t n, double* out, cudaStream_t s);
 int launch_power_norm_bwd_f32(const float* g, const float* y, float* dx, size_t n, const double* sums, const double* stats,
                               const float* mean_std, cudaStream_t s);

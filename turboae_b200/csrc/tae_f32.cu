@@ -429,6 +429,49 @@ __global__ void power_norm_bwd_kernel(const float* __restrict__ g, const float* 
     dx[idx] = (g[idx] - mg - y[idx] * cy) / stdf;
 }
 
+// ---- glue of the decoder's / encoder's backward around the fused kernels (loss.backward() of trainer.py:74) -----------------
+// out = sigmoid(deinterleave(o_last)) (decoders.py:263-267)  =>  d o_last[b, i] = (d_out * out * (1 - out))[b, perm[i]]
+__global__ void dec_out_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ out, const int32_t* __restrict__ perm,
+                                   float* __restrict__ d_last, size_t n, int L) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t src = (idx / L) * L + perm[idx % L];
+    const float y = out[src];
+    d_last[idx] = d_out[src] * y * (1.f - y);
+  }
+}
+
+// d received (B, L, 3) from the gradients w.r.t. the stack inputs, dxin_all (2I, B, L, 8): even stacks read [r_sys, r_par1, ...]
+// (decoders.py:230), odd stacks [interleave(r_sys), r_par2, ...] (:222, :240), so
+//   d r_sys[b, l] = sum_even dxin[s, b, l, 0] + sum_odd dxin[s, b, inv_perm[l], 0],  d r_par1 = sum_even [.., 1],  d r_par2 = sum_odd [.., 1]
+__global__ void dec_input_grad_kernel(const float* __restrict__ dxin, const int32_t* __restrict__ inv_perm, float* __restrict__ d_rec,
+                                      size_t n_rows, int L, int n_stacks) {
+  for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < n_rows; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t gi = (g / L) * L + inv_perm[g % L];
+    float sys = 0.f, p1 = 0.f, sys_i = 0.f, p2 = 0.f;
+    for (int st = 0; st < n_stacks; st += 2) {
+      const float2 e = *reinterpret_cast<const float2*>(dxin + ((size_t)st * n_rows + g) * 8);
+      sys += e.x;
+      p1 += e.y;
+      if (st + 1 < n_stacks) {
+        sys_i += dxin[((size_t)(st + 1) * n_rows + gi) * 8];
+        p2 += dxin[((size_t)(st + 1) * n_rows + g) * 8 + 1];
+      }
+    }
+    d_rec[g * 3 + 0] = sys + sys_i;
+    d_rec[g * 3 + 1] = p1;
+    d_rec[g * 3 + 2] = p2;
+  }
+}
+
+// x_tx = ELU(Linear(h)) (encoders.py:364-371)  =>  dlin[branch, b, l] = d x_tx[b, l, branch] * (x_tx > 0 ? 1 : x_tx + 1)
+__global__ void enc_out_bwd_kernel(const float* __restrict__ d_x, const float* __restrict__ x_tx, float* __restrict__ dlin, size_t n_rows) {
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < 3 * n_rows; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t br = idx / n_rows, g = idx - br * n_rows;
+    const float x = x_tx[g * 3 + br];
+    dlin[idx] = d_x[g * 3 + br] * (x > 0.f ? 1.f : x + 1.f);
+  }
+}
+
 inline int grid_for(size_t n, int block, int max_blocks = 148 * 16) {
   size_t g = (n + block - 1) / block;
   if (g < 1) g = 1;
@@ -703,6 +746,27 @@ int launch_power_norm_f32(const float* x, float* codes, size_t n, const double* 
   if (n == 0) return TAE_OK;
   power_norm_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, codes, n, stats, mean_std, limit, q);
   return after_launch("power_norm_kernel");
+}
+
+int launch_dec_out_bwd_f32(const float* d_out, const float* out, const int32_t* perm, float* d_last, int B, int L, cudaStream_t s) {
+  const size_t n = (size_t)B * L;
+  if (n == 0) return TAE_OK;
+  dec_out_bwd_kernel<<<grid_for(n, 256), 256, 0, s>>>(d_out, out, perm, d_last, n, L);
+  return after_launch("dec_out_bwd_kernel");
+}
+
+int launch_dec_input_grad_f32(const float* dxin_all, const int32_t* inv_perm, float* d_received, int n_stacks, int B, int L, cudaStream_t s) {
+  const size_t n = (size_t)B * L;
+  if (n == 0) return TAE_OK;
+  dec_input_grad_kernel<<<grid_for(n, 256), 256, 0, s>>>(dxin_all, inv_perm, d_received, n, L, n_stacks);
+  return after_launch("dec_input_grad_kernel");
+}
+
+int launch_enc_out_bwd_f32(const float* d_x, const float* x_tx, float* dlin, int B, int L, cudaStream_t s) {
+  const size_t n = (size_t)B * L;
+  if (n == 0) return TAE_OK;
+  enc_out_bwd_kernel<<<grid_for(3 * n, 256), 256, 0, s>>>(d_x, x_tx, dlin, n);
+  return after_launch("enc_out_bwd_kernel");
 }
 
 int launch_power_sums_f32(const float* a, const float* y, size_t n, double* out, cudaStream_t s) {

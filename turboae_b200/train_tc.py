@@ -309,7 +309,9 @@ class DecoderTrainFn(torch.autograd.Function):
             gflat, _ = _flat_grad(buf, flat, params)
             offsets, fouts = _dec_offsets(a)
             # out = sigmoid(deinterleave(o_last))  (decoders.py:267)  =>  d o_last = interleave(d_out * out * (1 - out))
-            d_o = (d_out.to(torch.float32) * out * (1.0 - out)).index_select(1, perm.long()).contiguous()
+            d_out = d_out.to(torch.float32).contiguous()
+            d_o = torch.empty_like(out)
+            _lib.check(lib.tae_dec_out_backward_f32(_lib.ptr(d_out), _lib.ptr(out), _lib.ptr(perm), _lib.ptr(d_o), B, L, _lib.stream_ptr(dev)))
             # all 2I stacks in one launch, schedule walked backwards (the glue between stacks runs inside the kernel) -- or in two
             # launches over disjoint work units when the last wave of units would leave most SMs idle (backward_split): the weight
             # gradients of the first launch's groups then run on a side stream beside the second launch
@@ -355,8 +357,8 @@ class DecoderTrainFn(torch.autograd.Function):
             d_rec = None
             if ctx.need_input:
                 # stack inputs: even [r_sys, r_par1, prior] (decoders.py:230), odd [interleave(r_sys), r_par2, ...] (:240)
-                ev, od = buf.dxin[0::2].sum(0), buf.dxin[1::2].sum(0)
-                d_rec = torch.stack([ev[:, :, 0] + od[:, :, 0].index_select(1, inv.long()), ev[:, :, 1], od[:, :, 1]], dim=2)
+                d_rec = torch.empty((B, L, 3), dtype=torch.float32, device=dev)
+                _lib.check(lib.tae_dec_input_grad_f32(_lib.ptr(buf.dxin), _lib.ptr(inv), _lib.ptr(d_rec), n_stacks, B, L, _lib.stream_ptr(dev)))
             grads = _grad_views(gflat, params) if ctx.need_params else [None] * len(params)
         ctx.tok.done = True
         return (None, d_rec, *grads)
@@ -436,7 +438,9 @@ class EncoderTrainFn(torch.autograd.Function):
             params = enc.ordered_parameters()
             gflat, _ = _flat_grad(buf, flat, params)
             # x_tx = ELU(Linear(h))  =>  d lin = d x_tx * ELU'   (ELU' = x_tx + 1 where x_tx < 0); one (B, L, 1) slab per branch
-            d_lin = (d_x.to(torch.float32) * torch.where(x_tx > 0, torch.ones_like(x_tx), x_tx + 1.0)).permute(2, 0, 1).contiguous()
+            d_x = d_x.to(torch.float32).contiguous()
+            d_lin = torch.empty((3, B, L, 1), dtype=torch.float32, device=dev)
+            _lib.check(lib.tae_enc_out_backward_f32(_lib.ptr(d_x), _lib.ptr(x_tx), _lib.ptr(d_lin), B, L, _lib.stream_ptr(dev)))
             offsets, off = [], 0
             for br in range(3):
                 layers = []

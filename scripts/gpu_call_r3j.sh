@@ -1,6 +1,6 @@
 #!/bin/bash
 # closing run #2 (after the split backward): full GPU suite, smoke, bench; compute-sanitizer memcheck over small training steps
-TAG=${1:-r02_close2}
+TAG=${1:-r02_close3}
 mkdir -p gpurun_out
 echo "== tests"; timeout 1700 python -m pytest tests -m gpu -q -x 2>&1 | tail -4 | tee gpurun_out/${TAG}_tests.log
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/${TAG}_smoke.log

@@ -257,9 +257,10 @@ int tae_enc_backward_bf16(const TaeEncConfig* cfg, const void* packed_bwd, const
                           void* stash_d, float* dxin_all, float* grad_flat, int32_t B, void* workspace, size_t workspace_bytes,
                           void* stream);
 /* Weight gradients as tensor-core GEMMs over group images (one CTA per job):
- *   grad[m*s_m + (n0+n)*s_n + t*s_t] += sum_{group in [g0,g1)} sum_rows A[row, m] * B[row + t - taps/2, b_c0*8 + n]
- * for m < m_valid, n < n_valid, t < taps; bias_grad[m] += sum_rows A[row, m] (NULL to skip; needs 8*b_nc < n_cols).
- * a_img has 13 chunks per group, b_img has b_chunks; the job reads chunks [b_c0, b_c0 + b_nc) of B (b_nc <= 8).
+ *   grad[m*s_m + (n0+n)*s_n + t*s_t] += sum_{group in [g0,g1)} sum_rows A[row, m] * B[row + t - taps/2 + tap_shift, b_c0*8 + n]
+ * for m < m_valid, n < n_valid, t < taps (row offsets t - taps/2 + tap_shift must stay within [-2, 2]: a job may cover a SUBSET of a
+ * 5-tap kernel's taps, e.g. taps = 3, tap_shift = -1 for taps 0..2 and taps = 2, tap_shift = 2, grad advanced by 3*s_t for taps 3..4); bias_grad[m] += sum_rows A[row, m] (NULL to skip; needs 8*b_nc < n_cols).
+ * a_img has 13 chunks per group, b_img has b_chunks; the job reads chunks [b_c0, b_c0 + b_nc) of B (b_nc <= 13).
  * n_cols = UMMA N: a multiple of 16, 8*b_nc <= n_cols <= 8*(b_nc+1), taps * n_cols <= 512.
  * Conv layer: A = stash_g layer, B = its input image (stash_y of the layer below, or stash_x), taps = 5, grad = dW
  * (Cout, Cin, 5): s_m = 5*Cin, s_n = 5, s_t = 1.  Linear: A = last stash_y, B = stash_d, taps = 1, grad = dV (F, units):
@@ -276,7 +277,7 @@ typedef struct TaeWgradJob {
   int32_t m_valid, n_valid, n0;
   int32_t s_m, s_n, s_t;
   int32_t g0, g1;
-  int32_t reserved;
+  int32_t tap_shift;
 } TaeWgradJob;
 int tae_wgrad_bf16(const TaeWgradJob* jobs_host, int32_t n_jobs, const void* jobs_dev, void* workspace, size_t workspace_bytes,
                    void* stream);

@@ -35,14 +35,15 @@ def _jobs(units, n_layer, cin0, fouts, groups, splits=None):
 def test_wgrad_jobs_cover_every_parameter_exactly_once(units, n_layer, cin0, fouts, groups):
     jobs, offsets, gflat = _jobs(units, n_layer, cin0, fouts, groups)
     base = gflat.data_ptr()
-    seen = {}                      # (grad offset in floats, channel, group) -> count
+    seen = {}                      # (flat index of the gradient element of output channel 0, group) -> count
     bias_jobs = {}
     last_cost = None
     last_job = None
     for j in jobs:
         # constraints of tae_wgrad_bf16 (include/turboae_b200.h)
         assert j.n_cols % 16 == 0 and 8 * j.b_nc <= j.n_cols <= 8 * (j.b_nc + 1) and j.taps * j.n_cols <= 512
-        assert 1 <= j.b_nc <= 8 and 0 <= j.b_c0 and j.b_c0 + j.b_nc <= j.b_chunks and j.taps in (1, 5)
+        assert 1 <= j.b_nc <= 13 and 0 <= j.b_c0 and j.b_c0 + j.b_nc <= j.b_chunks and 1 <= j.taps <= 5
+        assert 0 <= 2 - j.taps // 2 + j.tap_shift and 2 - j.taps // 2 + j.tap_shift + j.taps - 1 <= 4      # row offsets within the halo
         assert 0 <= j.n_valid <= 8 * j.b_nc and 1 <= j.m_valid <= 104 and 0 <= j.g0 < j.g1 <= groups
         if j.bias_grad:
             assert 8 * j.b_nc < j.n_cols                                  # the spare column that carries the bias gradient exists
@@ -50,11 +51,12 @@ def test_wgrad_jobs_cover_every_parameter_exactly_once(units, n_layer, cin0, fou
                 bias_jobs[(j.bias_grad, g)] = bias_jobs.get((j.bias_grad, g), 0) + 1
         goff = (j.grad - base) // 4
         for n in range(j.n_valid):
-            for g in range(j.g0, j.g1):
-                k = (goff, j.n0 + n, g)
-                seen[k] = seen.get(k, 0) + 1
+            for t in range(j.taps):
+                for g in range(j.g0, j.g1):
+                    k = (goff + (j.n0 + n) * j.s_n + t * j.s_t, g)
+                    seen[k] = seen.get(k, 0) + 1
         cost = train_tc._job_cost_us(j.b_chunks, j.n_cols, j.taps) * (j.g1 - j.g0)
-        # longest first; the slabs of one layer (same A image, same group range) follow their longest member directly
+        # longest first; the jobs of one layer (same A image, same group range) follow their longest member directly
         follower = last_job is not None and (j.a_img, j.g0, j.g1) == (last_job.a_img, last_job.g0, last_job.g1)
         assert last_cost is None or cost <= last_cost + 1e-9
         if not follower:
@@ -64,12 +66,12 @@ def test_wgrad_jobs_cover_every_parameter_exactly_once(units, n_layer, cin0, fou
     for st, (layers, lin_w_off) in enumerate(offsets):
         for jl, (w_off, b_off) in enumerate(layers):
             cin = cin0 if jl == 0 else units
-            for c in range(cin):
+            for e in range(cin * 5):                                      # every (input channel, tap) of output channel 0
                 for g in (0, groups - 1):
-                    assert seen.get((w_off, c, g)) == 1, (st, jl, c, g)
+                    assert seen.get((w_off + e, g)) == 1, (st, jl, e, g)
             assert bias_jobs.get((base + 4 * b_off, 0)) == 1 and bias_jobs.get((base + 4 * b_off, groups - 1)) == 1
         for f in range(fouts[st]):
-            assert seen.get((lin_w_off, f, 0)) == 1
+            assert seen.get((lin_w_off + f * units, 0)) == 1
 
 
 def test_wgrad_jobs_forced_splits_partition_the_groups():
@@ -116,8 +118,8 @@ def test_cabi_geometry_and_validation_without_a_gpu():
     assert lib.tae_gru_packed_bytes(100, 300, 100) == 0                     # 39 input chunks > 26
     # malformed weight-gradient jobs are rejected before anything touches the device
     good = dict(a_img=8, b_img=8, grad=8, bias_grad=None, b_chunks=13, b_c0=0, b_nc=8, taps=5, n_cols=64, m_valid=100, n_valid=64, n0=0,
-                s_m=500, s_n=5, s_t=1, g0=0, g1=4, reserved=0)
-    for bad in (dict(n_cols=72), dict(b_nc=9), dict(b_c0=6), dict(taps=4), dict(n_cols=112), dict(m_valid=105), dict(g1=-1), dict(grad=None)):
+                s_m=500, s_n=5, s_t=1, g0=0, g1=4, tap_shift=0)
+    for bad in (dict(n_cols=72), dict(b_nc=9), dict(b_c0=6), dict(taps=6), dict(tap_shift=1), dict(taps=3, tap_shift=-2), dict(b_nc=14, n_cols=112), dict(n_cols=112), dict(m_valid=105), dict(g1=-1), dict(grad=None)):
         job = _lib.TaeWgradJob(**{**good, **bad})
         arr = (_lib.TaeWgradJob * 1)(job)
         assert lib.tae_wgrad_bf16(arr, 1, None, C.c_void_p(8), 4096, None) == -1, bad
@@ -258,7 +260,7 @@ def test_backward_split_and_group_range_job_lists_partition_the_batch():
     gflat = torch.zeros(off)
     mk = lambda rng: train_tc.wgrad_jobs(n_layer, units, cin0, fouts, groups, stash_y, stash_y, stash_y, stash_y, gflat, offsets, group_range=rng)
     whole, head, tail = mk(None), mk((0, 148)), mk((148, 200))
-    cover = lambda jobs: sorted((j.grad, j.n0, j.b_c0, g) for j in jobs for g in range(j.g0, j.g1))
+    cover = lambda jobs: sorted((j.grad, j.n0, j.b_c0, j.taps, g) for j in jobs for g in range(j.g0, j.g1))
     assert cover(head + tail) == cover(whole) and len(set(cover(whole))) == len(cover(whole))
     assert all(j.g1 <= 148 for j in head) and all(j.g0 >= 148 for j in tail) and head and tail
     assert mk((5, 5)) == []

@@ -28,7 +28,7 @@ class TaeEncConfig(C.Structure):
 class TaeWgradJob(C.Structure):
     _fields_ = [("a_img", C.c_void_p), ("b_img", C.c_void_p), ("grad", C.c_void_p), ("bias_grad", C.c_void_p)] + \
                [(n, C.c_int32) for n in ("b_chunks", "b_c0", "b_nc", "taps", "n_cols", "m_valid", "n_valid", "n0",
-                                         "s_m", "s_n", "s_t", "g0", "g1", "reserved")]
+                                         "s_m", "s_n", "s_t", "g0", "g1", "tap_shift")]
 
 
 IMG_CHUNK_BYTES = 8256

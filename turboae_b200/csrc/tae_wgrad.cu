@@ -12,8 +12,11 @@
 // the images are consumed exactly as they were written, no transpose.  Tap t of the convolution is the B operand's start
 // address moved by 16*t bytes; the zero separator rows make the shifted products vanish across codeword borders.
 //     D_t[m = o][n = c]  +=  A[rows, o]^T  B[rows + t - 2, c]        (M = 128, N = 16..64, K = 16 rows per MMA)
-// One CTA = one job (a layer, a slab of input channels, a range of groups): accumulators of all taps stay in TMEM for
-// the whole range (5 x 64 columns), then go out as fp32 atomics.  Half groups stream through a 2-stage bulk-copy pipeline
+// One CTA = one job (a layer, a slab of input channels or -- for layers wider than 64 channels -- a SUBSET OF THE TAPS over all
+// input channels, a range of groups): accumulators of the job's taps stay in TMEM for the whole range (5 x 64 or 3 x 112
+// columns), then go out as fp32 atomics.  The MMAs are bound by operand fetch through the 128 B/clk shared-memory port: an
+// M128 x N64 MMA reads 6 KB for 32 tensor cycles (port: 48), an M128 x N112 one 7.5 KB for 56 (port: 59), which is why a
+// 100-channel layer runs as taps {0,1,2} and {3,4} at N = 112 rather than as channel slabs 64 + 36 at all five taps.  Half groups stream through a 2-stage bulk-copy pipeline
 // (the copies of half i+1 overlap the 80 MMAs of half i).  A constant all-ones chunk appended to B yields db in
 // a spare column.
 #include <cuda_bf16.h>
@@ -25,12 +28,12 @@ namespace tae {
 
 namespace {
 
-constexpr uint32_t W_ROWS = 516, W_CHUNK_B = W_ROWS * 16, W_A_CHUNKS = 13, W_B_CHUNKS_MAX = 8;
+constexpr uint32_t W_ROWS = 516, W_CHUNK_B = W_ROWS * 16, W_A_CHUNKS = 13, W_B_CHUNKS_MAX = 13;
 // One pipeline stage holds HALF a group: a 260-row window (256 reduction rows + 2 halo rows each side for the taps) of the
-// 13 A chunks and of up to 8 B chunks, followed by the constant ones chunk; chunks are W_WIN_B apart (= SBO).  The three
+// 13 A chunks and of up to 13 B chunks, followed by the constant ones chunk; chunks are W_WIN_B apart (= SBO).  The three
 // A chunks that M = 128 reads past channel 103 fall into the stage's own B region (their output rows are never stored).
 constexpr uint32_t W_WIN_ROWS = 260, W_WIN_B = W_WIN_ROWS * 16;                 // 4160
-constexpr uint32_t W_STAGE_B = (W_A_CHUNKS + W_B_CHUNKS_MAX + 1) * W_WIN_B;     // 91 520
+constexpr uint32_t W_STAGE_B = (W_A_CHUNKS + W_B_CHUNKS_MAX + 1) * W_WIN_B;     // 112 320
 constexpr uint32_t W_BAR_OFF = 2 * W_STAGE_B;
 constexpr uint32_t W_SMEM = W_BAR_OFF + 64;
 constexpr int W_KSTEPS = 16;                                                   // 256 rows / 16 per half
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(128, 1) wgrad_kernel(const TaeWgradJob* __rest
         const uint32_t stage = sbase + (uint32_t)st * W_STAGE_B;
         const uint64_t a0 = mn_desc(stage + 2 * 16, 128u, W_WIN_B);
         for (int t = 0; t < J.taps; ++t) {
-          const uint64_t b0 = mn_desc(stage + W_A_CHUNKS * W_WIN_B + (uint32_t)(2 + t - half) * 16, 128u, W_WIN_B);
+          const uint64_t b0 = mn_desc(stage + W_A_CHUNKS * W_WIN_B + (uint32_t)(2 + t - half + J.tap_shift) * 16, 128u, W_WIN_B);
           const uint32_t d = tmem_base + (uint32_t)(t * J.n_cols);
 #pragma unroll
           for (int ks = 0; ks < W_KSTEPS; ++ks)
@@ -150,7 +153,7 @@ int launch_wgrad(const TaeWgradJob* jobs_host, int n_jobs, const void* jobs_dev,
   for (int i = 0; i < n_jobs; ++i) {
     const TaeWgradJob& J = jobs_host[i];
     if (!J.a_img || !J.b_img || !J.grad || J.b_nc < 1 || J.b_nc > (int)W_B_CHUNKS_MAX || J.b_c0 < 0 || J.b_c0 + J.b_nc > J.b_chunks ||
-        (J.taps != 1 && J.taps != 3 && J.taps != 5) || J.n_cols % 16 || J.n_cols < 16 || J.n_cols > 8 * (J.b_nc + 1) || J.n_cols < 8 * J.b_nc || J.taps * J.n_cols > 512 ||
+        J.taps < 1 || J.taps > 5 || 2 - J.taps / 2 + J.tap_shift < 0 || 2 - J.taps / 2 + J.tap_shift + J.taps - 1 > 4 || J.n_cols % 16 || J.n_cols < 16 || J.n_cols > 8 * (J.b_nc + 1) || J.n_cols < 8 * J.b_nc || J.taps * J.n_cols > 512 ||
         J.m_valid < 1 || J.m_valid > 104 || J.n_valid < 0 || J.n_valid > 8 * J.b_nc || J.g1 < J.g0) {
       set_error("tae_wgrad_bf16: job %d is malformed", i);
       return TAE_EINVAL;

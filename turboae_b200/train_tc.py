@@ -134,8 +134,15 @@ def _flat_grad(buf, flat, params):
 def _job_cost_us(b_chunks, n_cols, taps):
     """Measured cost of one group in one job (B200, microseconds): the MMAs are operand-fetch bound."""
     if b_chunks > 1:
+        if n_cols > 64:                      # tap-split job over all input channels (N = 112): ~60 cycles per MMA
+            return 1.1 * taps
         return 5.0 if n_cols > 48 else 4.4
     return 3.9 if taps > 1 else 1.1
+
+
+#: layers wider than 64 input channels: jobs split the TAPS ({0,1,2} and {3,4}) over all channels instead of the channels (64 + rest)
+#: over all taps -- fewer operand bytes per tensor-core cycle (tae_wgrad.cu); TURBOAE_B200_WGRAD_TAPSPLIT=0 keeps the channel slabs
+WGRAD_TAP_SPLIT = os.environ.get("TURBOAE_B200_WGRAD_TAPSPLIT", "1") != "0"
 
 
 def wgrad_jobs(n_layer, units, cin0, fouts, groups, stash_y, stash_x, stash_g, stash_d, gflat, offsets, splits=None, sm_count=None,
@@ -167,6 +174,15 @@ def wgrad_jobs(n_layer, units, cin0, fouts, groups, stash_y, stash_x, stash_g, s
             a_img, b_img = g + j * layer_img, y + (j - 1) * layer_img
             c0 = 0
             family[0] += 1
+            nc_all = _odd_chunks(units, 0)
+            if WGRAD_TAP_SPLIT and units > 64 and nc_all <= 13:
+                # all input channels at once (N = 8 * nc_all + 8, the spare column carries the bias gradient), taps 0..2 and 3..4:
+                # (fields: ..., taps, n_cols, m_valid, n_valid, n0, s_m, s_n, s_t) + tap_shift as the last job field
+                add(a_img, b_img, gp + 4 * w_off, gp + 4 * b_off, _lib.IMG_CHUNKS, 0, nc_all, 3, 8 * nc_all + 8, units, units, 0,
+                    5 * units, 5, 1, -1)
+                add(a_img, b_img, gp + 4 * (w_off + 3), None, _lib.IMG_CHUNKS, 0, nc_all, 2, 8 * nc_all + 8, units, units, 0,
+                    5 * units, 5, 1, 2)
+                continue
             while c0 * 8 < units:
                 rest = units - c0 * 8
                 if rest > 64:                        # a full 8-chunk slab, no spare column
@@ -203,7 +219,7 @@ def wgrad_jobs(n_layer, units, cin0, fouts, groups, stash_y, stash_x, stash_g, s
         for sp in range(n_split):
             g0, g1 = g_lo + n_g * sp // n_split, g_lo + n_g * (sp + 1) // n_split
             if g1 > g0:
-                jobs.append(((-fam_cost[fam] * (g1 - g0) / max(n_g, 1), fam, sp, i), _lib.TaeWgradJob(*f, g0, g1, 0)))
+                jobs.append(((-fam_cost[fam] * (g1 - g0) / max(n_g, 1), fam, sp, i), _lib.TaeWgradJob(*f[:15], g0, g1, f[15] if len(f) > 15 else 0)))
     jobs.sort(key=lambda t: t[0])
     return [j for _, j in jobs]
 

@@ -16,10 +16,12 @@
 // input channels, a range of groups): accumulators of the job's taps stay in TMEM for the whole range (5 x 64 or 3 x 112
 // columns), then go out as fp32 atomics.  The MMAs are bound by operand fetch through the 128 B/clk shared-memory port: an
 // M128 x N64 MMA reads 6 KB for 32 tensor cycles (port: 48), an M128 x N112 one 7.5 KB for 56 (port: 59), which is why a
-// 100-channel layer runs as taps {0,1,2} and {3,4} at N = 112 rather than as channel slabs 64 + 36 at all five taps.  Half groups stream through a 2-stage bulk-copy pipeline
-// (the copies of half i+1 overlap the 80 MMAs of half i).  A constant all-ones chunk appended to B yields db in
+// 100-channel layer runs as taps {0,1,2} and {3,4} at N = 112 rather than as channel slabs 64 + 36 at all five taps.  Half groups stream through a 2-stage bulk-copy
+// pipeline (the copies of half i+1 overlap the MMAs of half i).  A constant all-ones chunk appended to B yields db in
 // a spare column.
 #include <cuda_bf16.h>
+
+#include <cstdio>
 
 #include "tae_common.cuh"
 #include "tae_umma.cuh"
@@ -29,14 +31,24 @@ namespace tae {
 namespace {
 
 constexpr uint32_t W_ROWS = 516, W_CHUNK_B = W_ROWS * 16, W_A_CHUNKS = 13, W_B_CHUNKS_MAX = 13;
-// One pipeline stage holds HALF a group: a 260-row window (256 reduction rows + 2 halo rows each side for the taps) of the
+// One pipeline stage holds HALF (or a quarter) of a group: a 260-row window (256 reduction rows + 2 halo rows each side for the taps) of the
 // 13 A chunks and of up to 13 B chunks, followed by the constant ones chunk; chunks are W_WIN_B apart (= SBO).  The three
 // A chunks that M = 128 reads past channel 103 fall into the stage's own B region (their output rows are never stored).
-constexpr uint32_t W_WIN_ROWS = 260, W_WIN_B = W_WIN_ROWS * 16;                 // 4160
-constexpr uint32_t W_STAGE_B = (W_A_CHUNKS + W_B_CHUNKS_MAX + 1) * W_WIN_B;     // 112 320
-constexpr uint32_t W_BAR_OFF = 2 * W_STAGE_B;
-constexpr uint32_t W_SMEM = W_BAR_OFF + 64;
-constexpr int W_KSTEPS = 16;                                                   // 256 rows / 16 per half
+#ifndef TAE_WGRAD_STAGES
+#define TAE_WGRAD_STAGES 2
+#endif
+// 2 stages of half a group (shipped) or 4 stages of a quarter group (-DTAE_WGRAD_STAGES=4: three windows = 168 KB in flight instead
+// of one = 112 KB; measured SLOWER, 3.39 vs 3.16 ms per training step: the stage loads are not what limits the kernel, and twice as
+// many hand-overs cost more than the deeper pipeline buys).
+constexpr int W_STAGES = TAE_WGRAD_STAGES;                                      // 2 or 4 windows per group, one stage each
+constexpr uint32_t W_PART_ROWS = 512 / W_STAGES;                                // reduction rows of one window
+constexpr uint32_t W_WIN_ROWS = W_PART_ROWS + 4, W_WIN_B = W_WIN_ROWS * 16;     // + 2 halo rows each side: 260 rows = 4160 B (132 rows = 2112 B)
+constexpr uint32_t W_STAGE_B = (W_A_CHUNKS + W_B_CHUNKS_MAX + 1) * W_WIN_B;     // 112 320 (57 024)
+constexpr uint32_t W_BAR_OFF = W_STAGES * W_STAGE_B;
+constexpr uint32_t W_SMEM = W_BAR_OFF + 128;                                    // full[4] empty[4] final tmem-ptr
+constexpr int W_KSTEPS = W_PART_ROWS / 16;
+static_assert(W_STAGES == 2 || W_STAGES == 4, "2 or 4 stages");
+static_assert(W_SMEM <= 232448, "shared memory of a CTA");
 
 __device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) |
@@ -49,21 +61,21 @@ __global__ void __launch_bounds__(128, 1) wgrad_kernel(const TaeWgradJob* __rest
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto bar_full = [&](int s) { return sbase + W_BAR_OFF + 8u * (uint32_t)s; };
-  auto bar_empty = [&](int s) { return sbase + W_BAR_OFF + 16u + 8u * (uint32_t)s; };
-  const uint32_t bar_final = sbase + W_BAR_OFF + 32, tptr = sbase + W_BAR_OFF + 40;
-  const int n_it = 2 * (J.g1 - J.g0);                   // half groups
+  auto bar_empty = [&](int s) { return sbase + W_BAR_OFF + 32u + 8u * (uint32_t)s; };
+  const uint32_t bar_final = sbase + W_BAR_OFF + 64, tptr = sbase + W_BAR_OFF + 72;
+  const int n_it = W_STAGES * (J.g1 - J.g0);            // windows (half or quarter groups)
 
   // B regions of both stages: zeros, then the ones chunk right behind the slab (channel 0 of every row = 1.0)
-  for (int st = 0; st < 2; ++st) {
+  for (int st = 0; st < W_STAGES; ++st) {
     const uint32_t b_off = sbase + (uint32_t)st * W_STAGE_B + W_A_CHUNKS * W_WIN_B;
     for (uint32_t i = threadIdx.x * 16; i < (W_B_CHUNKS_MAX + 1) * W_WIN_B; i += blockDim.x * 16) st_shared_v4(b_off + i, 0u, 0u, 0u, 0u);
   }
   __syncthreads();
-  for (int st = 0; st < 2; ++st)
+  for (int st = 0; st < W_STAGES; ++st)
     for (uint32_t r = threadIdx.x; r < W_WIN_ROWS; r += blockDim.x)
       st_shared_v4(sbase + (uint32_t)st * W_STAGE_B + (W_A_CHUNKS + (uint32_t)J.b_nc) * W_WIN_B + r * 16, 0x00003F80u, 0u, 0u, 0u);
   if (threadIdx.x == 0) {
-    for (int st = 0; st < 2; ++st) { mbar_init(bar_full(st), 1); mbar_init(bar_empty(st), 1); }
+    for (int st = 0; st < W_STAGES; ++st) { mbar_init(bar_full(st), 1); mbar_init(bar_empty(st), 1); }
     mbar_init(bar_final, 1);
     fence_barrier_init();
   }
@@ -80,10 +92,10 @@ __global__ void __launch_bounds__(128, 1) wgrad_kernel(const TaeWgradJob* __rest
       // producer: half h of group g = rows [256 h, 256 h + 260) of every chunk
       const uint32_t bytes = (W_A_CHUNKS + (uint32_t)J.b_nc) * W_WIN_B;
       for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1;
-        const size_t g = (size_t)(J.g0 + (it >> 1));
-        const uint32_t row_off = (uint32_t)(it & 1) * 256u * 16u;
-        if (it >= 2) mbar_wait(bar_empty(st), (uint32_t)((it >> 1) - 1) & 1u, err, 21);    // the MMAs that read this stage are done
+        const int st = it % W_STAGES;
+        const size_t g = (size_t)(J.g0 + it / W_STAGES);
+        const uint32_t row_off = (uint32_t)st * W_PART_ROWS * 16u;
+        if (it >= W_STAGES) mbar_wait(bar_empty(st), (uint32_t)(it / W_STAGES - 1) & 1u, err, 21);    // the MMAs that read this stage are done
         mbar_arrive_expect_tx(bar_full(st), bytes);
         const uint32_t dst = sbase + (uint32_t)st * W_STAGE_B;
         const uint8_t* a = reinterpret_cast<const uint8_t*>(J.a_img) + g * W_A_CHUNKS * W_CHUNK_B + row_off;
@@ -97,9 +109,19 @@ __global__ void __launch_bounds__(128, 1) wgrad_kernel(const TaeWgradJob* __rest
     // MMA issuer.  Both operands MN-major: LBO = 128 B between 8-row blocks of the reduction, SBO = one chunk window.
     const uint32_t idesc = make_idesc(128, J.n_cols) | (1u << 15) | (1u << 16);
     const int half = J.taps / 2;
+#ifdef TAE_WGRAD_PROBE
+    long long t_wait = 0, t_first = 0;
+    const long long t_begin = clock64();
+#endif
     for (int it = 0; it < n_it; ++it) {
-      const int st = it & 1;
-      mbar_wait(bar_full(st), (uint32_t)(it >> 1) & 1u, err, 22);
+      const int st = it % W_STAGES;
+#ifdef TAE_WGRAD_PROBE
+      const long long tw = clock64();
+#endif
+      mbar_wait(bar_full(st), (uint32_t)(it / W_STAGES) & 1u, err, 22);
+#ifdef TAE_WGRAD_PROBE
+      if (it == 0) t_first = clock64() - tw; else t_wait += clock64() - tw;
+#endif
       tc_fence_after();
       if (elect_one()) {
         const uint32_t stage = sbase + (uint32_t)st * W_STAGE_B;
@@ -116,6 +138,12 @@ __global__ void __launch_bounds__(128, 1) wgrad_kernel(const TaeWgradJob* __rest
       }
       __syncwarp();
     }
+#ifdef TAE_WGRAD_PROBE
+    // (issue-side view: the last window's MMAs are still running when the loop ends)
+    if (lane == 0 && (blockIdx.x % 37) == 0)
+      printf("wgrad job %4d taps %d N %3d windows %3d: first load %6lld  waits for loads %8lld  loop %8lld cycles (%.0f per MMA issued)\n", (int)blockIdx.x, J.taps,
+             J.n_cols, n_it, t_first, t_wait, clock64() - t_begin, (double)(clock64() - t_begin) / ((double)n_it * J.taps * W_KSTEPS));
+#endif
   }
   __syncwarp();
   // ---- drain: every thread owns TMEM lane m = output row -------------------------------------------------------------

@@ -134,10 +134,10 @@ def _flat_grad(buf, flat, params):
 def _job_cost_us(b_chunks, n_cols, taps):
     """Measured cost of one group in one job (B200, microseconds): the MMAs are operand-fetch bound."""
     if b_chunks > 1:
-        if n_cols > 64:                      # tap-split job over all input channels (N = 112): ~60 cycles per MMA
-            return 1.1 * taps
+        if n_cols > 64:                      # tap-split job over all input channels (N = 112): ~69 cycles per MMA; the 2-tap job waits
+            return 3.2 + 0.5 * (taps - 2)    # for its loads a fifth of the time (profiles/r02_wgrad_probe.log: 3.7 / 3.2 us per group)
         return 5.0 if n_cols > 48 else 4.4
-    return 3.9 if taps > 1 else 1.1
+    return 3.9 if taps > 1 else 1.9
 
 
 #: layers wider than 64 input channels: jobs split the TAPS ({0,1,2} and {3,4}) over all channels instead of the channels (64 + rest)

@@ -150,22 +150,61 @@ __global__ void __launch_bounds__(128, 1) wgrad_kernel(const TaeWgradJob* __rest
   if (n_it > 0) {
     mbar_wait(bar_final, 0u, err, 23);
     tc_fence_after();
+#ifdef TAE_WGRAD_PROBE
+    const long long t_drain = clock64();
+#endif
     const int m = 32 * warp + lane;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * warp) << 16);
-    for (int t = 0; t < J.taps; ++t)
-      for (int cb = 0; cb < J.n_cols / 16; ++cb) {
-        uint32_t r[16];
-        tmem_ld16(lane_addr + (uint32_t)(t * J.n_cols + cb * 16), r);
-        tmem_ld_wait();
-        if (m < J.m_valid) {
+    const uint32_t s_row = (uint32_t)(J.taps * J.n_cols) | 1u;
+    if (J.s_m == 1 || 512u * s_row > W_BAR_OFF) {
+      // Linear (dV is (F, units): consecutive output rows m are consecutive floats): straight from the registers, lanes across m
+      // (also the fallback for a job whose transposed tile would not fit the stage memory)
+      for (int t = 0; t < J.taps; ++t)
+        for (int cb = 0; cb < J.n_cols / 16; ++cb) {
+          uint32_t r[16];
+          tmem_ld16(lane_addr + (uint32_t)(t * J.n_cols + cb * 16), r);
+          tmem_ld_wait();
+          if (m < J.m_valid) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = cb * 16 + j;
-            if (n < J.n_valid) atomicAdd(J.grad + (size_t)m * J.s_m + (size_t)(J.n0 + n) * J.s_n + (size_t)t * J.s_t, __uint_as_float(r[j]));
-            else if (J.bias_grad && t == 0 && n == 8 * J.b_nc) atomicAdd(J.bias_grad + m, __uint_as_float(r[j]));
+            for (int j = 0; j < 16; ++j) {
+              const int n = cb * 16 + j;
+              if (n < J.n_valid) atomicAdd(J.grad + (size_t)m * J.s_m + (size_t)(J.n0 + n) * J.s_n + (size_t)t * J.s_t, __uint_as_float(r[j]));
+              else if (J.bias_grad && t == 0 && n == 8 * J.b_nc) atomicAdd(J.bias_grad + m, __uint_as_float(r[j]));
+            }
           }
         }
+    } else {
+      // Conv (dW is (Cout, Cin, taps): one output row m owns Cin * taps CONTIGUOUS floats, this job a (tap subset x channel range) of
+      // them).  A thread holds one row in TMEM, so atomics issued from the registers hit 32 different rows per warp instruction
+      // (32 sectors; measured: the drain took as long as the MMA loop).  Transpose through the now idle stage memory instead:
+      // S[m][t * n_cols + n] (row stride odd: conflict-free both ways), then each warp walks whole rows with its lanes across
+      // (n, t), t fastest -- runs of `taps` adjacent floats every s_n: ~7 sectors per warp instruction.
+      for (int t = 0; t < J.taps; ++t)
+        for (int cb = 0; cb < J.n_cols / 16; ++cb) {
+          uint32_t r[16];
+          tmem_ld16(lane_addr + (uint32_t)(t * J.n_cols + cb * 16), r);
+          tmem_ld_wait();
+          const uint32_t dst = sbase + 4u * ((uint32_t)m * s_row + (uint32_t)(t * J.n_cols + cb * 16));
+#pragma unroll
+          for (int j = 0; j < 16; ++j) st_shared_f32(dst + 4u * (uint32_t)j, __uint_as_float(r[j]));
+        }
+      __syncthreads();
+      const int items = J.n_valid * J.taps;
+      for (int mm = warp; mm < J.m_valid; mm += 4) {
+        const uint32_t src = sbase + 4u * (uint32_t)mm * s_row;
+        float* g_row = J.grad + (size_t)mm * J.s_m + (size_t)J.n0 * J.s_n;
+        for (int idx = lane; idx < items; idx += 32) {
+          const int n = idx / J.taps, t = idx - n * J.taps;
+          atomicAdd(g_row + (size_t)n * J.s_n + (size_t)t * J.s_t, ld_shared_f32(src + 4u * (uint32_t)(t * J.n_cols + n)));
+        }
+        if (J.bias_grad && lane == 0) atomicAdd(J.bias_grad + mm, ld_shared_f32(src + 4u * (uint32_t)(8 * J.b_nc)));
       }
+    }
+#ifdef TAE_WGRAD_PROBE
+    __syncthreads();
+    if (threadIdx.x == 0 && (blockIdx.x % 37) == 0)
+      printf("wgrad job %4d taps %d N %3d: drain %8lld cycles\n", (int)blockIdx.x, J.taps, J.n_cols, clock64() - t_drain);
+#endif
   }
   tc_fence_before();
   __syncthreads();

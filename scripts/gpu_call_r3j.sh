@@ -13,3 +13,6 @@ print({k: v for k, v in d.get('secondary', {}).items() if 'train' in k})
 for b in 23 745; do
   echo "== memcheck, training step B=$b"; timeout 900 compute-sanitizer --tool memcheck python scripts/train_small.py $b 2>&1 | grep -v "^$" | tail -4 | tee gpurun_out/${TAG}_memcheck_train_b$b.log
 done
+if [ -n "$2" ]; then
+  echo "== ncu wgrad"; bash scripts/gpu_call_r3o.sh 2>&1 | tail -10 | tee gpurun_out/${TAG}_wgrad_ncu.txt
+fi

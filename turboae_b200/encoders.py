@@ -202,9 +202,10 @@ class ENC_interCNN(OrderedParameters, ENCBase):
         return x_tx
 
     def _forward_train(self, u):
-        """Autograd path (reference encoders.py:362-375 under trainer.py:74): conv stacks through this package's forward /
-        backward kernels, torch glue for the 100->1 Linear, ELU, concat and the power constraint (whose statistics and
-        gradient sums are all-reduced when the batch is sharded across ranks)."""
+        """Autograd path (reference encoders.py:362-375 under trainer.py:74).  'bf16': the three branches incl. Linear + ELU in one
+        fused forward / backward on the tensor cores (train_tc.EncoderTrainFn); 'fp32' (and the dense variant): the conv stacks
+        through the fp32 kernels with torch glue for the 100->1 Linear, ELU and concat.  The power constraint is shard.PowerNorm
+        (this package's kernels on the device; statistics and gradient sums all-reduced when the batch is sharded across ranks)."""
         own_stats = None                      # (sum, sum of squares, count) of this rank's x_tx when a kernel already delivered them
         if self.train_precision == "bf16":
             from . import train_tc

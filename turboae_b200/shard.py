@@ -59,8 +59,9 @@ class PowerNorm(torch.autograd.Function):
 
     On a CUDA device both directions are this package's kernels (``tae_power_stats_f32`` unless the encoder kernel already
     delivered ``own_stats``, ``tae_power_norm_f32``, ``tae_power_norm_bwd_sums_f32``, ``tae_power_norm_bwd_f32``): three launches
-    forward and backward together instead of ~25 small torch operators.  The torch spelling below serves the host-side tests of
-    the collective logic (gloo, CPU tensors)."""
+    forward and backward together instead of ~25 small torch operators.  ``own_stats`` (3 device doubles: this rank's sum, sum of
+    squares, count) is merged across the ranks IN PLACE and kept for the backward: pass a tensor nobody else reads afterwards.  The
+    torch spelling below serves the host-side tests of the collective logic (gloo, CPU tensors)."""
 
     @staticmethod
     def forward(ctx, x, group, own_stats=None):
